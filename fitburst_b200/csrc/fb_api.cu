@@ -1,0 +1,598 @@
+// C ABI of fitburst_b200 (see include/fitburst_b200.h). Host-side plan management and the
+// launch logic for the kernels in fb_kernels.cuh / fb_hessian.cuh / fb_batched.cuh.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <new>
+#include <vector>
+
+#include "fb_kernels.cuh"
+#include "fb_trf.h"
+
+using namespace fb;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e_ = (expr);                                                             \
+    if (e_ != cudaSuccess)                                                               \
+      return fail(FB_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),   \
+                  __FILE__, __LINE__);                                                   \
+  } while (0)
+
+struct fb_plan_s {
+  fb_plan_desc desc;
+  PlanConst pc;
+  double* d_freqs = nullptr;
+  double* d_subfreqs = nullptr;
+  double* d_params = nullptr;
+  double* d_weights = nullptr;
+  double* d_chan_sumsq = nullptr;
+  double* d_partials = nullptr;
+  size_t partials_cap = 0;
+  double* d_gram = nullptr;  // (FB_MAX_FREE+1)^2
+  double* h_gram = nullptr;  // pinned
+  int* d_chan_list = nullptr;
+  int num_good = 0;
+  bool have_weights = false;
+  int* d_err = nullptr;
+  uint8_t* d_good = nullptr;
+  double h_params[FB_NUM_PARAMETERS * FB_MAX_COMPONENTS];
+  int free_mask[9];
+  int col_of[9];
+  int n_free = 0;
+  int sm_count = 148;
+  int64_t launches = 0;
+  std::vector<double> h_weights;
+};
+
+extern "C" const char* fb_last_error(void) { return g_err; }
+extern "C" int fb_version(void) { return 100; }
+
+static void layout_free(fb_plan_s* p) {
+  int col = 0;
+  for (int k = 0; k < 9; ++k) {
+    if (p->free_mask[k]) {
+      p->col_of[k] = col;
+      col += is_fit_global(k) ? 1 : p->desc.num_components;
+    } else {
+      p->col_of[k] = -1;
+    }
+  }
+  p->n_free = col;
+}
+
+extern "C" int fb_plan_create(const fb_plan_desc* desc, const double* freqs_host,
+                              const double* times_host, fb_plan_t* plan_out) {
+  if (!desc || !freqs_host || !times_host || !plan_out) return fail(FB_ERR_INVALID, "null argument");
+  if (desc->num_freq < 2 || desc->num_time < 2)
+    return fail(FB_ERR_INVALID, "need at least two channels and two samples (res_freq/res_time come "
+                                "from the first two labels)");
+  if (desc->num_components < 1 || desc->num_components > FB_MAX_COMPONENTS)
+    return fail(FB_ERR_INVALID, "num_components must be in 1..%d", FB_MAX_COMPONENTS);
+  if (desc->factor_freq_upsample < 1 || desc->factor_time_upsample < 1)
+    return fail(FB_ERR_INVALID, "up-sampling factors must be >= 1");
+  if ((long long)desc->num_time * desc->factor_time_upsample > 2000000000LL)
+    return fail(FB_ERR_INVALID, "num_time * factor_time_upsample overflows int32");
+  int dev_count = 0;
+  if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
+    return fail(FB_ERR_CUDA, "no CUDA device: fitburst_b200 has no CPU fallback");
+  fb_plan_s* p = new (std::nothrow) fb_plan_s();
+  if (!p) return fail(FB_ERR_NOMEM, "out of host memory");
+  p->desc = *desc;
+  const int nf = desc->num_freq, nt = desc->num_time, kf = desc->factor_freq_upsample;
+  PlanConst& pc = p->pc;
+  pc.num_freq = nf;
+  pc.num_time = nt;
+  pc.num_comp = desc->num_components;
+  pc.kf = kf;
+  pc.kt = desc->factor_time_upsample;
+  pc.is_folded = desc->is_folded;
+  pc.scintillation = desc->scintillation;
+  pc.normalize_pbf = desc->normalize_pbf;
+  pc.ntk = nt * pc.kt;
+  pc.dm_incoherent = desc->dm_incoherent;
+  pc.dm_const = desc->dispersion_constant;
+  pc.res_freq = fabs(freqs_host[1] - freqs_host[0]);  // analysis/model.py:87
+  pc.res_time = fabs(times_host[1] - times_host[0]);  // analysis/model.py:88
+  pc.time_first = times_host[0];
+  pc.time_last = times_host[nt - 1];
+  // sub-frequency labels, routines/manipulate.py:99-105 with np.linspace semantics:
+  // arange(K) * step + lo (two roundings), last element forced to hi when K > 1.
+  std::vector<double> sub((size_t)nf * kf);
+  const double diff_new = pc.res_freq / (double)kf;
+  for (int i = 0; i < nf; ++i) {
+    volatile double lo = freqs_host[i] - (pc.res_freq / 2);
+    lo = lo + (diff_new / 2);
+    volatile double hi = freqs_host[i] + (pc.res_freq / 2);
+    hi = hi - (diff_new / 2);
+    const double step = kf > 1 ? (hi - lo) / (double)(kf - 1) : 0.0;
+    for (int a = 0; a < kf; ++a) {
+      volatile double v = (double)a * step;
+      v = v + lo;
+      sub[(size_t)i * kf + a] = (a == kf - 1 && kf > 1) ? (double)hi : (double)v;
+    }
+  }
+  cudaDeviceProp prop;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (cudaGetDeviceProperties(&prop, dev) == cudaSuccess) p->sm_count = prop.multiProcessorCount;
+  const size_t gsz = sizeof(double) * (FB_MAX_FREE + 1) * (FB_MAX_FREE + 1);
+  cudaError_t e = cudaSuccess;
+  auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  chk(cudaMalloc(&p->d_freqs, sizeof(double) * nf));
+  chk(cudaMalloc(&p->d_subfreqs, sizeof(double) * nf * kf));
+  chk(cudaMalloc(&p->d_params, sizeof(double) * FB_NUM_PARAMETERS * FB_MAX_COMPONENTS));
+  chk(cudaMalloc(&p->d_weights, sizeof(double) * nf));
+  chk(cudaMalloc(&p->d_chan_sumsq, sizeof(double) * nf));
+  chk(cudaMalloc(&p->d_chan_list, sizeof(int) * nf));
+  chk(cudaMalloc(&p->d_good, nf));
+  chk(cudaMalloc(&p->d_err, sizeof(int)));
+  chk(cudaMalloc(&p->d_gram, gsz));
+  chk(cudaMallocHost(&p->h_gram, gsz));
+  if (e == cudaSuccess) chk(cudaMemcpy(p->d_freqs, freqs_host, sizeof(double) * nf, cudaMemcpyHostToDevice));
+  if (e == cudaSuccess) chk(cudaMemcpy(p->d_subfreqs, sub.data(), sizeof(double) * nf * kf, cudaMemcpyHostToDevice));
+  if (e == cudaSuccess) chk(cudaMemset(p->d_err, 0, sizeof(int)));
+  if (e != cudaSuccess) {
+    fb_plan_destroy(p);
+    return fail(FB_ERR_CUDA, "plan allocation failed: %s", cudaGetErrorString(e));
+  }
+  pc.freqs = p->d_freqs;
+  pc.subfreqs = p->d_subfreqs;
+  memset(p->h_params, 0, sizeof(p->h_params));
+  for (int k = 0; k < 9; ++k) p->free_mask[k] = 1;
+  layout_free(p);
+  *plan_out = p;
+  return FB_OK;
+}
+
+extern "C" int fb_plan_destroy(fb_plan_t p) {
+  if (!p) return FB_OK;
+  cudaFree(p->d_freqs);
+  cudaFree(p->d_subfreqs);
+  cudaFree(p->d_params);
+  cudaFree(p->d_weights);
+  cudaFree(p->d_chan_sumsq);
+  cudaFree(p->d_chan_list);
+  cudaFree(p->d_good);
+  cudaFree(p->d_err);
+  cudaFree(p->d_gram);
+  cudaFree(p->d_partials);
+  if (p->h_gram) cudaFreeHost(p->h_gram);
+  delete p;
+  return FB_OK;
+}
+
+extern "C" int fb_set_parameters(fb_plan_t p, const double* params_host, void* stream) {
+  if (!p || !params_host) return fail(FB_ERR_INVALID, "null argument");
+  const size_t n = (size_t)FB_NUM_PARAMETERS * p->desc.num_components;
+  memcpy(p->h_params, params_host, sizeof(double) * n);
+  CUDA_TRY(cudaMemcpyAsync(p->d_params, p->h_params, sizeof(double) * n, cudaMemcpyHostToDevice,
+                           (cudaStream_t)stream));
+  return FB_OK;
+}
+
+extern "C" int fb_get_parameters(fb_plan_t p, double* params_host, void* stream) {
+  if (!p || !params_host) return fail(FB_ERR_INVALID, "null argument");
+  const size_t n = (size_t)FB_NUM_PARAMETERS * p->desc.num_components;
+  CUDA_TRY(cudaMemcpyAsync(params_host, p->d_params, sizeof(double) * n, cudaMemcpyDeviceToHost,
+                           (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  memcpy(p->h_params, params_host, sizeof(double) * n);
+  return FB_OK;
+}
+
+static EvalArgs base_args(fb_plan_s* p) {
+  EvalArgs A;
+  memset(&A, 0, sizeof(A));
+  A.pc = p->pc;
+  A.params = p->d_params;
+  A.chan_list = nullptr;
+  A.num_chan = p->desc.num_freq;
+  A.n_free = p->n_free;
+  for (int k = 0; k < 9; ++k) A.col_of[k] = p->col_of[k];
+  A.err_flag = p->d_err;
+  return A;
+}
+
+template <int MODE>
+static int launch_eval(fb_plan_s* p, const EvalArgs& A, int ncols_main, cudaStream_t st, int* grid_out) {
+  const size_t smem = smem_bytes(p->pc.num_comp, p->pc.kf, ncols_main, p->pc.scintillation != 0);
+  if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request %zu B exceeds 227 KB", smem);
+  static thread_local size_t configured[4] = {0, 0, 0, 0};
+  if (smem > 48 * 1024 && smem > configured[MODE]) {
+    CUDA_TRY(cudaFuncSetAttribute(k_eval<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[MODE] = smem;
+  }
+  int occ = 1;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_eval<MODE>, kBlock, smem));
+  if (occ < 1) occ = 1;
+  const int tiles = (p->pc.num_time + kBlock - 1) / kBlock;
+  long long items = p->pc.scintillation ? (long long)A.num_chan : (long long)A.num_chan * tiles;
+  if (items < 1) items = 1;
+  long long grid = (long long)p->sm_count * occ;
+  if (MODE != MODE_GRAM) grid *= 8;  // short blocks balance better when nothing is kept in registers
+  if (grid > items) grid = items;
+  if (grid_out) *grid_out = (int)grid;
+  EvalArgs B = A;
+  if (MODE == MODE_GRAM) {
+    const size_t need = (size_t)grid * gram_ntiles(ncols_main) * kTile * kTile;
+    if (need > p->partials_cap) {
+      cudaFree(p->d_partials);
+      p->d_partials = nullptr;
+      p->partials_cap = 0;
+      CUDA_TRY(cudaMalloc(&p->d_partials, sizeof(double) * need));
+      p->partials_cap = need;
+    }
+    B.partials = p->d_partials;
+  }
+  k_eval<MODE><<<(int)grid, kBlock, smem, st>>>(B);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 1;
+  return FB_OK;
+}
+
+static int check_err_flag(fb_plan_s* p, cudaStream_t st) {
+  if (!p->pc.scintillation) return FB_OK;
+  int flag = 0;
+  CUDA_TRY(cudaMemcpyAsync(&flag, p->d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (flag) {
+    CUDA_TRY(cudaMemsetAsync(p->d_err, 0, sizeof(int), st));
+    return fail(FB_ERR_SINGULAR, "Singular matrix");  // numpy.linalg.LinAlgError text, routines/ism.py:46
+  }
+  return FB_OK;
+}
+
+extern "C" int fb_model_eval(fb_plan_t p, const double* data_dev, double* model_dev,
+                             double* amplitude_dev, double* spectrum_dev, double* timediff_dev,
+                             double* timeprof_dev, void* stream) {
+  if (!p || !model_dev) return fail(FB_ERR_INVALID, "null argument");
+  if (p->pc.scintillation && !data_dev)
+    return fail(FB_ERR_INVALID, "ERROR: scintillation modelling is desired by data are missing!");
+  EvalArgs A = base_args(p);
+  A.data = data_dev;
+  A.model = model_dev;
+  A.c_amp = amplitude_dev;
+  A.c_spec = spectrum_dev;
+  A.c_td = timediff_dev;
+  A.c_tp = timeprof_dev;
+  A.n_free = 0;
+  int rc = launch_eval<MODE_MODEL>(p, A, 1, (cudaStream_t)stream, nullptr);
+  if (rc != FB_OK) return rc;
+  return check_err_flag(p, (cudaStream_t)stream);
+}
+
+static int rebuild_channel_list(fb_plan_s* p, cudaStream_t st) {
+  std::vector<int> list;
+  list.reserve(p->h_weights.size());
+  for (size_t i = 0; i < p->h_weights.size(); ++i)
+    if (p->h_weights[i] != 0.0) list.push_back((int)i);  // NaN weights are kept (they propagate)
+  p->num_good = (int)list.size();
+  if (!list.empty())
+    CUDA_TRY(cudaMemcpyAsync(p->d_chan_list, list.data(), sizeof(int) * list.size(),
+                             cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  p->have_weights = true;
+  return FB_OK;
+}
+
+extern "C" int fb_set_weights(fb_plan_t p, const double* data_dev, const uint8_t* good_host,
+                              int32_t weighted_fit, int32_t range_lo, int32_t range_hi,
+                              double* weights_host, double* chisq_initial_host, void* stream) {
+  if (!p || !data_dev || !good_host) return fail(FB_ERR_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nf = p->desc.num_freq, nt = p->desc.num_time;
+  // python slice semantics of data[:, lo:hi] (analysis/fitter.py:528)
+  int lo = range_lo, hi = range_hi;
+  if (lo < 0) lo += nt;
+  if (hi < 0) hi += nt;
+  lo = std::max(0, std::min(lo, nt));
+  hi = std::max(0, std::min(hi, nt));
+  if (hi < lo) hi = lo;
+  CUDA_TRY(cudaMemcpyAsync(p->d_good, good_host, nf, cudaMemcpyHostToDevice, st));
+  k_weights<<<nf, kBlock, 0, st>>>(data_dev, nf, nt, p->d_good, weighted_fit, lo, hi, p->d_weights,
+                                   p->d_chan_sumsq);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 1;
+  p->h_weights.resize(nf);
+  std::vector<double> sumsq(nf);
+  CUDA_TRY(cudaMemcpyAsync(p->h_weights.data(), p->d_weights, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(sumsq.data(), p->d_chan_sumsq, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (weights_host) memcpy(weights_host, p->h_weights.data(), sizeof(double) * nf);
+  if (chisq_initial_host) {
+    double s = 0.0;
+    for (int i = 0; i < nf; ++i) s += sumsq[i];
+    *chisq_initial_host = s;
+  }
+  return rebuild_channel_list(p, st);
+}
+
+extern "C" int fb_load_weights(fb_plan_t p, const double* weights_host, void* stream) {
+  if (!p || !weights_host) return fail(FB_ERR_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nf = p->desc.num_freq;
+  p->h_weights.assign(weights_host, weights_host + nf);
+  CUDA_TRY(cudaMemcpyAsync(p->d_weights, p->h_weights.data(), sizeof(double) * nf, cudaMemcpyHostToDevice, st));
+  return rebuild_channel_list(p, st);
+}
+
+extern "C" int fb_set_free_parameters(fb_plan_t p, const int32_t* free_mask, int32_t* num_free_out) {
+  if (!p || !free_mask) return fail(FB_ERR_INVALID, "null argument");
+  int saved[9];
+  for (int k = 0; k < 9; ++k) {
+    saved[k] = p->free_mask[k];
+    p->free_mask[k] = free_mask[k] != 0;
+  }
+  layout_free(p);
+  if (p->n_free > FB_MAX_FREE) {
+    const int n = p->n_free;
+    for (int k = 0; k < 9; ++k) p->free_mask[k] = saved[k];
+    layout_free(p);
+    return fail(FB_ERR_INVALID, "%d free parameters exceed FB_MAX_FREE=%d", n, FB_MAX_FREE);
+  }
+  if (num_free_out) *num_free_out = p->n_free;
+  return FB_OK;
+}
+
+static int normal_equations_async(fb_plan_s* p, const double* data_dev, double* gram_dev, cudaStream_t st) {
+  if (!p->have_weights) return fail(FB_ERR_INVALID, "fb_set_weights / fb_load_weights must be called first");
+  if (p->n_free < 1) return fail(FB_ERR_INVALID, "no free parameters");
+  const int ncols = p->n_free + 1;
+  if (p->num_good == 0) {
+    CUDA_TRY(cudaMemsetAsync(gram_dev, 0, sizeof(double) * ncols * ncols, st));
+    return FB_OK;
+  }
+  EvalArgs A = base_args(p);
+  A.data = data_dev;
+  A.weights = p->d_weights;
+  A.chan_list = p->d_chan_list;
+  A.num_chan = p->num_good;
+  int grid = 0;
+  int rc = launch_eval<MODE_GRAM>(p, A, ncols, st, &grid);
+  if (rc != FB_OK) return rc;
+  k_gram_finalize<<<1, 256, 0, st>>>(p->d_partials, grid, ncols, gram_dev);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 1;
+  return FB_OK;
+}
+
+extern "C" int fb_normal_equations_dev(fb_plan_t p, const double* data_dev, double* gram_dev, void* stream) {
+  if (!p || !data_dev || !gram_dev) return fail(FB_ERR_INVALID, "null argument");
+  return normal_equations_async(p, data_dev, gram_dev, (cudaStream_t)stream);
+}
+
+extern "C" int fb_normal_equations(fb_plan_t p, const double* data_dev, double* gram_host, void* stream) {
+  if (!p || !data_dev || !gram_host) return fail(FB_ERR_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = normal_equations_async(p, data_dev, p->d_gram, st);
+  if (rc != FB_OK) return rc;
+  const int ncols = p->n_free + 1;
+  CUDA_TRY(cudaMemcpyAsync(p->h_gram, p->d_gram, sizeof(double) * ncols * ncols, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  memcpy(gram_host, p->h_gram, sizeof(double) * ncols * ncols);
+  return check_err_flag(p, st);
+}
+
+static int dense_common(fb_plan_s* p, const double* data_dev, double* jac_dev, double* resid_dev, cudaStream_t st) {
+  if (!p->have_weights) return fail(FB_ERR_INVALID, "fb_set_weights / fb_load_weights must be called first");
+  EvalArgs A = base_args(p);
+  A.data = data_dev;
+  A.weights = p->d_weights;
+  A.jac = jac_dev;
+  A.resid = resid_dev;
+  if (!jac_dev) {
+    A.n_free = 0;
+    for (int k = 0; k < 9; ++k) A.col_of[k] = -1;
+  }
+  int rc = launch_eval<MODE_JAC>(p, A, A.n_free + 1, st, nullptr);
+  if (rc != FB_OK) return rc;
+  return check_err_flag(p, st);
+}
+
+extern "C" int fb_residuals(fb_plan_t p, const double* data_dev, double* resid_dev, void* stream) {
+  if (!p || !data_dev || !resid_dev) return fail(FB_ERR_INVALID, "null argument");
+  return dense_common(p, data_dev, nullptr, resid_dev, (cudaStream_t)stream);
+}
+
+extern "C" int fb_jacobian_dense(fb_plan_t p, const double* data_dev, double* jac_dev, void* stream) {
+  if (!p || !data_dev || !jac_dev) return fail(FB_ERR_INVALID, "null argument");
+  if (p->n_free < 1) return fail(FB_ERR_INVALID, "no free parameters");
+  return dense_common(p, data_dev, jac_dev, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int fb_derivative_map(fb_plan_t p, const double* data_dev, int32_t param, int32_t component,
+                                 int32_t add_all, double* out_dev, void* stream) {
+  if (!p || !out_dev) return fail(FB_ERR_INVALID, "null argument");
+  if (param < 0 || param > 8) return fail(FB_ERR_INVALID, "parameter index %d out of range", param);
+  if (component < 0 || component >= p->desc.num_components)
+    return fail(FB_ERR_INVALID, "component %d out of range", component);
+  if (p->pc.scintillation && !data_dev) return fail(FB_ERR_INVALID, "scintillation mode needs data");
+  EvalArgs A = base_args(p);
+  A.data = data_dev;
+  A.d_param = param;
+  A.d_comp = component;
+  A.d_addall = add_all;
+  A.d_out = out_dev;
+  A.n_free = 0;
+  int rc = launch_eval<MODE_DERIV>(p, A, 1, (cudaStream_t)stream, nullptr);
+  if (rc != FB_OK) return rc;
+  return check_err_flag(p, (cudaStream_t)stream);
+}
+
+// Packs / unpacks the free vector in LSFitter.get_fit_parameters_list order
+// (analysis/fitter.py:353-430) against the plan's host copy of the parameter block.
+static void pack_free(const fb_plan_s* p, double* x) {
+  const int nc = p->desc.num_components;
+  for (int k = 0; k < 9; ++k) {
+    if (p->col_of[k] < 0) continue;
+    if (is_fit_global(k)) x[p->col_of[k]] = p->h_params[k * nc];
+    else
+      for (int c = 0; c < nc; ++c) x[p->col_of[k] + c] = p->h_params[k * nc + c];
+  }
+}
+
+static void unpack_free(fb_plan_s* p, const double* x) {
+  const int nc = p->desc.num_components;
+  for (int k = 0; k < 9; ++k) {
+    if (p->col_of[k] < 0) continue;
+    if (is_fit_global(k)) {
+      // load_fit_parameters_list returns a length-1 list; update_parameters then stores that
+      // list, and the model reads element 0 (analysis/model.py:155-159).
+      for (int c = 0; c < nc; ++c) p->h_params[k * nc + c] = x[p->col_of[k]];
+    } else {
+      for (int c = 0; c < nc; ++c) p->h_params[k * nc + c] = x[p->col_of[k] + c];
+    }
+  }
+}
+
+int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, cudaStream_t st);
+
+extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options* options,
+                      fb_fit_result* result, double* gram_final_host, double* hessian_host,
+                      void* stream) {
+  if (!p || !data_dev || !result) return fail(FB_ERR_INVALID, "null argument");
+  if (!p->have_weights) return fail(FB_ERR_INVALID, "fb_set_weights / fb_load_weights must be called first");
+  const int n = p->n_free;
+  if (n < 1) return fail(FB_ERR_INVALID, "no free parameters");
+  cudaStream_t st = (cudaStream_t)stream;
+  fb_fit_options opt;
+  opt.ftol = opt.xtol = opt.gtol = 1e-8;
+  opt.max_nfev = 0;
+  opt.compute_hessian = 0;
+  if (options) opt = *options;
+  const int ncols = n + 1;
+  std::vector<double> gram((size_t)ncols * ncols), accepted((size_t)ncols * ncols);
+  TrfState* stt = new (std::nothrow) TrfState();
+  if (!stt) return fail(FB_ERR_NOMEM, "out of host memory");
+  TrfState& S = *stt;
+  double x0[FB_MAX_FREE];
+  pack_free(p, x0);
+  int rc = fb_set_parameters(p, p->h_params, stream);
+  if (rc == FB_OK) rc = fb_normal_equations(p, data_dev, gram.data(), stream);
+  if (rc != FB_OK) {
+    delete stt;
+    return rc;
+  }
+  memset(result, 0, sizeof(*result));
+  result->num_free = n;
+  const long long m = (long long)p->desc.num_freq * p->desc.num_time;
+  trf_init(S, n, m, x0, opt.ftol, opt.xtol, opt.gtol, opt.max_nfev);
+  if (!std::isfinite(gram[(size_t)n * ncols + n])) {
+    // scipy raises "Residuals are not finite in the initial point." (least_squares.py:945-946)
+    delete stt;
+    result->status = -1;
+    return fail(FB_ERR_INVALID, "Residuals are not finite in the initial point.");
+  }
+  trf_load_accepted(S, gram.data());
+  accepted = gram;
+  S.nfev = 1;
+  S.njev = 1;
+  while (trf_propose(S)) {
+    unpack_free(p, S.x_new);
+    rc = fb_set_parameters(p, p->h_params, stream);
+    if (rc == FB_OK) rc = fb_normal_equations(p, data_dev, gram.data(), stream);
+    if (rc != FB_OK) {
+      delete stt;
+      return rc;
+    }
+    const int njev_before = S.njev;
+    trf_update(S, gram.data());
+    if (S.njev != njev_before) accepted = gram;
+  }
+  result->status = S.status;
+  result->nfev = S.nfev;
+  result->njev = S.njev;
+  result->cost = S.cost;
+  result->optimality = S.g_norm;
+  for (int i = 0; i < n; ++i) {
+    result->x[i] = S.x[i];
+    result->grad[i] = S.g[i];
+  }
+  if (gram_final_host) memcpy(gram_final_host, accepted.data(), sizeof(double) * ncols * ncols);
+  delete stt;
+  // the model is left at the LAST EVALUATED point, like analysis/fitter.py:258 leaves it.
+  if (opt.compute_hessian || hessian_host) {
+    std::vector<double> H((size_t)n * n);
+    rc = fb_hessian_impl(p, data_dev, H.data(), st);
+    if (rc != FB_OK) return rc;
+    if (hessian_host) memcpy(hessian_host, H.data(), sizeof(double) * n * n);
+  }
+  return FB_OK;
+}
+
+extern "C" int fb_measure_fp64_peak(double* tflops_out, void* stream) {
+  if (!tflops_out) return fail(FB_ERR_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaDeviceProp prop;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+  double* d_out = nullptr;
+  CUDA_TRY(cudaMalloc(&d_out, sizeof(double) * blocks * threads));
+  cudaEvent_t e0, e1;
+  CUDA_TRY(cudaEventCreate(&e0));
+  CUDA_TRY(cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CUDA_TRY(cudaEventRecord(e0, st));
+    k_dfma_peak<<<blocks, threads, 0, st>>>(d_out, iters);
+    CUDA_TRY(cudaEventRecord(e1, st));
+    CUDA_TRY(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 8.0 * (double)iters * blocks * threads;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  *tflops_out = best;
+  return FB_OK;
+}
+
+extern "C" int fb_launch_count(fb_plan_t p, int64_t* count_out, int32_t reset) {
+  if (!p || !count_out) return fail(FB_ERR_INVALID, "null argument");
+  *count_out = p->launches;
+  if (reset) p->launches = 0;
+  return FB_OK;
+}
+
+// ---- entry points implemented in later translation units / sections ---------------------------
+#ifndef FB_HAVE_HESSIAN
+int fb_hessian_impl(fb_plan_s*, const double*, double*, cudaStream_t) {
+  return fail(FB_ERR_INVALID, "fb_hessian: not built");
+}
+extern "C" int fb_hessian(fb_plan_t, const double*, double*, void*) {
+  return fail(FB_ERR_INVALID, "fb_hessian: not built");
+}
+extern "C" int fb_derivative2_map(fb_plan_t, const double*, int32_t, int32_t, int32_t, double*, void*) {
+  return fail(FB_ERR_INVALID, "fb_derivative2_map: not built");
+}
+#endif
+#ifndef FB_HAVE_BATCHED
+extern "C" int fb_fit_batched(fb_plan_t, int32_t, const double*, const double*, double*,
+                              const fb_fit_options*, fb_fit_result*, void*) {
+  return fail(FB_ERR_INVALID, "fb_fit_batched: not built");
+}
+extern "C" int fb_chisq_grid(fb_plan_t, const double*, const double*, int32_t, const double*, int32_t,
+                             double*, void*) {
+  return fail(FB_ERR_INVALID, "fb_chisq_grid: not built");
+}
+#endif

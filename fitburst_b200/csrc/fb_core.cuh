@@ -1,0 +1,283 @@
+// fitburst_b200 device core: per-channel tables, the scatter-broadened profile and the
+// per-sample model / first-derivative evaluation shared by every kernel.
+//
+// Reference citations are path:line under fitburst/ in CHIMEFRB/fitburst (pure Python); this
+// file restates WHAT those lines compute, laid out for one thread per output sample.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/fitburst_b200.h"
+
+namespace fb {
+
+constexpr double kSqrtHalf = 0.70710678118654752440;       // 1/sqrt(2)
+constexpr double kSqrtHalfPi = 1.25331413731550025121;     // sqrt(pi/2)
+constexpr double kTwoOverSqrtPi = 1.12837916709551257390;  // 2/sqrt(pi)
+constexpr double kLn10 = 2.30258509299404568402;
+
+// Static (per-plan) configuration, passed by value to kernels.
+struct PlanConst {
+  int num_freq, num_time, num_comp;
+  int kf, kt;
+  int is_folded, scintillation, normalize_pbf;
+  int ntk;  // num_time * kt
+  double dm_incoherent, dm_const;
+  double res_freq, res_time;
+  double time_first, time_last;  // times[0], times[num_time - 1]
+  const double* freqs;           // (num_freq) channel centres
+  const double* subfreqs;        // (num_freq, kf) routines/manipulate.py:99-105 labels
+};
+
+// Per-component constants (depend on parameters only).
+struct CompTab {
+  double t_start, t_step, t_stop;  // linspace of the up-sampled, arrival-corrected time labels
+  double w, inv_w, neg5w;
+  double amp10;                    // 10 ** amplitude (analysis/model.py:255-256)
+  double ref_freq;
+};
+
+// Per (channel, sub-frequency, component) constants.
+struct SubTab {
+  double delay;     // analysis/model.py:184-199
+  double ratio;     // width / sc_time(f_ia)             routines/profile.py:93
+  double amp_term;  // sc_time_ref / sc_time, or sqrt(pi/2) * ratio   routines/profile.py:96
+  double sed;       // running power law at f_ia         routines/spectrum.py:39-41
+  double fold_start, fold_step, fold_stop;  // second realisation, analysis/model.py:327-332
+};
+
+// Per (channel, component) constants at the channel CENTRE, used by the derivatives
+// (routines/derivative.py evaluates everything at model.freqs, not at the sub-frequencies).
+struct ChanTab {
+  double amp;        // amplitude_per_component value: 10**A * S(f_i)   analysis/model.py:250-255
+  double logf;       // ln(f_i / ref_freq)
+  double sc_time;    // sc_time_ref * (f_i / ref_freq) ** sc_index
+  double amp_pbf;    // routines/derivative.py:71-103
+  double d_dm;       // deriv_time_dm("dm")        routines/derivative.py:244-246
+  double d_dmidx;    // deriv_time_dm("dm_index")  routines/derivative.py:248-250
+  double dap_w, dap_tau, dap_alpha;  // deriv_amplitude_pbf for burst_width / scattering_timescale /
+                                     // scattering_index with THIS component as the one looked up
+                                     // (routines/derivative.py:105-152)
+  int scattered;     // any(sc_time(f_ia) > 0) over the sub-frequencies, analysis/model.py:339
+};
+
+__host__ __device__ inline double global_param(const double* params, int nc, int p) {
+  return params[p * nc];  // element 0 is used for all components, analysis/model.py:155-159
+}
+
+// np.linspace(lo, hi, num)[m]: arange * step + start with two roundings, last element = stop.
+__device__ __forceinline__ double linspace_at(double start, double step, double stop, int m, int num) {
+  double v = __dadd_rn(__dmul_rn((double)m, step), start);
+  return (m == num - 1 && num > 1) ? stop : v;
+}
+
+__device__ inline void make_comp_tab(const PlanConst& pc, const double* params, int c, CompTab& ct) {
+  const int nc = pc.num_comp;
+  const double t_arr = params[FB_ARRIVAL_TIME * nc + c];
+  const double w = params[FB_BURST_WIDTH * nc + c];
+  // analysis/model.py:202-206 + routines/manipulate.py:99-105, same operation order.
+  const double diff_new = pc.res_time / (double)pc.kt;
+  const double first = pc.time_first - t_arr;
+  const double last = pc.time_last - t_arr;
+  const double lo = __dadd_rn(__dsub_rn(first, pc.res_time / 2), diff_new / 2);
+  const double hi = __dsub_rn(__dadd_rn(last, pc.res_time / 2), diff_new / 2);
+  ct.t_start = lo;
+  ct.t_stop = hi;
+  ct.t_step = (pc.ntk > 1) ? (hi - lo) / (double)(pc.ntk - 1) : 0.0;
+  ct.w = w;
+  ct.inv_w = 1.0 / w;
+  ct.neg5w = -5 * w;
+  ct.amp10 = pow(10.0, params[FB_AMPLITUDE * nc + c]);
+  ct.ref_freq = params[FB_REF_FREQ * nc + c];
+}
+
+__device__ inline void make_sub_tab(const PlanConst& pc, const double* params, const CompTab& ct,
+                                    int i, int a, int c, SubTab& st) {
+  const int nc = pc.num_comp;
+  const double f = pc.subfreqs[(size_t)i * pc.kf + a];
+  const double fc = pc.freqs[i];
+  const double dm = global_param(params, nc, FB_DM);
+  const double beta = global_param(params, nc, FB_DM_INDEX);
+  const double tau0 = global_param(params, nc, FB_SCATTERING_TIMESCALE);
+  const double alpha = global_param(params, nc, FB_SCATTERING_INDEX);
+  const double fref = ct.ref_freq;
+  const double fref_b = pow(fref, beta);
+  // routines/ism.py:78: dm_value * dm_const * (freq1 ** dm_idx - freq2 ** dm_idx)
+  double delay = ((pc.dm_incoherent + dm) * pc.dm_const) * (pow(f, beta) - fref_b);
+  delay -= (pc.dm_incoherent * pc.dm_const) * (pow(fc, beta) - fref_b);
+  st.delay = delay;
+  const double fr = f / fref;
+  const double sc_time = tau0 * pow(fr, alpha);  // analysis/model.py:336
+  st.ratio = ct.w / sc_time;
+  st.amp_term = pc.normalize_pbf ? kSqrtHalfPi * st.ratio : tau0 / sc_time;
+  const double lf = log(fr);
+  const double sp_idx = params[FB_SPECTRAL_INDEX * nc + c];
+  const double sp_run = params[FB_SPECTRAL_RUNNING * nc + c];
+  st.sed = exp(sp_idx * lf + sp_run * (lf * lf));
+  if (pc.is_folded) {
+    // analysis/model.py:327-331 on the delay-corrected labels of this sub-frequency row.
+    const int n = pc.ntk;
+    const double t0 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, 0, n) - delay;
+    const double t1 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, 1, n) - delay;
+    const double tl = linspace_at(ct.t_start, ct.t_step, ct.t_stop, n - 1, n) - delay;
+    const double res = t1 - t0;
+    st.fold_start = tl + res;
+    st.fold_stop = tl + res * (double)n;
+    st.fold_step = (n > 1) ? (st.fold_stop - st.fold_start) / (double)(n - 1) : 0.0;
+  } else {
+    st.fold_start = st.fold_step = st.fold_stop = 0.0;
+  }
+}
+
+__device__ inline void make_chan_tab(const PlanConst& pc, const double* params, const CompTab& ct,
+                                     int i, int c, ChanTab& ch) {
+  const int nc = pc.num_comp;
+  const double fc = pc.freqs[i];
+  const double dm = global_param(params, nc, FB_DM);
+  const double beta = global_param(params, nc, FB_DM_INDEX);
+  const double tau0 = global_param(params, nc, FB_SCATTERING_TIMESCALE);
+  const double alpha = global_param(params, nc, FB_SCATTERING_INDEX);
+  const double fref = ct.ref_freq;
+  const double fr = fc / fref;
+  const double lf = log(fr);
+  const double sp_idx = params[FB_SPECTRAL_INDEX * nc + c];
+  const double sp_run = params[FB_SPECTRAL_RUNNING * nc + c];
+  ch.amp = exp(sp_idx * lf + sp_run * (lf * lf)) * ct.amp10;
+  ch.logf = lf;
+  ch.sc_time = tau0 * pow(fr, alpha);
+  double amp_pbf = pow(fr, -alpha);
+  if (pc.normalize_pbf) amp_pbf *= kSqrtHalfPi * ct.w / tau0;
+  ch.amp_pbf = amp_pbf;
+  if (pc.normalize_pbf) {
+    ch.dap_w = kSqrtHalfPi / ch.sc_time;
+    ch.dap_alpha = -kSqrtHalfPi * lf * ct.w / ch.sc_time;
+    ch.dap_tau = -kSqrtHalfPi * ct.w / (ch.sc_time * tau0);
+  } else {
+    ch.dap_w = 0.0;
+    ch.dap_tau = 0.0;
+    ch.dap_alpha = -lf * pow(fr, -alpha);
+  }
+  const double fc_b = pow(fc, beta), fref_b = pow(fref, beta);
+  ch.d_dm = -pc.dm_const * (fc_b - fref_b);
+  ch.d_dmidx = -pc.dm_const * dm * (log(fc) * fc_b - log(fref) * fref_b);
+  int scattered = 0;
+  for (int a = 0; a < pc.kf; ++a) {
+    const double f = pc.subfreqs[(size_t)i * pc.kf + a];
+    if (tau0 * pow(f / fref, alpha) > 0.0) scattered = 1;
+  }
+  ch.scattered = scattered;
+}
+
+// Exponentially-modified Gaussian without its amplitude term, routines/profile.py:90-112:
+//   exp(-z^2/2) * erfcx((ratio - z)/sqrt(2))          == exp((ratio/2 - z) ratio) * erfc(.)
+// evaluated so that neither factor over/underflows (the reference switches formula at
+// arg <= -20; here the split is at arg = 0, exact to rounding):
+//   arg >= 0       exp(-z^2/2) erfcx(arg)
+//   -6 < arg < 0   2 exp(ratio (ratio/2 - z)) - exp(-z^2/2) erfcx(-arg)     [erfcx(-y) = 2e^{y^2} - erfcx(y)]
+//   arg <= -6      2 exp(ratio (ratio/2 - z))                               [erfc(6)/2 = 1.1e-17 < ulp/2]
+__device__ __forceinline__ double emg_shape(double z, double ratio) {
+  const double arg = (ratio - z) * kSqrtHalf;
+  if (arg >= 0.0) return exp(-0.5 * z * z) * erfcx(arg);
+  const double tail = 2.0 * exp(ratio * (0.5 * ratio - z));
+  if (arg <= -6.0) return tail;
+  return tail - exp(-0.5 * z * z) * erfcx(-arg);
+}
+
+// Per-sample, per-component result: the three cached maps of analysis/model.py:212-256.
+struct SampleComp {
+  double timediff;  // mean over sub-freq / sub-time of the UNCLAMPED time difference
+  double timeprof;  // mean profile
+  double spectrum;  // 10**A * mean(profile * sed)   (scintillation rescales later)
+};
+
+// One (channel, sample, component): loops the kf x kt sub-grid. `sub` points at this
+// component's kf SubTab entries (shared memory).
+__device__ __forceinline__ SampleComp eval_sample_component(const PlanConst& pc, const CompTab& ct,
+                                                            const SubTab* __restrict__ sub,
+                                                            int scattered, int j) {
+  const int kf = pc.kf, kt = pc.kt, n = pc.ntk;
+  const double inv_kf = 1.0 / (double)kf, inv_kt = 1.0 / (double)kt;
+  double acc_t = 0.0, acc_p = 0.0, acc_ps = 0.0;
+  for (int b = 0; b < kt; ++b) {
+    const int m = j * kt + b;
+    const double u = linspace_at(ct.t_start, ct.t_step, ct.t_stop, m, n);
+    double s_t = 0.0, s_p = 0.0, s_ps = 0.0;
+    for (int a = 0; a < kf; ++a) {
+      const SubTab& st = sub[a];
+      const double t = u - st.delay;  // analysis/model.py:208-209
+      s_t += t;
+      double p;
+      if (scattered) {
+        const double tc = (t < ct.neg5w) ? ct.neg5w : t;  // analysis/model.py:340
+        p = st.amp_term * emg_shape(tc * ct.inv_w, st.ratio);
+        if (pc.is_folded) {
+          double t2 = linspace_at(st.fold_start, st.fold_step, st.fold_stop, m, n);
+          t2 = (t2 < ct.neg5w) ? ct.neg5w : t2;
+          p = 0.5 * (p + st.amp_term * emg_shape(t2 * ct.inv_w, st.ratio));
+        }
+      } else {
+        const double z = t * ct.inv_w;  // routines/profile.py:47
+        p = exp(-0.5 * z * z);
+        if (pc.is_folded) {
+          const double z2 = linspace_at(st.fold_start, st.fold_step, st.fold_stop, m, n) * ct.inv_w;
+          p = 0.5 * (p + exp(-0.5 * z2 * z2));
+        }
+      }
+      s_p += p;
+      s_ps += p * st.sed;
+    }
+    acc_t += s_t * inv_kf;
+    acc_p += s_p * inv_kf;
+    acc_ps += s_ps * inv_kf;
+  }
+  SampleComp out;
+  out.timediff = acc_t * inv_kt;
+  out.timeprof = acc_p * inv_kt;
+  out.spectrum = ct.amp10 * (acc_ps * inv_kt);
+  return out;
+}
+
+// First derivatives of ONE component's spectrum at one sample, routines/derivative.py:454-936.
+// m = spectrum_per_component value, td = timediff_per_component value, ch = this component's
+// channel-centre table, cho = the table of the component the reference passes to
+// deriv_amplitude_pbf (the four "global" functions pass the OUTER component,
+// routines/derivative.py:707,779,847,916). d[] is indexed by fb_parameter. gfac_out returns
+// the shared factor amp * amp_pbf * exp(arg_exp) * 2/sqrt(pi) for the second derivatives.
+__device__ __forceinline__ void first_derivatives(const ChanTab& ch, const ChanTab& cho, double w,
+                                                  double tau0, double m, double td, double* d,
+                                                  double* gfac_out) {
+  const double lf = ch.logf;
+  d[FB_AMPLITUDE] = kLn10 * m;
+  d[FB_SPECTRAL_INDEX] = lf * m;
+  d[FB_SPECTRAL_RUNNING] = (lf * lf) * m;
+  const double tau = ch.sc_time;
+  // shared scattered-branch factor, routines/derivative.py:14-69 (arg_exp evaluated as written).
+  const double arg_erf = (td - w * w / tau) / w * kSqrtHalf;
+  const double ws = w / tau;
+  const double arg_exp = 0.5 * ws * ws - td / tau - arg_erf * arg_erf;
+  const double g = ch.amp * ch.amp_pbf * exp(arg_exp) * kTwoOverSqrtPi;
+  *gfac_out = g;
+  const double inv_amp_pbf = 1.0 / ch.amp_pbf;
+  if (tau == 0.0) {  // per-channel Gaussian branch, routines/derivative.py:568,629,695,767
+    const double w2 = w * w;
+    d[FB_BURST_WIDTH] = td * td * m / (w2 * w);
+    d[FB_ARRIVAL_TIME] = td * m / w2;
+    d[FB_DM] = -td * m / w2 * ch.d_dm;
+    d[FB_DM_INDEX] = -td * m / w2 * ch.d_dmidx;
+  } else {
+    d[FB_BURST_WIDTH] = m * cho.dap_w * inv_amp_pbf + (w / (tau * tau)) * m +
+                        g * (-(td / (w * w) + 1.0 / tau) * kSqrtHalf);
+    d[FB_ARRIVAL_TIME] = m / tau + g * (-1.0 / w * kSqrtHalf);
+    d[FB_DM] = -ch.d_dm * m / tau + g * (ch.d_dm / w * kSqrtHalf);
+    d[FB_DM_INDEX] = -ch.d_dmidx * m / tau + g * (ch.d_dmidx / w * kSqrtHalf);
+  }
+  // no Gaussian branch in the reference for these two (routines/derivative.py:800-936):
+  // sc_time == 0 yields inf/nan there and here alike.
+  d[FB_SCATTERING_TIMESCALE] = m * cho.dap_tau * inv_amp_pbf + (-(ws * ws) + td / tau) * m / tau0 +
+                               g * (w / tau0 / tau * kSqrtHalf);
+  d[FB_SCATTERING_INDEX] = m * cho.dap_alpha * inv_amp_pbf - lf * m * (ws * ws - td / tau) +
+                           g * (lf * w / tau * kSqrtHalf);
+}
+
+}  // namespace fb

@@ -1,0 +1,485 @@
+// fitburst_b200 kernels: one thread per output sample, one block per (channel, 256-sample
+// tile) work item, channel tables staged in shared memory, [J r]^T [J r] accumulated in
+// registers through a shared-memory row stage and reduced deterministically in two stages.
+#pragma once
+#include "fb_core.cuh"
+
+namespace fb {
+
+constexpr int kBlock = 256;
+constexpr int kTile = 4;  // register tile edge of the Gram accumulation
+
+enum EvalMode { MODE_MODEL = 0, MODE_GRAM = 1, MODE_JAC = 2, MODE_DERIV = 3 };
+
+struct EvalArgs {
+  PlanConst pc;
+  const double* params;  // device, (FB_NUM_PARAMETERS, num_comp)
+  const int* chan_list;  // channels to visit (nullptr = all)
+  int num_chan;
+  const double* data;     // (num_freq, num_time) or nullptr
+  const double* weights;  // (num_freq) or nullptr
+  // free-parameter layout (LSFitter.get_fit_parameters_list order, analysis/fitter.py:353-384)
+  int n_free;
+  int col_of[9];  // first packed column of parameter p, -1 if fixed
+  // MODE_MODEL outputs
+  double* model;
+  double* c_amp;
+  double* c_spec;
+  double* c_td;
+  double* c_tp;
+  // MODE_GRAM output: per-block partial tiles
+  double* partials;
+  // MODE_JAC outputs
+  double* jac;
+  double* resid;
+  // MODE_DERIV
+  int d_param, d_comp, d_addall;
+  double* d_out;
+  int* err_flag;  // set to 1 on a singular scintillation system (routines/ism.py:46)
+};
+
+__host__ __device__ inline bool is_fit_global(int p) {
+  // LSFitter.global_parameters, analysis/fitter.py:72
+  return p == FB_DM || p == FB_DM_INDEX || p == FB_SCATTERING_TIMESCALE || p == FB_SCATTERING_INDEX;
+}
+
+__host__ __device__ inline int gram_side(int ncols) { return (ncols + kTile - 1) / kTile; }
+__host__ __device__ inline int gram_ntiles(int ncols) {
+  const int s = gram_side(ncols);
+  return s * (s + 1) / 2;
+}
+__host__ __device__ inline int gram_stride(int ncols) { return (gram_side(ncols) * kTile) | 1; }
+
+// Maps a linear upper-triangle tile index to (ti <= tj).
+__device__ inline void tile_coords(int t, int side, int& ti, int& tj) {
+  int row = 0, rem = t;
+  while (rem >= side - row) {
+    rem -= side - row;
+    ++row;
+  }
+  ti = row;
+  tj = row + rem;
+}
+
+// Accumulates X^T X over `rows` staged rows. Thread layout: tile = tid % ntiles,
+// slice = tid / ntiles; each thread owns a kTile x kTile register block.
+__device__ __forceinline__ void gram_accumulate(const double* __restrict__ X, int stride, int rows,
+                                                int ntiles, int nslices, int ti, int tj, int slice,
+                                                bool active, double (&acc)[kTile * kTile]) {
+  if (!active) return;
+  const double* xa = X + ti * kTile;
+  const double* xb = X + tj * kTile;
+  for (int s = slice; s < rows; s += nslices) {
+    const double* ra = xa + s * stride;
+    const double* rb = xb + s * stride;
+    double a[kTile], b[kTile];
+#pragma unroll
+    for (int k = 0; k < kTile; ++k) {
+      a[k] = ra[k];
+      b[k] = rb[k];
+    }
+#pragma unroll
+    for (int r = 0; r < kTile; ++r)
+#pragma unroll
+      for (int q = 0; q < kTile; ++q) acc[r * kTile + q] = fma(a[r], b[q], acc[r * kTile + q]);
+  }
+}
+
+// Sums the per-slice register tiles of a block in slice order (deterministic) and leaves
+// tile-major sums out[tile * 16 + k] in `out` (shared or global).
+__device__ inline void gram_block_reduce(double* scratch, int ntiles, int nslices, int tile,
+                                         int slice, bool active, const double (&acc)[kTile * kTile],
+                                         double* out) {
+  constexpr int kk = kTile * kTile;
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < kk; ++k) scratch[(slice * ntiles + tile) * kk + k] = acc[k];
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < ntiles * kk; e += blockDim.x) {
+    double s = 0.0;
+    for (int sl = 0; sl < nslices; ++sl) s += scratch[sl * ntiles * kk + e];
+    out[e] = s;
+  }
+  __syncthreads();
+}
+
+// Gaussian elimination with partial pivoting on an n x n system held in shared memory
+// (n <= FB_MAX_COMPONENTS); one thread. Returns false on an exactly-zero pivot, the condition
+// under which LAPACK gesv (np.linalg.solve, routines/ism.py:46) reports a singular matrix.
+__device__ inline bool solve_small(double* a, double* b, int n, int ld) {
+  for (int k = 0; k < n; ++k) {
+    int piv = k;
+    double best = fabs(a[k * ld + k]);
+    for (int r = k + 1; r < n; ++r)
+      if (fabs(a[r * ld + k]) > best) {
+        best = fabs(a[r * ld + k]);
+        piv = r;
+      }
+    if (best == 0.0 || best != best) return false;
+    if (piv != k) {
+      for (int c = 0; c < n; ++c) {
+        const double t = a[k * ld + c];
+        a[k * ld + c] = a[piv * ld + c];
+        a[piv * ld + c] = t;
+      }
+      const double t = b[k];
+      b[k] = b[piv];
+      b[piv] = t;
+    }
+    for (int r = k + 1; r < n; ++r) {
+      const double f = a[r * ld + k] / a[k * ld + k];
+      for (int c = k + 1; c < n; ++c) a[r * ld + c] -= f * a[k * ld + c];
+      b[r] -= f * b[k];
+    }
+  }
+  for (int k = n - 1; k >= 0; --k) {
+    double s = b[k];
+    for (int c = k + 1; c < n; ++c) s -= a[k * ld + c] * b[c];
+    b[k] = s / a[k * ld + k];
+  }
+  return true;
+}
+
+struct SmemLayout {
+  CompTab* comp;
+  ChanTab* chan;
+  SubTab* sub;
+  double* scint_amp;
+  double* small;    // (nc+1)^2 + nc scratch for the scintillation solve
+  double* tilesum;  // block-summed Gram tiles of the scintillation system
+  double* X;
+};
+
+__host__ __device__ inline size_t smem_bytes(int nc, int kf, int ncols_main, bool scint) {
+  size_t n = 0;
+  n += sizeof(CompTab) * nc;
+  n += sizeof(ChanTab) * nc;
+  n += sizeof(SubTab) * nc * kf;
+  n += sizeof(double) * nc;
+  n += sizeof(double) * ((nc + 1) * (nc + 1) + nc + 2);
+  n += sizeof(double) * gram_ntiles(nc + 1) * kTile * kTile;
+  int stride = gram_stride(ncols_main);
+  if (scint) {
+    const int s2 = gram_stride(nc + 1);
+    stride = stride > s2 ? stride : s2;
+  }
+  size_t xr = (size_t)kBlock * stride;
+  if (xr < (size_t)kBlock * kTile * kTile) xr = (size_t)kBlock * kTile * kTile;
+  n += sizeof(double) * xr;
+  return n;
+}
+
+__device__ inline SmemLayout carve(double* base, int nc, int kf) {
+  SmemLayout L;
+  char* p = reinterpret_cast<char*>(base);
+  L.comp = reinterpret_cast<CompTab*>(p);
+  p += sizeof(CompTab) * nc;
+  L.chan = reinterpret_cast<ChanTab*>(p);
+  p += sizeof(ChanTab) * nc;
+  L.sub = reinterpret_cast<SubTab*>(p);
+  p += sizeof(SubTab) * nc * kf;
+  L.scint_amp = reinterpret_cast<double*>(p);
+  p += sizeof(double) * nc;
+  L.small = reinterpret_cast<double*>(p);
+  p += sizeof(double) * ((nc + 1) * (nc + 1) + nc + 2);
+  L.tilesum = reinterpret_cast<double*>(p);
+  p += sizeof(double) * gram_ntiles(nc + 1) * kTile * kTile;
+  L.X = reinterpret_cast<double*>(p);
+  return L;
+}
+
+__device__ inline void load_channel_tables(const EvalArgs& A, const SmemLayout& L, int i) {
+  const PlanConst& pc = A.pc;
+  const int nc = pc.num_comp, kf = pc.kf;
+  __syncthreads();
+  for (int e = threadIdx.x; e < nc * kf; e += blockDim.x) {
+    const int c = e / kf, a = e % kf;
+    make_sub_tab(pc, A.params, L.comp[c], i, a, c, L.sub[c * kf + a]);
+  }
+  // channel-centre tables are computed by the LAST threads of the block so that they run
+  // concurrently with the sub-frequency tables built by the first ones.
+  for (int e = (int)blockDim.x - 1 - (int)threadIdx.x; e < nc; e += blockDim.x) {
+    make_chan_tab(pc, A.params, L.comp[e], i, e, L.chan[e]);
+  }
+  __syncthreads();
+}
+
+// Everything a thread does for one sample of one channel, for every mode.
+template <int MODE>
+__device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayout& L, int i, int j,
+                                               bool valid, double* row, int stride) {
+  const PlanConst& pc = A.pc;
+  const int nc = pc.num_comp, kf = pc.kf, n = A.n_free;
+  const double wi = (A.weights != nullptr) ? A.weights[i] : 1.0;
+  const double tau0 = global_param(A.params, nc, FB_SCATTERING_TIMESCALE);
+  if (MODE == MODE_GRAM || MODE == MODE_JAC) {
+    for (int k = 0; k <= n; ++k) row[k] = 0.0;
+    if (MODE == MODE_GRAM)
+      for (int k = n + 1; k < stride; ++k) row[k] = 0.0;
+  }
+  if (!valid) return;
+  double msum = 0.0, dsum = 0.0;
+  const size_t s_idx = (size_t)i * pc.num_time + j;
+  for (int c = 0; c < nc; ++c) {
+    const CompTab& ct = L.comp[c];
+    const ChanTab& ch = L.chan[c];
+    SampleComp sc = eval_sample_component(pc, ct, L.sub + c * kf, ch.scattered, j);
+    double amp = ch.amp;
+    if (pc.scintillation) {  // analysis/model.py:274-277
+      amp = L.scint_amp[c];
+      sc.spectrum = amp * sc.timeprof;
+    }
+    msum += sc.spectrum;
+    if (MODE == MODE_MODEL) {
+      const size_t o = s_idx * nc + c;
+      if (A.c_amp) A.c_amp[o] = amp;
+      if (A.c_spec) A.c_spec[o] = sc.spectrum;
+      if (A.c_td) A.c_td[o] = sc.timediff;
+      if (A.c_tp) A.c_tp[o] = sc.timeprof;
+    } else {
+      ChanTab chl = ch;
+      chl.amp = amp;
+      double d[9], g;
+      if (MODE == MODE_DERIV) {
+        // the reference looks deriv_amplitude_pbf up with the requested component.
+        first_derivatives(chl, L.chan[A.d_comp], ct.w, tau0, sc.spectrum, sc.timediff, d, &g);
+        const bool all = A.d_addall && is_fit_global(A.d_param);
+        if (all || c == A.d_comp) dsum += d[A.d_param];
+      } else {
+        // LSFitter.compute_jacobian calls the global derivatives with component = 0
+        // (analysis/fitter.py:213-223), per-component ones with their own index.
+        double dg[9];
+        first_derivatives(chl, ch, ct.w, tau0, sc.spectrum, sc.timediff, d, &g);
+        if (c == 0) {
+          for (int p = 0; p < 9; ++p) dg[p] = d[p];
+        } else {
+          first_derivatives(chl, L.chan[0], ct.w, tau0, sc.spectrum, sc.timediff, dg, &g);
+        }
+#pragma unroll
+        for (int p = 0; p < 9; ++p) {
+          const int col = A.col_of[p];
+          if (col < 0) continue;
+          if (is_fit_global(p)) row[col] += -dg[p] * wi;
+          else row[col + c] = -d[p] * wi;
+        }
+      }
+    }
+  }
+  if (MODE == MODE_MODEL) {
+    A.model[s_idx] = msum;
+  } else if (MODE == MODE_DERIV) {
+    A.d_out[s_idx] = dsum;
+  } else {
+    const double r = (A.data[s_idx] - msum) * wi;  // analysis/fitter.py:262-264
+    row[n] = r;
+    if (MODE == MODE_JAC) {
+      if (A.jac)
+        for (int k = 0; k < n; ++k) A.jac[s_idx * n + k] = row[k];
+      if (A.resid) A.resid[s_idx] = r;
+    }
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
+  extern __shared__ double smem_raw[];
+  const PlanConst& pc = A.pc;
+  const int nc = pc.num_comp, kf = pc.kf, tid = threadIdx.x;
+  SmemLayout L = carve(smem_raw, nc, kf);
+  for (int c = tid; c < nc; c += blockDim.x) make_comp_tab(pc, A.params, c, L.comp[c]);
+  __syncthreads();
+
+  const int ncols = A.n_free + 1;
+  const int stride = gram_stride(ncols);
+  const int side = gram_side(ncols);
+  const int ntiles = gram_ntiles(ncols);
+  const int nslices = kBlock / ntiles;
+  const int g_tile = tid % ntiles, g_slice = tid / ntiles;
+  const bool g_active = (MODE == MODE_GRAM) && g_slice < nslices;
+  int g_ti = 0, g_tj = 0;
+  if (MODE == MODE_GRAM) tile_coords(g_tile, side, g_ti, g_tj);
+  double acc[kTile * kTile];
+#pragma unroll
+  for (int k = 0; k < kTile * kTile; ++k) acc[k] = 0.0;
+
+  const int tiles = (pc.num_time + kBlock - 1) / kBlock;
+  double* row = L.X + (size_t)tid * stride;
+
+  if (!pc.scintillation) {
+    const long long total = (long long)A.num_chan * tiles;
+    const long long begin = total * blockIdx.x / gridDim.x;
+    const long long end = total * (blockIdx.x + 1) / gridDim.x;
+    int cur = -1;
+    for (long long item = begin; item < end; ++item) {
+      const int chi = (int)(item / tiles), tile = (int)(item % tiles);
+      const int i = A.chan_list ? A.chan_list[chi] : chi;
+      if (chi != cur) {
+        load_channel_tables(A, L, i);
+        cur = chi;
+      }
+      const int j = tile * kBlock + tid;
+      process_sample<MODE>(A, L, i, j, j < pc.num_time, row, stride);
+      if (MODE == MODE_GRAM) {
+        __syncthreads();
+        gram_accumulate(L.X, stride, kBlock, ntiles, nslices, g_ti, g_tj, g_slice, g_active, acc);
+        __syncthreads();
+      }
+    }
+  } else {
+    // Scintillation: per-channel amplitudes come from a least-squares solve over ALL samples of
+    // the channel (routines/ism.py:11-48), so a block owns whole channels and makes two passes.
+    const int ncols2 = nc + 1;
+    const int stride2 = gram_stride(ncols2);
+    const int side2 = gram_side(ncols2);
+    const int ntiles2 = gram_ntiles(ncols2);
+    const int nslices2 = kBlock / ntiles2;
+    const int s_tile = tid % ntiles2, s_slice = tid / ntiles2;
+    const bool s_active = s_slice < nslices2;
+    int s_ti, s_tj;
+    tile_coords(s_tile, side2, s_ti, s_tj);
+    double* row2 = L.X + (size_t)tid * stride2;
+    for (int chi = blockIdx.x; chi < A.num_chan; chi += gridDim.x) {
+      const int i = A.chan_list ? A.chan_list[chi] : chi;
+      load_channel_tables(A, L, i);
+      double acc2[kTile * kTile];
+#pragma unroll
+      for (int k = 0; k < kTile * kTile; ++k) acc2[k] = 0.0;
+      for (int tile = 0; tile < tiles; ++tile) {
+        const int j = tile * kBlock + tid;
+        for (int k = 0; k < stride2; ++k) row2[k] = 0.0;
+        if (j < pc.num_time) {
+          for (int c = 0; c < nc; ++c) {
+            const SampleComp sc =
+                eval_sample_component(pc, L.comp[c], L.sub + c * kf, L.chan[c].scattered, j);
+            row2[c] = sc.timeprof;
+          }
+          row2[nc] = A.data[(size_t)i * pc.num_time + j];
+        }
+        __syncthreads();
+        gram_accumulate(L.X, stride2, kBlock, ntiles2, nslices2, s_ti, s_tj, s_slice, s_active, acc2);
+        __syncthreads();
+      }
+      // block sums land tile-major in X, then thread 0 assembles and solves.
+      double* sums = L.tilesum;
+      gram_block_reduce(L.X, ntiles2, nslices2, s_tile, s_slice, s_active, acc2, sums);
+      if (tid == 0) {
+        double* G = L.small;            // nc x nc
+        double* b = L.small + nc * nc;  // nc
+        for (int t = 0; t < ntiles2; ++t) {
+          int ti, tj;
+          tile_coords(t, side2, ti, tj);
+          for (int r = 0; r < kTile; ++r)
+            for (int q = 0; q < kTile; ++q) {
+              const int gr = ti * kTile + r, gc = tj * kTile + q;
+              const double v = sums[t * kTile * kTile + r * kTile + q];
+              if (gr < nc && gc < nc) {
+                G[gr * nc + gc] = v;
+                G[gc * nc + gr] = v;
+              } else if (gr < nc && gc == nc) {
+                b[gr] = v;
+              }
+            }
+        }
+        const bool ok = solve_small(G, b, nc, nc);
+        for (int c = 0; c < nc; ++c) L.scint_amp[c] = ok ? b[c] : nan("");
+        if (!ok && A.err_flag) atomicExch(A.err_flag, 1);
+      }
+      __syncthreads();
+      for (int tile = 0; tile < tiles; ++tile) {
+        const int j = tile * kBlock + tid;
+        process_sample<MODE>(A, L, i, j, j < pc.num_time, row, stride);
+        if (MODE == MODE_GRAM) {
+          __syncthreads();
+          gram_accumulate(L.X, stride, kBlock, ntiles, nslices, g_ti, g_tj, g_slice, g_active, acc);
+          __syncthreads();
+        }
+      }
+    }
+  }
+
+  if (MODE == MODE_GRAM) {
+    gram_block_reduce(L.X, ntiles, nslices, g_tile, g_slice, g_active, acc,
+                      A.partials + (size_t)blockIdx.x * ntiles * kTile * kTile);
+  }
+}
+
+// Second stage: sums the per-block partial tiles in block order and writes the symmetric
+// (ncols x ncols) matrix.
+__global__ void k_gram_finalize(const double* __restrict__ partials, int nblocks, int ncols,
+                                double* __restrict__ gram) {
+  const int side = gram_side(ncols), ntiles = gram_ntiles(ncols);
+  constexpr int kk = kTile * kTile;
+  for (int e = threadIdx.x; e < ntiles * kk; e += blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * ntiles * kk + e];
+    const int t = e / kk, r = (e % kk) / kTile, q = e % kTile;
+    int ti, tj;
+    tile_coords(t, side, ti, tj);
+    const int gr = ti * kTile + r, gc = tj * kTile + q;
+    if (gr < ncols && gc < ncols) {
+      if (ti != tj || gr <= gc) {
+        gram[gr * ncols + gc] = s;
+        gram[gc * ncols + gr] = s;
+      }
+    }
+  }
+}
+
+// LSFitter._set_weights (analysis/fitter.py:506-542): one block per channel.
+__global__ void __launch_bounds__(kBlock) k_weights(const double* __restrict__ data, int num_freq,
+                                                   int num_time, const uint8_t* __restrict__ good,
+                                                   int weighted, int lo, int hi,
+                                                   double* __restrict__ weights,
+                                                   double* __restrict__ chan_sumsq) {
+  __shared__ double red[2][kBlock];
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const double* rowp = data + (size_t)i * num_time;
+  double s_range = 0.0, s_all = 0.0;
+  for (int j = tid; j < num_time; j += kBlock) {
+    const double v = rowp[j];
+    const double v2 = v * v;
+    s_all += v2;
+    if (j >= lo && j < hi) s_range += v2;
+  }
+  red[0][tid] = s_range;
+  red[1][tid] = s_all;
+  __syncthreads();
+  for (int off = kBlock / 2; off > 0; off >>= 1) {
+    if (tid < off) {
+      red[0][tid] += red[0][tid + off];
+      red[1][tid] += red[1][tid + off];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    double w = 0.0;
+    if (good[i]) {
+      const int cnt = hi - lo;
+      w = weighted ? 1.0 / sqrt(red[0][0] / (double)cnt) : 1.0;
+    }
+    weights[i] = w;
+    chan_sumsq[i] = red[1][0] * w * w;
+  }
+}
+
+// Dependent-free FP64 FMA chains: the measured roofline denominator for the model kernels.
+__global__ void k_dfma_peak(double* out, int iters) {
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double m = 0.999999, b = 1e-7;
+  for (int it = 0; it < iters; ++it) {
+    a0 = fma(a0, m, b);
+    a1 = fma(a1, m, b);
+    a2 = fma(a2, m, b);
+    a3 = fma(a3, m, b);
+    a4 = fma(a4, m, b);
+    a5 = fma(a5, m, b);
+    a6 = fma(a6, m, b);
+    a7 = fma(a7, m, b);
+  }
+  out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+}  // namespace fb

@@ -1,0 +1,141 @@
+"""
+Parity of the CUDA path (through the SpectrumModeler / LSFitter mirror, i.e. through the C ABI)
+against the CPU oracle on seeded inputs. Tolerances are BASELINE.json's: model 1e-10 relative,
+best-fit parameters 1e-6 relative.
+"""
+import numpy as np
+import pytest
+
+from fitburst_b200 import synthetic as syn
+from tests.helpers import assert_close, make_case, model_pair, rel_to_max
+
+pytestmark = pytest.mark.gpu
+
+MODEL_CASES = {
+    "config2_shape": dict(),
+    "no_upsampling": dict(kf=1, kt=1),
+    "odd_factors": dict(kf=3, kt=5, num_comp=2),
+    "gaussian": dict(tau=0.0, kf=4, kt=2),
+    "folded": dict(folded=True, kf=2, kt=3, num_comp=2),
+    "folded_gaussian": dict(folded=True, tau=0.0, kf=2, kt=2, num_comp=1),
+    "dedispersed_offset": dict(dm=0.3, kf=4, kt=2),
+    "incoherent_dm": dict(dm_inc=50.0, dm=0.05, kf=4, kt=2, num_comp=1),
+    "ragged_time": dict(num_time=301, num_freq=19, kf=2, kt=2),
+    "eight_components": dict(num_comp=3, kf=1, kt=1, num_time=640),
+}
+
+
+@pytest.mark.parametrize("name", list(MODEL_CASES))
+def test_model_and_caches(name, native_lib):
+    freqs, times, truth, kwargs = make_case(**MODEL_CASES[name])
+    cuda, oracle = model_pair(freqs, times, kwargs, truth)
+    got = cuda.compute_model()
+    want = oracle.compute_model()
+    assert_close(got, want, 1e-10, f"{name} model")
+    assert_close(cuda.spectrum_per_component, oracle.spectrum_per_component, 1e-10, f"{name} spectrum")
+    assert_close(cuda.timeprof_per_component, oracle.timeprof_per_component, 1e-10, f"{name} timeprof")
+    assert_close(cuda.amplitude_per_component, oracle.amplitude_per_component, 1e-10, f"{name} amplitude")
+    # timediff is a difference of O(second) terms: absolute 1e-15 s is its rounding floor
+    assert np.max(np.abs(cuda.timediff_per_component - oracle.timediff_per_component)) < 1e-13
+
+
+def test_normalize_pbf_flag(native_lib):
+    from fitburst_b200.backend import general
+    freqs, times, truth, kwargs = make_case(kf=2, kt=2)
+    general["flags"]["normalize_pbf"] = True
+    try:
+        cuda, oracle = model_pair(freqs, times, kwargs, truth)
+        oracle.normalize_pbf = True
+        assert_close(cuda.compute_model(), oracle.compute_model(), 1e-10, "normalize_pbf")
+    finally:
+        general["flags"]["normalize_pbf"] = False
+
+
+def _fitters(case, fixed, bad_fraction=0.3, sigma=0.1, seed=2, weighted=True, start=None):
+    from fitburst_b200.analysis.fitter import LSFitter
+    from oracle.fitburst_oracle import OracleFitter
+
+    freqs, times, truth, kwargs = make_case(**case)
+    cuda, oracle = model_pair(freqs, times, kwargs, truth)
+    clean = oracle.compute_model() if not kwargs["scintillation"] else None
+    if clean is None:
+        kw2 = dict(kwargs, scintillation=False)
+        _, plain = model_pair(freqs, times, kw2, truth)
+        clean = plain.compute_model()
+    good = syn.make_good_freq(len(freqs), bad_fraction, seed)
+    data = syn.add_noise(clean, good, sigma, seed)
+    begin = start if start is not None else syn.config2_start(truth)
+    cuda.update_parameters(begin)
+    oracle.update_parameters(begin)
+    fc = LSFitter(data, cuda, good, weighted_fit=weighted)
+    fo = OracleFitter(data, oracle, good, weighted_fit=weighted)
+    fc.fix_parameter(list(fixed))
+    fo.fix_parameter(list(fixed))
+    return fc, fo
+
+
+def test_weights(native_lib):
+    fc, fo = _fitters(dict(kf=2, kt=2), ["dm_index", "scattering_index"])
+    np.testing.assert_allclose(fc.weights, fo.weights, rtol=1e-13, atol=0)
+    assert np.all(fc.weights[~fo.good_freq] == 0.0)
+
+
+@pytest.mark.parametrize("case,fixed", [
+    (dict(), ["dm_index", "scattering_index"]),
+    (dict(kf=1, kt=1), []),
+    (dict(tau=0.0, kf=2, kt=2), ["dm_index", "scattering_index", "scattering_timescale"]),
+    (dict(dm=0.2, kf=2, kt=2, num_comp=2), ["dm_index", "scattering_index"]),
+])
+def test_residuals_jacobian_and_normal_equations(case, fixed, native_lib):
+    import ctypes, torch
+    from fitburst_b200 import _lib
+    fc, fo = _fitters(case, fixed)
+    x0 = fo.get_fit_parameters_list()
+    assert fc.get_fit_parameters_list() == x0
+    r_c, r_o = fc.compute_residuals(x0), fo.compute_residuals(x0)
+    assert_close(r_c, r_o, 1e-9, "residuals")
+    j_c, j_o = fc.compute_jacobian(x0), fo.compute_jacobian(x0)
+    assert j_c.shape == j_o.shape
+    for col in range(j_o.shape[1]):
+        assert rel_to_max(j_c[:, col], j_o[:, col]) < 1e-9, f"jacobian column {col}"
+    # fused normal equations against the oracle's dense J and r
+    plan, n = fc._prepare()
+    fc.model._push_parameters()
+    gram = np.zeros((n + 1, n + 1))
+    _lib.check(native_lib.fb_normal_equations(plan, fc._data_on_device().data_ptr(), _lib.dptr(gram), fc._stream()))
+    full = np.concatenate([j_o, r_o[:, None]], axis=1)
+    want = full.T @ full
+    scale = np.sqrt(np.outer(np.diag(want), np.diag(want)))
+    assert np.max(np.abs(gram - want) / scale) < 1e-9
+
+
+@pytest.mark.parametrize("case,fixed", [
+    (dict(num_freq=64, num_time=128), ["dm_index", "scattering_index"]),
+    (dict(num_freq=64, num_time=128, kf=1, kt=1, num_comp=1), ["dm_index", "scattering_index", "scattering_timescale"]),
+    (dict(num_freq=64, num_time=128, tau=0.0, kf=2, kt=2, num_comp=2), ["dm_index", "scattering_index", "scattering_timescale"]),
+])
+def test_fit_matches_scipy_trajectory(case, fixed, native_lib):
+    fc, fo = _fitters(case, fixed)
+    fc.fit()
+    fo.fit(with_statistics=False)
+    rc, ro = fc.results, fo.results
+    assert rc.status == ro.status
+    assert rc.nfev == ro.nfev and rc.njev == ro.njev
+    np.testing.assert_allclose(rc.x, ro.x, rtol=1e-6)
+    assert abs(rc.cost - ro.cost) <= 1e-9 * abs(ro.cost)
+    stats = fc.fit_statistics
+    assert stats["num_fit_parameters"] == len(ro.x)
+    assert abs(stats["chisq_final"] - float(np.sum(ro.fun ** 2))) <= 1e-9 * stats["chisq_final"]
+
+
+def test_scintillation_model(native_lib):
+    case = dict(scint=True, kf=1, kt=1, num_comp=2, num_time=160)
+    freqs, times, truth, kwargs = make_case(**case)
+    cuda, oracle = model_pair(freqs, times, kwargs, truth)
+    _, plain = model_pair(freqs, times, dict(kwargs, scintillation=False), truth)
+    rng = np.random.default_rng(5)
+    data = plain.compute_model() * np.exp(rng.normal(0, 0.5, size=(len(freqs), 1))) + rng.normal(0, 0.05, size=(len(freqs), len(times)))
+    got = cuda.compute_model(data=data)
+    want = oracle.compute_model(data=data)
+    assert_close(got, want, 1e-9, "scintillation model")
+    assert_close(cuda.amplitude_per_component, oracle.amplitude_per_component, 1e-9, "scintillation amplitudes")
