@@ -1,0 +1,402 @@
+"""
+Benchmark of the fitburst hot path on B200 (contract: see the task brief and DESIGN.md section 6).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--nfreq 16384 ...]
+
+A "step" is ONE complete LSFitter fit of one synthetic CHIME-shaped burst at BASELINE.json
+config 2 (16384 channels x 1024 samples, 3 scattered components with running power law, 8x
+frequency / 4x time up-sampling, 17 free parameters, ~35 % flagged channels): trust-region loop
++ exact Hessian + uncertainties. `value` = fits/s with the spectrum already resident in HBM;
+`e2e` = fits/s through LSFitter(data_host, ...).fit() with the host->device copy of the spectrum
+and the device->host read of the results inside the timed region. With --gpus N every rank fits
+its own bursts (config 3 sharding, no data-path collective): weak scaling.
+
+The `roofline` object describes the dominant kernel (the fused model + Jacobian + normal-equation
+pass), timed alone with CUDA events; `cpu_baseline` is the numpy oracle (a port of the
+reference's algorithm) timed on this box's host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FLOP_PER_PE_SCATTERED = 110.0  # SURVEY.md section 8d / BASELINE.md section 3
+FLOP_PER_PE_GAUSSIAN = 40.0
+FIXED = ["dm_index", "scattering_index"]  # config 2: 17 free parameters
+
+
+def jacobian_flop_per_sample(num_comp, p_c, p_g):
+    n = num_comp * p_c + p_g
+    return num_comp * (38 + 8 * p_c) + 8 * p_g * num_comp + n * (n + 1) + 2 * n + 6
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--nfreq", type=int, default=16384)
+    ap.add_argument("--ntime", type=int, default=1024)
+    ap.add_argument("--ncomp", type=int, default=3)
+    ap.add_argument("--kf", type=int, default=8)
+    ap.add_argument("--kt", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-stride", type=int, default=64, help="CPU sample: every k-th channel")
+    ap.add_argument("--eval-reps", type=int, default=20)
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(
+                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
+                    capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([s.strip() for s in out.split(",")])
+            except Exception:  # noqa: BLE001
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for name, val in zip(names, s[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def make_burst(args, seed, model_fn):
+    """Config 2 burst with seed-dependent noise and flag mask. model_fn(parameters) -> clean model."""
+    from fitburst_b200 import synthetic as syn
+
+    truth = syn.truncate_components(syn.config2_truth(args.ntime), args.ncomp)
+    clean = model_fn(truth)
+    good = syn.make_good_freq(args.nfreq, 0.35, seed)
+    data = syn.add_noise(clean, good, 0.1, seed)
+    return truth, syn.config2_start(truth), good, data
+
+
+# ------------------------------------------------------------------------------------------
+# CPU baseline (oracle port of the reference) -- the only place bench.py executes oracle/.
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(payload):
+    """One full oracle fit (trust-region loop + exact Hessian) of a channel-decimated burst."""
+    import warnings
+
+    warnings.filterwarnings("ignore")
+    from oracle.fitburst_oracle import OracleFitter, OracleModel
+    try:
+        from oracle import hessian_oracle
+    except Exception:  # noqa: BLE001
+        hessian_oracle = None
+    freqs, times, kwargs, start, good, data, fixed = payload
+    model = OracleModel(freqs, times, **kwargs)
+    model.update_parameters(start)
+    fitter = OracleFitter(data, model, good)
+    fitter.fix_parameter(list(fixed))
+    if hessian_oracle is not None:
+        fitter.hessian_fn = hessian_oracle.compute_hessian
+    t0 = time.perf_counter()
+    fitter.fit(with_statistics=True)
+    return time.perf_counter() - t0, int(fitter.results.nfev)
+
+
+def cpu_baseline(args, cores=None):
+    """Times `cores` concurrent oracle fits (one process per core) on every `stride`-th channel of
+    the config-2 workload and scales to the full channel count."""
+    import multiprocessing as mp
+
+    from fitburst_b200 import synthetic as syn
+    from oracle.fitburst_oracle import OracleModel
+
+    cores = cores or os.cpu_count() or 1
+    stride = args.cpu_stride
+    freqs_full, times = syn.chime_axes(args.nfreq, args.ntime)
+    kwargs = dict(factor_freq_upsample=args.kf, factor_time_upsample=args.kt, num_components=args.ncomp)
+    payloads = []
+    for worker in range(cores):
+        # decimated channel set; the model needs the ORIGINAL channel width, so hand it the
+        # first two labels of the full axis via a two-channel-consistent subset: the oracle (like
+        # the reference) takes res_freq from freqs[1]-freqs[0], so the subset keeps channel pairs.
+        idx = np.arange(worker % stride, args.nfreq - 1, stride)
+        idx = np.unique(np.concatenate([idx[:1], idx[:1] + 1, idx[1:]]))
+        freqs = freqs_full[idx]
+
+        def model_fn(parameters, freqs=freqs):
+            model = OracleModel(freqs, times, **kwargs)
+            model.update_parameters(parameters)
+            return model.compute_model()
+
+        truth = syn.truncate_components(syn.config2_truth(args.ntime), args.ncomp)
+        clean = model_fn(truth)
+        good = syn.make_good_freq(len(freqs), 0.35, 100 + worker)
+        data = syn.add_noise(clean, good, 0.1, 100 + worker)
+        payloads.append((freqs, times, kwargs, syn.config2_start(truth), good, data, FIXED))
+    nchan = len(payloads[0][0])
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(cores) as pool:
+        out = pool.map(_cpu_worker, payloads)
+    wall = time.perf_counter() - t0
+    scale = args.nfreq / nchan
+    fits_per_s = cores / (wall * scale)
+    return {
+        "value": fits_per_s, "unit": "fits/s", "cores": cores, "kind": "port",
+        "sample": (f"{cores} concurrent oracle fits (one process per core), each on {nchan} of {args.nfreq} "
+                   f"channels (every {stride}th) x {args.ntime} samples, {args.ncomp} comps, {args.kf}x{args.kt} "
+                   f"up-sampling, incl. exact Hessian; wall {wall:.1f}s, mean nfev "
+                   f"{np.mean([o[1] for o in out]):.1f}; time scaled x{scale:.1f} to the full channel count"),
+    }, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = []
+    base = None
+    for _ in range(max(1, min(args.steps, 2))):
+        base, wall = cpu_baseline(args)
+        per_step.append(wall)
+    value = base["value"]
+    line = {
+        "impl": "reference", "metric": "LSFitter fits/s at 16384ch x 1024t 3-comp", "value": value, "unit": "fits/s",
+        "n_gpus": args.gpus, "steps": len(per_step), "warmup": 0, "ms_per_step": 1e3 / value,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args), "cpu_baseline": base,
+        "e2e": {"value": value, "unit": "fits/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args):
+    return {
+        "workload": (f"BASELINE.json configs[1]: synthetic CHIME-shape {args.nfreq} ch x {args.ntime} samples, "
+                     f"{args.ncomp}-component scattered burst, running power law, {args.kf}x freq / {args.kt}x time "
+                     "up-sampling, single LSFitter fit (17 free parameters) incl. exact Hessian"),
+        "num_freq": args.nfreq, "num_time": args.ntime, "num_components": args.ncomp,
+        "factor_freq_upsample": args.kf, "factor_time_upsample": args.kt, "free_parameters": 17,
+        "flagged_channel_fraction": 0.35, "sharding": "one independent burst per GPU per step",
+        "l2_note": "134 MB spectrum per fit > 126 MB L2; a different burst buffer is fitted on consecutive steps",
+    }
+
+
+# ------------------------------------------------------------------------------------------
+def run_cuda(args):
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as entry
+    entry.build()
+    from fitburst_b200 import _lib
+    from fitburst_b200.analysis.fitter import LSFitter
+    from fitburst_b200.analysis.model import SpectrumModeler
+    from fitburst_b200 import synthetic as syn
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    lib = _lib.load_library()
+
+    freqs, times = syn.chime_axes(args.nfreq, args.ntime)
+    kwargs = dict(factor_freq_upsample=args.kf, factor_time_upsample=args.kt, num_components=args.ncomp)
+    model = SpectrumModeler(freqs, times, device=device, **kwargs)
+
+    def model_fn(parameters):
+        model.update_parameters(parameters)
+        return model.compute_model()
+
+    # two different bursts per rank, alternated between steps (each 134 MB > L2).
+    bursts = [make_burst(args, 1000 * rank + k, model_fn) for k in range(2)]
+    pinned = [torch.from_numpy(b[3]).pin_memory() for b in bursts]
+    host_data = [p.numpy() for p in pinned]
+
+    import contextlib, io
+
+    def one_fit_resident(fitter, start):
+        model.update_parameters(start)
+        with contextlib.redirect_stdout(io.StringIO()):
+            fitter.fit()
+        return fitter
+
+    def one_fit_e2e(k):
+        truth, start, good, _ = bursts[k]
+        model.update_parameters(start)
+        with contextlib.redirect_stdout(io.StringIO()):
+            fitter = LSFitter(host_data[k], model, good, weighted_fit=True)
+            fitter.fix_parameter(FIXED)
+            fitter.fit()
+        stats = fitter.fit_statistics
+        return fitter, stats
+
+    # resident fitters (data uploaded, weights computed) outside the timed region
+    resident = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for k in range(2):
+            model.update_parameters(bursts[k][1])
+            f = LSFitter(host_data[k], model, bursts[k][2], weighted_fit=True)
+            f.fix_parameter(FIXED)
+            resident.append(f)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for s in range(warmup):
+            fn(s)
+        barrier()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        ev0.record()
+        for s in range(steps):
+            fn(s)
+        ev1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = ev0.elapsed_time(ev1)
+        ms = max(ms, 0.0)
+        t = torch.tensor([ms, wall * 1e3], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1])
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    plan = model._ensure_plan()
+    launches = __import__("ctypes").c_int64(0)
+    lib.fb_launch_count(plan, launches, 1)
+    last = {}
+
+    def step_resident(s):
+        last["fitter"] = one_fit_resident(resident[s % 2], bursts[s % 2][1])
+
+    ms_dev, ms_wall = timed(step_resident, args.steps, args.warmup)
+    lib.fb_launch_count(plan, launches, 1)
+    # launches were counted over warmup + timed steps: keep the timed share
+    gpu_launches = int(round(launches.value * args.steps / max(1, args.steps + args.warmup)))
+    ms_step = max(ms_dev, ms_wall) / args.steps  # host-driven loop: wall and device agree; take the larger
+    value = world * 1e3 / ms_step
+
+    def step_e2e(s):
+        last["e2e"] = one_fit_e2e(s % 2)
+
+    ms_dev_e, ms_wall_e = timed(step_e2e, args.steps, args.warmup)
+    ms_step_e = max(ms_dev_e, ms_wall_e) / args.steps
+    e2e_value = world * 1e3 / ms_step_e
+    sampler.stop_flag.set()
+    sampler.join(timeout=2)
+
+    fitter = last["fitter"]
+    res = fitter.results
+    nfev = int(res.nfev)
+    n_free = len(res.x)
+    h2d = int(host_data[0].nbytes + args.nfreq)  # spectrum + flag mask
+    d2h = int(8 * ((n_free + 1) ** 2 * nfev + n_free * n_free + args.nfreq + 10 * args.ncomp))
+
+    # ---- dominant kernel alone: fused model + Jacobian + normal equations --------------------
+    fitter0 = resident[0]
+    plan0, n = fitter0._prepare()
+    model.update_parameters(bursts[0][1])
+    model._push_parameters()
+    gram_dev = torch.empty((n + 1) * (n + 1), dtype=torch.float64, device=device)
+    stream = model._stream()
+    data_ptrs = [f._data_on_device().data_ptr() for f in resident]
+    for r in range(3):
+        _lib.check(lib.fb_normal_equations_dev(plan0, data_ptrs[r % 2], gram_dev.data_ptr(), stream))
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for r in range(args.eval_reps):
+        _lib.check(lib.fb_normal_equations_dev(plan0, data_ptrs[r % 2], gram_dev.data_ptr(), stream))
+    ev1.record()
+    torch.cuda.synchronize()
+    eval_ms = ev0.elapsed_time(ev1) / args.eval_reps
+    num_good = int(np.sum(bursts[0][2]))
+    n_pe = float(args.ncomp) * num_good * args.kf * args.ntime * args.kt
+    flop = n_pe * FLOP_PER_PE_SCATTERED + float(num_good) * args.ntime * jacobian_flop_per_sample(args.ncomp, 5, 2)
+    peak = __import__("ctypes").c_double(0.0)
+    _lib.check(lib.fb_measure_fp64_peak(peak, stream))
+    achieved = flop / (eval_ms * 1e-3) / 1e12
+    roofline = {
+        "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
+        "frac": achieved / peak.value if peak.value > 0 else None, "traffic": None,
+        "kernel": "fb::k_eval<MODE_GRAM> (fused model + analytic Jacobian + [J r]^T[J r])",
+        "ms_per_launch": eval_ms, "algorithmic_flop_per_launch": flop,
+        "units_per_launch": {"profile_evaluations": n_pe, "good_channels": num_good},
+        "peak_source": "measured live: dependent-free DFMA chains on all SMs (MEASURED_PEAKS.json has no FP64 entry)",
+        "hbm_algorithmic_bytes_per_launch": 8.0 * num_good * args.ntime,
+        "evals_per_s": 1e3 / eval_ms,
+    }
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "LSFitter fits/s at 16384ch x 1024t 3-comp", "value": value, "unit": "fits/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_step_e},
+            "gpu_launches": gpu_launches, "clocks": sampler.summary(), "roofline": roofline,
+            "fit": {"status": int(res.status), "nfev": nfev, "njev": int(res.njev),
+                    "chisq_final_reduced": fitter.fit_statistics.get("chisq_final_reduced"),
+                    "uncertainties_computed": fitter.fit_statistics.get("bestfit_uncertainties") is not None},
+            "model_jacobian_evals_per_s": 1e3 / eval_ms,
+        }
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"], _ = cpu_baseline(args)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()
