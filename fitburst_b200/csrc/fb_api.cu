@@ -11,6 +11,8 @@
 #include <vector>
 
 #include "fb_kernels.cuh"
+#include "fb_hessian.cuh"
+#define FB_HAVE_HESSIAN 1
 #include "fb_trf.h"
 
 using namespace fb;
@@ -45,6 +47,10 @@ struct fb_plan_s {
   size_t partials_cap = 0;
   double* d_gram = nullptr;  // (FB_MAX_FREE+1)^2
   double* h_gram = nullptr;  // pinned
+  double* d_hess_partials = nullptr;
+  size_t hess_partials_cap = 0;
+  HessPair* d_pairs = nullptr;
+  size_t pairs_cap = 0;
   int* d_chan_list = nullptr;
   int num_good = 0;
   bool have_weights = false;
@@ -171,6 +177,8 @@ extern "C" int fb_plan_destroy(fb_plan_t p) {
   cudaFree(p->d_err);
   cudaFree(p->d_gram);
   cudaFree(p->d_partials);
+  cudaFree(p->d_hess_partials);
+  cudaFree(p->d_pairs);
   if (p->h_gram) cudaFreeHost(p->h_gram);
   delete p;
   return FB_OK;
@@ -572,6 +580,144 @@ extern "C" int fb_launch_count(fb_plan_t p, int64_t* count_out, int32_t reset) {
   *count_out = p->launches;
   if (reset) p->launches = 0;
   return FB_OK;
+}
+
+
+// ---- exact Hessian (analysis/fitter.py:81-178) --------------------------------------------------
+template <bool MAP>
+static int launch_hessian(fb_plan_s* p, HessArgs& H, cudaStream_t st, int* grid_out) {
+  const size_t smem = hess_smem_bytes(p->pc.num_comp, p->pc.kf, MAP ? 0 : H.num_pairs);
+  if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "Hessian shared-memory request %zu B exceeds 227 KB", smem);
+  if (smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(k_hessian<MAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_hessian<MAP>, kBlock, smem));
+  if (occ < 1) occ = 1;
+  const int tiles = (p->pc.num_time + kBlock - 1) / kBlock;
+  long long items = p->pc.scintillation ? (long long)H.E.num_chan : (long long)H.E.num_chan * tiles;
+  if (items < 1) items = 1;
+  long long grid = (long long)p->sm_count * occ;
+  if (MAP) grid *= 8;
+  if (grid > items) grid = items;
+  if (!MAP) {
+    const size_t need = (size_t)grid * H.num_pairs;
+    if (need > p->hess_partials_cap) {
+      cudaFree(p->d_hess_partials);
+      p->d_hess_partials = nullptr;
+      p->hess_partials_cap = 0;
+      CUDA_TRY(cudaMalloc(&p->d_hess_partials, sizeof(double) * need));
+      p->hess_partials_cap = need;
+    }
+    H.partials = p->d_hess_partials;
+  }
+  k_hessian<MAP><<<(int)grid, kBlock, smem, st>>>(H);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 1;
+  if (grid_out) *grid_out = (int)grid;
+  return FB_OK;
+}
+
+int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, cudaStream_t st) {
+  if (!p->have_weights) return fail(FB_ERR_INVALID, "fb_set_weights / fb_load_weights must be called first");
+  const int n = p->n_free, nc = p->desc.num_components;
+  if (n < 1) return fail(FB_ERR_INVALID, "no free parameters");
+  // packed columns -> (parameter, component), analysis/fitter.py:116-127
+  std::vector<int> cp(n), cc(n);
+  for (int k = 0; k < 9; ++k) {
+    if (p->col_of[k] < 0) continue;
+    if (is_fit_global(k)) {
+      cp[p->col_of[k]] = k;
+      cc[p->col_of[k]] = -1;
+    } else {
+      for (int c = 0; c < nc; ++c) {
+        cp[p->col_of[k] + c] = k;
+        cc[p->col_of[k] + c] = c;
+      }
+    }
+  }
+  std::vector<HessPair> pairs;
+  std::vector<int> pair_a, pair_b;
+  for (int a = 0; a < n; ++a)
+    for (int b = a; b < n; ++b) {
+      const bool la = cc[a] >= 0, lb = cc[b] >= 0;
+      if (la && lb && cc[a] != cc[b]) continue;  // mixed partial skipped, analysis/fitter.py:158-160
+      HessPair hp;
+      hp.pa = (int8_t)cp[a];
+      hp.pb = (int8_t)cp[b];
+      hp.component = (int8_t)(lb ? cc[b] : (la ? cc[a] : 0));  // analysis/fitter.py:163-168
+      hp.is_sum = d2_is_sum(cp[a], cp[b]) ? 1 : 0;
+      pairs.push_back(hp);
+      pair_a.push_back(a);
+      pair_b.push_back(b);
+    }
+  const int npairs = (int)pairs.size();
+  if ((size_t)npairs > p->pairs_cap) {
+    cudaFree(p->d_pairs);
+    p->d_pairs = nullptr;
+    p->pairs_cap = 0;
+    CUDA_TRY(cudaMalloc(&p->d_pairs, sizeof(HessPair) * npairs));
+    p->pairs_cap = npairs;
+  }
+  CUDA_TRY(cudaMemcpyAsync(p->d_pairs, pairs.data(), sizeof(HessPair) * npairs, cudaMemcpyHostToDevice, st));
+  const int ncols = n + 1;
+  std::vector<double> gram((size_t)ncols * ncols), S(npairs, 0.0);
+  // first-derivative products = J^T J of the weighted Jacobian at the model's current state
+  int rc = normal_equations_async(p, data_dev, p->d_gram, st);
+  if (rc != FB_OK) return rc;
+  CUDA_TRY(cudaMemcpyAsync(gram.data(), p->d_gram, sizeof(double) * ncols * ncols, cudaMemcpyDeviceToHost, st));
+  if (p->num_good > 0) {
+    HessArgs H;
+    memset(&H, 0, sizeof(H));
+    H.E = base_args(p);
+    H.E.data = data_dev;
+    H.E.weights = p->d_weights;
+    H.E.chan_list = p->d_chan_list;
+    H.E.num_chan = p->num_good;
+    H.pairs = p->d_pairs;
+    H.num_pairs = npairs;
+    int grid = 0;
+    rc = launch_hessian<false>(p, H, st, &grid);
+    if (rc != FB_OK) return rc;
+    double* d_out = p->d_gram;  // reuse: npairs <= (n+1)^2
+    CUDA_TRY(cudaStreamSynchronize(st));
+    k_hess_finalize<<<(npairs + 127) / 128, 128, 0, st>>>(p->d_hess_partials, grid, npairs, d_out);
+    CUDA_TRY(cudaGetLastError());
+    p->launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(S.data(), d_out, sizeof(double) * npairs, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (int a = 0; a < n; ++a)
+    for (int b = 0; b < n; ++b) hessian_host[a * n + b] = 2.0 * gram[(size_t)a * ncols + b];
+  for (int k = 0; k < npairs; ++k) {
+    const int a = pair_a[k], b = pair_b[k];
+    hessian_host[a * n + b] -= 2.0 * S[k];
+    if (a != b) hessian_host[b * n + a] -= 2.0 * S[k];
+  }
+  return check_err_flag(p, st);
+}
+
+extern "C" int fb_hessian(fb_plan_t p, const double* data_dev, double* hessian_host, void* stream) {
+  if (!p || !data_dev || !hessian_host) return fail(FB_ERR_INVALID, "null argument");
+  return fb_hessian_impl(p, data_dev, hessian_host, (cudaStream_t)stream);
+}
+
+extern "C" int fb_derivative2_map(fb_plan_t p, const double* data_dev, int32_t param1, int32_t param2,
+                                  int32_t component, double* out_dev, void* stream) {
+  if (!p || !out_dev) return fail(FB_ERR_INVALID, "null argument");
+  if (param1 < 0 || param1 > 8 || param2 < 0 || param2 > 8) return fail(FB_ERR_INVALID, "parameter index out of range");
+  if (component < 0 || component >= p->desc.num_components) return fail(FB_ERR_INVALID, "component out of range");
+  if (p->pc.scintillation && !data_dev) return fail(FB_ERR_INVALID, "scintillation mode needs data");
+  HessArgs H;
+  memset(&H, 0, sizeof(H));
+  H.E = base_args(p);
+  H.E.data = data_dev;
+  H.map_pa = param1;
+  H.map_pb = param2;
+  H.map_component = component;
+  H.map_out = out_dev;
+  int rc = launch_hessian<true>(p, H, (cudaStream_t)stream, nullptr);
+  if (rc != FB_OK) return rc;
+  return check_err_flag(p, (cudaStream_t)stream);
 }
 
 // ---- entry points implemented in later translation units / sections ---------------------------

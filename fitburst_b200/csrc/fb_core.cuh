@@ -59,6 +59,10 @@ struct ChanTab {
   double dap_w, dap_tau, dap_alpha;  // deriv_amplitude_pbf for burst_width / scattering_timescale /
                                      // scattering_index with THIS component as the one looked up
                                      // (routines/derivative.py:105-152)
+  double d2ap_alpha; // deriv2_amplitude_pbf(scattering_index, scattering_index), :154-209
+  double fpow, refpow;  // f_i ** dm_index, ref_freq ** dm_index
+  double q1, q2;     // ln f f^b - ln fr fr^b  and  ln^2 f f^b - ln^2 fr fr^b (derivative.py:2267,2822)
+  double ref_freq;
   int scattered;     // any(sc_time(f_ia) > 0) over the sub-frequencies, analysis/model.py:339
 };
 
@@ -153,14 +157,21 @@ __device__ inline void make_chan_tab(const PlanConst& pc, const double* params, 
     ch.dap_w = kSqrtHalfPi / ch.sc_time;
     ch.dap_alpha = -kSqrtHalfPi * lf * ct.w / ch.sc_time;
     ch.dap_tau = -kSqrtHalfPi * ct.w / (ch.sc_time * tau0);
+    ch.d2ap_alpha = kSqrtHalfPi * lf * lf * ct.w / ch.sc_time;
   } else {
     ch.dap_w = 0.0;
     ch.dap_tau = 0.0;
     ch.dap_alpha = -lf * pow(fr, -alpha);
+    ch.d2ap_alpha = lf * lf * pow(fr, -alpha);
   }
   const double fc_b = pow(fc, beta), fref_b = pow(fref, beta);
   ch.d_dm = -pc.dm_const * (fc_b - fref_b);
-  ch.d_dmidx = -pc.dm_const * dm * (log(fc) * fc_b - log(fref) * fref_b);
+  ch.q1 = log(fc) * fc_b - log(fref) * fref_b;
+  ch.q2 = log(fc) * log(fc) * fc_b - log(fref) * log(fref) * fref_b;
+  ch.d_dmidx = -pc.dm_const * dm * ch.q1;
+  ch.fpow = fc_b;
+  ch.refpow = fref_b;
+  ch.ref_freq = fref;
   int scattered = 0;
   for (int a = 0; a < pc.kf; ++a) {
     const double f = pc.subfreqs[(size_t)i * pc.kf + a];
@@ -246,7 +257,7 @@ __device__ __forceinline__ SampleComp eval_sample_component(const PlanConst& pc,
 // the shared factor amp * amp_pbf * exp(arg_exp) * 2/sqrt(pi) for the second derivatives.
 __device__ __forceinline__ void first_derivatives(const ChanTab& ch, const ChanTab& cho, double w,
                                                   double tau0, double m, double td, double* d,
-                                                  double* gfac_out) {
+                                                  double* gfac_out, double* arg_erf_out = nullptr) {
   const double lf = ch.logf;
   d[FB_AMPLITUDE] = kLn10 * m;
   d[FB_SPECTRAL_INDEX] = lf * m;
@@ -258,6 +269,7 @@ __device__ __forceinline__ void first_derivatives(const ChanTab& ch, const ChanT
   const double arg_exp = 0.5 * ws * ws - td / tau - arg_erf * arg_erf;
   const double g = ch.amp * ch.amp_pbf * exp(arg_exp) * kTwoOverSqrtPi;
   *gfac_out = g;
+  if (arg_erf_out) *arg_erf_out = arg_erf;
   const double inv_amp_pbf = 1.0 / ch.amp_pbf;
   if (tau == 0.0) {  // per-channel Gaussian branch, routines/derivative.py:568,629,695,767
     const double w2 = w * w;

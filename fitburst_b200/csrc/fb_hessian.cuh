@@ -1,0 +1,403 @@
+// Exact chi^2 Hessian: the 45 mixed partials of routines/derivative.py:938-2836 evaluated per
+// (sample, component) from the same three quantities the first derivatives use (spectrum,
+// amplitude, time difference), contracted on the fly with the weighted residual so that no
+// (Nf, Nt) derivative map is ever stored:   S_ab = sum (data - model) w^2 d2m/dadb,
+//   H = 2 J^T J - 2 S   (LSFitter.compute_hessian, analysis/fitter.py:81-178).
+// The reference's quirks are reproduced deliberately (they define bestfit_uncertainties); each
+// is flagged "quirk" with its line.
+#pragma once
+#include "fb_kernels.cuh"
+
+namespace fb {
+
+struct D2Ctx {
+  double M, T, w, tau, tau0, L, apbf, D, Dp, G, arg_erf;
+  double d1[9];
+  double fpow, ref_freq, q1, q2, k, dm;
+  double dap_alpha, d2ap_alpha;
+  double sum_dmidx;   // component-summed d model / d dm_index (quirk: derivative.py:2110, 2266)
+  double apbf_outer;  // amp_pbf of the function's `component` argument (quirk: derivative.py:2807)
+};
+
+__host__ __device__ inline bool is_scalar_row(int p) {
+  return p == FB_AMPLITUDE || p == FB_SPECTRAL_INDEX || p == FB_SPECTRAL_RUNNING;
+}
+
+// Functions of the reference that return the SUM over components whatever `component` is.
+__host__ __device__ inline bool d2_is_sum(int pa, int pb) {
+  if (pa > pb) {
+    const int t = pa;
+    pa = pb;
+    pb = t;
+  }
+  if (is_scalar_row(pa) || is_scalar_row(pb)) return false;
+  if (pa == FB_ARRIVAL_TIME || pa == FB_BURST_WIDTH) return false;
+  if (pa == FB_DM && pb == FB_DM_INDEX) return false;
+  return true;  // dm_dm, dm x scattering_*, dm_index x {dm_index, scattering_*}, scattering_* x scattering_*
+}
+
+__device__ __forceinline__ double d2_dae(int p, const D2Ctx& c) {  // deriv_argument_erf, :252-307
+  switch (p) {
+    case FB_ARRIVAL_TIME: return -1.0 / c.w * kSqrtHalf;
+    case FB_BURST_WIDTH: return -(c.T / (c.w * c.w) + 1.0 / c.tau) * kSqrtHalf;
+    case FB_DM: return c.D / c.w * kSqrtHalf;
+    case FB_DM_INDEX: return c.Dp / c.w * kSqrtHalf;
+    case FB_SCATTERING_TIMESCALE: return c.w / c.tau0 / c.tau * kSqrtHalf;
+    case FB_SCATTERING_INDEX: return c.L * c.w / c.tau * kSqrtHalf;
+  }
+  return 0.0;
+}
+
+__device__ __forceinline__ double d2_dax(int p, const D2Ctx& c) {  // deriv_argument_exp, :309-371
+  double base = 0.0;
+  const double ws = c.w / c.tau;
+  switch (p) {
+    case FB_ARRIVAL_TIME: base = 1.0 / c.tau; break;
+    case FB_BURST_WIDTH: base = c.w / (c.tau * c.tau); break;
+    case FB_DM: base = -c.D / c.tau; break;
+    case FB_DM_INDEX: base = -c.Dp / c.tau; break;
+    case FB_SCATTERING_TIMESCALE: base = -(ws * ws) / c.tau0 + c.T / c.tau / c.tau0; break;
+    case FB_SCATTERING_INDEX: base = c.L * (-(ws * ws) + c.T / c.tau); break;
+  }
+  return base - 2.0 * c.arg_erf * d2_dae(p, c);
+}
+
+// One component's term of deriv2_model_wrt_<pa>_<pb> (unordered pair).
+__device__ double d2_term(int pa, int pb, const D2Ctx& c) {
+  if (pa > pb) {
+    const int t = pa;
+    pa = pb;
+    pb = t;
+  }
+  const double M = c.M, T = c.T, w = c.w, tau = c.tau, tau0 = c.tau0, L = c.L, G = c.G;
+  // rows that are scalar multiples of a first derivative, :938-1573
+  if (is_scalar_row(pa) || is_scalar_row(pb)) {
+    int s, o;  // the reference names amplitude first, then spectral_running, then spectral_index
+    if (pa == FB_AMPLITUDE) { s = pa; o = pb; }
+    else if (pb == FB_SPECTRAL_RUNNING) { s = pb; o = pa; }
+    else if (pa == FB_SPECTRAL_RUNNING) { s = pa; o = pb; }
+    else if (pb == FB_SPECTRAL_INDEX) { s = pb; o = pa; }
+    else { s = pa; o = pb; }
+    const double factor = (s == FB_AMPLITUDE) ? kLn10 : (s == FB_SPECTRAL_RUNNING ? L * L : L);
+    return factor * c.d1[o];
+  }
+  const bool gauss = (tau == 0.0);
+  const double w2 = w * w, ws = w / tau;
+  const int key = pa * 16 + pb;
+  switch (key) {
+    case FB_ARRIVAL_TIME * 16 + FB_ARRIVAL_TIME:  // :1957-2014
+      if (gauss) return T * T * M / (w2 * w2) - M / w2;
+      return c.d1[FB_ARRIVAL_TIME] / tau + G * d2_dae(FB_ARRIVAL_TIME, c) * d2_dax(FB_ARRIVAL_TIME, c);
+    case FB_ARRIVAL_TIME * 16 + FB_BURST_WIDTH:  // :1639-1700
+      if (gauss) return -2.0 * T * M / (w2 * w) + T * T * T * M / (w2 * w2 * w);
+      return w * c.d1[FB_ARRIVAL_TIME] / (tau * tau) + G * (1.0 / w2 * kSqrtHalf) +
+             G * d2_dae(FB_BURST_WIDTH, c) * d2_dax(FB_ARRIVAL_TIME, c);
+    case FB_ARRIVAL_TIME * 16 + FB_DM:  // :2016-2080
+      if (gauss) return T * c.d1[FB_DM] / w2 + c.D * M / w2;
+      return c.d1[FB_DM] / tau + G * d2_dae(FB_ARRIVAL_TIME, c) * d2_dax(FB_DM, c);
+    case FB_ARRIVAL_TIME * 16 + FB_DM_INDEX:  // :2082-2115 quirk: Gaussian form always, summed first derivative
+      return T * c.sum_dmidx / w2 + (c.k * c.dm * c.q1) * M / w2;
+    case FB_ARRIVAL_TIME * 16 + FB_SCATTERING_TIMESCALE:  // :2117-2174
+      return -M / tau0 / tau + c.d1[FB_SCATTERING_TIMESCALE] / tau +
+             G * d2_dae(FB_ARRIVAL_TIME, c) * d2_dax(FB_SCATTERING_TIMESCALE, c);
+    case FB_ARRIVAL_TIME * 16 + FB_SCATTERING_INDEX:  // :2176-2234
+      return -M * L / tau + c.d1[FB_SCATTERING_INDEX] / tau +
+             (G / c.apbf) * c.dap_alpha * d2_dae(FB_ARRIVAL_TIME, c) +
+             G * d2_dae(FB_ARRIVAL_TIME, c) * d2_dax(FB_SCATTERING_INDEX, c);
+    case FB_BURST_WIDTH * 16 + FB_BURST_WIDTH:  // :1575-1637
+      if (gauss) return -3.0 * T * T * M / (w2 * w2) + T * T * T * T * M / (w2 * w2 * w2);
+      return M / (tau * tau) + w * c.d1[FB_BURST_WIDTH] / (tau * tau) + G * (1.41421356237309504880 * T / (w2 * w)) +
+             G * d2_dae(FB_BURST_WIDTH, c) * d2_dax(FB_BURST_WIDTH, c);
+    case FB_BURST_WIDTH * 16 + FB_DM:  // :1822-1887
+      if (gauss) return 2.0 * T * c.D * M / (w2 * w) + T * T * c.d1[FB_DM] / (w2 * w);
+      return w * c.d1[FB_DM] / (tau * tau) + G * (-c.D / w2 * kSqrtHalf) +
+             G * d2_dae(FB_BURST_WIDTH, c) * d2_dax(FB_DM, c);
+    case FB_BURST_WIDTH * 16 + FB_DM_INDEX:  // :1889-1955 quirk: -2 where the dm twin has +2
+      if (gauss) return -2.0 * T * c.Dp * M / (w2 * w) + T * T * c.d1[FB_DM_INDEX] / (w2 * w);
+      return w * c.d1[FB_DM_INDEX] / (tau * tau) + G * (-c.Dp / w2 * kSqrtHalf) +
+             G * d2_dae(FB_BURST_WIDTH, c) * d2_dax(FB_DM_INDEX, c);
+    case FB_BURST_WIDTH * 16 + FB_SCATTERING_TIMESCALE:  // :1702-1759
+      return -2.0 * w * M / tau0 / (tau * tau) + w * c.d1[FB_SCATTERING_TIMESCALE] / (tau * tau) +
+             G * (1.0 / tau0 / tau * kSqrtHalf) + G * d2_dae(FB_BURST_WIDTH, c) * d2_dax(FB_SCATTERING_TIMESCALE, c);
+    case FB_BURST_WIDTH * 16 + FB_SCATTERING_INDEX:  // :1761-1820
+      return -2.0 * L * w * M / (tau * tau) + w * c.d1[FB_SCATTERING_INDEX] / (tau * tau) -
+             G * d2_dae(FB_BURST_WIDTH, c) * L + G * (L * kSqrtHalf / tau) +
+             G * d2_dae(FB_BURST_WIDTH, c) * d2_dax(FB_SCATTERING_INDEX, c);
+    case FB_DM * 16 + FB_DM:  // :2275-2341
+      if (gauss) return (c.D * T) * (c.D * T) * M / (w2 * w2) - (c.D / w) * (c.D / w) * M;
+      return -c.D * c.d1[FB_DM] / tau + G * d2_dae(FB_DM, c) * d2_dax(FB_DM, c);
+    case FB_DM * 16 + FB_DM_INDEX: {  // :2236-2273 quirks: Gaussian form, summed derivative, ref_freq ** 2
+      double out = (-c.D) * T * c.sum_dmidx / w2;
+      out += c.k * c.k * c.dm * M / w2 * (c.fpow - c.ref_freq * c.ref_freq) * c.q1;
+      out -= c.k * c.q1 * T * M / w2;
+      return out;
+    }
+    case FB_DM * 16 + FB_SCATTERING_TIMESCALE:  // :2474-2535
+      return -c.D * c.d1[FB_SCATTERING_TIMESCALE] / tau + c.D * M / tau0 / tau +
+             G * d2_dae(FB_DM, c) * d2_dax(FB_SCATTERING_TIMESCALE, c);
+    case FB_DM * 16 + FB_SCATTERING_INDEX: {  // :2666-2720
+      const double t0 = -(1.0 + ws * ws - T / tau) * L;
+      return (L * c.D / tau) * M + t0 * c.d1[FB_DM] + G * d2_dae(FB_SCATTERING_INDEX, c) * d2_dax(FB_DM, c);
+    }
+    case FB_DM_INDEX * 16 + FB_DM_INDEX: {  // :2779-2836 quirk: amp_pbf of the outer component
+      const double product = c.k * c.dm * c.q1, product_d = c.k * c.dm * c.q2;
+      const double gs = G * (c.apbf_outer / c.apbf) * kSqrtHalf;
+      return product_d * M / tau + product * c.d1[FB_DM_INDEX] / tau - product_d * gs / w / tau -
+             product * gs / w / tau * d2_dax(FB_DM_INDEX, c);
+    }
+    case FB_DM_INDEX * 16 + FB_SCATTERING_TIMESCALE: {  // :2537-2594
+      const double t0 = -1.0 / tau0 - ws * ws / tau0 + T / tau0 / tau;
+      return (c.Dp / tau / tau0) * M + t0 * c.d1[FB_DM_INDEX] +
+             G * d2_dae(FB_SCATTERING_TIMESCALE, c) * d2_dax(FB_DM_INDEX, c);
+    }
+    case FB_DM_INDEX * 16 + FB_SCATTERING_INDEX: {  // :2722-2777
+      const double t0 = -(1.0 + ws * ws - T / tau) * L;
+      return (L * c.Dp / tau) * M + t0 * c.d1[FB_DM_INDEX] +
+             G * d2_dae(FB_SCATTERING_INDEX, c) * d2_dax(FB_DM_INDEX, c);
+    }
+    case FB_SCATTERING_TIMESCALE * 16 + FB_SCATTERING_TIMESCALE: {  // :2343-2404
+      const double u = T / tau - ws * ws;
+      const double t0 = u / tau0;
+      const double t0d = -u / (tau0 * tau0) + (-T / tau + 2.0 * ws * ws) / (tau0 * tau0);
+      return t0d * M + t0 * c.d1[FB_SCATTERING_TIMESCALE] +
+             G * (-1.41421356237309504880 * w / tau / (tau0 * tau0)) +
+             G * d2_dae(FB_SCATTERING_TIMESCALE, c) * d2_dax(FB_SCATTERING_TIMESCALE, c);
+    }
+    case FB_SCATTERING_TIMESCALE * 16 + FB_SCATTERING_INDEX: {  // :2406-2472
+      const double e1 = d2_dae(FB_SCATTERING_TIMESCALE, c);
+      const double t0 = -(ws * ws) / tau0 + T / tau0 / tau;
+      const double t0d2 = 2.0 * ws * ws / tau0 * L - T * L / tau / tau0;
+      return t0d2 * M + t0 * c.d1[FB_SCATTERING_INDEX] + (G / c.apbf) * c.dap_alpha * e1 +
+             G * e1 * d2_dax(FB_SCATTERING_INDEX, c) + G * (-L * e1);
+    }
+    case FB_SCATTERING_INDEX * 16 + FB_SCATTERING_INDEX: {  // :2596-2664
+      const double ad = c.dap_alpha / c.apbf, ed = d2_dae(FB_SCATTERING_INDEX, c);
+      const double t0 = ad - (ws * ws - T / tau) * L;
+      const double t0d = c.d2ap_alpha / c.apbf - ad * ad - L * (-2.0 * L * ws * ws + T * L / tau);
+      return t0d * M + t0 * c.d1[FB_SCATTERING_INDEX] + (G / c.apbf) * c.dap_alpha * ed +
+             G * ed * d2_dax(FB_SCATTERING_INDEX, c) + G * (-w * L * L / tau * kSqrtHalf);
+    }
+  }
+  return 0.0;
+}
+
+__device__ __forceinline__ void make_d2ctx(const EvalArgs& A, const ChanTab& ch, double amp, double w,
+                                           double m, double td, double sum_dmidx, double apbf_outer,
+                                           D2Ctx& c) {
+  const int nc = A.pc.num_comp;
+  ChanTab chl = ch;
+  chl.amp = amp;
+  c.tau0 = global_param(A.params, nc, FB_SCATTERING_TIMESCALE);
+  first_derivatives(chl, ch, w, c.tau0, m, td, c.d1, &c.G, &c.arg_erf);
+  c.M = m;
+  c.T = td;
+  c.w = w;
+  c.tau = ch.sc_time;
+  c.L = ch.logf;
+  c.apbf = ch.amp_pbf;
+  c.D = ch.d_dm;
+  c.Dp = ch.d_dmidx;
+  c.fpow = ch.fpow;
+  c.ref_freq = ch.ref_freq;
+  c.q1 = ch.q1;
+  c.q2 = ch.q2;
+  c.k = A.pc.dm_const;
+  c.dm = global_param(A.params, nc, FB_DM);
+  c.dap_alpha = ch.dap_alpha;
+  c.d2ap_alpha = ch.d2ap_alpha;
+  c.sum_dmidx = sum_dmidx;
+  c.apbf_outer = apbf_outer;
+}
+
+// Pair table entry (built on the host): unordered parameter pair, the `component` the reference
+// would pass (analysis/fitter.py:163-168) and whether the function sums over components.
+struct HessPair {
+  int8_t pa, pb;
+  int8_t component;
+  int8_t is_sum;
+};
+
+struct HessArgs {
+  EvalArgs E;
+  const HessPair* pairs;
+  int num_pairs;
+  double* partials;  // [grid][num_pairs]
+  // single-map mode (fb_derivative2_map)
+  int map_pa, map_pb, map_component;
+  double* map_out;
+};
+
+__host__ __device__ inline size_t hess_smem_bytes(int nc, int kf, int num_pairs) {
+  size_t n = smem_bytes(nc, kf, 1, true);
+  n += sizeof(double) * (size_t)kBlock * (2 * nc + 1);  // per-thread (M_c, T_c) rows, odd stride
+  n += sizeof(double) * (size_t)(kBlock / 32) * num_pairs;
+  return n;
+}
+
+template <bool MAP>
+__global__ void __launch_bounds__(kBlock) k_hessian(const HessArgs H) {
+  extern __shared__ double smem_raw[];
+  const EvalArgs& A = H.E;
+  const PlanConst& pc = A.pc;
+  const int nc = pc.num_comp, kf = pc.kf, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  SmemLayout L = carve(smem_raw, nc, kf);
+  const size_t base_doubles = smem_bytes(nc, kf, 1, true) / sizeof(double);
+  const int rstride = 2 * nc + 1;
+  double* rows = smem_raw + base_doubles;
+  double* wacc = rows + (size_t)kBlock * rstride;  // [warps][num_pairs]
+  double* row = rows + (size_t)tid * rstride;
+  const int npairs = H.num_pairs;
+  if (!MAP)
+    for (int e = tid; e < (kBlock / 32) * npairs; e += kBlock) wacc[e] = 0.0;
+  for (int c = tid; c < nc; c += blockDim.x) make_comp_tab(pc, A.params, c, L.comp[c]);
+  __syncthreads();
+  const int tiles = (pc.num_time + kBlock - 1) / kBlock;
+  const double tau0 = global_param(A.params, nc, FB_SCATTERING_TIMESCALE);
+
+  // scintillation needs whole channels per block (two passes); otherwise (channel, tile) items.
+  const long long total = pc.scintillation ? (long long)A.num_chan : (long long)A.num_chan * tiles;
+  const long long begin = total * blockIdx.x / gridDim.x, end = total * (blockIdx.x + 1) / gridDim.x;
+  int cur = -1;
+  for (long long item = begin; item < end; ++item) {
+    const int chi = pc.scintillation ? (int)item : (int)(item / tiles);
+    const int i = A.chan_list ? A.chan_list[chi] : chi;
+    const int tile_lo = pc.scintillation ? 0 : (int)(item % tiles);
+    const int tile_hi = pc.scintillation ? tiles : tile_lo + 1;
+    if (chi != cur) {
+      load_channel_tables(A, L, i);
+      cur = chi;
+      if (pc.scintillation) {
+        // amplitudes from the per-channel least-squares solve (routines/ism.py:11-48)
+        const int ncols2 = nc + 1, stride2 = gram_stride(ncols2), side2 = gram_side(ncols2);
+        const int ntiles2 = gram_ntiles(ncols2), nslices2 = kBlock / ntiles2;
+        const int s_tile = tid % ntiles2, s_slice = tid / ntiles2;
+        const bool s_active = s_slice < nslices2;
+        int s_ti, s_tj;
+        tile_coords(s_tile, side2, s_ti, s_tj);
+        double* row2 = L.X + (size_t)tid * stride2;
+        double acc2[kTile * kTile];
+#pragma unroll
+        for (int k = 0; k < kTile * kTile; ++k) acc2[k] = 0.0;
+        for (int tile = 0; tile < tiles; ++tile) {
+          const int j = tile * kBlock + tid;
+          for (int k = 0; k < stride2; ++k) row2[k] = 0.0;
+          if (j < pc.num_time) {
+            for (int c = 0; c < nc; ++c)
+              row2[c] = eval_sample_component(pc, L.comp[c], L.sub + c * kf, L.chan[c].scattered, j).timeprof;
+            row2[nc] = A.data[(size_t)i * pc.num_time + j];
+          }
+          __syncthreads();
+          gram_accumulate(L.X, stride2, kBlock, ntiles2, nslices2, s_ti, s_tj, s_slice, s_active, acc2);
+          __syncthreads();
+        }
+        gram_block_reduce(L.X, ntiles2, nslices2, s_tile, s_slice, s_active, acc2, L.tilesum);
+        if (tid == 0) {
+          double* G = L.small;
+          double* b = L.small + nc * nc;
+          for (int t = 0; t < ntiles2; ++t) {
+            int ti, tj;
+            tile_coords(t, side2, ti, tj);
+            for (int r = 0; r < kTile; ++r)
+              for (int q = 0; q < kTile; ++q) {
+                const int gr = ti * kTile + r, gc = tj * kTile + q;
+                const double v = L.tilesum[t * kTile * kTile + r * kTile + q];
+                if (gr < nc && gc < nc) {
+                  G[gr * nc + gc] = v;
+                  G[gc * nc + gr] = v;
+                } else if (gr < nc && gc == nc) {
+                  b[gr] = v;
+                }
+              }
+          }
+          const bool ok = solve_small(G, b, nc, nc);
+          for (int c = 0; c < nc; ++c) L.scint_amp[c] = ok ? b[c] : nan("");
+          if (!ok && A.err_flag) atomicExch(A.err_flag, 1);
+        }
+        __syncthreads();
+      }
+    }
+    for (int tile = tile_lo; tile < tile_hi; ++tile) {
+      const int j = tile * kBlock + tid;
+      const bool valid = j < pc.num_time;
+      const size_t s_idx = (size_t)i * pc.num_time + (valid ? j : 0);
+      double msum = 0.0, sum_dmidx = 0.0;
+      if (valid) {
+        for (int c = 0; c < nc; ++c) {
+          SampleComp sc = eval_sample_component(pc, L.comp[c], L.sub + c * kf, L.chan[c].scattered, j);
+          double amp = L.chan[c].amp;
+          if (pc.scintillation) {
+            amp = L.scint_amp[c];
+            sc.spectrum = amp * sc.timeprof;
+          }
+          row[2 * c] = sc.spectrum;
+          row[2 * c + 1] = sc.timediff;
+          msum += sc.spectrum;
+          ChanTab chl = L.chan[c];
+          chl.amp = amp;
+          double d[9], g;
+          first_derivatives(chl, L.chan[c], L.comp[c].w, tau0, sc.spectrum, sc.timediff, d, &g);
+          sum_dmidx += d[FB_DM_INDEX];
+        }
+      }
+      if (MAP) {
+        if (valid) {
+          const bool sum = d2_is_sum(H.map_pa, H.map_pb);
+          double out = 0.0;
+          for (int c = 0; c < nc; ++c) {
+            if (!sum && c != H.map_component) continue;
+            D2Ctx ctx;
+            const double amp = pc.scintillation ? L.scint_amp[c] : L.chan[c].amp;
+            make_d2ctx(A, L.chan[c], amp, L.comp[c].w, row[2 * c], row[2 * c + 1], sum_dmidx,
+                       L.chan[H.map_component].amp_pbf, ctx);
+            out += d2_term(H.map_pa, H.map_pb, ctx);
+          }
+          H.map_out[s_idx] = out;
+        }
+        continue;
+      }
+      double rho = 0.0;
+      if (valid) {
+        const double wi = A.weights[i];
+        rho = (A.data[s_idx] - msum) * wi * wi;
+      }
+      for (int c = 0; c < nc; ++c) {
+        D2Ctx ctx;
+        if (valid) {
+          const double amp = pc.scintillation ? L.scint_amp[c] : L.chan[c].amp;
+          make_d2ctx(A, L.chan[c], amp, L.comp[c].w, row[2 * c], row[2 * c + 1], sum_dmidx, 0.0, ctx);
+        }
+        for (int pi = 0; pi < npairs; ++pi) {
+          const HessPair hp = H.pairs[pi];
+          if (!hp.is_sum && hp.component != c) continue;  // uniform across the block
+          double v = 0.0;
+          if (valid) {
+            ctx.apbf_outer = L.chan[hp.component].amp_pbf;
+            v = rho * d2_term(hp.pa, hp.pb, ctx);
+          }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+          if (lane == 0) wacc[warp * npairs + pi] += v;
+        }
+      }
+    }
+  }
+  if (!MAP) {
+    __syncthreads();
+    for (int pi = tid; pi < npairs; pi += kBlock) {
+      double s = 0.0;
+      for (int wv = 0; wv < kBlock / 32; ++wv) s += wacc[wv * npairs + pi];
+      H.partials[(size_t)blockIdx.x * npairs + pi] = s;
+    }
+  }
+}
+
+__global__ void k_hess_finalize(const double* __restrict__ partials, int nblocks, int npairs,
+                                double* __restrict__ out) {
+  for (int pi = blockIdx.x * blockDim.x + threadIdx.x; pi < npairs; pi += gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * npairs + pi];
+    out[pi] = s;
+  }
+}
+
+}  // namespace fb

@@ -139,3 +139,85 @@ def test_scintillation_model(native_lib):
     want = oracle.compute_model(data=data)
     assert_close(got, want, 1e-9, "scintillation model")
     assert_close(cuda.amplitude_per_component, oracle.amplitude_per_component, 1e-9, "scintillation amplitudes")
+
+
+@pytest.mark.parametrize("case", [dict(kf=2, kt=2), dict(kf=2, kt=2, tau=0.0, num_comp=2), dict(kf=1, kt=1, dm=0.2, num_comp=2)])
+@pytest.mark.parametrize("normalize", [False, True])
+def test_first_and_second_derivative_maps(case, normalize, native_lib):
+    """All 9 first- and 45 second-derivative maps through fitburst_b200.routines.derivative."""
+    import fitburst_b200.routines.derivative as deriv
+    from fitburst_b200.backend import general
+    from oracle.hessian_oracle import REFERENCE_PAIRS, OracleSecondDerivatives
+
+    if normalize and case.get("tau", 1.0) == 0.0:
+        pytest.skip("normalised PBF with zero scattering time divides by zero in the reference")
+    general["flags"]["normalize_pbf"] = normalize
+    try:
+        freqs, times, truth, kwargs = make_case(num_freq=16, num_time=48, **case)
+        cuda, oracle = model_pair(freqs, times, kwargs, truth)
+        oracle.normalize_pbf = normalize
+        cuda.compute_model()
+        oracle.compute_model()
+        second = OracleSecondDerivatives(oracle)
+        P = oracle.get_parameters_dict()
+
+        def close(got, want, what):
+            want = np.broadcast_to(np.asarray(want, dtype=float), got.shape)
+            finite = np.isfinite(want)
+            if not finite.any():
+                return
+            scale = np.max(np.abs(want[finite]))
+            err = np.max(np.abs(got[finite] - want[finite]))
+            assert err <= 1e-9 * max(scale, 1e-300), f"{what}: {err / max(scale, 1e-300):.2e}"
+
+        with np.errstate(all="ignore"):
+            for name in oracle.parameters:
+                for comp in range(oracle.num_components):
+                    try:
+                        want = second.first.first(name, P, comp)
+                    except ZeroDivisionError:
+                        continue
+                    close(getattr(deriv, f"deriv_model_wrt_{name}")(P, cuda, comp), want, f"d/d{name}[{comp}]")
+            for n1, seconds in REFERENCE_PAIRS.items():
+                for n2 in seconds:
+                    for comp in range(oracle.num_components):
+                        try:
+                            want = second.second(n1, n2, P, comp)
+                        except ZeroDivisionError:
+                            continue
+                        got = getattr(deriv, f"deriv2_model_wrt_{n1}_{n2}")(P, cuda, comp)
+                        close(got, want, f"d2/d{n1}d{n2}[{comp}]")
+    finally:
+        general["flags"]["normalize_pbf"] = False
+
+
+@pytest.mark.parametrize("case,fixed", [
+    (dict(num_freq=48, num_time=96), ["dm_index", "scattering_index"]),
+    (dict(num_freq=32, num_time=64, kf=2, kt=2, num_comp=2), ["dm_index"]),
+    (dict(num_freq=32, num_time=64, tau=0.0, kf=2, kt=2, num_comp=2), ["dm_index", "scattering_index", "scattering_timescale"]),
+])
+def test_hessian_and_fit_statistics(case, fixed, native_lib):
+    from oracle import hessian_oracle
+    fc, fo = _fitters(case, fixed)
+    fo.hessian_fn = hessian_oracle.compute_hessian
+    fc.fit()
+    fo.fit()
+    assert fc.results.status == fo.results.status
+    np.testing.assert_allclose(fc.results.x, fo.results.x, rtol=1e-6)
+    scale = np.sqrt(np.outer(np.abs(np.diag(fo.hessian)), np.abs(np.diag(fo.hessian))))
+    assert np.max(np.abs(fc.hessian - fo.hessian) / scale) < 1e-6
+    assert np.max(np.abs(fc.hessian_approx - fo.hessian_approx) / scale) < 1e-6
+    assert fc.covariance_labels == fo.covariance_labels
+    sc, so = fc.fit_statistics, fo.fit_statistics
+    assert set(sc) == set(so)
+    for key in ("num_freq", "num_freq_good", "num_fit_parameters", "num_observations", "num_time"):
+        assert sc[key] == so[key]
+    for key in ("chisq_initial", "chisq_final", "chisq_final_reduced", "snr"):
+        assert abs(sc[key] - so[key]) <= 1e-8 * abs(so[key])
+    for name, values in so["bestfit_uncertainties"].items():
+        np.testing.assert_allclose(sc["bestfit_uncertainties"][name], values, rtol=1e-5)
+        # best fit agrees far inside one sigma
+        diff = np.abs(np.asarray(sc["bestfit_parameters"][name]) - np.asarray(so["bestfit_parameters"][name]))
+        assert np.all(diff < 1e-3 * np.asarray(values))
+    import json
+    json.dumps(sc)  # the pipeline dumps fit_statistics as JSON (fitburst_pipeline.py:560-573)
