@@ -47,6 +47,10 @@ struct fb_plan_s {
   size_t partials_cap = 0;
   double* d_gram = nullptr;  // (FB_MAX_FREE+1)^2
   double* h_gram = nullptr;  // pinned
+  CompTab* d_comp = nullptr;
+  SubTab* d_sub = nullptr;
+  ChanTab* d_chan = nullptr;
+  bool tables_dirty = true;
   double* d_hess_partials = nullptr;
   size_t hess_partials_cap = 0;
   HessPair* d_pairs = nullptr;
@@ -148,6 +152,9 @@ extern "C" int fb_plan_create(const fb_plan_desc* desc, const double* freqs_host
   chk(cudaMalloc(&p->d_good, nf));
   chk(cudaMalloc(&p->d_err, sizeof(int)));
   chk(cudaMalloc(&p->d_gram, gsz));
+  chk(cudaMalloc(&p->d_comp, sizeof(CompTab) * FB_MAX_COMPONENTS));
+  chk(cudaMalloc(&p->d_sub, sizeof(SubTab) * (size_t)nf * desc->num_components * kf));
+  chk(cudaMalloc(&p->d_chan, sizeof(ChanTab) * (size_t)nf * desc->num_components));
   chk(cudaMallocHost(&p->h_gram, gsz));
   if (e == cudaSuccess) chk(cudaMemcpy(p->d_freqs, freqs_host, sizeof(double) * nf, cudaMemcpyHostToDevice));
   if (e == cudaSuccess) chk(cudaMemcpy(p->d_subfreqs, sub.data(), sizeof(double) * nf * kf, cudaMemcpyHostToDevice));
@@ -179,6 +186,9 @@ extern "C" int fb_plan_destroy(fb_plan_t p) {
   cudaFree(p->d_partials);
   cudaFree(p->d_hess_partials);
   cudaFree(p->d_pairs);
+  cudaFree(p->d_comp);
+  cudaFree(p->d_sub);
+  cudaFree(p->d_chan);
   if (p->h_gram) cudaFreeHost(p->h_gram);
   delete p;
   return FB_OK;
@@ -190,6 +200,18 @@ extern "C" int fb_set_parameters(fb_plan_t p, const double* params_host, void* s
   memcpy(p->h_params, params_host, sizeof(double) * n);
   CUDA_TRY(cudaMemcpyAsync(p->d_params, p->h_params, sizeof(double) * n, cudaMemcpyHostToDevice,
                            (cudaStream_t)stream));
+  p->tables_dirty = true;
+  return FB_OK;
+}
+
+// Rebuilds the per-channel tables when the parameters changed since the last build.
+static int ensure_tables(fb_plan_s* p, cudaStream_t st) {
+  if (!p->tables_dirty) return FB_OK;
+  const int total = p->desc.num_freq * p->desc.num_components;
+  k_tables<<<(total + 127) / 128, 128, 0, st>>>(p->pc, p->d_params, p->d_comp, p->d_sub, p->d_chan);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 1;
+  p->tables_dirty = false;
   return FB_OK;
 }
 
@@ -213,11 +235,18 @@ static EvalArgs base_args(fb_plan_s* p) {
   A.n_free = p->n_free;
   for (int k = 0; k < 9; ++k) A.col_of[k] = p->col_of[k];
   A.err_flag = p->d_err;
+  A.g_comp = p->d_comp;
+  A.g_sub = p->d_sub;
+  A.g_chan = p->d_chan;
   return A;
 }
 
 template <int MODE>
 static int launch_eval(fb_plan_s* p, const EvalArgs& A, int ncols_main, cudaStream_t st, int* grid_out) {
+  {
+    const int rc_t = ensure_tables(p, st);
+    if (rc_t != FB_OK) return rc_t;
+  }
   const size_t smem = smem_bytes(p->pc.num_comp, p->pc.kf, ncols_main, p->pc.scintillation != 0);
   if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request %zu B exceeds 227 KB", smem);
   static thread_local size_t configured[4] = {0, 0, 0, 0};
@@ -586,6 +615,10 @@ extern "C" int fb_launch_count(fb_plan_t p, int64_t* count_out, int32_t reset) {
 // ---- exact Hessian (analysis/fitter.py:81-178) --------------------------------------------------
 template <bool MAP>
 static int launch_hessian(fb_plan_s* p, HessArgs& H, cudaStream_t st, int* grid_out) {
+  {
+    const int rc_t = ensure_tables(p, st);
+    if (rc_t != FB_OK) return rc_t;
+  }
   const size_t smem = hess_smem_bytes(p->pc.num_comp, p->pc.kf, MAP ? 0 : H.num_pairs);
   if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "Hessian shared-memory request %zu B exceeds 227 KB", smem);
   if (smem > 48 * 1024)

@@ -13,9 +13,11 @@
 namespace fb {
 
 constexpr double kSqrtHalf = 0.70710678118654752440;       // 1/sqrt(2)
+constexpr double kSqrt2 = 1.41421356237309504880;
 constexpr double kSqrtHalfPi = 1.25331413731550025121;     // sqrt(pi/2)
 constexpr double kTwoOverSqrtPi = 1.12837916709551257390;  // 2/sqrt(pi)
 constexpr double kLn10 = 2.30258509299404568402;
+constexpr double kTailArg = -6.0;  // erfc(6)/2 = 1.1e-17 < ulp/2: below this the EMG is its pure exponential tail
 
 // Static (per-plan) configuration, passed by value to kernels.
 struct PlanConst {
@@ -44,26 +46,34 @@ struct SubTab {
   double ratio;     // width / sc_time(f_ia)             routines/profile.py:93
   double amp_term;  // sc_time_ref / sc_time, or sqrt(pi/2) * ratio   routines/profile.py:96
   double sed;       // running power law at f_ia         routines/spectrum.py:39-41
+  // pure-exponential-tail fast path: sum_b P_ab / (kf kt) = tail_c * exp(tail_e - u0 * inv_tau)
+  double inv_tau, tail_e, tail_c;
   double fold_start, fold_step, fold_stop;  // second realisation, analysis/model.py:327-332
 };
 
-// Per (channel, component) constants at the channel CENTRE, used by the derivatives
-// (routines/derivative.py evaluates everything at model.freqs, not at the sub-frequencies).
+// Per (channel, component) constants: regime boundaries of the model along the time axis and
+// the channel-CENTRE quantities of the derivatives (routines/derivative.py evaluates everything
+// at model.freqs, not at the sub-frequencies).
 struct ChanTab {
-  double amp;        // amplitude_per_component value: 10**A * S(f_i)   analysis/model.py:250-255
-  double logf;       // ln(f_i / ref_freq)
-  double sc_time;    // sc_time_ref * (f_i / ref_freq) ** sc_index
-  double amp_pbf;    // routines/derivative.py:71-103
-  double d_dm;       // deriv_time_dm("dm")        routines/derivative.py:244-246
-  double d_dmidx;    // deriv_time_dm("dm_index")  routines/derivative.py:248-250
-  double dap_w, dap_tau, dap_alpha;  // deriv_amplitude_pbf for burst_width / scattering_timescale /
-                                     // scattering_index with THIS component as the one looked up
-                                     // (routines/derivative.py:105-152)
-  double d2ap_alpha; // deriv2_amplitude_pbf(scattering_index, scattering_index), :154-209
+  double amp;         // amplitude_per_component value: 10**A * S(f_i)   analysis/model.py:250-255
+  // regimes (scattered branch, not folded): every sub-sample of a time bin is clamped at -5w
+  // (analysis/model.py:340) when u_last - min_delay < -5w; every one is pure tail when u0 >= tail_lo.
+  double min_delay, mean_delay, tail_lo;
+  double plateau_p, plateau_ps;  // mean profile / 10**A * mean(profile * sed) on the clamp plateau
+  double logf;        // ln(f_i / ref_freq)
+  double sc_time;     // sc_time_ref * (f_i / ref_freq) ** sc_index
+  double inv_tau;     // 1 / sc_time
+  double amp_pbf;     // routines/derivative.py:71-103
+  double inv_apbf;
+  double d_dm;        // deriv_time_dm("dm")        routines/derivative.py:244-246
+  double d_dmidx;     // deriv_time_dm("dm_index")  routines/derivative.py:248-250
+  double dap_w, dap_tau, dap_alpha;  // deriv_amplitude_pbf with THIS component looked up (:105-152)
+  double d2ap_alpha;  // deriv2_amplitude_pbf(scattering_index, scattering_index), :154-209
   double fpow, refpow;  // f_i ** dm_index, ref_freq ** dm_index
-  double q1, q2;     // ln f f^b - ln fr fr^b  and  ln^2 f f^b - ln^2 fr fr^b (derivative.py:2267,2822)
+  double q1, q2;      // ln f f^b - ln fr fr^b  and  ln^2 f f^b - ln^2 fr fr^b (derivative.py:2267,2822)
   double ref_freq;
-  int scattered;     // any(sc_time(f_ia) > 0) over the sub-frequencies, analysis/model.py:339
+  int scattered;      // any(sc_time(f_ia) > 0) over the sub-frequencies, analysis/model.py:339
+  int fast_ok;        // regime fast paths usable (scattered, not folded, finite tables)
 };
 
 __host__ __device__ inline double global_param(const double* params, int nc, int p) {
@@ -74,6 +84,21 @@ __host__ __device__ inline double global_param(const double* params, int nc, int
 __device__ __forceinline__ double linspace_at(double start, double step, double stop, int m, int num) {
   double v = __dadd_rn(__dmul_rn((double)m, step), start);
   return (m == num - 1 && num > 1) ? stop : v;
+}
+
+// Exponentially-modified Gaussian without its amplitude term, routines/profile.py:90-112:
+//   exp(-z^2/2) * erfcx((ratio - z)/sqrt(2))          == exp((ratio/2 - z) ratio) * erfc(.)
+// evaluated so that neither factor over/underflows (the reference switches formula at
+// arg <= -20; here the split is at arg = 0, exact to rounding):
+//   arg >= 0       exp(-z^2/2) erfcx(arg)
+//   -6 < arg < 0   2 exp(ratio (ratio/2 - z)) - exp(-z^2/2) erfcx(-arg)     [erfcx(-y) = 2e^{y^2} - erfcx(y)]
+//   arg <= -6      2 exp(ratio (ratio/2 - z))                               [erfc(6)/2 = 1.1e-17 < ulp/2]
+__device__ __forceinline__ double emg_shape(double z, double ratio) {
+  const double arg = (ratio - z) * kSqrtHalf;
+  if (arg >= 0.0) return exp(-0.5 * z * z) * erfcx(arg);
+  const double tail = 2.0 * exp(ratio * (0.5 * ratio - z));
+  if (arg <= kTailArg) return tail;
+  return tail - exp(-0.5 * z * z) * erfcx(-arg);
 }
 
 __device__ inline void make_comp_tab(const PlanConst& pc, const double* params, int c, CompTab& ct) {
@@ -96,75 +121,94 @@ __device__ inline void make_comp_tab(const PlanConst& pc, const double* params, 
   ct.ref_freq = params[FB_REF_FREQ * nc + c];
 }
 
-__device__ inline void make_sub_tab(const PlanConst& pc, const double* params, const CompTab& ct,
-                                    int i, int a, int c, SubTab& st) {
-  const int nc = pc.num_comp;
-  const double f = pc.subfreqs[(size_t)i * pc.kf + a];
+// All tables of one (channel, component): kf SubTab entries + the ChanTab. One thread.
+__device__ inline void make_channel_tables(const PlanConst& pc, const double* params, const CompTab& ct,
+                                           int i, int c, SubTab* sub, ChanTab& ch) {
+  const int nc = pc.num_comp, kf = pc.kf, kt = pc.kt;
   const double fc = pc.freqs[i];
   const double dm = global_param(params, nc, FB_DM);
   const double beta = global_param(params, nc, FB_DM_INDEX);
   const double tau0 = global_param(params, nc, FB_SCATTERING_TIMESCALE);
   const double alpha = global_param(params, nc, FB_SCATTERING_INDEX);
+  const double sp_idx = params[FB_SPECTRAL_INDEX * nc + c];
+  const double sp_run = params[FB_SPECTRAL_RUNNING * nc + c];
   const double fref = ct.ref_freq;
   const double fref_b = pow(fref, beta);
-  // routines/ism.py:78: dm_value * dm_const * (freq1 ** dm_idx - freq2 ** dm_idx)
-  double delay = ((pc.dm_incoherent + dm) * pc.dm_const) * (pow(f, beta) - fref_b);
-  delay -= (pc.dm_incoherent * pc.dm_const) * (pow(fc, beta) - fref_b);
-  st.delay = delay;
-  const double fr = f / fref;
-  const double sc_time = tau0 * pow(fr, alpha);  // analysis/model.py:336
-  st.ratio = ct.w / sc_time;
-  st.amp_term = pc.normalize_pbf ? kSqrtHalfPi * st.ratio : tau0 / sc_time;
-  const double lf = log(fr);
-  const double sp_idx = params[FB_SPECTRAL_INDEX * nc + c];
-  const double sp_run = params[FB_SPECTRAL_RUNNING * nc + c];
-  st.sed = exp(sp_idx * lf + sp_run * (lf * lf));
-  if (pc.is_folded) {
-    // analysis/model.py:327-331 on the delay-corrected labels of this sub-frequency row.
-    const int n = pc.ntk;
-    const double t0 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, 0, n) - delay;
-    const double t1 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, 1, n) - delay;
-    const double tl = linspace_at(ct.t_start, ct.t_step, ct.t_stop, n - 1, n) - delay;
-    const double res = t1 - t0;
-    st.fold_start = tl + res;
-    st.fold_stop = tl + res * (double)n;
-    st.fold_step = (n > 1) ? (st.fold_stop - st.fold_start) / (double)(n - 1) : 0.0;
-  } else {
-    st.fold_start = st.fold_step = st.fold_stop = 0.0;
-  }
-}
+  const double fc_b = pow(fc, beta);
+  const double w = ct.w;
 
-__device__ inline void make_chan_tab(const PlanConst& pc, const double* params, const CompTab& ct,
-                                     int i, int c, ChanTab& ch) {
-  const int nc = pc.num_comp;
-  const double fc = pc.freqs[i];
-  const double dm = global_param(params, nc, FB_DM);
-  const double beta = global_param(params, nc, FB_DM_INDEX);
-  const double tau0 = global_param(params, nc, FB_SCATTERING_TIMESCALE);
-  const double alpha = global_param(params, nc, FB_SCATTERING_INDEX);
-  const double fref = ct.ref_freq;
+  int scattered = 0;
+  double min_delay = INFINITY, max_delay = -INFINITY, sum_delay = 0.0, max_wr = 0.0;
+  double plat_p = 0.0, plat_ps = 0.0;
+  const double z_clamp = ct.neg5w * ct.inv_w;
+  for (int a = 0; a < kf; ++a) {
+    SubTab st;
+    const double f = pc.subfreqs[(size_t)i * kf + a];
+    // routines/ism.py:78: dm_value * dm_const * (freq1 ** dm_idx - freq2 ** dm_idx)
+    double delay = ((pc.dm_incoherent + dm) * pc.dm_const) * (pow(f, beta) - fref_b);
+    delay -= (pc.dm_incoherent * pc.dm_const) * (fc_b - fref_b);
+    st.delay = delay;
+    const double fr = f / fref;
+    const double sc_time = tau0 * pow(fr, alpha);  // analysis/model.py:336
+    if (sc_time > 0.0) scattered = 1;
+    st.ratio = w / sc_time;
+    st.amp_term = pc.normalize_pbf ? kSqrtHalfPi * st.ratio : tau0 / sc_time;
+    const double lf = log(fr);
+    st.sed = exp(sp_idx * lf + sp_run * (lf * lf));
+    st.inv_tau = 1.0 / sc_time;
+    st.tail_e = 0.5 * st.ratio * st.ratio + delay * st.inv_tau;
+    double geom = 0.0;
+    for (int b = 0; b < kt; ++b) geom += exp(-(double)b * ct.t_step * st.inv_tau);
+    st.tail_c = 2.0 * st.amp_term * geom / ((double)kt * (double)kf);
+    if (pc.is_folded) {
+      // analysis/model.py:327-331 on the delay-corrected labels of this sub-frequency row.
+      const int n = pc.ntk;
+      const double t0 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, 0, n) - delay;
+      const double t1 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, 1, n) - delay;
+      const double tl = linspace_at(ct.t_start, ct.t_step, ct.t_stop, n - 1, n) - delay;
+      const double res = t1 - t0;
+      st.fold_start = tl + res;
+      st.fold_stop = tl + res * (double)n;
+      st.fold_step = (n > 1) ? (st.fold_stop - st.fold_start) / (double)(n - 1) : 0.0;
+    } else {
+      st.fold_start = st.fold_step = st.fold_stop = 0.0;
+    }
+    sub[a] = st;
+    min_delay = fmin(min_delay, delay);
+    max_delay = fmax(max_delay, delay);
+    sum_delay += delay;
+    max_wr = fmax(max_wr, w * st.ratio);
+    const double p = st.amp_term * emg_shape(z_clamp, st.ratio);
+    plat_p += p;
+    plat_ps += p * st.sed;
+  }
   const double fr = fc / fref;
   const double lf = log(fr);
-  const double sp_idx = params[FB_SPECTRAL_INDEX * nc + c];
-  const double sp_run = params[FB_SPECTRAL_RUNNING * nc + c];
   ch.amp = exp(sp_idx * lf + sp_run * (lf * lf)) * ct.amp10;
+  ch.min_delay = min_delay;
+  ch.mean_delay = sum_delay / (double)kf;
+  // pure tail for every sub-sample:  (T/w - ratio)/sqrt(2) >= 6  <=  T >= w*ratio + 6 sqrt(2) w
+  ch.tail_lo = max_delay + max_wr + (6.0 * kSqrt2 + 1e-6) * w;
+  ch.plateau_p = plat_p / (double)kf;
+  ch.plateau_ps = ct.amp10 * (plat_ps / (double)kf);
   ch.logf = lf;
   ch.sc_time = tau0 * pow(fr, alpha);
+  ch.inv_tau = 1.0 / ch.sc_time;
   double amp_pbf = pow(fr, -alpha);
-  if (pc.normalize_pbf) amp_pbf *= kSqrtHalfPi * ct.w / tau0;
+  if (pc.normalize_pbf) amp_pbf *= kSqrtHalfPi * w / tau0;
   ch.amp_pbf = amp_pbf;
+  ch.inv_apbf = 1.0 / amp_pbf;
   if (pc.normalize_pbf) {
     ch.dap_w = kSqrtHalfPi / ch.sc_time;
-    ch.dap_alpha = -kSqrtHalfPi * lf * ct.w / ch.sc_time;
-    ch.dap_tau = -kSqrtHalfPi * ct.w / (ch.sc_time * tau0);
-    ch.d2ap_alpha = kSqrtHalfPi * lf * lf * ct.w / ch.sc_time;
+    ch.dap_alpha = -kSqrtHalfPi * lf * w / ch.sc_time;
+    ch.dap_tau = -kSqrtHalfPi * w / (ch.sc_time * tau0);
+    ch.d2ap_alpha = kSqrtHalfPi * lf * lf * w / ch.sc_time;
   } else {
     ch.dap_w = 0.0;
     ch.dap_tau = 0.0;
     ch.dap_alpha = -lf * pow(fr, -alpha);
     ch.d2ap_alpha = lf * lf * pow(fr, -alpha);
   }
-  const double fc_b = pow(fc, beta), fref_b = pow(fref, beta);
   ch.d_dm = -pc.dm_const * (fc_b - fref_b);
   ch.q1 = log(fc) * fc_b - log(fref) * fref_b;
   ch.q2 = log(fc) * log(fc) * fc_b - log(fref) * log(fref) * fref_b;
@@ -172,27 +216,9 @@ __device__ inline void make_chan_tab(const PlanConst& pc, const double* params, 
   ch.fpow = fc_b;
   ch.refpow = fref_b;
   ch.ref_freq = fref;
-  int scattered = 0;
-  for (int a = 0; a < pc.kf; ++a) {
-    const double f = pc.subfreqs[(size_t)i * pc.kf + a];
-    if (tau0 * pow(f / fref, alpha) > 0.0) scattered = 1;
-  }
   ch.scattered = scattered;
-}
-
-// Exponentially-modified Gaussian without its amplitude term, routines/profile.py:90-112:
-//   exp(-z^2/2) * erfcx((ratio - z)/sqrt(2))          == exp((ratio/2 - z) ratio) * erfc(.)
-// evaluated so that neither factor over/underflows (the reference switches formula at
-// arg <= -20; here the split is at arg = 0, exact to rounding):
-//   arg >= 0       exp(-z^2/2) erfcx(arg)
-//   -6 < arg < 0   2 exp(ratio (ratio/2 - z)) - exp(-z^2/2) erfcx(-arg)     [erfcx(-y) = 2e^{y^2} - erfcx(y)]
-//   arg <= -6      2 exp(ratio (ratio/2 - z))                               [erfc(6)/2 = 1.1e-17 < ulp/2]
-__device__ __forceinline__ double emg_shape(double z, double ratio) {
-  const double arg = (ratio - z) * kSqrtHalf;
-  if (arg >= 0.0) return exp(-0.5 * z * z) * erfcx(arg);
-  const double tail = 2.0 * exp(ratio * (0.5 * ratio - z));
-  if (arg <= -6.0) return tail;
-  return tail - exp(-0.5 * z * z) * erfcx(-arg);
+  ch.fast_ok = scattered && !pc.is_folded && isfinite(ch.tail_lo) && isfinite(ch.plateau_ps) &&
+               isfinite(min_delay) && w > 0.0 && tau0 > 0.0;
 }
 
 // Per-sample, per-component result: the three cached maps of analysis/model.py:212-256.
@@ -204,14 +230,51 @@ struct SampleComp {
 
 // One (channel, sample, component): loops the kf x kt sub-grid. `sub` points at this
 // component's kf SubTab entries (shared memory).
+//
+// Along the time axis a scattered component has three regimes and only the middle one needs the
+// special functions (the split is exact to rounding, see emg_shape):
+//   plateau  every sub-sample is clamped to -5w (analysis/model.py:340): the profile is a
+//            per-(channel, component) constant, tabulated;
+//   rise     general case: exp + erfcx per sub-sample;
+//   tail     every sub-sample has erfc == 2 to rounding: the kt sub-samples of one sub-frequency
+//            form a geometric series, one exp per (sample, sub-frequency).
 __device__ __forceinline__ SampleComp eval_sample_component(const PlanConst& pc, const CompTab& ct,
-                                                            const SubTab* __restrict__ sub,
-                                                            int scattered, int j) {
+                                                            const ChanTab& ch,
+                                                            const SubTab* __restrict__ sub, int j) {
   const int kf = pc.kf, kt = pc.kt, n = pc.ntk;
   const double inv_kf = 1.0 / (double)kf, inv_kt = 1.0 / (double)kt;
+  const int m0 = j * kt;
+  SampleComp out;
+  if (ch.fast_ok) {
+    const double u0 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, m0, n);
+    const double u_last = linspace_at(ct.t_start, ct.t_step, ct.t_stop, m0 + kt - 1, n);
+    const bool plateau = (u_last - ch.min_delay) < ct.neg5w;
+    const bool tail = u0 >= ch.tail_lo;
+    if (plateau || tail) {
+      double su = 0.0;
+      for (int b = 0; b < kt; ++b) su += linspace_at(ct.t_start, ct.t_step, ct.t_stop, m0 + b, n);
+      out.timediff = su * inv_kt - ch.mean_delay;
+      if (plateau) {
+        out.timeprof = ch.plateau_p;
+        out.spectrum = ch.plateau_ps;
+      } else {
+        double s_p = 0.0, s_ps = 0.0;
+        for (int a = 0; a < kf; ++a) {
+          const SubTab& st = sub[a];
+          const double p = st.tail_c * exp(fma(-u0, st.inv_tau, st.tail_e));
+          s_p += p;
+          s_ps = fma(p, st.sed, s_ps);
+        }
+        out.timeprof = s_p;
+        out.spectrum = ct.amp10 * s_ps;
+      }
+      return out;
+    }
+  }
+  const int scattered = ch.scattered;
   double acc_t = 0.0, acc_p = 0.0, acc_ps = 0.0;
   for (int b = 0; b < kt; ++b) {
-    const int m = j * kt + b;
+    const int m = m0 + b;
     const double u = linspace_at(ct.t_start, ct.t_step, ct.t_stop, m, n);
     double s_t = 0.0, s_p = 0.0, s_ps = 0.0;
     for (int a = 0; a < kf; ++a) {
@@ -242,7 +305,6 @@ __device__ __forceinline__ SampleComp eval_sample_component(const PlanConst& pc,
     acc_p += s_p * inv_kf;
     acc_ps += s_ps * inv_kf;
   }
-  SampleComp out;
   out.timediff = acc_t * inv_kt;
   out.timeprof = acc_p * inv_kt;
   out.spectrum = ct.amp10 * (acc_ps * inv_kt);
@@ -250,46 +312,47 @@ __device__ __forceinline__ SampleComp eval_sample_component(const PlanConst& pc,
 }
 
 // First derivatives of ONE component's spectrum at one sample, routines/derivative.py:454-936.
-// m = spectrum_per_component value, td = timediff_per_component value, ch = this component's
-// channel-centre table, cho = the table of the component the reference passes to
-// deriv_amplitude_pbf (the four "global" functions pass the OUTER component,
-// routines/derivative.py:707,779,847,916). d[] is indexed by fb_parameter. gfac_out returns
-// the shared factor amp * amp_pbf * exp(arg_exp) * 2/sqrt(pi) for the second derivatives.
-__device__ __forceinline__ void first_derivatives(const ChanTab& ch, const ChanTab& cho, double w,
-                                                  double tau0, double m, double td, double* d,
+// m = spectrum_per_component value, td = timediff_per_component value, amp = the
+// amplitude_per_component value, ch = this component's table, cho = the table of the component
+// the reference passes to deriv_amplitude_pbf (the four "global" functions pass the OUTER
+// component, routines/derivative.py:707,779,847,916). d[] is indexed by fb_parameter. gfac_out
+// returns the shared factor amp * amp_pbf * exp(arg_exp) * 2/sqrt(pi) for the second derivatives.
+__device__ __forceinline__ void first_derivatives(const ChanTab& ch, const ChanTab& cho, const CompTab& ct,
+                                                  double tau0, double amp, double m, double td, double* d,
                                                   double* gfac_out, double* arg_erf_out = nullptr) {
-  const double lf = ch.logf;
+  const double lf = ch.logf, w = ct.w, inv_w = ct.inv_w;
   d[FB_AMPLITUDE] = kLn10 * m;
   d[FB_SPECTRAL_INDEX] = lf * m;
   d[FB_SPECTRAL_RUNNING] = (lf * lf) * m;
-  const double tau = ch.sc_time;
+  const double inv_tau = ch.inv_tau;
   // shared scattered-branch factor, routines/derivative.py:14-69 (arg_exp evaluated as written).
-  const double arg_erf = (td - w * w / tau) / w * kSqrtHalf;
-  const double ws = w / tau;
-  const double arg_exp = 0.5 * ws * ws - td / tau - arg_erf * arg_erf;
-  const double g = ch.amp * ch.amp_pbf * exp(arg_exp) * kTwoOverSqrtPi;
+  const double arg_erf = (td - w * w * inv_tau) * inv_w * kSqrtHalf;
+  const double ws = w * inv_tau;
+  const double arg_exp = 0.5 * ws * ws - td * inv_tau - arg_erf * arg_erf;
+  const double g = amp * ch.amp_pbf * exp(arg_exp) * kTwoOverSqrtPi;
   *gfac_out = g;
   if (arg_erf_out) *arg_erf_out = arg_erf;
-  const double inv_amp_pbf = 1.0 / ch.amp_pbf;
-  if (tau == 0.0) {  // per-channel Gaussian branch, routines/derivative.py:568,629,695,767
-    const double w2 = w * w;
-    d[FB_BURST_WIDTH] = td * td * m / (w2 * w);
-    d[FB_ARRIVAL_TIME] = td * m / w2;
-    d[FB_DM] = -td * m / w2 * ch.d_dm;
-    d[FB_DM_INDEX] = -td * m / w2 * ch.d_dmidx;
+  if (ch.sc_time == 0.0) {  // per-channel Gaussian branch, routines/derivative.py:568,629,695,767
+    const double inv_w2 = inv_w * inv_w;
+    const double tm = td * m * inv_w2;
+    d[FB_BURST_WIDTH] = td * tm * inv_w;
+    d[FB_ARRIVAL_TIME] = tm;
+    d[FB_DM] = -tm * ch.d_dm;
+    d[FB_DM_INDEX] = -tm * ch.d_dmidx;
   } else {
-    d[FB_BURST_WIDTH] = m * cho.dap_w * inv_amp_pbf + (w / (tau * tau)) * m +
-                        g * (-(td / (w * w) + 1.0 / tau) * kSqrtHalf);
-    d[FB_ARRIVAL_TIME] = m / tau + g * (-1.0 / w * kSqrtHalf);
-    d[FB_DM] = -ch.d_dm * m / tau + g * (ch.d_dm / w * kSqrtHalf);
-    d[FB_DM_INDEX] = -ch.d_dmidx * m / tau + g * (ch.d_dmidx / w * kSqrtHalf);
+    const double gs = g * inv_w * kSqrtHalf;
+    d[FB_BURST_WIDTH] = m * (cho.dap_w * ch.inv_apbf + ws * inv_tau) - gs * (td * inv_w + ws);
+    d[FB_ARRIVAL_TIME] = m * inv_tau - gs;
+    d[FB_DM] = ch.d_dm * (gs - m * inv_tau);
+    d[FB_DM_INDEX] = ch.d_dmidx * (gs - m * inv_tau);
   }
   // no Gaussian branch in the reference for these two (routines/derivative.py:800-936):
   // sc_time == 0 yields inf/nan there and here alike.
-  d[FB_SCATTERING_TIMESCALE] = m * cho.dap_tau * inv_amp_pbf + (-(ws * ws) + td / tau) * m / tau0 +
-                               g * (w / tau0 / tau * kSqrtHalf);
-  d[FB_SCATTERING_INDEX] = m * cho.dap_alpha * inv_amp_pbf - lf * m * (ws * ws - td / tau) +
-                           g * (lf * w / tau * kSqrtHalf);
+  const double inv_tau0 = 1.0 / tau0;
+  const double gt = g * ws * kSqrtHalf;
+  const double u = td * inv_tau - ws * ws;
+  d[FB_SCATTERING_TIMESCALE] = m * (cho.dap_tau * ch.inv_apbf + u * inv_tau0) + gt * inv_tau0;
+  d[FB_SCATTERING_INDEX] = m * (cho.dap_alpha * ch.inv_apbf + lf * u) + gt * lf;
 }
 
 }  // namespace fb

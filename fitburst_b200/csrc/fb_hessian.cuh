@@ -181,14 +181,13 @@ __device__ double d2_term(int pa, int pb, const D2Ctx& c) {
   return 0.0;
 }
 
-__device__ __forceinline__ void make_d2ctx(const EvalArgs& A, const ChanTab& ch, double amp, double w,
+__device__ __forceinline__ void make_d2ctx(const EvalArgs& A, const ChanTab& ch, const CompTab& ct, double amp,
                                            double m, double td, double sum_dmidx, double apbf_outer,
                                            D2Ctx& c) {
   const int nc = A.pc.num_comp;
-  ChanTab chl = ch;
-  chl.amp = amp;
   c.tau0 = global_param(A.params, nc, FB_SCATTERING_TIMESCALE);
-  first_derivatives(chl, ch, w, c.tau0, m, td, c.d1, &c.G, &c.arg_erf);
+  first_derivatives(ch, ch, ct, c.tau0, amp, m, td, c.d1, &c.G, &c.arg_erf);
+  const double w = ct.w;
   c.M = m;
   c.T = td;
   c.w = w;
@@ -249,8 +248,7 @@ __global__ void __launch_bounds__(kBlock) k_hessian(const HessArgs H) {
   const int npairs = H.num_pairs;
   if (!MAP)
     for (int e = tid; e < (kBlock / 32) * npairs; e += kBlock) wacc[e] = 0.0;
-  for (int c = tid; c < nc; c += blockDim.x) make_comp_tab(pc, A.params, c, L.comp[c]);
-  __syncthreads();
+  load_comp_tables(A, L);
   const int tiles = (pc.num_time + kBlock - 1) / kBlock;
   const double tau0 = global_param(A.params, nc, FB_SCATTERING_TIMESCALE);
 
@@ -283,7 +281,7 @@ __global__ void __launch_bounds__(kBlock) k_hessian(const HessArgs H) {
           for (int k = 0; k < stride2; ++k) row2[k] = 0.0;
           if (j < pc.num_time) {
             for (int c = 0; c < nc; ++c)
-              row2[c] = eval_sample_component(pc, L.comp[c], L.sub + c * kf, L.chan[c].scattered, j).timeprof;
+              row2[c] = eval_sample_component(pc, L.comp[c], L.chan[c], L.sub + c * kf, j).timeprof;
             row2[nc] = A.data[(size_t)i * pc.num_time + j];
           }
           __syncthreads();
@@ -323,7 +321,7 @@ __global__ void __launch_bounds__(kBlock) k_hessian(const HessArgs H) {
       double msum = 0.0, sum_dmidx = 0.0;
       if (valid) {
         for (int c = 0; c < nc; ++c) {
-          SampleComp sc = eval_sample_component(pc, L.comp[c], L.sub + c * kf, L.chan[c].scattered, j);
+          SampleComp sc = eval_sample_component(pc, L.comp[c], L.chan[c], L.sub + c * kf, j);
           double amp = L.chan[c].amp;
           if (pc.scintillation) {
             amp = L.scint_amp[c];
@@ -332,10 +330,8 @@ __global__ void __launch_bounds__(kBlock) k_hessian(const HessArgs H) {
           row[2 * c] = sc.spectrum;
           row[2 * c + 1] = sc.timediff;
           msum += sc.spectrum;
-          ChanTab chl = L.chan[c];
-          chl.amp = amp;
           double d[9], g;
-          first_derivatives(chl, L.chan[c], L.comp[c].w, tau0, sc.spectrum, sc.timediff, d, &g);
+          first_derivatives(L.chan[c], L.chan[c], L.comp[c], tau0, amp, sc.spectrum, sc.timediff, d, &g);
           sum_dmidx += d[FB_DM_INDEX];
         }
       }
@@ -347,7 +343,7 @@ __global__ void __launch_bounds__(kBlock) k_hessian(const HessArgs H) {
             if (!sum && c != H.map_component) continue;
             D2Ctx ctx;
             const double amp = pc.scintillation ? L.scint_amp[c] : L.chan[c].amp;
-            make_d2ctx(A, L.chan[c], amp, L.comp[c].w, row[2 * c], row[2 * c + 1], sum_dmidx,
+            make_d2ctx(A, L.chan[c], L.comp[c], amp, row[2 * c], row[2 * c + 1], sum_dmidx,
                        L.chan[H.map_component].amp_pbf, ctx);
             out += d2_term(H.map_pa, H.map_pb, ctx);
           }
@@ -364,7 +360,7 @@ __global__ void __launch_bounds__(kBlock) k_hessian(const HessArgs H) {
         D2Ctx ctx;
         if (valid) {
           const double amp = pc.scintillation ? L.scint_amp[c] : L.chan[c].amp;
-          make_d2ctx(A, L.chan[c], amp, L.comp[c].w, row[2 * c], row[2 * c + 1], sum_dmidx, 0.0, ctx);
+          make_d2ctx(A, L.chan[c], L.comp[c], amp, row[2 * c], row[2 * c + 1], sum_dmidx, 0.0, ctx);
         }
         for (int pi = 0; pi < npairs; ++pi) {
           const HessPair hp = H.pairs[pi];

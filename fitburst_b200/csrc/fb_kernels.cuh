@@ -14,6 +14,10 @@ enum EvalMode { MODE_MODEL = 0, MODE_GRAM = 1, MODE_JAC = 2, MODE_DERIV = 3 };
 struct EvalArgs {
   PlanConst pc;
   const double* params;  // device, (FB_NUM_PARAMETERS, num_comp)
+  // tables built by k_tables for the current parameters, indexed by channel number
+  const CompTab* g_comp;  // (num_comp)
+  const SubTab* g_sub;    // (num_freq, num_comp, kf)
+  const ChanTab* g_chan;  // (num_freq, num_comp)
   const int* chan_list;  // channels to visit (nullptr = all)
   int num_chan;
   const double* data;     // (num_freq, num_time) or nullptr
@@ -190,19 +194,45 @@ __device__ inline SmemLayout carve(double* base, int nc, int kf) {
   return L;
 }
 
+// Builds every table of the current parameter set: one thread per (channel, component).
+__global__ void __launch_bounds__(128) k_tables(const PlanConst pc, const double* __restrict__ params,
+                                                CompTab* __restrict__ g_comp, SubTab* __restrict__ g_sub,
+                                                ChanTab* __restrict__ g_chan) {
+  const int nc = pc.num_comp;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= pc.num_freq * nc) return;
+  const int i = e / nc, c = e % nc;
+  CompTab ct;
+  make_comp_tab(pc, params, c, ct);
+  if (i == 0) g_comp[c] = ct;
+  make_channel_tables(pc, params, ct, i, c, g_sub + (size_t)e * pc.kf, g_chan[e]);
+}
+
+// Stages one channel's tables from global memory (L2-resident, written by k_tables).
 __device__ inline void load_channel_tables(const EvalArgs& A, const SmemLayout& L, int i) {
   const PlanConst& pc = A.pc;
   const int nc = pc.num_comp, kf = pc.kf;
   __syncthreads();
-  for (int e = threadIdx.x; e < nc * kf; e += blockDim.x) {
-    const int c = e / kf, a = e % kf;
-    make_sub_tab(pc, A.params, L.comp[c], i, a, c, L.sub[c * kf + a]);
+  {
+    const double* src = reinterpret_cast<const double*>(A.g_sub + (size_t)i * nc * kf);
+    double* dst = reinterpret_cast<double*>(L.sub);
+    const int nd = nc * kf * (int)(sizeof(SubTab) / sizeof(double));
+    for (int e = threadIdx.x; e < nd; e += blockDim.x) dst[e] = src[e];
   }
-  // channel-centre tables are computed by the LAST threads of the block so that they run
-  // concurrently with the sub-frequency tables built by the first ones.
-  for (int e = (int)blockDim.x - 1 - (int)threadIdx.x; e < nc; e += blockDim.x) {
-    make_chan_tab(pc, A.params, L.comp[e], i, e, L.chan[e]);
+  {
+    const double* src = reinterpret_cast<const double*>(A.g_chan + (size_t)i * nc);
+    double* dst = reinterpret_cast<double*>(L.chan);
+    const int nd = nc * (int)(sizeof(ChanTab) / sizeof(double));
+    for (int e = threadIdx.x; e < nd; e += blockDim.x) dst[e] = src[e];
   }
+  __syncthreads();
+}
+
+__device__ inline void load_comp_tables(const EvalArgs& A, const SmemLayout& L) {
+  const double* src = reinterpret_cast<const double*>(A.g_comp);
+  double* dst = reinterpret_cast<double*>(L.comp);
+  const int nd = A.pc.num_comp * (int)(sizeof(CompTab) / sizeof(double));
+  for (int e = threadIdx.x; e < nd; e += blockDim.x) dst[e] = src[e];
   __syncthreads();
 }
 
@@ -225,7 +255,7 @@ __device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayo
   for (int c = 0; c < nc; ++c) {
     const CompTab& ct = L.comp[c];
     const ChanTab& ch = L.chan[c];
-    SampleComp sc = eval_sample_component(pc, ct, L.sub + c * kf, ch.scattered, j);
+    SampleComp sc = eval_sample_component(pc, ct, ch, L.sub + c * kf, j);
     double amp = ch.amp;
     if (pc.scintillation) {  // analysis/model.py:274-277
       amp = L.scint_amp[c];
@@ -239,29 +269,26 @@ __device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayo
       if (A.c_td) A.c_td[o] = sc.timediff;
       if (A.c_tp) A.c_tp[o] = sc.timeprof;
     } else {
-      ChanTab chl = ch;
-      chl.amp = amp;
       double d[9], g;
       if (MODE == MODE_DERIV) {
         // the reference looks deriv_amplitude_pbf up with the requested component.
-        first_derivatives(chl, L.chan[A.d_comp], ct.w, tau0, sc.spectrum, sc.timediff, d, &g);
+        first_derivatives(ch, L.chan[A.d_comp], ct, tau0, amp, sc.spectrum, sc.timediff, d, &g);
         const bool all = A.d_addall && is_fit_global(A.d_param);
         if (all || c == A.d_comp) dsum += d[A.d_param];
       } else {
         // LSFitter.compute_jacobian calls the global derivatives with component = 0
         // (analysis/fitter.py:213-223), per-component ones with their own index.
-        double dg[9];
-        first_derivatives(chl, ch, ct.w, tau0, sc.spectrum, sc.timediff, d, &g);
-        if (c == 0) {
-          for (int p = 0; p < 9; ++p) dg[p] = d[p];
-        } else {
-          first_derivatives(chl, L.chan[0], ct.w, tau0, sc.spectrum, sc.timediff, dg, &g);
-        }
+        first_derivatives(ch, ch, ct, tau0, amp, sc.spectrum, sc.timediff, d, &g);
+        // the scattering_* columns look deriv_amplitude_pbf up with component 0: correct them
+        // when that differs from the own-component value (only if ref_freq / width differ).
+        const ChanTab& ch0 = L.chan[0];
+        d[FB_SCATTERING_TIMESCALE] += sc.spectrum * (ch0.dap_tau - ch.dap_tau) * ch.inv_apbf;
+        d[FB_SCATTERING_INDEX] += sc.spectrum * (ch0.dap_alpha - ch.dap_alpha) * ch.inv_apbf;
 #pragma unroll
         for (int p = 0; p < 9; ++p) {
           const int col = A.col_of[p];
           if (col < 0) continue;
-          if (is_fit_global(p)) row[col] += -dg[p] * wi;
+          if (is_fit_global(p)) row[col] += -d[p] * wi;
           else row[col + c] = -d[p] * wi;
         }
       }
@@ -288,8 +315,7 @@ __global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
   const PlanConst& pc = A.pc;
   const int nc = pc.num_comp, kf = pc.kf, tid = threadIdx.x;
   SmemLayout L = carve(smem_raw, nc, kf);
-  for (int c = tid; c < nc; c += blockDim.x) make_comp_tab(pc, A.params, c, L.comp[c]);
-  __syncthreads();
+  load_comp_tables(A, L);
 
   const int ncols = A.n_free + 1;
   const int stride = gram_stride(ncols);
@@ -351,8 +377,7 @@ __global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
         for (int k = 0; k < stride2; ++k) row2[k] = 0.0;
         if (j < pc.num_time) {
           for (int c = 0; c < nc; ++c) {
-            const SampleComp sc =
-                eval_sample_component(pc, L.comp[c], L.sub + c * kf, L.chan[c].scattered, j);
+            const SampleComp sc = eval_sample_component(pc, L.comp[c], L.chan[c], L.sub + c * kf, j);
             row2[c] = sc.timeprof;
           }
           row2[nc] = A.data[(size_t)i * pc.num_time + j];
