@@ -228,9 +228,6 @@ struct SampleComp {
   double spectrum;  // 10**A * mean(profile * sed)   (scintillation rescales later)
 };
 
-// One (channel, sample, component): loops the kf x kt sub-grid. `sub` points at this
-// component's kf SubTab entries (shared memory).
-//
 // Along the time axis a scattered component has three regimes and only the middle one needs the
 // special functions (the split is exact to rounding, see emg_shape):
 //   plateau  every sub-sample is clamped to -5w (analysis/model.py:340): the profile is a
@@ -238,77 +235,96 @@ struct SampleComp {
 //   rise     general case: exp + erfcx per sub-sample;
 //   tail     every sub-sample has erfc == 2 to rounding: the kt sub-samples of one sub-frequency
 //            form a geometric series, one exp per (sample, sub-frequency).
-__device__ __forceinline__ SampleComp eval_sample_component(const PlanConst& pc, const CompTab& ct,
-                                                            const ChanTab& ch,
-                                                            const SubTab* __restrict__ sub, int j) {
+// Returns true and fills `out` when sample j lies in the plateau or the tail.
+__device__ __forceinline__ bool eval_sample_fast(const PlanConst& pc, const CompTab& ct, const ChanTab& ch,
+                                                 const SubTab* __restrict__ sub, int j, SampleComp& out) {
+  if (!ch.fast_ok) return false;
   const int kf = pc.kf, kt = pc.kt, n = pc.ntk;
-  const double inv_kf = 1.0 / (double)kf, inv_kt = 1.0 / (double)kt;
   const int m0 = j * kt;
-  SampleComp out;
-  if (ch.fast_ok) {
-    const double u0 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, m0, n);
-    const double u_last = linspace_at(ct.t_start, ct.t_step, ct.t_stop, m0 + kt - 1, n);
-    const bool plateau = (u_last - ch.min_delay) < ct.neg5w;
-    const bool tail = u0 >= ch.tail_lo;
-    if (plateau || tail) {
-      double su = 0.0;
-      for (int b = 0; b < kt; ++b) su += linspace_at(ct.t_start, ct.t_step, ct.t_stop, m0 + b, n);
-      out.timediff = su * inv_kt - ch.mean_delay;
-      if (plateau) {
-        out.timeprof = ch.plateau_p;
-        out.spectrum = ch.plateau_ps;
-      } else {
-        double s_p = 0.0, s_ps = 0.0;
-        for (int a = 0; a < kf; ++a) {
-          const SubTab& st = sub[a];
-          const double p = st.tail_c * exp(fma(-u0, st.inv_tau, st.tail_e));
-          s_p += p;
-          s_ps = fma(p, st.sed, s_ps);
-        }
-        out.timeprof = s_p;
-        out.spectrum = ct.amp10 * s_ps;
-      }
-      return out;
-    }
-  }
-  const int scattered = ch.scattered;
-  double acc_t = 0.0, acc_p = 0.0, acc_ps = 0.0;
-  for (int b = 0; b < kt; ++b) {
-    const int m = m0 + b;
-    const double u = linspace_at(ct.t_start, ct.t_step, ct.t_stop, m, n);
-    double s_t = 0.0, s_p = 0.0, s_ps = 0.0;
+  const double u0 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, m0, n);
+  const double u_last = linspace_at(ct.t_start, ct.t_step, ct.t_stop, m0 + kt - 1, n);
+  const bool plateau = (u_last - ch.min_delay) < ct.neg5w;
+  const bool tail = u0 >= ch.tail_lo;
+  if (!(plateau || tail)) return false;
+  double su = 0.0;
+  for (int b = 0; b < kt; ++b) su += linspace_at(ct.t_start, ct.t_step, ct.t_stop, m0 + b, n);
+  out.timediff = su * (1.0 / (double)kt) - ch.mean_delay;
+  if (plateau) {
+    out.timeprof = ch.plateau_p;
+    out.spectrum = ch.plateau_ps;
+  } else {
+    double s_p = 0.0, s_ps = 0.0;
     for (int a = 0; a < kf; ++a) {
       const SubTab& st = sub[a];
-      const double t = u - st.delay;  // analysis/model.py:208-209
-      s_t += t;
-      double p;
-      if (scattered) {
-        const double tc = (t < ct.neg5w) ? ct.neg5w : t;  // analysis/model.py:340
-        p = st.amp_term * emg_shape(tc * ct.inv_w, st.ratio);
-        if (pc.is_folded) {
-          double t2 = linspace_at(st.fold_start, st.fold_step, st.fold_stop, m, n);
-          t2 = (t2 < ct.neg5w) ? ct.neg5w : t2;
-          p = 0.5 * (p + st.amp_term * emg_shape(t2 * ct.inv_w, st.ratio));
-        }
-      } else {
-        const double z = t * ct.inv_w;  // routines/profile.py:47
-        p = exp(-0.5 * z * z);
-        if (pc.is_folded) {
-          const double z2 = linspace_at(st.fold_start, st.fold_step, st.fold_stop, m, n) * ct.inv_w;
-          p = 0.5 * (p + exp(-0.5 * z2 * z2));
-        }
-      }
+      const double p = st.tail_c * exp(fma(-u0, st.inv_tau, st.tail_e));
       s_p += p;
-      s_ps += p * st.sed;
+      s_ps = fma(p, st.sed, s_ps);
+    }
+    out.timeprof = s_p;
+    out.spectrum = ct.amp10 * s_ps;
+  }
+  return true;
+}
+
+// One sub-sample (sub-frequency entry st, up-sampled time index m) of the general case:
+// time difference t (analysis/model.py:208-209) and profile p (analysis/model.py:336-350).
+__device__ __forceinline__ void eval_subsample(const PlanConst& pc, const CompTab& ct, int scattered,
+                                               const SubTab& st, int m, double& t, double& p) {
+  const int n = pc.ntk;
+  const double u = linspace_at(ct.t_start, ct.t_step, ct.t_stop, m, n);
+  t = u - st.delay;
+  if (scattered) {
+    const double tc = (t < ct.neg5w) ? ct.neg5w : t;  // analysis/model.py:340
+    p = st.amp_term * emg_shape(tc * ct.inv_w, st.ratio);
+    if (pc.is_folded) {
+      double t2 = linspace_at(st.fold_start, st.fold_step, st.fold_stop, m, n);
+      t2 = (t2 < ct.neg5w) ? ct.neg5w : t2;
+      p = 0.5 * (p + st.amp_term * emg_shape(t2 * ct.inv_w, st.ratio));
+    }
+  } else {
+    const double z = t * ct.inv_w;  // routines/profile.py:47
+    p = exp(-0.5 * z * z);
+    if (pc.is_folded) {
+      const double z2 = linspace_at(st.fold_start, st.fold_step, st.fold_stop, m, n) * ct.inv_w;
+      p = 0.5 * (p + exp(-0.5 * z2 * z2));
+    }
+  }
+}
+
+// General case of one (channel, sample, component) by a single thread: loops the kf x kt
+// sub-grid in the reference's order (mean over sub-frequencies, then over sub-times).
+__device__ __forceinline__ SampleComp eval_sample_general(const PlanConst& pc, const CompTab& ct,
+                                                          const ChanTab& ch,
+                                                          const SubTab* __restrict__ sub, int j) {
+  const int kf = pc.kf, kt = pc.kt;
+  const double inv_kf = 1.0 / (double)kf, inv_kt = 1.0 / (double)kt;
+  double acc_t = 0.0, acc_p = 0.0, acc_ps = 0.0;
+  for (int b = 0; b < kt; ++b) {
+    double s_t = 0.0, s_p = 0.0, s_ps = 0.0;
+    for (int a = 0; a < kf; ++a) {
+      double t, p;
+      eval_subsample(pc, ct, ch.scattered, sub[a], j * kt + b, t, p);
+      s_t += t;
+      s_p += p;
+      s_ps += p * sub[a].sed;
     }
     acc_t += s_t * inv_kf;
     acc_p += s_p * inv_kf;
     acc_ps += s_ps * inv_kf;
   }
+  SampleComp out;
   out.timediff = acc_t * inv_kt;
   out.timeprof = acc_p * inv_kt;
   out.spectrum = ct.amp10 * (acc_ps * inv_kt);
   return out;
+}
+
+__device__ __forceinline__ SampleComp eval_sample_component(const PlanConst& pc, const CompTab& ct,
+                                                            const ChanTab& ch,
+                                                            const SubTab* __restrict__ sub, int j) {
+  SampleComp out;
+  if (eval_sample_fast(pc, ct, ch, sub, j, out)) return out;
+  return eval_sample_general(pc, ct, ch, sub, j);
 }
 
 // First derivatives of ONE component's spectrum at one sample, routines/derivative.py:454-936.

@@ -278,10 +278,11 @@ __global__ void __launch_bounds__(kBlock) k_hessian(const HessArgs H) {
         for (int k = 0; k < kTile * kTile; ++k) acc2[k] = 0.0;
         for (int tile = 0; tile < tiles; ++tile) {
           const int j = tile * kBlock + tid;
+          eval_tile(A, L, i, tile);
           for (int k = 0; k < stride2; ++k) row2[k] = 0.0;
           if (j < pc.num_time) {
-            for (int c = 0; c < nc; ++c)
-              row2[c] = eval_sample_component(pc, L.comp[c], L.chan[c], L.sub + c * kf, j).timeprof;
+            const double* vrow = L.vals + (size_t)tid * val_stride(nc);
+            for (int c = 0; c < nc; ++c) row2[c] = vrow[3 * c + 2];
             row2[nc] = A.data[(size_t)i * pc.num_time + j];
           }
           __syncthreads();
@@ -319,9 +320,14 @@ __global__ void __launch_bounds__(kBlock) k_hessian(const HessArgs H) {
       const bool valid = j < pc.num_time;
       const size_t s_idx = (size_t)i * pc.num_time + (valid ? j : 0);
       double msum = 0.0, sum_dmidx = 0.0;
+      eval_tile(A, L, i, tile);
       if (valid) {
+        const double* vrow = L.vals + (size_t)tid * val_stride(nc);
         for (int c = 0; c < nc; ++c) {
-          SampleComp sc = eval_sample_component(pc, L.comp[c], L.chan[c], L.sub + c * kf, j);
+          SampleComp sc;
+          sc.spectrum = vrow[3 * c];
+          sc.timediff = vrow[3 * c + 1];
+          sc.timeprof = vrow[3 * c + 2];
           double amp = L.chan[c].amp;
           if (pc.scintillation) {
             amp = L.scint_amp[c];

@@ -153,8 +153,13 @@ struct SmemLayout {
   double* scint_amp;
   double* small;    // (nc+1)^2 + nc scratch for the scintillation solve
   double* tilesum;  // block-summed Gram tiles of the scintillation system
+  double* vals;     // per-thread (spectrum, timediff, timeprof) per component, stride val_stride
+  int* queue;       // (thread, component) items of the current tile that need the general case
+  int* qcount;
   double* X;
 };
+
+__host__ __device__ inline int val_stride(int nc) { return (3 * nc) | 1; }
 
 __host__ __device__ inline size_t smem_bytes(int nc, int kf, int ncols_main, bool scint) {
   size_t n = 0;
@@ -164,6 +169,8 @@ __host__ __device__ inline size_t smem_bytes(int nc, int kf, int ncols_main, boo
   n += sizeof(double) * nc;
   n += sizeof(double) * ((nc + 1) * (nc + 1) + nc + 2);
   n += sizeof(double) * gram_ntiles(nc + 1) * kTile * kTile;
+  n += sizeof(double) * (size_t)kBlock * val_stride(nc);
+  n += sizeof(int) * ((size_t)kBlock * nc + 2);
   int stride = gram_stride(ncols_main);
   if (scint) {
     const int s2 = gram_stride(nc + 1);
@@ -190,6 +197,11 @@ __device__ inline SmemLayout carve(double* base, int nc, int kf) {
   p += sizeof(double) * ((nc + 1) * (nc + 1) + nc + 2);
   L.tilesum = reinterpret_cast<double*>(p);
   p += sizeof(double) * gram_ntiles(nc + 1) * kTile * kTile;
+  L.vals = reinterpret_cast<double*>(p);
+  p += sizeof(double) * (size_t)kBlock * val_stride(nc);
+  L.queue = reinterpret_cast<int*>(p);
+  L.qcount = L.queue + (size_t)kBlock * nc;
+  p += sizeof(int) * ((size_t)kBlock * nc + 2);
   L.X = reinterpret_cast<double*>(p);
   return L;
 }
@@ -236,6 +248,87 @@ __device__ inline void load_comp_tables(const EvalArgs& A, const SmemLayout& L) 
   __syncthreads();
 }
 
+// Evaluates (spectrum, timediff, timeprof) of every component for the kBlock samples of one time
+// tile of channel i into L.vals. Samples on the clamp plateau or in the exponential tail are
+// closed-form and done by their own thread; the few samples per (channel, component) that need
+// the general exp + erfcx sub-grid are pushed on a block-wide queue and evaluated one sub-sample
+// per LANE, so that the expensive work is spread over the whole block instead of stalling
+// every other warp at the next barrier.
+__device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, int tile) {
+  const PlanConst& pc = A.pc;
+  const int nc = pc.num_comp, kf = pc.kf, kt = pc.kt, tid = threadIdx.x;
+  const int vs = val_stride(nc);
+  const int npe = kf * kt;
+  const bool use_queue = npe >= 8;
+  const int j = tile * kBlock + tid;
+  if (tid == 0) *L.qcount = 0;
+  __syncthreads();
+  double* v = L.vals + (size_t)tid * vs;
+  if (j < pc.num_time) {
+    for (int c = 0; c < nc; ++c) {
+      SampleComp sc;
+      if (eval_sample_fast(pc, L.comp[c], L.chan[c], L.sub + c * kf, j, sc)) {
+        v[3 * c] = sc.spectrum;
+        v[3 * c + 1] = sc.timediff;
+        v[3 * c + 2] = sc.timeprof;
+      } else if (use_queue) {
+        L.queue[atomicAdd(L.qcount, 1)] = tid * nc + c;
+      } else {
+        sc = eval_sample_general(pc, L.comp[c], L.chan[c], L.sub + c * kf, j);
+        v[3 * c] = sc.spectrum;
+        v[3 * c + 1] = sc.timediff;
+        v[3 * c + 2] = sc.timeprof;
+      }
+    }
+  }
+  __syncthreads();
+  if (!use_queue) return;
+  const int qn = *L.qcount;
+  if (qn > 0) {
+    // group of gs lanes per item (gs = power of two >= min(npe, 32)), 32/gs items per warp pass.
+    int gs = 8;
+    while (gs < npe && gs < 32) gs <<= 1;
+    const int lane = tid & 31, warp = tid >> 5, nwarps = kBlock / 32;
+    const int gpw = 32 / gs, g = lane / gs, gl = lane % gs;
+    const double inv_n = 1.0 / (double)npe;
+    for (int base = warp * gpw; base < qn; base += nwarps * gpw) {
+      const int q = base + g;
+      const bool active = q < qn;
+      double s_t = 0.0, s_p = 0.0, s_ps = 0.0;
+      int t_idx = 0, c = 0;
+      if (active) {
+        const int item = L.queue[q];
+        t_idx = item / nc;
+        c = item % nc;
+        const CompTab& ct = L.comp[c];
+        const SubTab* sub = L.sub + c * kf;
+        const int scattered = L.chan[c].scattered;
+        const int jj = tile * kBlock + t_idx;
+        for (int pe = gl; pe < npe; pe += gs) {
+          const int b = pe / kf, a = pe - b * kf;
+          double t, p;
+          eval_subsample(pc, ct, scattered, sub[a], jj * kt + b, t, p);
+          s_t += t;
+          s_p += p;
+          s_ps = fma(p, sub[a].sed, s_ps);
+        }
+      }
+      for (int off = gs >> 1; off > 0; off >>= 1) {
+        s_t += __shfl_xor_sync(0xffffffffu, s_t, off);
+        s_p += __shfl_xor_sync(0xffffffffu, s_p, off);
+        s_ps += __shfl_xor_sync(0xffffffffu, s_ps, off);
+      }
+      if (active && gl == 0) {
+        double* o = L.vals + (size_t)t_idx * vs + 3 * c;
+        o[0] = L.comp[c].amp10 * (s_ps * inv_n);
+        o[1] = s_t * inv_n;
+        o[2] = s_p * inv_n;
+      }
+    }
+  }
+  __syncthreads();
+}
+
 // Everything a thread does for one sample of one channel, for every mode.
 template <int MODE>
 __device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayout& L, int i, int j,
@@ -244,6 +337,7 @@ __device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayo
   const int nc = pc.num_comp, kf = pc.kf, n = A.n_free;
   const double wi = (A.weights != nullptr) ? A.weights[i] : 1.0;
   const double tau0 = global_param(A.params, nc, FB_SCATTERING_TIMESCALE);
+  const double* vrow = L.vals + (size_t)threadIdx.x * val_stride(nc);
   if (MODE == MODE_GRAM || MODE == MODE_JAC) {
     for (int k = 0; k <= n; ++k) row[k] = 0.0;
     if (MODE == MODE_GRAM)
@@ -255,7 +349,10 @@ __device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayo
   for (int c = 0; c < nc; ++c) {
     const CompTab& ct = L.comp[c];
     const ChanTab& ch = L.chan[c];
-    SampleComp sc = eval_sample_component(pc, ct, ch, L.sub + c * kf, j);
+    SampleComp sc;
+    sc.spectrum = vrow[3 * c];
+    sc.timediff = vrow[3 * c + 1];
+    sc.timeprof = vrow[3 * c + 2];
     double amp = ch.amp;
     if (pc.scintillation) {  // analysis/model.py:274-277
       amp = L.scint_amp[c];
@@ -346,6 +443,7 @@ __global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
         cur = chi;
       }
       const int j = tile * kBlock + tid;
+      eval_tile(A, L, i, tile);
       process_sample<MODE>(A, L, i, j, j < pc.num_time, row, stride);
       if (MODE == MODE_GRAM) {
         __syncthreads();
@@ -374,12 +472,11 @@ __global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
       for (int k = 0; k < kTile * kTile; ++k) acc2[k] = 0.0;
       for (int tile = 0; tile < tiles; ++tile) {
         const int j = tile * kBlock + tid;
+        eval_tile(A, L, i, tile);
         for (int k = 0; k < stride2; ++k) row2[k] = 0.0;
         if (j < pc.num_time) {
-          for (int c = 0; c < nc; ++c) {
-            const SampleComp sc = eval_sample_component(pc, L.comp[c], L.chan[c], L.sub + c * kf, j);
-            row2[c] = sc.timeprof;
-          }
+          const double* vrow = L.vals + (size_t)tid * val_stride(nc);
+          for (int c = 0; c < nc; ++c) row2[c] = vrow[3 * c + 2];
           row2[nc] = A.data[(size_t)i * pc.num_time + j];
         }
         __syncthreads();
@@ -414,6 +511,7 @@ __global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
       __syncthreads();
       for (int tile = 0; tile < tiles; ++tile) {
         const int j = tile * kBlock + tid;
+        eval_tile(A, L, i, tile);
         process_sample<MODE>(A, L, i, j, j < pc.num_time, row, stride);
         if (MODE == MODE_GRAM) {
           __syncthreads();
