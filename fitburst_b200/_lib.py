@@ -99,6 +99,12 @@ SIGNATURES = {
     "fb_hessian": (ctypes.c_int, [_P, _P, _D, _P]),
     "fb_derivative2_map": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
     "fb_fit": (ctypes.c_int, [_P, _P, ctypes.POINTER(FitOptions), ctypes.POINTER(FitResult), _D, _D, _P]),
+    "fb_trf_create": (ctypes.c_int, [_I32, ctypes.c_int64, _D, ctypes.POINTER(FitOptions), ctypes.POINTER(_P)]),
+    "fb_trf_destroy": (ctypes.c_int, [_P]),
+    "fb_trf_start": (ctypes.c_int, [_P, _D]),
+    "fb_trf_propose": (ctypes.c_int, [_P, _D]),
+    "fb_trf_update": (ctypes.c_int, [_P, _D]),
+    "fb_trf_result": (ctypes.c_int, [_P, ctypes.POINTER(FitResult), _D]),
     "fb_fit_batched": (ctypes.c_int, [_P, _I32, _P, _P, _P, ctypes.POINTER(FitOptions), ctypes.POINTER(FitResult), _P]),
     "fb_chisq_grid": (ctypes.c_int, [_P, _P, _D, _I32, _D, _I32, _P, _P]),
     "fb_measure_fp64_peak": (ctypes.c_int, [_D, _P]),

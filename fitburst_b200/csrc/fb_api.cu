@@ -765,13 +765,200 @@ extern "C" int fb_derivative2_map(fb_plan_t, const double*, int32_t, int32_t, in
   return fail(FB_ERR_INVALID, "fb_derivative2_map: not built");
 }
 #endif
-#ifndef FB_HAVE_BATCHED
-extern "C" int fb_fit_batched(fb_plan_t, int32_t, const double*, const double*, double*,
-                              const fb_fit_options*, fb_fit_result*, void*) {
-  return fail(FB_ERR_INVALID, "fb_fit_batched: not built");
+// ---- trust-region state machine (see fb_trf.h) ---------------------------------------------------
+struct fb_trf_s {
+  TrfState S;
+  std::vector<double> accepted;
+  bool started = false;
+};
+
+static fb_fit_options default_options(const fb_fit_options* options) {
+  fb_fit_options opt;
+  opt.ftol = opt.xtol = opt.gtol = 1e-8;
+  opt.max_nfev = 0;
+  opt.compute_hessian = 0;
+  if (options) opt = *options;
+  return opt;
 }
-extern "C" int fb_chisq_grid(fb_plan_t, const double*, const double*, int32_t, const double*, int32_t,
-                             double*, void*) {
-  return fail(FB_ERR_INVALID, "fb_chisq_grid: not built");
+
+extern "C" int fb_trf_create(int32_t num_free, int64_t num_residuals, const double* x0_host,
+                             const fb_fit_options* options, fb_trf_t* trf_out) {
+  if (!x0_host || !trf_out) return fail(FB_ERR_INVALID, "null argument");
+  if (num_free < 1 || num_free > FB_MAX_FREE) return fail(FB_ERR_INVALID, "num_free must be in 1..%d", FB_MAX_FREE);
+  fb_trf_s* t = new (std::nothrow) fb_trf_s();
+  if (!t) return fail(FB_ERR_NOMEM, "out of host memory");
+  const fb_fit_options opt = default_options(options);
+  trf_init(t->S, num_free, num_residuals, x0_host, opt.ftol, opt.xtol, opt.gtol, opt.max_nfev);
+  t->accepted.assign((size_t)(num_free + 1) * (num_free + 1), 0.0);
+  *trf_out = t;
+  return FB_OK;
 }
-#endif
+
+extern "C" int fb_trf_destroy(fb_trf_t t) {
+  delete t;
+  return FB_OK;
+}
+
+extern "C" int fb_trf_start(fb_trf_t t, const double* gram_host) {
+  if (!t || !gram_host) return fail(FB_ERR_INVALID, "null argument");
+  const int n = t->S.n, ncols = n + 1;
+  if (!std::isfinite(gram_host[(size_t)n * ncols + n]))
+    return fail(FB_ERR_INVALID, "Residuals are not finite in the initial point.");  // least_squares.py:945-946
+  trf_load_accepted(t->S, gram_host);
+  t->accepted.assign(gram_host, gram_host + (size_t)ncols * ncols);
+  t->S.nfev = 1;
+  t->S.njev = 1;
+  t->started = true;
+  return FB_OK;
+}
+
+extern "C" int fb_trf_propose(fb_trf_t t, double* x_trial_host) {
+  if (!t || !x_trial_host || !t->started) {
+    fail(FB_ERR_INVALID, "fb_trf_propose before fb_trf_start");
+    return FB_ERR_INVALID;
+  }
+  if (!trf_propose(t->S)) return 0;
+  for (int i = 0; i < t->S.n; ++i) x_trial_host[i] = t->S.x_new[i];
+  return 1;
+}
+
+extern "C" int fb_trf_update(fb_trf_t t, const double* gram_host) {
+  if (!t || !gram_host || !t->started) return fail(FB_ERR_INVALID, "fb_trf_update before fb_trf_start");
+  const int njev_before = t->S.njev, ncols = t->S.n + 1;
+  trf_update(t->S, gram_host);
+  if (t->S.njev != njev_before) t->accepted.assign(gram_host, gram_host + (size_t)ncols * ncols);
+  return FB_OK;
+}
+
+extern "C" int fb_trf_result(fb_trf_t t, fb_fit_result* result, double* gram_accepted_host) {
+  if (!t || !result) return fail(FB_ERR_INVALID, "null argument");
+  const TrfState& S = t->S;
+  memset(result, 0, sizeof(*result));
+  result->num_free = S.n;
+  result->status = S.finished ? S.status : -100;
+  result->nfev = S.nfev;
+  result->njev = S.njev;
+  result->cost = S.cost;
+  result->optimality = S.g_norm;
+  for (int i = 0; i < S.n; ++i) {
+    result->x[i] = S.x[i];
+    result->grad[i] = S.g[i];
+  }
+  if (gram_accepted_host) memcpy(gram_accepted_host, t->accepted.data(), sizeof(double) * t->accepted.size());
+  return FB_OK;
+}
+
+// ---- chi^2 grid sweep (BASELINE.json config 4) ----------------------------------------------------
+extern "C" int fb_chisq_grid(fb_plan_t p, const double* data_dev, const double* dm_values_host, int32_t num_dm,
+                             const double* sc_values_host, int32_t num_sc, double* chisq_dev, void* stream) {
+  if (!p || !data_dev || !dm_values_host || !sc_values_host || !chisq_dev) return fail(FB_ERR_INVALID, "null argument");
+  if (!p->have_weights) return fail(FB_ERR_INVALID, "fb_set_weights / fb_load_weights must be called first");
+  if (num_dm < 1 || num_sc < 1) return fail(FB_ERR_INVALID, "empty grid");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nc = p->desc.num_components;
+  if (p->num_good == 0) {
+    CUDA_TRY(cudaMemsetAsync(chisq_dev, 0, sizeof(double) * (size_t)num_dm * num_sc, st));
+    return FB_OK;
+  }
+  for (int a = 0; a < num_dm; ++a)
+    for (int b = 0; b < num_sc; ++b) {
+      // the whole sweep is enqueued without a host round trip: the grid point is written into
+      // the device parameter block by a kernel, tables and chi^2 follow on the same stream.
+      k_set_grid_point<<<1, 32, 0, st>>>(p->d_params, nc, dm_values_host[a], sc_values_host[b]);
+      p->launches += 1;
+      p->tables_dirty = true;
+      EvalArgs A = base_args(p);
+      A.data = data_dev;
+      A.weights = p->d_weights;
+      A.chan_list = p->d_chan_list;
+      A.num_chan = p->num_good;
+      A.n_free = 0;
+      int grid = 0;
+      // per-block partials live in the Gram partial buffer
+      const size_t need = (size_t)p->sm_count * 64;
+      if (need > p->partials_cap) {
+        cudaFree(p->d_partials);
+        p->d_partials = nullptr;
+        p->partials_cap = 0;
+        CUDA_TRY(cudaMalloc(&p->d_partials, sizeof(double) * need));
+        p->partials_cap = need;
+      }
+      A.chi2_partials = p->d_partials;
+      int rc = launch_eval<MODE_CHI2>(p, A, 1, st, &grid);
+      if (rc != FB_OK) return rc;
+      k_chi2_finalize<<<1, 32, 0, st>>>(p->d_partials, grid, chisq_dev + (size_t)a * num_sc + b);
+      CUDA_TRY(cudaGetLastError());
+      p->launches += 1;
+    }
+  // restore the plan's own parameters on the device
+  const size_t n = (size_t)FB_NUM_PARAMETERS * nc;
+  CUDA_TRY(cudaMemcpyAsync(p->d_params, p->h_params, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  p->tables_dirty = true;
+  return check_err_flag(p, st);
+}
+
+// ---- batched independent fits (BASELINE.json config 3) ---------------------------------------------
+extern "C" int fb_fit_batched(fb_plan_t p, int32_t count, const double* data_dev, const double* weights_dev,
+                              double* params_dev, const fb_fit_options* options, fb_fit_result* results_host,
+                              void* stream) {
+  if (!p || !data_dev || !weights_dev || !params_dev || !results_host) return fail(FB_ERR_INVALID, "null argument");
+  if (count < 0) return fail(FB_ERR_INVALID, "negative count");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nf = p->desc.num_freq, nc = p->desc.num_components, n = p->n_free;
+  const size_t spec = (size_t)nf * p->desc.num_time, nparam = (size_t)FB_NUM_PARAMETERS * nc;
+  fb_fit_options opt = default_options(options);
+  std::vector<double> w(nf), pr(nparam), H((size_t)n * n);
+  for (int b = 0; b < count; ++b) {
+    CUDA_TRY(cudaMemcpyAsync(w.data(), weights_dev + (size_t)b * nf, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(pr.data(), params_dev + (size_t)b * nparam, sizeof(double) * nparam, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    int rc = fb_load_weights(p, w.data(), stream);
+    if (rc == FB_OK) rc = fb_set_parameters(p, pr.data(), stream);
+    if (rc != FB_OK) return rc;
+    fb_fit_options o1 = opt;
+    o1.compute_hessian = 0;
+    rc = fb_fit(p, data_dev + (size_t)b * spec, &o1, &results_host[b], nullptr, nullptr, stream);
+    if (rc != FB_OK) {
+      results_host[b].status = -1;
+      continue;  // one bad burst must not abort the batch (fit() never raises, analysis/fitter.py:320-322)
+    }
+    // best fit back into the caller's parameter block
+    unpack_free(p, results_host[b].x);
+    CUDA_TRY(cudaMemcpyAsync(params_dev + (size_t)b * nparam, p->h_params, sizeof(double) * nparam,
+                             cudaMemcpyHostToDevice, st));
+    if (opt.compute_hessian) {
+      rc = fb_set_parameters(p, p->h_params, stream);
+      if (rc == FB_OK) rc = fb_hessian_impl(p, data_dev + (size_t)b * spec, H.data(), st);
+      if (rc == FB_OK) {
+        // uncertainties = sqrt(diag(inv(0.5 H))), analysis/fitter.py:484-485 (Gauss-Jordan on the small matrix)
+        std::vector<double> M((size_t)n * 2 * n, 0.0);
+        for (int i = 0; i < n; ++i) {
+          for (int j = 0; j < n; ++j) M[(size_t)i * 2 * n + j] = 0.5 * H[(size_t)i * n + j];
+          M[(size_t)i * 2 * n + n + i] = 1.0;
+        }
+        bool ok = true;
+        for (int k = 0; k < n && ok; ++k) {
+          int piv = k;
+          for (int r = k + 1; r < n; ++r)
+            if (std::fabs(M[(size_t)r * 2 * n + k]) > std::fabs(M[(size_t)piv * 2 * n + k])) piv = r;
+          if (M[(size_t)piv * 2 * n + k] == 0.0) { ok = false; break; }
+          if (piv != k)
+            for (int j = 0; j < 2 * n; ++j) std::swap(M[(size_t)k * 2 * n + j], M[(size_t)piv * 2 * n + j]);
+          const double d = M[(size_t)k * 2 * n + k];
+          for (int j = 0; j < 2 * n; ++j) M[(size_t)k * 2 * n + j] /= d;
+          for (int r = 0; r < n; ++r) {
+            if (r == k) continue;
+            const double f = M[(size_t)r * 2 * n + k];
+            if (f != 0.0)
+              for (int j = 0; j < 2 * n; ++j) M[(size_t)r * 2 * n + j] -= f * M[(size_t)k * 2 * n + j];
+          }
+        }
+        for (int i = 0; i < n; ++i)
+          results_host[b].uncertainty[i] = ok ? std::sqrt(M[(size_t)i * 2 * n + n + i]) : NAN;
+      }
+    }
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return FB_OK;
+}
+

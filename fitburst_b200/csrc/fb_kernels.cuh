@@ -9,7 +9,7 @@ namespace fb {
 constexpr int kBlock = 256;
 constexpr int kTile = 4;  // register tile edge of the Gram accumulation
 
-enum EvalMode { MODE_MODEL = 0, MODE_GRAM = 1, MODE_JAC = 2, MODE_DERIV = 3 };
+enum EvalMode { MODE_MODEL = 0, MODE_GRAM = 1, MODE_JAC = 2, MODE_DERIV = 3, MODE_CHI2 = 4 };
 
 struct EvalArgs {
   PlanConst pc;
@@ -40,6 +40,8 @@ struct EvalArgs {
   int d_param, d_comp, d_addall;
   double* d_out;
   int* err_flag;  // set to 1 on a singular scintillation system (routines/ism.py:46)
+  // MODE_CHI2: per-block partial sums of ((data - model) w)^2
+  double* chi2_partials;
 };
 
 __host__ __device__ inline bool is_fit_global(int p) {
@@ -343,6 +345,7 @@ __device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayo
     if (MODE == MODE_GRAM)
       for (int k = n + 1; k < stride; ++k) row[k] = 0.0;
   }
+  if (MODE == MODE_CHI2) row[0] = 0.0;
   if (!valid) return;
   double msum = 0.0, dsum = 0.0;
   const size_t s_idx = (size_t)i * pc.num_time + j;
@@ -359,6 +362,7 @@ __device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayo
       sc.spectrum = amp * sc.timeprof;
     }
     msum += sc.spectrum;
+    if (MODE == MODE_CHI2) continue;
     if (MODE == MODE_MODEL) {
       const size_t o = s_idx * nc + c;
       if (A.c_amp) A.c_amp[o] = amp;
@@ -393,6 +397,9 @@ __device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayo
   }
   if (MODE == MODE_MODEL) {
     A.model[s_idx] = msum;
+  } else if (MODE == MODE_CHI2) {
+    const double r = (A.data[s_idx] - msum) * wi;
+    row[0] = r * r;
   } else if (MODE == MODE_DERIV) {
     A.d_out[s_idx] = dsum;
   } else {
@@ -429,6 +436,7 @@ __global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
 
   const int tiles = (pc.num_time + kBlock - 1) / kBlock;
   double* row = L.X + (size_t)tid * stride;
+  double chi2_acc = 0.0;
 
   if (!pc.scintillation) {
     const long long total = (long long)A.num_chan * tiles;
@@ -445,6 +453,7 @@ __global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
       const int j = tile * kBlock + tid;
       eval_tile(A, L, i, tile);
       process_sample<MODE>(A, L, i, j, j < pc.num_time, row, stride);
+      if (MODE == MODE_CHI2) chi2_acc += row[0];
       if (MODE == MODE_GRAM) {
         __syncthreads();
         gram_accumulate(L.X, stride, kBlock, ntiles, nslices, g_ti, g_tj, g_slice, g_active, acc);
@@ -513,6 +522,7 @@ __global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
         const int j = tile * kBlock + tid;
         eval_tile(A, L, i, tile);
         process_sample<MODE>(A, L, i, j, j < pc.num_time, row, stride);
+        if (MODE == MODE_CHI2) chi2_acc += row[0];
         if (MODE == MODE_GRAM) {
           __syncthreads();
           gram_accumulate(L.X, stride, kBlock, ntiles, nslices, g_ti, g_tj, g_slice, g_active, acc);
@@ -520,6 +530,17 @@ __global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
         }
       }
     }
+  }
+  if (MODE == MODE_CHI2) {
+    // deterministic block tree-sum of the per-thread partial chi^2
+    __syncthreads();
+    L.X[tid] = chi2_acc;
+    __syncthreads();
+    for (int off = kBlock / 2; off > 0; off >>= 1) {
+      if (tid < off) L.X[tid] += L.X[tid + off];
+      __syncthreads();
+    }
+    if (tid == 0) A.chi2_partials[blockIdx.x] = L.X[0];
   }
 
   if (MODE == MODE_GRAM) {
@@ -547,6 +568,24 @@ __global__ void k_gram_finalize(const double* __restrict__ partials, int nblocks
         gram[gc * ncols + gr] = s;
       }
     }
+  }
+}
+
+// Sums per-block chi^2 partials in block order into out[0].
+__global__ void k_chi2_finalize(const double* __restrict__ partials, int nblocks, double* __restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partials[b];
+    out[0] = s;
+  }
+}
+
+// Overrides the global dm / scattering_timescale rows of a parameter block (chi^2 grid sweep).
+__global__ void k_set_grid_point(double* params, int nc, double dm, double sc_time) {
+  const int c = threadIdx.x;
+  if (c < nc) {
+    params[FB_DM * nc + c] = dm;
+    params[FB_SCATTERING_TIMESCALE * nc + c] = sc_time;
   }
 }
 

@@ -178,10 +178,27 @@ typedef struct fb_fit_options {
 int fb_fit(fb_plan_t plan, const double* data_dev, const fb_fit_options* options,
            fb_fit_result* result, double* gram_final_host, double* hessian_host, void* stream);
 
+/* The trust-region state machine behind fb_fit, exposed so that a caller can insert its own
+ * reduction between the evaluation and the step -- the channel-sharded multi-GPU fit
+ * (BASELINE.json config 5) all-reduces the (n+1)^2 normal-equation matrix over NCCL and then every
+ * rank advances an identical copy of this state (scipy/optimize/_lsq/trf.py:415-587 restated,
+ * see fitburst_b200/csrc/fb_trf.h). Protocol: create(x0) -> start(gram at x0) ->
+ * while (propose(x_trial) == 1) { evaluate gram at x_trial; update(gram); } -> result(). */
+typedef struct fb_trf_s* fb_trf_t;
+int fb_trf_create(int32_t num_free, int64_t num_residuals, const double* x0_host,
+                  const fb_fit_options* options, fb_trf_t* trf_out);
+int fb_trf_destroy(fb_trf_t trf);
+int fb_trf_start(fb_trf_t trf, const double* gram_host);
+/* returns 1 and fills x_trial_host when a trial point must be evaluated, 0 when finished */
+int fb_trf_propose(fb_trf_t trf, double* x_trial_host);
+int fb_trf_update(fb_trf_t trf, const double* gram_host);
+int fb_trf_result(fb_trf_t trf, fb_fit_result* result, double* gram_accepted_host);
+
 /* Batched independent fits (BASELINE.json config 3): `count` bursts of identical shape, burst b
  * occupying data_dev + b*num_freq*num_time, weights_dev + b*num_freq, params_dev + b *
- * FB_NUM_PARAMETERS*num_components (start point in, best fit out). One thread-block cluster
- * owns each burst and runs the whole trust-region loop on the device. */
+ * FB_NUM_PARAMETERS*num_components (start point in, best fit out; all on the device). Bursts
+ * are fitted back to back, each using the whole GPU; results_host[b] receives the scalar fields
+ * and, when options->compute_hessian is set, the 1-sigma uncertainties. */
 int fb_fit_batched(fb_plan_t plan, int32_t count, const double* data_dev, const double* weights_dev,
                    double* params_dev, const fb_fit_options* options, fb_fit_result* results_host,
                    void* stream);

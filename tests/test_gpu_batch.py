@@ -1,0 +1,84 @@
+"""GPU tests of the batched workloads: chi^2 grid (config 4), batched fits (config 3) and the
+channel-sharded driver on one rank (config 5's code path; the all-reduce is a no-op at world 1)."""
+import numpy as np
+import pytest
+
+from fitburst_b200 import synthetic as syn
+from tests.helpers import make_case, model_pair
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(case, fixed=("dm_index", "scattering_index"), seed=2):
+    from fitburst_b200.analysis.fitter import LSFitter
+    from oracle.fitburst_oracle import OracleFitter
+    freqs, times, truth, kwargs = make_case(**case)
+    cuda, oracle = model_pair(freqs, times, kwargs, truth)
+    clean = oracle.compute_model()
+    good = syn.make_good_freq(len(freqs), 0.3, seed)
+    data = syn.add_noise(clean, good, 0.1, seed)
+    start = syn.config2_start(truth)
+    cuda.update_parameters(start)
+    oracle.update_parameters(start)
+    fc = LSFitter(data, cuda, good)
+    fo = OracleFitter(data, oracle, good)
+    fc.fix_parameter(list(fixed))
+    fo.fix_parameter(list(fixed))
+    return fc, fo, truth, start, good, data
+
+
+def test_chisq_grid_matches_reference_definition(native_lib):
+    from fitburst_b200.batch import chisq_grid
+    fc, fo, truth, start, good, data = _setup(dict(num_freq=32, num_time=64, kf=2, kt=2, num_comp=2))
+    dm_values = np.linspace(-0.05, 0.05, 5)
+    sc_values = np.logspace(-3.5, -2.0, 4)
+    got = chisq_grid(fc, dm_values, sc_values)
+    want = np.zeros_like(got)
+    fo.fit_parameters = ["dm", "scattering_timescale"]
+    for a, dm in enumerate(dm_values):
+        for b, sc in enumerate(sc_values):
+            want[a, b] = np.sum(fo.compute_residuals([dm, sc]) ** 2)  # the reference's definition
+    np.testing.assert_allclose(got, want, rtol=1e-10)
+    assert np.unravel_index(np.argmin(got), got.shape) == np.unravel_index(np.argmin(want), want.shape)
+
+
+def test_fit_batched_matches_individual_fits(native_lib):
+    from fitburst_b200.analysis.model import SpectrumModeler
+    from fitburst_b200.batch import fit_batched
+    from oracle.fitburst_oracle import OracleFitter, OracleModel
+    num_freq, num_time, count = 32, 64, 3
+    freqs, times = syn.chime_axes(num_freq, num_time)
+    kwargs = dict(factor_freq_upsample=2, factor_time_upsample=2, num_components=2)
+    datas, goods, starts, oracles = [], [], [], []
+    truth = syn.truncate_components(syn.config2_truth(num_time), 2)
+    for b in range(count):
+        t = {k: list(v) for k, v in truth.items()}
+        t["amplitude"] = [a + 0.05 * b for a in t["amplitude"]]
+        om = OracleModel(freqs, times, **kwargs)
+        om.update_parameters(t)
+        good = syn.make_good_freq(num_freq, 0.2, 10 + b)
+        data = syn.add_noise(om.compute_model(), good, 0.1, 10 + b)
+        start = syn.config2_start(t)
+        om.update_parameters(start)
+        fo = OracleFitter(data, om, good)
+        fo.fix_parameter(["dm_index", "scattering_index"])
+        fo.fit(with_statistics=False)
+        datas.append(data); goods.append(good); starts.append(start); oracles.append(fo)
+    model = SpectrumModeler(freqs, times, **kwargs)
+    out = fit_batched(model, np.stack(datas), np.stack(goods), starts, ["dm_index", "scattering_index"])
+    for b in range(count):
+        assert out[b]["status"] == oracles[b].results.status
+        assert out[b]["nfev"] == oracles[b].results.nfev
+        np.testing.assert_allclose(out[b]["x"], oracles[b].results.x, rtol=1e-6)
+        assert np.all(np.isfinite(out[b]["uncertainties"])) and np.all(out[b]["uncertainties"] > 0)
+
+
+def test_channel_sharded_driver_single_rank(native_lib):
+    from fitburst_b200.distributed import ChannelShardedFitter
+    fc, fo, truth, start, good, data = _setup(dict(num_freq=32, num_time=64, kf=2, kt=2, num_comp=2))
+    sharded = ChannelShardedFitter(fc, num_freq_total=32)
+    res = sharded.fit()
+    fo.fit(with_statistics=False)
+    assert res["status"] == fo.results.status and res["nfev"] == fo.results.nfev
+    np.testing.assert_allclose(res["x"], fo.results.x, rtol=1e-6)
+    assert np.all(res["uncertainties"] > 0)
