@@ -55,6 +55,8 @@ struct fb_plan_s {
   size_t hess_partials_cap = 0;
   HessPair* d_pairs = nullptr;
   size_t pairs_cap = 0;
+  int* d_comp_list = nullptr;
+  size_t comp_list_cap = 0;
   int* d_chan_list = nullptr;
   int num_good = 0;
   bool have_weights = false;
@@ -186,6 +188,7 @@ extern "C" int fb_plan_destroy(fb_plan_t p) {
   cudaFree(p->d_partials);
   cudaFree(p->d_hess_partials);
   cudaFree(p->d_pairs);
+  cudaFree(p->d_comp_list);
   cudaFree(p->d_comp);
   cudaFree(p->d_sub);
   cudaFree(p->d_chan);
@@ -692,6 +695,26 @@ int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, 
     p->pairs_cap = npairs;
   }
   CUDA_TRY(cudaMemcpyAsync(p->d_pairs, pairs.data(), sizeof(HessPair) * npairs, cudaMemcpyHostToDevice, st));
+  // per component: the pairs it contributes to (summing functions: all components; others: the
+  // one `component` the reference passes)
+  std::vector<int> comp_list;
+  int comp_off[FB_MAX_COMPONENTS + 1];
+  for (int c = 0; c < nc; ++c) {
+    comp_off[c] = (int)comp_list.size();
+    for (int k = 0; k < npairs; ++k)
+      if (pairs[k].is_sum || pairs[k].component == c) comp_list.push_back(k);
+  }
+  comp_off[nc] = (int)comp_list.size();
+  if (comp_list.size() > p->comp_list_cap) {
+    cudaFree(p->d_comp_list);
+    p->d_comp_list = nullptr;
+    p->comp_list_cap = 0;
+    CUDA_TRY(cudaMalloc(&p->d_comp_list, sizeof(int) * comp_list.size()));
+    p->comp_list_cap = comp_list.size();
+  }
+  CUDA_TRY(cudaMemcpyAsync(p->d_comp_list, comp_list.data(), sizeof(int) * comp_list.size(),
+                           cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));  // host vectors go out of scope
   const int ncols = n + 1;
   std::vector<double> gram((size_t)ncols * ncols), S(npairs, 0.0);
   // first-derivative products = J^T J of the weighted Jacobian at the model's current state
@@ -708,6 +731,8 @@ int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, 
     H.E.num_chan = p->num_good;
     H.pairs = p->d_pairs;
     H.num_pairs = npairs;
+    H.comp_list = p->d_comp_list;
+    for (int c = 0; c <= nc; ++c) H.comp_off[c] = comp_off[c];
     int grid = 0;
     rc = launch_hessian<false>(p, H, st, &grid);
     if (rc != FB_OK) return rc;

@@ -12,6 +12,7 @@ namespace fb {
 
 struct D2Ctx {
   double M, T, w, tau, tau0, L, apbf, D, Dp, G, arg_erf;
+  double it, iw, iw2, it0, ws, iap;  // 1/tau, 1/w, 1/w^2, 1/tau0, w/tau, 1/amp_pbf
   double d1[9];
   double fpow, ref_freq, q1, q2, k, dm;
   double dap_alpha, d2ap_alpha;
@@ -38,38 +39,40 @@ __host__ __device__ inline bool d2_is_sum(int pa, int pb) {
 
 __device__ __forceinline__ double d2_dae(int p, const D2Ctx& c) {  // deriv_argument_erf, :252-307
   switch (p) {
-    case FB_ARRIVAL_TIME: return -1.0 / c.w * kSqrtHalf;
-    case FB_BURST_WIDTH: return -(c.T / (c.w * c.w) + 1.0 / c.tau) * kSqrtHalf;
-    case FB_DM: return c.D / c.w * kSqrtHalf;
-    case FB_DM_INDEX: return c.Dp / c.w * kSqrtHalf;
-    case FB_SCATTERING_TIMESCALE: return c.w / c.tau0 / c.tau * kSqrtHalf;
-    case FB_SCATTERING_INDEX: return c.L * c.w / c.tau * kSqrtHalf;
+    case FB_ARRIVAL_TIME: return -c.iw * kSqrtHalf;
+    case FB_BURST_WIDTH: return -(c.T * c.iw2 + c.it) * kSqrtHalf;
+    case FB_DM: return c.D * c.iw * kSqrtHalf;
+    case FB_DM_INDEX: return c.Dp * c.iw * kSqrtHalf;
+    case FB_SCATTERING_TIMESCALE: return c.ws * c.it0 * kSqrtHalf;
+    case FB_SCATTERING_INDEX: return c.L * c.ws * kSqrtHalf;
   }
   return 0.0;
 }
 
 __device__ __forceinline__ double d2_dax(int p, const D2Ctx& c) {  // deriv_argument_exp, :309-371
   double base = 0.0;
-  const double ws = c.w / c.tau;
+  const double ws = c.ws;
   switch (p) {
-    case FB_ARRIVAL_TIME: base = 1.0 / c.tau; break;
-    case FB_BURST_WIDTH: base = c.w / (c.tau * c.tau); break;
-    case FB_DM: base = -c.D / c.tau; break;
-    case FB_DM_INDEX: base = -c.Dp / c.tau; break;
-    case FB_SCATTERING_TIMESCALE: base = -(ws * ws) / c.tau0 + c.T / c.tau / c.tau0; break;
-    case FB_SCATTERING_INDEX: base = c.L * (-(ws * ws) + c.T / c.tau); break;
+    case FB_ARRIVAL_TIME: base = c.it; break;
+    case FB_BURST_WIDTH: base = ws * c.it; break;
+    case FB_DM: base = -c.D * c.it; break;
+    case FB_DM_INDEX: base = -c.Dp * c.it; break;
+    case FB_SCATTERING_TIMESCALE: base = (c.T * c.it - ws * ws) * c.it0; break;
+    case FB_SCATTERING_INDEX: base = c.L * (c.T * c.it - ws * ws); break;
   }
   return base - 2.0 * c.arg_erf * d2_dae(p, c);
 }
 
-// One component's term of deriv2_model_wrt_<pa>_<pb> (unordered pair).
-__device__ double d2_term(int pa, int pb, const D2Ctx& c) {
+// One component's term of deriv2_model_wrt_<pa>_<pb> (unordered pair). Divisions of the
+// reference are multiplications by the reciprocals held in the context.
+__device__ __forceinline__ double d2_term(int pa, int pb, const D2Ctx& c) {
   if (pa > pb) {
     const int t = pa;
     pa = pb;
     pb = t;
   }
-  const double M = c.M, T = c.T, w = c.w, tau = c.tau, tau0 = c.tau0, L = c.L, G = c.G;
+  const double M = c.M, T = c.T, w = c.w, L = c.L, G = c.G;
+  const double it = c.it, iw = c.iw, iw2 = c.iw2, it0 = c.it0, ws = c.ws;
   // rows that are scalar multiples of a first derivative, :938-1573
   if (is_scalar_row(pa) || is_scalar_row(pb)) {
     int s, o;  // the reference names amplitude first, then spectral_running, then spectral_index
@@ -81,101 +84,100 @@ __device__ double d2_term(int pa, int pb, const D2Ctx& c) {
     const double factor = (s == FB_AMPLITUDE) ? kLn10 : (s == FB_SPECTRAL_RUNNING ? L * L : L);
     return factor * c.d1[o];
   }
-  const bool gauss = (tau == 0.0);
-  const double w2 = w * w, ws = w / tau;
+  const bool gauss = (c.tau == 0.0);
+  const double it2 = it * it;
   const int key = pa * 16 + pb;
   switch (key) {
     case FB_ARRIVAL_TIME * 16 + FB_ARRIVAL_TIME:  // :1957-2014
-      if (gauss) return T * T * M / (w2 * w2) - M / w2;
-      return c.d1[FB_ARRIVAL_TIME] / tau + G * d2_dae(FB_ARRIVAL_TIME, c) * d2_dax(FB_ARRIVAL_TIME, c);
+      if (gauss) return T * T * M * (iw2 * iw2) - M * iw2;
+      return c.d1[FB_ARRIVAL_TIME] * it + G * d2_dae(FB_ARRIVAL_TIME, c) * d2_dax(FB_ARRIVAL_TIME, c);
     case FB_ARRIVAL_TIME * 16 + FB_BURST_WIDTH:  // :1639-1700
-      if (gauss) return -2.0 * T * M / (w2 * w) + T * T * T * M / (w2 * w2 * w);
-      return w * c.d1[FB_ARRIVAL_TIME] / (tau * tau) + G * (1.0 / w2 * kSqrtHalf) +
+      if (gauss) return -2.0 * T * M * (iw2 * iw) + T * T * T * M * (iw2 * iw2 * iw);
+      return w * c.d1[FB_ARRIVAL_TIME] * it2 + G * (iw2 * kSqrtHalf) +
              G * d2_dae(FB_BURST_WIDTH, c) * d2_dax(FB_ARRIVAL_TIME, c);
     case FB_ARRIVAL_TIME * 16 + FB_DM:  // :2016-2080
-      if (gauss) return T * c.d1[FB_DM] / w2 + c.D * M / w2;
-      return c.d1[FB_DM] / tau + G * d2_dae(FB_ARRIVAL_TIME, c) * d2_dax(FB_DM, c);
+      if (gauss) return T * c.d1[FB_DM] * iw2 + c.D * M * iw2;
+      return c.d1[FB_DM] * it + G * d2_dae(FB_ARRIVAL_TIME, c) * d2_dax(FB_DM, c);
     case FB_ARRIVAL_TIME * 16 + FB_DM_INDEX:  // :2082-2115 quirk: Gaussian form always, summed first derivative
-      return T * c.sum_dmidx / w2 + (c.k * c.dm * c.q1) * M / w2;
+      return T * c.sum_dmidx * iw2 + (c.k * c.dm * c.q1) * M * iw2;
     case FB_ARRIVAL_TIME * 16 + FB_SCATTERING_TIMESCALE:  // :2117-2174
-      return -M / tau0 / tau + c.d1[FB_SCATTERING_TIMESCALE] / tau +
+      return -M * it0 * it + c.d1[FB_SCATTERING_TIMESCALE] * it +
              G * d2_dae(FB_ARRIVAL_TIME, c) * d2_dax(FB_SCATTERING_TIMESCALE, c);
     case FB_ARRIVAL_TIME * 16 + FB_SCATTERING_INDEX:  // :2176-2234
-      return -M * L / tau + c.d1[FB_SCATTERING_INDEX] / tau +
-             (G / c.apbf) * c.dap_alpha * d2_dae(FB_ARRIVAL_TIME, c) +
+      return -M * L * it + c.d1[FB_SCATTERING_INDEX] * it +
+             (G * c.iap) * c.dap_alpha * d2_dae(FB_ARRIVAL_TIME, c) +
              G * d2_dae(FB_ARRIVAL_TIME, c) * d2_dax(FB_SCATTERING_INDEX, c);
     case FB_BURST_WIDTH * 16 + FB_BURST_WIDTH:  // :1575-1637
-      if (gauss) return -3.0 * T * T * M / (w2 * w2) + T * T * T * T * M / (w2 * w2 * w2);
-      return M / (tau * tau) + w * c.d1[FB_BURST_WIDTH] / (tau * tau) + G * (1.41421356237309504880 * T / (w2 * w)) +
+      if (gauss) return -3.0 * T * T * M * (iw2 * iw2) + T * T * T * T * M * (iw2 * iw2 * iw2);
+      return M * it2 + w * c.d1[FB_BURST_WIDTH] * it2 + G * (kSqrt2 * T * (iw2 * iw)) +
              G * d2_dae(FB_BURST_WIDTH, c) * d2_dax(FB_BURST_WIDTH, c);
     case FB_BURST_WIDTH * 16 + FB_DM:  // :1822-1887
-      if (gauss) return 2.0 * T * c.D * M / (w2 * w) + T * T * c.d1[FB_DM] / (w2 * w);
-      return w * c.d1[FB_DM] / (tau * tau) + G * (-c.D / w2 * kSqrtHalf) +
+      if (gauss) return 2.0 * T * c.D * M * (iw2 * iw) + T * T * c.d1[FB_DM] * (iw2 * iw);
+      return w * c.d1[FB_DM] * it2 + G * (-c.D * iw2 * kSqrtHalf) +
              G * d2_dae(FB_BURST_WIDTH, c) * d2_dax(FB_DM, c);
     case FB_BURST_WIDTH * 16 + FB_DM_INDEX:  // :1889-1955 quirk: -2 where the dm twin has +2
-      if (gauss) return -2.0 * T * c.Dp * M / (w2 * w) + T * T * c.d1[FB_DM_INDEX] / (w2 * w);
-      return w * c.d1[FB_DM_INDEX] / (tau * tau) + G * (-c.Dp / w2 * kSqrtHalf) +
+      if (gauss) return -2.0 * T * c.Dp * M * (iw2 * iw) + T * T * c.d1[FB_DM_INDEX] * (iw2 * iw);
+      return w * c.d1[FB_DM_INDEX] * it2 + G * (-c.Dp * iw2 * kSqrtHalf) +
              G * d2_dae(FB_BURST_WIDTH, c) * d2_dax(FB_DM_INDEX, c);
     case FB_BURST_WIDTH * 16 + FB_SCATTERING_TIMESCALE:  // :1702-1759
-      return -2.0 * w * M / tau0 / (tau * tau) + w * c.d1[FB_SCATTERING_TIMESCALE] / (tau * tau) +
-             G * (1.0 / tau0 / tau * kSqrtHalf) + G * d2_dae(FB_BURST_WIDTH, c) * d2_dax(FB_SCATTERING_TIMESCALE, c);
+      return -2.0 * w * M * it0 * it2 + w * c.d1[FB_SCATTERING_TIMESCALE] * it2 +
+             G * (it0 * it * kSqrtHalf) + G * d2_dae(FB_BURST_WIDTH, c) * d2_dax(FB_SCATTERING_TIMESCALE, c);
     case FB_BURST_WIDTH * 16 + FB_SCATTERING_INDEX:  // :1761-1820
-      return -2.0 * L * w * M / (tau * tau) + w * c.d1[FB_SCATTERING_INDEX] / (tau * tau) -
-             G * d2_dae(FB_BURST_WIDTH, c) * L + G * (L * kSqrtHalf / tau) +
+      return -2.0 * L * w * M * it2 + w * c.d1[FB_SCATTERING_INDEX] * it2 -
+             G * d2_dae(FB_BURST_WIDTH, c) * L + G * (L * kSqrtHalf * it) +
              G * d2_dae(FB_BURST_WIDTH, c) * d2_dax(FB_SCATTERING_INDEX, c);
     case FB_DM * 16 + FB_DM:  // :2275-2341
-      if (gauss) return (c.D * T) * (c.D * T) * M / (w2 * w2) - (c.D / w) * (c.D / w) * M;
-      return -c.D * c.d1[FB_DM] / tau + G * d2_dae(FB_DM, c) * d2_dax(FB_DM, c);
+      if (gauss) return (c.D * T) * (c.D * T) * M * (iw2 * iw2) - (c.D * iw) * (c.D * iw) * M;
+      return -c.D * c.d1[FB_DM] * it + G * d2_dae(FB_DM, c) * d2_dax(FB_DM, c);
     case FB_DM * 16 + FB_DM_INDEX: {  // :2236-2273 quirks: Gaussian form, summed derivative, ref_freq ** 2
-      double out = (-c.D) * T * c.sum_dmidx / w2;
-      out += c.k * c.k * c.dm * M / w2 * (c.fpow - c.ref_freq * c.ref_freq) * c.q1;
-      out -= c.k * c.q1 * T * M / w2;
+      double out = (-c.D) * T * c.sum_dmidx * iw2;
+      out += c.k * c.k * c.dm * M * iw2 * (c.fpow - c.ref_freq * c.ref_freq) * c.q1;
+      out -= c.k * c.q1 * T * M * iw2;
       return out;
     }
     case FB_DM * 16 + FB_SCATTERING_TIMESCALE:  // :2474-2535
-      return -c.D * c.d1[FB_SCATTERING_TIMESCALE] / tau + c.D * M / tau0 / tau +
+      return -c.D * c.d1[FB_SCATTERING_TIMESCALE] * it + c.D * M * it0 * it +
              G * d2_dae(FB_DM, c) * d2_dax(FB_SCATTERING_TIMESCALE, c);
     case FB_DM * 16 + FB_SCATTERING_INDEX: {  // :2666-2720
-      const double t0 = -(1.0 + ws * ws - T / tau) * L;
-      return (L * c.D / tau) * M + t0 * c.d1[FB_DM] + G * d2_dae(FB_SCATTERING_INDEX, c) * d2_dax(FB_DM, c);
+      const double t0 = -(1.0 + ws * ws - T * it) * L;
+      return (L * c.D * it) * M + t0 * c.d1[FB_DM] + G * d2_dae(FB_SCATTERING_INDEX, c) * d2_dax(FB_DM, c);
     }
     case FB_DM_INDEX * 16 + FB_DM_INDEX: {  // :2779-2836 quirk: amp_pbf of the outer component
       const double product = c.k * c.dm * c.q1, product_d = c.k * c.dm * c.q2;
-      const double gs = G * (c.apbf_outer / c.apbf) * kSqrtHalf;
-      return product_d * M / tau + product * c.d1[FB_DM_INDEX] / tau - product_d * gs / w / tau -
-             product * gs / w / tau * d2_dax(FB_DM_INDEX, c);
+      const double gs = G * (c.apbf_outer * c.iap) * kSqrtHalf;
+      return product_d * M * it + product * c.d1[FB_DM_INDEX] * it - product_d * gs * iw * it -
+             product * gs * iw * it * d2_dax(FB_DM_INDEX, c);
     }
     case FB_DM_INDEX * 16 + FB_SCATTERING_TIMESCALE: {  // :2537-2594
-      const double t0 = -1.0 / tau0 - ws * ws / tau0 + T / tau0 / tau;
-      return (c.Dp / tau / tau0) * M + t0 * c.d1[FB_DM_INDEX] +
+      const double t0 = -it0 - ws * ws * it0 + T * it0 * it;
+      return (c.Dp * it * it0) * M + t0 * c.d1[FB_DM_INDEX] +
              G * d2_dae(FB_SCATTERING_TIMESCALE, c) * d2_dax(FB_DM_INDEX, c);
     }
     case FB_DM_INDEX * 16 + FB_SCATTERING_INDEX: {  // :2722-2777
-      const double t0 = -(1.0 + ws * ws - T / tau) * L;
-      return (L * c.Dp / tau) * M + t0 * c.d1[FB_DM_INDEX] +
+      const double t0 = -(1.0 + ws * ws - T * it) * L;
+      return (L * c.Dp * it) * M + t0 * c.d1[FB_DM_INDEX] +
              G * d2_dae(FB_SCATTERING_INDEX, c) * d2_dax(FB_DM_INDEX, c);
     }
     case FB_SCATTERING_TIMESCALE * 16 + FB_SCATTERING_TIMESCALE: {  // :2343-2404
-      const double u = T / tau - ws * ws;
-      const double t0 = u / tau0;
-      const double t0d = -u / (tau0 * tau0) + (-T / tau + 2.0 * ws * ws) / (tau0 * tau0);
-      return t0d * M + t0 * c.d1[FB_SCATTERING_TIMESCALE] +
-             G * (-1.41421356237309504880 * w / tau / (tau0 * tau0)) +
+      const double u = T * it - ws * ws;
+      const double t0 = u * it0;
+      const double t0d = -u * (it0 * it0) + (-T * it + 2.0 * ws * ws) * (it0 * it0);
+      return t0d * M + t0 * c.d1[FB_SCATTERING_TIMESCALE] + G * (-kSqrt2 * ws * (it0 * it0)) +
              G * d2_dae(FB_SCATTERING_TIMESCALE, c) * d2_dax(FB_SCATTERING_TIMESCALE, c);
     }
     case FB_SCATTERING_TIMESCALE * 16 + FB_SCATTERING_INDEX: {  // :2406-2472
       const double e1 = d2_dae(FB_SCATTERING_TIMESCALE, c);
-      const double t0 = -(ws * ws) / tau0 + T / tau0 / tau;
-      const double t0d2 = 2.0 * ws * ws / tau0 * L - T * L / tau / tau0;
-      return t0d2 * M + t0 * c.d1[FB_SCATTERING_INDEX] + (G / c.apbf) * c.dap_alpha * e1 +
+      const double t0 = -(ws * ws) * it0 + T * it0 * it;
+      const double t0d2 = 2.0 * ws * ws * it0 * L - T * L * it * it0;
+      return t0d2 * M + t0 * c.d1[FB_SCATTERING_INDEX] + (G * c.iap) * c.dap_alpha * e1 +
              G * e1 * d2_dax(FB_SCATTERING_INDEX, c) + G * (-L * e1);
     }
     case FB_SCATTERING_INDEX * 16 + FB_SCATTERING_INDEX: {  // :2596-2664
-      const double ad = c.dap_alpha / c.apbf, ed = d2_dae(FB_SCATTERING_INDEX, c);
-      const double t0 = ad - (ws * ws - T / tau) * L;
-      const double t0d = c.d2ap_alpha / c.apbf - ad * ad - L * (-2.0 * L * ws * ws + T * L / tau);
-      return t0d * M + t0 * c.d1[FB_SCATTERING_INDEX] + (G / c.apbf) * c.dap_alpha * ed +
-             G * ed * d2_dax(FB_SCATTERING_INDEX, c) + G * (-w * L * L / tau * kSqrtHalf);
+      const double ad = c.dap_alpha * c.iap, ed = d2_dae(FB_SCATTERING_INDEX, c);
+      const double t0 = ad - (ws * ws - T * it) * L;
+      const double t0d = c.d2ap_alpha * c.iap - ad * ad - L * (-2.0 * L * ws * ws + T * L * it);
+      return t0d * M + t0 * c.d1[FB_SCATTERING_INDEX] + (G * c.iap) * c.dap_alpha * ed +
+             G * ed * d2_dax(FB_SCATTERING_INDEX, c) + G * (-ws * L * L * kSqrtHalf);
     }
   }
   return 0.0;
@@ -206,6 +208,12 @@ __device__ __forceinline__ void make_d2ctx(const EvalArgs& A, const ChanTab& ch,
   c.d2ap_alpha = ch.d2ap_alpha;
   c.sum_dmidx = sum_dmidx;
   c.apbf_outer = apbf_outer;
+  c.it = ch.inv_tau;
+  c.iw = ct.inv_w;
+  c.iw2 = ct.inv_w * ct.inv_w;
+  c.it0 = 1.0 / c.tau0;
+  c.ws = ct.w * ch.inv_tau;
+  c.iap = ch.inv_apbf;
 }
 
 // Pair table entry (built on the host): unordered parameter pair, the `component` the reference
@@ -216,10 +224,15 @@ struct HessPair {
   int8_t is_sum;
 };
 
+constexpr int kHessChunk = 32;             // pairs staged per reduction round
+constexpr int kHessStageStride = kBlock + 1;  // odd stride: conflict-free column sums
+
 struct HessArgs {
   EvalArgs E;
   const HessPair* pairs;
   int num_pairs;
+  const int* comp_list;  // pair indices applicable to each component, concatenated
+  int comp_off[FB_MAX_COMPONENTS + 1];
   double* partials;  // [grid][num_pairs]
   // single-map mode (fb_derivative2_map)
   int map_pa, map_pb, map_component;
@@ -228,8 +241,8 @@ struct HessArgs {
 
 __host__ __device__ inline size_t hess_smem_bytes(int nc, int kf, int num_pairs) {
   size_t n = smem_bytes(nc, kf, 1, true);
-  n += sizeof(double) * (size_t)kBlock * (2 * nc + 1);  // per-thread (M_c, T_c) rows, odd stride
-  n += sizeof(double) * (size_t)(kBlock / 32) * num_pairs;
+  n += sizeof(double) * (size_t)kHessChunk * kHessStageStride;   // staged rho * d2 values
+  n += sizeof(double) * (size_t)(kBlock / 32) * num_pairs;       // per-segment accumulators
   return n;
 }
 
@@ -241,11 +254,10 @@ __global__ void __launch_bounds__(kBlock) k_hessian(const HessArgs H) {
   const int nc = pc.num_comp, kf = pc.kf, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   SmemLayout L = carve(smem_raw, nc, kf);
   const size_t base_doubles = smem_bytes(nc, kf, 1, true) / sizeof(double);
-  const int rstride = 2 * nc + 1;
-  double* rows = smem_raw + base_doubles;
-  double* wacc = rows + (size_t)kBlock * rstride;  // [warps][num_pairs]
-  double* row = rows + (size_t)tid * rstride;
+  double* stage = smem_raw + base_doubles;                        // [kHessChunk][kHessStageStride]
+  double* wacc = stage + (size_t)kHessChunk * kHessStageStride;   // [segments][num_pairs]
   const int npairs = H.num_pairs;
+  const double* vrow = L.vals + (size_t)tid * val_stride(nc);
   if (!MAP)
     for (int e = tid; e < (kBlock / 32) * npairs; e += kBlock) wacc[e] = 0.0;
   load_comp_tables(A, L);
@@ -322,7 +334,6 @@ __global__ void __launch_bounds__(kBlock) k_hessian(const HessArgs H) {
       double msum = 0.0, sum_dmidx = 0.0;
       eval_tile(A, L, i, tile);
       if (valid) {
-        const double* vrow = L.vals + (size_t)tid * val_stride(nc);
         for (int c = 0; c < nc; ++c) {
           SampleComp sc;
           sc.spectrum = vrow[3 * c];
@@ -333,8 +344,6 @@ __global__ void __launch_bounds__(kBlock) k_hessian(const HessArgs H) {
             amp = L.scint_amp[c];
             sc.spectrum = amp * sc.timeprof;
           }
-          row[2 * c] = sc.spectrum;
-          row[2 * c + 1] = sc.timediff;
           msum += sc.spectrum;
           double d[9], g;
           first_derivatives(L.chan[c], L.chan[c], L.comp[c], tau0, amp, sc.spectrum, sc.timediff, d, &g);
@@ -349,7 +358,8 @@ __global__ void __launch_bounds__(kBlock) k_hessian(const HessArgs H) {
             if (!sum && c != H.map_component) continue;
             D2Ctx ctx;
             const double amp = pc.scintillation ? L.scint_amp[c] : L.chan[c].amp;
-            make_d2ctx(A, L.chan[c], L.comp[c], amp, row[2 * c], row[2 * c + 1], sum_dmidx,
+            const double spec = pc.scintillation ? amp * vrow[3 * c + 2] : vrow[3 * c];
+            make_d2ctx(A, L.chan[c], L.comp[c], amp, spec, vrow[3 * c + 1], sum_dmidx,
                        L.chan[H.map_component].amp_pbf, ctx);
             out += d2_term(H.map_pa, H.map_pb, ctx);
           }
@@ -366,19 +376,36 @@ __global__ void __launch_bounds__(kBlock) k_hessian(const HessArgs H) {
         D2Ctx ctx;
         if (valid) {
           const double amp = pc.scintillation ? L.scint_amp[c] : L.chan[c].amp;
-          make_d2ctx(A, L.chan[c], L.comp[c], amp, row[2 * c], row[2 * c + 1], sum_dmidx, 0.0, ctx);
+          const double spec = pc.scintillation ? amp * vrow[3 * c + 2] : vrow[3 * c];
+          make_d2ctx(A, L.chan[c], L.comp[c], amp, spec, vrow[3 * c + 1], sum_dmidx, 0.0, ctx);
         }
-        for (int pi = 0; pi < npairs; ++pi) {
-          const HessPair hp = H.pairs[pi];
-          if (!hp.is_sum && hp.component != c) continue;  // uniform across the block
-          double v = 0.0;
-          if (valid) {
-            ctx.apbf_outer = L.chan[hp.component].amp_pbf;
-            v = rho * d2_term(hp.pa, hp.pb, ctx);
+        // pairs this component contributes to, staged kHessChunk at a time: every thread writes
+        // its rho * d2 values into a column of `stage`, then thread (k, seg) sums 32 rows of
+        // staged pair k -- no shuffles, fixed order, one owner per (segment, pair) accumulator.
+        const int lo = H.comp_off[c], cnt = H.comp_off[c + 1] - lo;
+        for (int chunk = 0; chunk < cnt; chunk += kHessChunk) {
+          const int m = min(kHessChunk, cnt - chunk);
+          for (int k = 0; k < m; ++k) {
+            double v = 0.0;
+            if (valid) {
+              const HessPair hp = H.pairs[H.comp_list[lo + chunk + k]];
+              ctx.apbf_outer = L.chan[hp.component].amp_pbf;
+              v = rho * d2_term(hp.pa, hp.pb, ctx);
+            }
+            stage[k * kHessStageStride + tid] = v;
           }
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-          if (lane == 0) wacc[warp * npairs + pi] += v;
+          __syncthreads();
+          {
+            const int k = tid & 31, seg = tid >> 5;
+            if (k < m) {
+              const double* col = stage + k * kHessStageStride + seg * 32;
+              double sum = 0.0;
+#pragma unroll 8
+              for (int r = 0; r < 32; ++r) sum += col[r];
+              wacc[seg * npairs + H.comp_list[lo + chunk + k]] += sum;
+            }
+          }
+          __syncthreads();
         }
       }
     }
