@@ -88,6 +88,8 @@ SIGNATURES = {
     "fb_set_parameters": (ctypes.c_int, [_P, _D, _P]),
     "fb_get_parameters": (ctypes.c_int, [_P, _D, _P]),
     "fb_model_eval": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P]),
+    "fb_profile_eval": (ctypes.c_int, [_P, _P, _I32, _I32, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                       ctypes.c_double, ctypes.c_double, _I32, _I32, _I32, _I32, _P, _P]),
     "fb_set_weights": (ctypes.c_int, [_P, _P, ctypes.POINTER(ctypes.c_uint8), _I32, _I32, _I32, _D, _D, _P]),
     "fb_load_weights": (ctypes.c_int, [_P, _D, _P]),
     "fb_set_free_parameters": (ctypes.c_int, [_P, ctypes.POINTER(_I32), ctypes.POINTER(_I32)]),

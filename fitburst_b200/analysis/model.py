@@ -229,6 +229,22 @@ class SpectrumModeler:
         lambda self: self._get_cache("timeprof"),
         lambda self, value: self._cache_host.__setitem__("timeprof", value))
 
+    def compute_profile(self, times: float, arrival_time: float, sc_time_ref: float, sc_index: float,
+        width: float, freqs: float, ref_freq: float, is_folded: bool = False) -> float:
+        """
+        Returns the temporal profile, depending on input values of width and scattering timescale
+        (analysis/model.py:281-352): pulse-broadening function with the -5 width clamp when any
+        scattering timescale is positive, Gaussian otherwise; optional folding.
+        """
+        # pylint: disable=too-many-arguments
+        from ..routines.profile import _evaluate
+        freqs = np.asarray(freqs, dtype=np.float64)
+        with np.errstate(all="ignore"):
+            sc_time = sc_time_ref * (freqs / ref_freq) ** sc_index
+        scattered = bool(np.any(sc_time > 0.0))
+        return _evaluate(times, arrival_time, width, freqs, ref_freq, sc_time_ref, sc_index, scattered, True,
+                         bool(is_folded), self._normalize_pbf())
+
     def get_parameters_dict(self) -> dict:
         """
         Returns model parameters as a dictionary, with keys set to the parameter names

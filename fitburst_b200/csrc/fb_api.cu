@@ -575,6 +575,21 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
   return FB_OK;
 }
 
+extern "C" int fb_profile_eval(const double* times_dev, const double* freqs_dev, int32_t num_rows,
+                               int32_t num_cols, double arrival_time, double sc_time_ref, double sc_index,
+                               double width, double ref_freq, int32_t scattered, int32_t clamp,
+                               int32_t is_folded, int32_t normalize_pbf, double* profile_dev, void* stream) {
+  if (!times_dev || !freqs_dev || !profile_dev) return fail(FB_ERR_INVALID, "null argument");
+  if (num_rows < 1 || num_cols < 1) return fail(FB_ERR_INVALID, "empty array");
+  if (is_folded && num_cols < 2) return fail(FB_ERR_INVALID, "folding needs at least two samples");
+  const size_t total = (size_t)num_rows * num_cols;
+  k_profile<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      times_dev, freqs_dev, num_rows, num_cols, arrival_time, sc_time_ref, sc_index, width, ref_freq,
+      scattered, clamp, is_folded, normalize_pbf, profile_dev);
+  CUDA_TRY(cudaGetLastError());
+  return FB_OK;
+}
+
 extern "C" int fb_measure_fp64_peak(double* tflops_out, void* stream) {
   if (!tflops_out) return fail(FB_ERR_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;

@@ -626,6 +626,38 @@ __global__ void __launch_bounds__(kBlock) k_weights(const double* __restrict__ d
   }
 }
 
+// Stand-alone temporal profile on an arbitrary (rows, cols) array of times
+// (SpectrumModeler.compute_profile, analysis/model.py:281-352; routines/profile.py:15-114).
+__global__ void k_profile(const double* __restrict__ times, const double* __restrict__ freqs, int rows,
+                          int cols, double toa, double sc_time_ref, double sc_index, double width,
+                          double ref_freq, int scattered, int clamp, int folded, int normalize,
+                          double* __restrict__ out) {
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (size_t)rows * cols) return;
+  const int r = (int)(e / cols), m = (int)(e % cols);
+  const double* row = times + (size_t)r * cols;
+  const double sc_time = sc_time_ref * pow(freqs[r] / ref_freq, sc_index);
+  const double ratio = width / sc_time;
+  const double amp = normalize ? kSqrtHalfPi * ratio : sc_time_ref / sc_time;
+  const double neg5w = -5 * width;
+  auto shape = [&](double t) {
+    if (scattered) {
+      if (clamp && t < neg5w) t = neg5w;  // analysis/model.py:340
+      return amp * emg_shape((t - toa) / width, ratio);
+    }
+    const double z = (t - toa) / width;
+    return exp(-0.5 * z * z);
+  };
+  double p = shape(row[m]);
+  if (folded) {  // analysis/model.py:327-332,349-350
+    const double res = row[1] - row[0];
+    const double start = row[cols - 1] + res, stop = row[cols - 1] + res * (double)cols;
+    const double step = cols > 1 ? (stop - start) / (double)(cols - 1) : 0.0;
+    p = 0.5 * (p + shape(linspace_at(start, step, stop, m, cols)));
+  }
+  out[e] = p;
+}
+
 // Dependent-free FP64 FMA chains: the measured roofline denominator for the model kernels.
 __global__ void k_dfma_peak(double* out, int iters) {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,

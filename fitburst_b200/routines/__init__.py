@@ -1,2 +1,2 @@
-"""Mirror of fitburst.routines for the hot path (derivative maps backed by the CUDA kernels)."""
-from . import derivative  # noqa: F401
+"""Mirror of fitburst.routines for the hot path (profiles and derivative maps backed by the CUDA kernels)."""
+from . import derivative, profile  # noqa: F401

@@ -97,6 +97,17 @@ int fb_model_eval(fb_plan_t plan, const double* data_dev, double* model_dev,
                   double* amplitude_dev, double* spectrum_dev, double* timediff_dev,
                   double* timeprof_dev, void* stream);
 
+/* SpectrumModeler.compute_profile (analysis/model.py:281-352) = routines/profile.py:15-114 on an
+ * arbitrary (num_rows, num_cols) array of times: row r is evaluated at frequency freqs_dev[r]
+ * (scattering time sc_time_ref * (f / ref_freq) ** sc_index). scattered != 0 selects the
+ * pulse-broadening function with the -5 width clamp (analysis/model.py:339-341), else the
+ * Gaussian; is_folded averages the second realisation (analysis/model.py:327-332,349-350);
+ * arrival_time is subtracted like routines/profile.py:91. */
+int fb_profile_eval(const double* times_dev, const double* freqs_dev, int32_t num_rows, int32_t num_cols,
+                    double arrival_time, double sc_time_ref, double sc_index, double width, double ref_freq,
+                    int32_t scattered, int32_t clamp, int32_t is_folded, int32_t normalize_pbf,
+                    double* profile_dev, void* stream);
+
 /* LSFitter._set_weights (analysis/fitter.py:506-542): w_i = 1/sqrt(mean(data[i, lo:hi]^2)) for
  * good channels (1 if not weighted_fit), 0 for flagged ones. good_host is a uint8 mask of length
  * num_freq. The plan keeps the weights on the device (and the list of channels with non-zero

@@ -82,3 +82,17 @@ def test_channel_sharded_driver_single_rank(native_lib):
     assert res["status"] == fo.results.status and res["nfev"] == fo.results.nfev
     np.testing.assert_allclose(res["x"], fo.results.x, rtol=1e-6)
     assert np.all(res["uncertainties"] > 0)
+
+
+def test_multi_gpu_nccl(native_lib):
+    """Runs tests/multi_gpu_check.py over NCCL when the box has at least two GPUs."""
+    import os, subprocess, sys, torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run(
+        [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+         "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(root, "tests", "multi_gpu_check.py")],
+        capture_output=True, text=True, timeout=600)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-4000:]
+    assert "MULTI_GPU_OK" in proc.stdout

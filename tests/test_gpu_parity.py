@@ -221,3 +221,26 @@ def test_hessian_and_fit_statistics(case, fixed, native_lib):
         assert np.all(diff < 1e-3 * np.asarray(values))
     import json
     json.dumps(sc)  # the pipeline dumps fit_statistics as JSON (fitburst_pipeline.py:560-573)
+
+
+@pytest.mark.parametrize("tau,folded", [(2e-3, False), (0.0, False), (2e-3, True), (0.0, True)])
+def test_compute_profile_and_routines_profile(tau, folded, native_lib):
+    """SpectrumModeler.compute_profile and fitburst_b200.routines.profile against the oracle's
+    restatement of analysis/model.py:281-352 / routines/profile.py."""
+    from fitburst_b200.analysis.model import SpectrumModeler
+    from fitburst_b200.routines import profile as gprof
+    from oracle.fitburst_oracle import OracleModel, profile_gaussian, profile_pbf
+    freqs, times = syn.chime_axes(8, 64)
+    cuda = SpectrumModeler(freqs, times, num_components=1, is_folded=folded)
+    oracle = OracleModel(freqs, times, num_components=1, is_folded=folded)
+    sub = np.linspace(590.0, 610.0, 4)[:, None]
+    tarr = (np.linspace(-0.02, 0.04, 96)[None, :] - np.linspace(0, 1e-3, 4)[:, None])
+    got = cuda.compute_profile(tarr, 0.0, tau, -4.0, 1.2e-3, sub, 600.0, is_folded=folded)
+    want = oracle._profile(tarr[None], tau, -4.0, 1.2e-3, sub[None], 600.0)[0]
+    assert_close(got, want, 1e-10, "compute_profile")
+    if not folded:
+        g = gprof.compute_profile_gaussian(tarr, 1e-3, 1.2e-3)
+        assert_close(g, profile_gaussian(tarr, 1e-3, 1.2e-3), 1e-12, "gaussian")
+        if tau > 0:
+            p = gprof.compute_profile_pbf(tarr, 0.0, 1.2e-3, sub, 600.0, tau, sc_index=-4.0)
+            assert_close(p, profile_pbf(tarr, 1.2e-3, sub, 600.0, tau, -4.0, False), 1e-10, "pbf")
