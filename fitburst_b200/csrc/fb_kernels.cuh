@@ -91,6 +91,7 @@ __device__ __forceinline__ void gram_accumulate(const double* __restrict__ X, in
   }
 }
 
+struct SmemLayout;
 // Sums the per-slice register tiles of a block in slice order (deterministic) and leaves
 // tile-major sums out[tile * 16 + k] in `out` (shared or global).
 __device__ inline void gram_block_reduce(double* scratch, int ntiles, int nslices, int tile,
@@ -155,6 +156,7 @@ struct SmemLayout {
   double* scint_amp;
   double* small;    // (nc+1)^2 + nc scratch for the scintillation solve
   double* tilesum;  // block-summed Gram tiles of the scintillation system
+  double* park;     // Gram register tiles parked between tiles: [kTile*kTile][kBlock]
   double* vals;     // per-thread (spectrum, timediff, timeprof) per component, stride val_stride
   int* queue;       // (thread, component) items of the current tile that need the general case
   int* qcount;
@@ -172,6 +174,7 @@ __host__ __device__ inline size_t smem_bytes(int nc, int kf, int ncols_main, boo
   n += sizeof(double) * ((nc + 1) * (nc + 1) + nc + 2);
   n += sizeof(double) * gram_ntiles(nc + 1) * kTile * kTile;
   n += sizeof(double) * (size_t)kBlock * val_stride(nc);
+  n += sizeof(double) * (size_t)kBlock * kTile * kTile;
   n += sizeof(int) * ((size_t)kBlock * nc + 2);
   int stride = gram_stride(ncols_main);
   if (scint) {
@@ -201,11 +204,27 @@ __device__ inline SmemLayout carve(double* base, int nc, int kf) {
   p += sizeof(double) * gram_ntiles(nc + 1) * kTile * kTile;
   L.vals = reinterpret_cast<double*>(p);
   p += sizeof(double) * (size_t)kBlock * val_stride(nc);
+  L.park = reinterpret_cast<double*>(p);
+  p += sizeof(double) * (size_t)kBlock * kTile * kTile;
   L.queue = reinterpret_cast<int*>(p);
   L.qcount = L.queue + (size_t)kBlock * nc;
   p += sizeof(int) * ((size_t)kBlock * nc + 2);
   L.X = reinterpret_cast<double*>(p);
   return L;
+}
+
+// Gram accumulation of one staged tile with the register tile parked in shared memory between
+// tiles ([k][tid] layout, conflict-free), so that it is not live across the model evaluation.
+__device__ __forceinline__ void gram_accumulate_parked(const SmemLayout& L, int stride, int ntiles, int nslices,
+                                                       int ti, int tj, int slice, bool active) {
+  if (!active) return;
+  double acc[kTile * kTile];
+  double* park = L.park + threadIdx.x;
+#pragma unroll
+  for (int k = 0; k < kTile * kTile; ++k) acc[k] = park[k * kBlock];
+  gram_accumulate(L.X, stride, kBlock, ntiles, nslices, ti, tj, slice, active, acc);
+#pragma unroll
+  for (int k = 0; k < kTile * kTile; ++k) park[k * kBlock] = acc[k];
 }
 
 // Builds every table of the current parameter set: one thread per (channel, component).
@@ -430,9 +449,8 @@ __global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
   const bool g_active = (MODE == MODE_GRAM) && g_slice < nslices;
   int g_ti = 0, g_tj = 0;
   if (MODE == MODE_GRAM) tile_coords(g_tile, side, g_ti, g_tj);
-  double acc[kTile * kTile];
 #pragma unroll
-  for (int k = 0; k < kTile * kTile; ++k) acc[k] = 0.0;
+  for (int k = 0; k < kTile * kTile; ++k) L.park[k * kBlock + tid] = 0.0;
 
   const int tiles = (pc.num_time + kBlock - 1) / kBlock;
   double* row = L.X + (size_t)tid * stride;
@@ -456,7 +474,7 @@ __global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
       if (MODE == MODE_CHI2) chi2_acc += row[0];
       if (MODE == MODE_GRAM) {
         __syncthreads();
-        gram_accumulate(L.X, stride, kBlock, ntiles, nslices, g_ti, g_tj, g_slice, g_active, acc);
+        gram_accumulate_parked(L, stride, ntiles, nslices, g_ti, g_tj, g_slice, g_active);
         __syncthreads();
       }
     }
@@ -525,7 +543,7 @@ __global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
         if (MODE == MODE_CHI2) chi2_acc += row[0];
         if (MODE == MODE_GRAM) {
           __syncthreads();
-          gram_accumulate(L.X, stride, kBlock, ntiles, nslices, g_ti, g_tj, g_slice, g_active, acc);
+          gram_accumulate_parked(L, stride, ntiles, nslices, g_ti, g_tj, g_slice, g_active);
           __syncthreads();
         }
       }
@@ -544,6 +562,9 @@ __global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
   }
 
   if (MODE == MODE_GRAM) {
+    double acc[kTile * kTile];
+#pragma unroll
+    for (int k = 0; k < kTile * kTile; ++k) acc[k] = L.park[k * kBlock + tid];
     gram_block_reduce(L.X, ntiles, nslices, g_tile, g_slice, g_active, acc,
                       A.partials + (size_t)blockIdx.x * ntiles * kTile * kTile);
   }

@@ -17,7 +17,7 @@ def _evaluate(time, toa, width, freq, ref_freq, sc_time_ref, sc_index, scattered
     time_b = np.ascontiguousarray(np.broadcast_to(time, shape)).reshape(-1, shape[-1] if shape else 1)
     freq_b = np.ascontiguousarray(np.broadcast_to(freq, shape)).reshape(-1, shape[-1] if shape else 1)[:, 0].copy()
     device = torch.device("cuda")
-    t_dev = torch.from_numpy(time_b).to(device)
+    t_dev = torch.from_numpy(time_b.copy()).to(device)
     f_dev = torch.from_numpy(freq_b).to(device)
     out = torch.empty_like(t_dev)
     with torch.cuda.device(device):
