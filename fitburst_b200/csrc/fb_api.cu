@@ -57,6 +57,8 @@ struct fb_plan_s {
   size_t pairs_cap = 0;
   int* d_comp_list = nullptr;
   size_t comp_list_cap = 0;
+  HessDesc* d_desc = nullptr;
+  size_t desc_cap = 0;
   int* d_chan_list = nullptr;
   int num_good = 0;
   bool have_weights = false;
@@ -189,6 +191,7 @@ extern "C" int fb_plan_destroy(fb_plan_t p) {
   cudaFree(p->d_hess_partials);
   cudaFree(p->d_pairs);
   cudaFree(p->d_comp_list);
+  cudaFree(p->d_desc);
   cudaFree(p->d_comp);
   cudaFree(p->d_sub);
   cudaFree(p->d_chan);
@@ -736,7 +739,71 @@ int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, 
   int rc = normal_equations_async(p, data_dev, p->d_gram, st);
   if (rc != FB_OK) return rc;
   CUDA_TRY(cudaMemcpyAsync(gram.data(), p->d_gram, sizeof(double) * ncols * ncols, cudaMemcpyDeviceToHost, st));
-  if (p->num_good > 0) {
+  if (p->num_good > 0 && !p->pc.scintillation) {
+    // fast path: register accumulation of the 30 term values per (sample, component)
+    std::vector<HessDesc> desc(npairs);
+    HessAccArgs H;
+    memset(&H, 0, sizeof(H));
+    for (int c = 0; c < nc; ++c) H.need[c] = 0u;
+    for (int k = 0; k < npairs; ++k) {
+      int code, idx;
+      pair_descriptor(pairs[k].pa, pairs[k].pb, code, idx);
+      desc[k].code = (int8_t)code;
+      desc[k].idx = (int8_t)idx;
+      for (int c = 0; c < nc; ++c)
+        if (pairs[k].is_sum || pairs[k].component == c) H.need[c] |= (1u << idx);
+      if (idx == 12 || idx == 21) H.need_sum_dmidx = 1;
+    }
+    if ((size_t)npairs > p->desc_cap) {
+      cudaFree(p->d_desc);
+      p->d_desc = nullptr;
+      p->desc_cap = 0;
+      CUDA_TRY(cudaMalloc(&p->d_desc, sizeof(HessDesc) * npairs));
+      p->desc_cap = npairs;
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->d_desc, desc.data(), sizeof(HessDesc) * npairs, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    H.E = base_args(p);
+    H.E.data = data_dev;
+    H.E.weights = p->d_weights;
+    H.E.chan_list = p->d_chan_list;
+    H.E.num_chan = p->num_good;
+    H.desc = p->d_desc;
+    H.num_pairs = npairs;
+    H.comp_list = p->d_comp_list;
+    for (int c = 0; c <= nc; ++c) H.comp_off[c] = comp_off[c];
+    rc = ensure_tables(p, st);
+    if (rc != FB_OK) return rc;
+    const size_t smem = hess_acc_smem_bytes(nc, p->pc.kf, npairs);
+    if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "Hessian shared-memory request %zu B exceeds 227 KB", smem);
+    if (smem > 48 * 1024)
+      CUDA_TRY(cudaFuncSetAttribute(k_hessian_acc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_hessian_acc, kBlock, smem));
+    if (occ < 1) occ = 1;
+    const int tiles = (p->pc.num_time + kBlock - 1) / kBlock;
+    long long items = (long long)p->num_good * ((tiles + kHessSuper - 1) / kHessSuper);
+    long long grid = (long long)p->sm_count * occ;
+    if (grid > items) grid = items;
+    const size_t need_cap = (size_t)grid * npairs;
+    if (need_cap > p->hess_partials_cap) {
+      cudaFree(p->d_hess_partials);
+      p->d_hess_partials = nullptr;
+      p->hess_partials_cap = 0;
+      CUDA_TRY(cudaMalloc(&p->d_hess_partials, sizeof(double) * need_cap));
+      p->hess_partials_cap = need_cap;
+    }
+    H.partials = p->d_hess_partials;
+    k_hessian_acc<<<(int)grid, kBlock, smem, st>>>(H);
+    CUDA_TRY(cudaGetLastError());
+    p->launches += 1;
+    double* d_out = p->d_gram;  // reuse: npairs <= (n+1)^2
+    CUDA_TRY(cudaStreamSynchronize(st));
+    k_hess_finalize<<<(npairs + 127) / 128, 128, 0, st>>>(p->d_hess_partials, (int)grid, npairs, d_out);
+    CUDA_TRY(cudaGetLastError());
+    p->launches += 1;
+    CUDA_TRY(cudaMemcpyAsync(S.data(), d_out, sizeof(double) * npairs, cudaMemcpyDeviceToHost, st));
+  } else if (p->num_good > 0) {
     HessArgs H;
     memset(&H, 0, sizeof(H));
     H.E = base_args(p);

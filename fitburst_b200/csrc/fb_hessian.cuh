@@ -247,7 +247,7 @@ __host__ __device__ inline size_t hess_smem_bytes(int nc, int kf, int num_pairs)
 }
 
 template <bool MAP>
-__global__ void __launch_bounds__(kBlock) k_hessian(const HessArgs H) {
+__global__ void __launch_bounds__(kBlock, 2) k_hessian(const HessArgs H) {
   extern __shared__ double smem_raw[];
   const EvalArgs& A = H.E;
   const PlanConst& pc = A.pc;
@@ -418,6 +418,207 @@ __global__ void __launch_bounds__(kBlock) k_hessian(const HessArgs H) {
       H.partials[(size_t)blockIdx.x * npairs + pi] = s;
     }
   }
+}
+
+// ---- accumulate path -------------------------------------------------------------------------
+// S_pair = sum_samples rho * d2 is linear in a small set of per-(sample, component) values: the
+// nine first derivatives and the 21 non-trivial mixed partials ("term values", tv[0..29]); every
+// one of the 45 functions is one of them times a per-CHANNEL factor (1, ln 10, L, L^2). So each
+// thread accumulates rho * tv[k] in registers over a super-tile of samples, the block sums the
+// columns once per (super-tile, component), and only then are the pair accumulators touched.
+constexpr int kNumTerms = 30;
+constexpr int kHessSuper = 2;      // tiles per super-tile
+constexpr int kFlushChunk = 15;    // accumulators staged per flush round (fits the X region)
+
+struct HessDesc {
+  int8_t code;  // 0: 1, 1: ln 10, 2: L, 3: L^2
+  int8_t idx;   // term-value index
+};
+
+__host__ __device__ inline void pair_descriptor(int pa, int pb, int& code, int& idx) {
+  if (pa > pb) {
+    const int t = pa;
+    pa = pb;
+    pb = t;
+  }
+  if (is_scalar_row(pa) || is_scalar_row(pb)) {
+    int s, o;
+    if (pa == FB_AMPLITUDE) { s = pa; o = pb; }
+    else if (pb == FB_SPECTRAL_RUNNING) { s = pb; o = pa; }
+    else if (pa == FB_SPECTRAL_RUNNING) { s = pa; o = pb; }
+    else if (pb == FB_SPECTRAL_INDEX) { s = pb; o = pa; }
+    else { s = pa; o = pb; }
+    code = (s == FB_AMPLITUDE) ? 1 : (s == FB_SPECTRAL_RUNNING ? 3 : 2);
+    idx = o;
+    return;
+  }
+  // pa <= pb both in {ARRIVAL_TIME=1 .. SCATTERING_INDEX=6}: position in the upper triangle
+  const int a = pa - 1, b = pb - 1;  // 0..5
+  code = 0;
+  idx = 9 + a * 6 - a * (a - 1) / 2 + (b - a);
+}
+
+// rho-weighted accumulation of every needed term value of one (sample, component).
+__device__ __forceinline__ void accumulate_terms(const D2Ctx& c, double rho, unsigned need,
+                                                 double (&acc)[kNumTerms]) {
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+    if (need & (1u << k)) acc[k] = fma(rho, c.d1[k], acc[k]);
+#define FB_TERM(IDX, PA, PB) \
+  if (need & (1u << (IDX))) acc[IDX] = fma(rho, d2_term(PA, PB, c), acc[IDX]);
+  FB_TERM(9, FB_ARRIVAL_TIME, FB_ARRIVAL_TIME)
+  FB_TERM(10, FB_ARRIVAL_TIME, FB_BURST_WIDTH)
+  FB_TERM(11, FB_ARRIVAL_TIME, FB_DM)
+  FB_TERM(12, FB_ARRIVAL_TIME, FB_DM_INDEX)
+  FB_TERM(13, FB_ARRIVAL_TIME, FB_SCATTERING_TIMESCALE)
+  FB_TERM(14, FB_ARRIVAL_TIME, FB_SCATTERING_INDEX)
+  FB_TERM(15, FB_BURST_WIDTH, FB_BURST_WIDTH)
+  FB_TERM(16, FB_BURST_WIDTH, FB_DM)
+  FB_TERM(17, FB_BURST_WIDTH, FB_DM_INDEX)
+  FB_TERM(18, FB_BURST_WIDTH, FB_SCATTERING_TIMESCALE)
+  FB_TERM(19, FB_BURST_WIDTH, FB_SCATTERING_INDEX)
+  FB_TERM(20, FB_DM, FB_DM)
+  FB_TERM(21, FB_DM, FB_DM_INDEX)
+  FB_TERM(22, FB_DM, FB_SCATTERING_TIMESCALE)
+  FB_TERM(23, FB_DM, FB_SCATTERING_INDEX)
+  FB_TERM(24, FB_DM_INDEX, FB_DM_INDEX)
+  FB_TERM(25, FB_DM_INDEX, FB_SCATTERING_TIMESCALE)
+  FB_TERM(26, FB_DM_INDEX, FB_SCATTERING_INDEX)
+  FB_TERM(27, FB_SCATTERING_TIMESCALE, FB_SCATTERING_TIMESCALE)
+  FB_TERM(28, FB_SCATTERING_TIMESCALE, FB_SCATTERING_INDEX)
+  FB_TERM(29, FB_SCATTERING_INDEX, FB_SCATTERING_INDEX)
+#undef FB_TERM
+}
+
+struct HessAccArgs {
+  EvalArgs E;
+  const HessDesc* desc;   // per pair
+  int num_pairs;
+  const int* comp_list;   // pair indices applicable to each component, concatenated
+  int comp_off[FB_MAX_COMPONENTS + 1];
+  unsigned need[FB_MAX_COMPONENTS];  // term values needed per component
+  int need_sum_dmidx;
+  double* partials;       // [grid][num_pairs]
+};
+
+__host__ __device__ inline size_t hess_acc_smem_bytes(int nc, int kf, int num_pairs) {
+  size_t n = smem_bytes(nc, kf, 1, false);
+  n += sizeof(double) * (size_t)kHessSuper * kBlock * val_stride(nc);  // term inputs of the super-tile
+  n += sizeof(double) * (size_t)kHessSuper * kBlock * 2;               // rho, sum_dmidx
+  n += sizeof(double) * ((size_t)(kBlock / 32) * 32 + 32);             // column partials, totals
+  n += sizeof(double) * (size_t)num_pairs;
+  return n;
+}
+
+__global__ void __launch_bounds__(kBlock, 2) k_hessian_acc(const HessAccArgs H) {
+  extern __shared__ double smem_raw[];
+  const EvalArgs& A = H.E;
+  const PlanConst& pc = A.pc;
+  const int nc = pc.num_comp, kf = pc.kf, tid = threadIdx.x;
+  SmemLayout L = carve(smem_raw, nc, kf);
+  const int vs = val_stride(nc);
+  double* big = smem_raw + smem_bytes(nc, kf, 1, false) / sizeof(double);  // [super rows][vs]
+  double* rho_s = big + (size_t)kHessSuper * kBlock * vs;
+  double* sdm_s = rho_s + (size_t)kHessSuper * kBlock;
+  double* part = sdm_s + (size_t)kHessSuper * kBlock;  // [8][32]
+  double* total = part + (kBlock / 32) * 32;           // [32]
+  double* pacc = total + 32;                           // [num_pairs]
+  double* stage = L.X;                                 // [kFlushChunk][kBlock + 1] (X region >= 32 KB)
+  const int npairs = H.num_pairs;
+  for (int e = tid; e < npairs; e += kBlock) pacc[e] = 0.0;
+  load_comp_tables(A, L);
+  const int tiles = (pc.num_time + kBlock - 1) / kBlock;
+  const int supers = (tiles + kHessSuper - 1) / kHessSuper;
+  const double tau0 = global_param(A.params, nc, FB_SCATTERING_TIMESCALE);
+  const long long total_items = (long long)A.num_chan * supers;
+  const long long begin = total_items * blockIdx.x / gridDim.x, end = total_items * (blockIdx.x + 1) / gridDim.x;
+  int cur = -1;
+  for (long long item = begin; item < end; ++item) {
+    const int chi = (int)(item / supers), sup = (int)(item % supers);
+    const int i = A.chan_list ? A.chan_list[chi] : chi;
+    if (chi != cur) {
+      load_channel_tables(A, L, i);
+      cur = chi;
+    }
+    const int t_lo = sup * kHessSuper, t_hi = min(tiles, t_lo + kHessSuper);
+    const double wi = A.weights[i];
+    // 1. term inputs (spectrum, timediff) of every component + rho for the super-tile
+    for (int t = t_lo; t < t_hi; ++t) {
+      double* dst = big + (size_t)(t - t_lo) * kBlock * vs;
+      eval_tile(A, L, i, t, dst);
+      const int j = t * kBlock + tid, r = (t - t_lo) * kBlock + tid;
+      double rho = 0.0, sdm = 0.0;
+      if (j < pc.num_time) {
+        const double* vrow = dst + (size_t)tid * vs;
+        double msum = 0.0;
+        for (int c = 0; c < nc; ++c) msum += vrow[3 * c];
+        rho = (A.data[(size_t)i * pc.num_time + j] - msum) * wi * wi;
+        if (H.need_sum_dmidx) {
+          for (int c = 0; c < nc; ++c) {
+            double d[9], g;
+            first_derivatives(L.chan[c], L.chan[c], L.comp[c], tau0, L.chan[c].amp, vrow[3 * c], vrow[3 * c + 1], d, &g);
+            sdm += d[FB_DM_INDEX];
+          }
+        }
+      }
+      rho_s[r] = rho;
+      sdm_s[r] = sdm;
+    }
+    __syncthreads();
+    // 2. per component: register accumulation over the super-tile, then one block flush
+    for (int c = 0; c < nc; ++c) {
+      double acc[kNumTerms];
+#pragma unroll
+      for (int k = 0; k < kNumTerms; ++k) acc[k] = 0.0;
+      const unsigned need = H.need[c];
+      for (int t = t_lo; t < t_hi; ++t) {
+        const int j = t * kBlock + tid, r = (t - t_lo) * kBlock + tid;
+        if (j < pc.num_time) {
+          const double* vrow = big + (size_t)r * vs;
+          D2Ctx ctx;
+          make_d2ctx(A, L.chan[c], L.comp[c], L.chan[c].amp, vrow[3 * c], vrow[3 * c + 1], sdm_s[r],
+                     L.chan[0].amp_pbf, ctx);
+          accumulate_terms(ctx, rho_s[r], need, acc);
+        }
+      }
+      // flush: column sums of the needed accumulators (fixed order), then the pair updates
+      for (int k0 = 0; k0 < kNumTerms; k0 += kFlushChunk) {
+#pragma unroll
+        for (int k = 0; k < kFlushChunk; ++k) stage[k * (kBlock + 1) + tid] = acc[k0 + k];
+        __syncthreads();
+        {
+          const int k = tid & 31, seg = tid >> 5;
+          if (k < kFlushChunk) {
+            const double* col = stage + k * (kBlock + 1) + seg * 32;
+            double sum = 0.0;
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) sum += col[r];
+            part[seg * 32 + k] = sum;
+          }
+        }
+        __syncthreads();
+        if (tid < kFlushChunk) {
+          double sum = 0.0;
+          for (int seg = 0; seg < kBlock / 32; ++seg) sum += part[seg * 32 + tid];
+          total[k0 + tid] = sum;
+        }
+        __syncthreads();
+      }
+      {
+        const double lf = L.chan[c].logf;
+        const int lo = H.comp_off[c], cnt = H.comp_off[c + 1] - lo;
+        for (int p = tid; p < cnt; p += kBlock) {
+          const int pair = H.comp_list[lo + p];
+          const HessDesc d = H.desc[pair];
+          const double factor = d.code == 0 ? 1.0 : (d.code == 1 ? kLn10 : (d.code == 2 ? lf : lf * lf));
+          pacc[pair] += factor * total[d.idx];
+        }
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < npairs; e += kBlock) H.partials[(size_t)blockIdx.x * npairs + e] = pacc[e];
 }
 
 __global__ void k_hess_finalize(const double* __restrict__ partials, int nblocks, int npairs,

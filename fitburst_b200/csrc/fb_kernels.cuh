@@ -275,7 +275,8 @@ __device__ inline void load_comp_tables(const EvalArgs& A, const SmemLayout& L) 
 // the general exp + erfcx sub-grid are pushed on a block-wide queue and evaluated one sub-sample
 // per LANE, so that the expensive work is spread over the whole block instead of stalling
 // every other warp at the next barrier.
-__device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, int tile) {
+__device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, int tile,
+                                 double* vals_out = nullptr) {
   const PlanConst& pc = A.pc;
   const int nc = pc.num_comp, kf = pc.kf, kt = pc.kt, tid = threadIdx.x;
   const int vs = val_stride(nc);
@@ -284,7 +285,8 @@ __device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, 
   const int j = tile * kBlock + tid;
   if (tid == 0) *L.qcount = 0;
   __syncthreads();
-  double* v = L.vals + (size_t)tid * vs;
+  double* vals = vals_out ? vals_out : L.vals;
+  double* v = vals + (size_t)tid * vs;
   if (j < pc.num_time) {
     for (int c = 0; c < nc; ++c) {
       SampleComp sc;
@@ -340,7 +342,7 @@ __device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, 
         s_ps += __shfl_xor_sync(0xffffffffu, s_ps, off);
       }
       if (active && gl == 0) {
-        double* o = L.vals + (size_t)t_idx * vs + 3 * c;
+        double* o = vals + (size_t)t_idx * vs + 3 * c;
         o[0] = L.comp[c].amp10 * (s_ps * inv_n);
         o[1] = s_t * inv_n;
         o[2] = s_p * inv_n;
