@@ -57,41 +57,57 @@ def parse_args():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
+    """Samples SM clocks / throttle reasons of one GPU through NVML while the timed region runs
+    (in-process NVML calls: spawning nvidia-smi every 200 ms was seen to stall CUDA API calls of
+    the timed loop for tens of milliseconds)."""
 
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    REASONS = {
+        "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4,
+    }
 
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.sm, self.reasons, self.sm_max = [], set(), None
         self.stop_flag = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:  # noqa: BLE001
+            self.nvml = None
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(
-                    ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits"],
-                    capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([s.strip() for s in out.split(",")])
+                if self.nvml is not None:
+                    self.sm.append(float(self.nvml.nvmlDeviceGetClockInfo(self.handle, self.nvml.NVML_CLOCK_SM)))
+                    try:
+                        mask = int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    except Exception:  # noqa: BLE001
+                        mask = int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    for name, bit in self.REASONS.items():
+                        if mask & bit:
+                            self.reasons.add(name)
+                else:
+                    out = subprocess.run(
+                        ["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm",
+                         "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        cur, mx = [float(x) for x in out.split(",")]
+                        self.sm.append(cur)
+                        self.sm_max = mx
             except Exception:  # noqa: BLE001
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05 if self.nvml is not None else 1.0)
 
     def summary(self):
-        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
-        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            for name, val in zip(names, s[3:7]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": sorted(self.reasons), "samples": len(self.sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def make_burst(args, seed, model_fn):
@@ -277,8 +293,10 @@ def run_cuda(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps, warmup):
+        import gc
         for s in range(warmup):
             fn(s)
+        gc.collect()
         barrier()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t0 = time.perf_counter()

@@ -10,6 +10,7 @@ convention ("fit() never raises") and fit_statistics keys as the reference.
 """
 import ctypes
 import traceback
+import weakref
 
 import numpy as np
 import torch
@@ -240,11 +241,16 @@ class LSFitter:
         self.model._cache_host = {}
         self._gram_final = gram
 
+        # the lazy members must not keep the fitter alive through a reference cycle
+        # (fitter -> results -> closure -> fitter): dead fitters would hold their 134 MB device
+        # spectrum until a cyclic-GC pass, which also stalls the caller for tens of milliseconds.
+        owner = weakref.ref(self)
+
         def lazy_fun():
-            return self._evaluate_at(x, want="fun")
+            return owner()._evaluate_at(x, want="fun")
 
         def lazy_jac():
-            return self._evaluate_at(x, want="jac")
+            return owner()._evaluate_at(x, want="jac")
 
         results = LazyOptimizeResult(
             x=x, cost=float(result.cost), grad=np.array(result.grad[:num_free]),
