@@ -246,15 +246,17 @@ __device__ __forceinline__ bool eval_sample_fast(const PlanConst& pc, const Comp
   const bool plateau = (u_last - ch.min_delay) < ct.neg5w;
   const bool tail = u0 >= ch.tail_lo;
   if (!(plateau || tail)) return false;
-  double su = 0.0;
-  for (int b = 0; b < kt; ++b) su += linspace_at(ct.t_start, ct.t_step, ct.t_stop, m0 + b, n);
-  out.timediff = su * (1.0 / (double)kt) - ch.mean_delay;
+  // mean over the kt sub-times of the arrival-corrected labels: start + step (m0 + (kt-1)/2)
+  // (identical to summing them up to rounding; the forced last label differs from the
+  // arithmetic one by an ulp of |stop|)
+  out.timediff = fma(ct.t_step, (double)m0 + 0.5 * (double)(kt - 1), ct.t_start) - ch.mean_delay;
   if (plateau) {
     out.timeprof = ch.plateau_p;
     out.spectrum = ch.plateau_ps;
   } else {
     double s_p = 0.0, s_ps = 0.0;
-    for (int a = 0; a < kf; ++a) {
+#pragma unroll 4
+    for (int a = 0; a < kf; ++a) {  // independent exps: unrolled for instruction-level parallelism
       const SubTab& st = sub[a];
       const double p = st.tail_c * exp(fma(-u0, st.inv_tau, st.tail_e));
       s_p += p;

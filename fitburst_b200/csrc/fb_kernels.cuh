@@ -295,7 +295,7 @@ __device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, 
         v[3 * c + 1] = sc.timediff;
         v[3 * c + 2] = sc.timeprof;
       } else if (use_queue) {
-        L.queue[atomicAdd(L.qcount, 1)] = tid * nc + c;
+        L.queue[atomicAdd(L.qcount, 1)] = (tid << 5) | c;
       } else {
         sc = eval_sample_general(pc, L.comp[c], L.chan[c], L.sub + c * kf, j);
         v[3 * c] = sc.spectrum;
@@ -321,19 +321,27 @@ __device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, 
       int t_idx = 0, c = 0;
       if (active) {
         const int item = L.queue[q];
-        t_idx = item / nc;
-        c = item % nc;
+        t_idx = item >> 5;
+        c = item & 31;
         const CompTab& ct = L.comp[c];
         const SubTab* sub = L.sub + c * kf;
         const int scattered = L.chan[c].scattered;
         const int jj = tile * kBlock + t_idx;
+        // sub-sample pe -> (sub-time b, sub-frequency a) without an integer division per step
+        int b = gl / kf, a = gl - b * kf;
+        const int db = gs / kf, da = gs - db * kf;
         for (int pe = gl; pe < npe; pe += gs) {
-          const int b = pe / kf, a = pe - b * kf;
           double t, p;
           eval_subsample(pc, ct, scattered, sub[a], jj * kt + b, t, p);
           s_t += t;
           s_p += p;
           s_ps = fma(p, sub[a].sed, s_ps);
+          b += db;
+          a += da;
+          if (a >= kf) {
+            a -= kf;
+            ++b;
+          }
         }
       }
       for (int off = gs >> 1; off > 0; off >>= 1) {
