@@ -71,6 +71,11 @@ struct fb_plan_s {
   int sm_count = 148;
   int64_t launches = 0;
   std::vector<double> h_weights;
+  // last [J r]^T [J r] returned to the host, keyed by what it was computed from: lets
+  // fb_hessian reuse the J^T J of the final trust-region evaluation instead of recomputing it.
+  bool gram_cache_valid = false;
+  std::vector<double> gram_cache, gram_cache_params;
+  const double* gram_cache_data = nullptr;
 };
 
 extern "C" const char* fb_last_error(void) { return g_err; }
@@ -330,6 +335,7 @@ static int rebuild_channel_list(fb_plan_s* p, cudaStream_t st) {
                              cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   p->have_weights = true;
+  p->gram_cache_valid = false;
   return FB_OK;
 }
 
@@ -382,6 +388,8 @@ extern "C" int fb_set_free_parameters(fb_plan_t p, const int32_t* free_mask, int
     p->free_mask[k] = free_mask[k] != 0;
   }
   layout_free(p);
+  for (int k = 0; k < 9; ++k)
+    if (saved[k] != p->free_mask[k]) p->gram_cache_valid = false;
   if (p->n_free > FB_MAX_FREE) {
     const int n = p->n_free;
     for (int k = 0; k < 9; ++k) p->free_mask[k] = saved[k];
@@ -428,6 +436,10 @@ extern "C" int fb_normal_equations(fb_plan_t p, const double* data_dev, double* 
   CUDA_TRY(cudaMemcpyAsync(p->h_gram, p->d_gram, sizeof(double) * ncols * ncols, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   memcpy(gram_host, p->h_gram, sizeof(double) * ncols * ncols);
+  p->gram_cache.assign(p->h_gram, p->h_gram + (size_t)ncols * ncols);
+  p->gram_cache_params.assign(p->h_params, p->h_params + (size_t)FB_NUM_PARAMETERS * p->desc.num_components);
+  p->gram_cache_data = data_dev;
+  p->gram_cache_valid = true;
   return check_err_flag(p, st);
 }
 
@@ -735,10 +747,20 @@ int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, 
   CUDA_TRY(cudaStreamSynchronize(st));  // host vectors go out of scope
   const int ncols = n + 1;
   std::vector<double> gram((size_t)ncols * ncols), S(npairs, 0.0);
-  // first-derivative products = J^T J of the weighted Jacobian at the model's current state
-  int rc = normal_equations_async(p, data_dev, p->d_gram, st);
-  if (rc != FB_OK) return rc;
-  CUDA_TRY(cudaMemcpyAsync(gram.data(), p->d_gram, sizeof(double) * ncols * ncols, cudaMemcpyDeviceToHost, st));
+  // first-derivative products = J^T J of the weighted Jacobian at the model's current state;
+  // after a fit that is normally the last trust-region evaluation, still cached.
+  int rc = FB_OK;
+  const size_t nparam = (size_t)FB_NUM_PARAMETERS * nc;
+  if (p->gram_cache_valid && p->gram_cache_data == data_dev && p->gram_cache.size() == (size_t)ncols * ncols &&
+      p->gram_cache_params.size() == nparam &&
+      memcmp(p->gram_cache_params.data(), p->h_params, sizeof(double) * nparam) == 0) {
+    gram = p->gram_cache;
+  } else {
+    rc = normal_equations_async(p, data_dev, p->d_gram, st);
+    if (rc != FB_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(gram.data(), p->d_gram, sizeof(double) * ncols * ncols, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
   if (p->num_good > 0 && !p->pc.scintillation) {
     // fast path: register accumulation of the 30 term values per (sample, component)
     std::vector<HessDesc> desc(npairs);
