@@ -502,7 +502,7 @@ struct HessAccArgs {
 };
 
 __host__ __device__ inline size_t hess_acc_smem_bytes(int nc, int kf, int num_pairs) {
-  size_t n = smem_bytes(nc, kf, 1, false);
+  size_t n = smem_bytes(nc, kf, 1, false, true);
   n += sizeof(double) * (size_t)kHessSuper * kBlock * val_stride(nc);  // term inputs of the super-tile
   n += sizeof(double) * (size_t)kHessSuper * kBlock * 2;               // rho, sum_dmidx
   n += sizeof(double) * ((size_t)(kBlock / 32) * 32 + 32);             // column partials, totals
@@ -515,9 +515,9 @@ __global__ void __launch_bounds__(kBlock, 2) k_hessian_acc(const HessAccArgs H) 
   const EvalArgs& A = H.E;
   const PlanConst& pc = A.pc;
   const int nc = pc.num_comp, kf = pc.kf, tid = threadIdx.x;
-  SmemLayout L = carve(smem_raw, nc, kf);
+  SmemLayout L = carve(smem_raw, nc, kf, true);
   const int vs = val_stride(nc);
-  double* big = smem_raw + smem_bytes(nc, kf, 1, false) / sizeof(double);  // [super rows][vs]
+  double* big = smem_raw + smem_bytes(nc, kf, 1, false, true) / sizeof(double);  // [super rows][vs]
   double* rho_s = big + (size_t)kHessSuper * kBlock * vs;
   double* sdm_s = rho_s + (size_t)kHessSuper * kBlock;
   double* part = sdm_s + (size_t)kHessSuper * kBlock;  // [8][32]

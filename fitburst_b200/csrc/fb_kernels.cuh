@@ -165,7 +165,7 @@ struct SmemLayout {
 
 __host__ __device__ inline int val_stride(int nc) { return (3 * nc) | 1; }
 
-__host__ __device__ inline size_t smem_bytes(int nc, int kf, int ncols_main, bool scint) {
+__host__ __device__ inline size_t smem_bytes(int nc, int kf, int ncols_main, bool scint, bool lean = false) {
   size_t n = 0;
   n += sizeof(CompTab) * nc;
   n += sizeof(ChanTab) * nc;
@@ -173,8 +173,9 @@ __host__ __device__ inline size_t smem_bytes(int nc, int kf, int ncols_main, boo
   n += sizeof(double) * nc;
   n += sizeof(double) * ((nc + 1) * (nc + 1) + nc + 2);
   n += sizeof(double) * gram_ntiles(nc + 1) * kTile * kTile;
-  n += sizeof(double) * (size_t)kBlock * val_stride(nc);
-  n += sizeof(double) * (size_t)kBlock * kTile * kTile;
+  // lean layout (Hessian accumulate kernel): no per-tile value rows, no parked Gram tiles
+  if (!lean) n += sizeof(double) * (size_t)kBlock * val_stride(nc);
+  if (!lean) n += sizeof(double) * (size_t)kBlock * kTile * kTile;
   n += sizeof(int) * ((size_t)kBlock * nc + 2);
   int stride = gram_stride(ncols_main);
   if (scint) {
@@ -187,7 +188,7 @@ __host__ __device__ inline size_t smem_bytes(int nc, int kf, int ncols_main, boo
   return n;
 }
 
-__device__ inline SmemLayout carve(double* base, int nc, int kf) {
+__device__ inline SmemLayout carve(double* base, int nc, int kf, bool lean = false) {
   SmemLayout L;
   char* p = reinterpret_cast<char*>(base);
   L.comp = reinterpret_cast<CompTab*>(p);
@@ -203,9 +204,9 @@ __device__ inline SmemLayout carve(double* base, int nc, int kf) {
   L.tilesum = reinterpret_cast<double*>(p);
   p += sizeof(double) * gram_ntiles(nc + 1) * kTile * kTile;
   L.vals = reinterpret_cast<double*>(p);
-  p += sizeof(double) * (size_t)kBlock * val_stride(nc);
+  if (!lean) p += sizeof(double) * (size_t)kBlock * val_stride(nc);
   L.park = reinterpret_cast<double*>(p);
-  p += sizeof(double) * (size_t)kBlock * kTile * kTile;
+  if (!lean) p += sizeof(double) * (size_t)kBlock * kTile * kTile;
   L.queue = reinterpret_cast<int*>(p);
   L.qcount = L.queue + (size_t)kBlock * nc;
   p += sizeof(int) * ((size_t)kBlock * nc + 2);
