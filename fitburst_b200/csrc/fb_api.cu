@@ -2,6 +2,7 @@
 // launch logic for the kernels in fb_kernels.cuh / fb_hessian.cuh / fb_batched.cuh.
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -12,6 +13,7 @@
 
 #include "fb_kernels.cuh"
 #include "fb_hessian.cuh"
+#include "fb_batched.cuh"
 #define FB_HAVE_HESSIAN 1
 #include "fb_trf.h"
 
@@ -1026,6 +1028,153 @@ extern "C" int fb_chisq_grid(fb_plan_t p, const double* data_dev, const double* 
   return check_err_flag(p, st);
 }
 
+// uncertainties = sqrt(diag(inv(0.5 H))), analysis/fitter.py:484-485 (Gauss-Jordan on the small matrix)
+static void invert_half_hessian(const std::vector<double>& H, int n, double* uncertainty) {
+  std::vector<double> M((size_t)n * 2 * n, 0.0);
+  for (int i = 0; i < n; ++i) {
+    for (int j = 0; j < n; ++j) M[(size_t)i * 2 * n + j] = 0.5 * H[(size_t)i * n + j];
+    M[(size_t)i * 2 * n + n + i] = 1.0;
+  }
+  bool ok = true;
+  for (int k = 0; k < n && ok; ++k) {
+    int piv = k;
+    for (int r = k + 1; r < n; ++r)
+      if (std::fabs(M[(size_t)r * 2 * n + k]) > std::fabs(M[(size_t)piv * 2 * n + k])) piv = r;
+    if (M[(size_t)piv * 2 * n + k] == 0.0) { ok = false; break; }
+    if (piv != k)
+      for (int j = 0; j < 2 * n; ++j) std::swap(M[(size_t)k * 2 * n + j], M[(size_t)piv * 2 * n + j]);
+    const double d = M[(size_t)k * 2 * n + k];
+    for (int j = 0; j < 2 * n; ++j) M[(size_t)k * 2 * n + j] /= d;
+    for (int r = 0; r < n; ++r) {
+      if (r == k) continue;
+      const double f = M[(size_t)r * 2 * n + k];
+      if (f != 0.0)
+        for (int j = 0; j < 2 * n; ++j) M[(size_t)r * 2 * n + j] -= f * M[(size_t)k * 2 * n + j];
+    }
+  }
+  for (int i = 0; i < n; ++i) uncertainty[i] = ok ? std::sqrt(M[(size_t)i * 2 * n + n + i]) : NAN;
+}
+
+// ---- on-device batched solver (fb_batched.cuh) -----------------------------------------------------
+struct DevBuf {
+  void* ptr = nullptr;
+  ~DevBuf() { cudaFree(ptr); }
+  cudaError_t alloc(size_t bytes) { return cudaMalloc(&ptr, bytes ? bytes : 1); }
+  template <typename T> T* as() { return reinterpret_cast<T*>(ptr); }
+};
+
+static int fit_batched_device(fb_plan_s* p, int count, const double* data_dev, const double* weights_dev,
+                              double* params_dev, const fb_fit_options& opt, fb_fit_result* results_host,
+                              cudaStream_t st) {
+  const int nf = p->desc.num_freq, nt = p->desc.num_time, nc = p->desc.num_components, kf = p->pc.kf;
+  const int n = p->n_free, ncols = n + 1;
+  // per-burst lists of channels with non-zero weight (host-built: deterministic order)
+  std::vector<double> w((size_t)count * nf);
+  CUDA_TRY(cudaMemcpyAsync(w.data(), weights_dev, sizeof(double) * w.size(), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  std::vector<int> lists((size_t)count * nf, 0), num_good(count, 0);
+  int max_good = 0;
+  for (int b = 0; b < count; ++b) {
+    int k = 0;
+    for (int i = 0; i < nf; ++i)
+      if (w[(size_t)b * nf + i] != 0.0) lists[(size_t)b * nf + k++] = i;
+    num_good[b] = k;
+    max_good = std::max(max_good, k);
+  }
+  const int tiles = (nt + kBlock - 1) / kBlock;
+  const long long items = p->pc.scintillation ? (long long)max_good : (long long)max_good * tiles;
+  int blocks = (int)std::max(1LL, std::min(64LL, (items + 3) / 4));
+  const int ntiles = gram_ntiles(ncols);
+  DevBuf d_lists, d_num_good, d_done, d_started, d_num_done, d_states, d_results, d_gram, d_comp, d_sub, d_chan, d_part;
+  cudaError_t e = cudaSuccess;
+  auto chk = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  chk(d_lists.alloc(sizeof(int) * lists.size()));
+  chk(d_num_good.alloc(sizeof(int) * count));
+  chk(d_done.alloc(sizeof(int) * count));
+  chk(d_started.alloc(sizeof(int) * count));
+  chk(d_num_done.alloc(sizeof(int)));
+  chk(d_states.alloc(sizeof(TrfState) * (size_t)count));
+  chk(d_results.alloc(sizeof(fb_fit_result) * (size_t)count));
+  chk(d_gram.alloc(sizeof(double) * (size_t)count * ncols * ncols));
+  chk(d_comp.alloc(sizeof(CompTab) * (size_t)count * nc));
+  chk(d_sub.alloc(sizeof(SubTab) * (size_t)count * nf * nc * kf));
+  chk(d_chan.alloc(sizeof(ChanTab) * (size_t)count * nf * nc));
+  chk(d_part.alloc(sizeof(double) * (size_t)count * blocks * ntiles * kTile * kTile));
+  if (e != cudaSuccess) return fail(FB_ERR_NOMEM, "batched fit allocation failed: %s", cudaGetErrorString(e));
+  CUDA_TRY(cudaMemcpyAsync(d_lists.ptr, lists.data(), sizeof(int) * lists.size(), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(d_num_good.ptr, num_good.data(), sizeof(int) * count, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(d_done.ptr, 0, sizeof(int) * count, st));
+  CUDA_TRY(cudaMemsetAsync(d_started.ptr, 0, sizeof(int) * count, st));
+  CUDA_TRY(cudaMemsetAsync(d_num_done.ptr, 0, sizeof(int), st));
+  CUDA_TRY(cudaMemsetAsync(d_results.ptr, 0, sizeof(fb_fit_result) * (size_t)count, st));
+
+  EvalArgs A = base_args(p);
+  A.data = data_dev;
+  A.weights = weights_dev;
+  A.params = params_dev;
+  A.g_comp = d_comp.as<CompTab>();
+  A.g_sub = d_sub.as<SubTab>();
+  A.g_chan = d_chan.as<ChanTab>();
+  A.chan_list = d_lists.as<int>();
+  A.partials = d_part.as<double>();
+  BatchArgs B;
+  B.done = d_done.as<int>();
+  B.num_good = d_num_good.as<int>();
+  B.data_stride = (size_t)nf * nt;
+  B.weights_stride = nf;
+  B.params_stride = (size_t)FB_NUM_PARAMETERS * nc;
+  B.comp_stride = nc;
+  B.sub_stride = (size_t)nf * nc * kf;
+  B.chan_stride = (size_t)nf * nc;
+  B.list_stride = nf;
+  B.partials_stride = (size_t)blocks * ntiles * kTile * kTile;
+  BatchedTrfArgs T;
+  memset(&T, 0, sizeof(T));
+  T.count = count;
+  T.nc = nc;
+  T.n_free = n;
+  for (int k = 0; k < 9; ++k) T.col_of[k] = p->col_of[k];
+  T.num_residuals = (long long)nf * nt;
+  T.ftol = opt.ftol;
+  T.xtol = opt.xtol;
+  T.gtol = opt.gtol;
+  T.max_nfev = opt.max_nfev;
+  T.partials = d_part.as<double>();
+  T.blocks = blocks;
+  T.gram = d_gram.as<double>();
+  T.params = params_dev;
+  T.states = d_states.as<TrfState>();
+  T.started = d_started.as<int>();
+  T.done = d_done.as<int>();
+  T.num_done = d_num_done.as<int>();
+  T.results = d_results.as<fb_fit_result>();
+
+  const size_t smem = smem_bytes(nc, kf, ncols, p->pc.scintillation != 0);
+  if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request %zu B exceeds 227 KB", smem);
+  if (smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(k_eval_batched<MODE_GRAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const size_t trf_smem = sizeof(double) * 2 * (size_t)n * n;
+  if (trf_smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(k_trf_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trf_smem));
+  const int max_iter = (opt.max_nfev > 0 ? opt.max_nfev : 100 * n) + 2;
+  const dim3 tgrid((nf * nc + 127) / 128, count), egrid(blocks, count);
+  int done_host = 0;
+  for (int it = 0; it < max_iter && done_host < count; ++it) {
+    k_tables_batched<<<tgrid, 128, 0, st>>>(p->pc, params_dev, d_comp.as<CompTab>(), d_sub.as<SubTab>(),
+                                            d_chan.as<ChanTab>(), d_done.as<int>());
+    k_eval_batched<MODE_GRAM><<<egrid, kBlock, smem, st>>>(A, B);
+    k_trf_batched<<<count, 32, trf_smem, st>>>(T);
+    CUDA_TRY(cudaGetLastError());
+    p->launches += 3;
+    CUDA_TRY(cudaMemcpyAsync(&done_host, d_num_done.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  CUDA_TRY(cudaMemcpyAsync(results_host, d_results.ptr, sizeof(fb_fit_result) * (size_t)count, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  p->tables_dirty = true;
+  return check_err_flag(p, st);
+}
+
 // ---- batched independent fits (BASELINE.json config 3) ---------------------------------------------
 extern "C" int fb_fit_batched(fb_plan_t p, int32_t count, const double* data_dev, const double* weights_dev,
                               double* params_dev, const fb_fit_options* options, fb_fit_result* results_host,
@@ -1037,7 +1186,33 @@ extern "C" int fb_fit_batched(fb_plan_t p, int32_t count, const double* data_dev
   const size_t spec = (size_t)nf * p->desc.num_time, nparam = (size_t)FB_NUM_PARAMETERS * nc;
   fb_fit_options opt = default_options(options);
   std::vector<double> w(nf), pr(nparam), H((size_t)n * n);
+  // Many small bursts: the whole trust-region loop runs on the device for all bursts at once.
+  // Large bursts already fill the GPU one at a time and their tables would not fit `count` times.
+  const char* mode = getenv("FITBURST_B200_BATCHED");
+  const size_t table_bytes = (size_t)count * nf * nc * (p->pc.kf * sizeof(SubTab) + sizeof(ChanTab));
+  bool device_path = count >= 2 && table_bytes <= ((size_t)8 << 30) && spec <= ((size_t)1 << 22);
+  if (mode && !strcmp(mode, "device")) device_path = true;
+  if (mode && !strcmp(mode, "sequential")) device_path = false;
+  bool fitted_on_device = false;
+  if (device_path && n >= 1 && count >= 1) {
+    int rc = fit_batched_device(p, count, data_dev, weights_dev, params_dev, opt, results_host, st);
+    if (rc != FB_OK) return rc;
+    fitted_on_device = true;
+  }
   for (int b = 0; b < count; ++b) {
+    if (fitted_on_device) {
+      if (!opt.compute_hessian || results_host[b].status < 0) continue;
+      // uncertainties: exact Hessian at the best fit, burst by burst
+      CUDA_TRY(cudaMemcpyAsync(w.data(), weights_dev + (size_t)b * nf, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaMemcpyAsync(pr.data(), params_dev + (size_t)b * nparam, sizeof(double) * nparam, cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      int rc = fb_load_weights(p, w.data(), stream);
+      if (rc == FB_OK) rc = fb_set_parameters(p, pr.data(), stream);
+      if (rc == FB_OK) rc = fb_hessian_impl(p, data_dev + (size_t)b * spec, H.data(), st);
+      if (rc != FB_OK) continue;
+      invert_half_hessian(H, n, results_host[b].uncertainty);
+      continue;
+    }
     CUDA_TRY(cudaMemcpyAsync(w.data(), weights_dev + (size_t)b * nf, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(pr.data(), params_dev + (size_t)b * nparam, sizeof(double) * nparam, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
@@ -1059,31 +1234,7 @@ extern "C" int fb_fit_batched(fb_plan_t p, int32_t count, const double* data_dev
       rc = fb_set_parameters(p, p->h_params, stream);
       if (rc == FB_OK) rc = fb_hessian_impl(p, data_dev + (size_t)b * spec, H.data(), st);
       if (rc == FB_OK) {
-        // uncertainties = sqrt(diag(inv(0.5 H))), analysis/fitter.py:484-485 (Gauss-Jordan on the small matrix)
-        std::vector<double> M((size_t)n * 2 * n, 0.0);
-        for (int i = 0; i < n; ++i) {
-          for (int j = 0; j < n; ++j) M[(size_t)i * 2 * n + j] = 0.5 * H[(size_t)i * n + j];
-          M[(size_t)i * 2 * n + n + i] = 1.0;
-        }
-        bool ok = true;
-        for (int k = 0; k < n && ok; ++k) {
-          int piv = k;
-          for (int r = k + 1; r < n; ++r)
-            if (std::fabs(M[(size_t)r * 2 * n + k]) > std::fabs(M[(size_t)piv * 2 * n + k])) piv = r;
-          if (M[(size_t)piv * 2 * n + k] == 0.0) { ok = false; break; }
-          if (piv != k)
-            for (int j = 0; j < 2 * n; ++j) std::swap(M[(size_t)k * 2 * n + j], M[(size_t)piv * 2 * n + j]);
-          const double d = M[(size_t)k * 2 * n + k];
-          for (int j = 0; j < 2 * n; ++j) M[(size_t)k * 2 * n + j] /= d;
-          for (int r = 0; r < n; ++r) {
-            if (r == k) continue;
-            const double f = M[(size_t)r * 2 * n + k];
-            if (f != 0.0)
-              for (int j = 0; j < 2 * n; ++j) M[(size_t)r * 2 * n + j] -= f * M[(size_t)k * 2 * n + j];
-          }
-        }
-        for (int i = 0; i < n; ++i)
-          results_host[b].uncertainty[i] = ok ? std::sqrt(M[(size_t)i * 2 * n + n + i]) : NAN;
+        invert_half_hessian(H, n, results_host[b].uncertainty);
       }
     }
     CUDA_TRY(cudaStreamSynchronize(st));

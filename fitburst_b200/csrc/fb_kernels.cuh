@@ -444,7 +444,7 @@ __device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayo
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
+__device__ __forceinline__ void eval_body(const EvalArgs& A, const int block_id, const int num_blocks) {
   extern __shared__ double smem_raw[];
   const PlanConst& pc = A.pc;
   const int nc = pc.num_comp, kf = pc.kf, tid = threadIdx.x;
@@ -469,8 +469,8 @@ __global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
 
   if (!pc.scintillation) {
     const long long total = (long long)A.num_chan * tiles;
-    const long long begin = total * blockIdx.x / gridDim.x;
-    const long long end = total * (blockIdx.x + 1) / gridDim.x;
+    const long long begin = total * block_id / num_blocks;
+    const long long end = total * (block_id + 1) / num_blocks;
     int cur = -1;
     for (long long item = begin; item < end; ++item) {
       const int chi = (int)(item / tiles), tile = (int)(item % tiles);
@@ -502,7 +502,7 @@ __global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
     int s_ti, s_tj;
     tile_coords(s_tile, side2, s_ti, s_tj);
     double* row2 = L.X + (size_t)tid * stride2;
-    for (int chi = blockIdx.x; chi < A.num_chan; chi += gridDim.x) {
+    for (int chi = block_id; chi < A.num_chan; chi += num_blocks) {
       const int i = A.chan_list ? A.chan_list[chi] : chi;
       load_channel_tables(A, L, i);
       double acc2[kTile * kTile];
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
       if (tid < off) L.X[tid] += L.X[tid + off];
       __syncthreads();
     }
-    if (tid == 0) A.chi2_partials[blockIdx.x] = L.X[0];
+    if (tid == 0) A.chi2_partials[block_id] = L.X[0];
   }
 
   if (MODE == MODE_GRAM) {
@@ -577,8 +577,55 @@ __global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
 #pragma unroll
     for (int k = 0; k < kTile * kTile; ++k) acc[k] = L.park[k * kBlock + tid];
     gram_block_reduce(L.X, ntiles, nslices, g_tile, g_slice, g_active, acc,
-                      A.partials + (size_t)blockIdx.x * ntiles * kTile * kTile);
+                      A.partials + (size_t)block_id * ntiles * kTile * kTile);
   }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
+  eval_body<MODE>(A, blockIdx.x, gridDim.x);
+}
+
+// Batched variant (many independent bursts of identical shape, blockIdx.y = burst): every
+// per-burst buffer is offset by the burst index; bursts whose fit has finished are skipped.
+struct BatchArgs {
+  const int* done;       // (count) 1 once the burst's fit has terminated
+  const int* num_good;   // (count) channels with non-zero weight
+  size_t data_stride, weights_stride, params_stride, comp_stride, sub_stride, chan_stride, list_stride,
+      partials_stride;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) k_eval_batched(const EvalArgs A, const BatchArgs B) {
+  const int y = blockIdx.y;
+  if (B.done[y]) return;
+  EvalArgs Ab = A;
+  Ab.data = A.data + y * B.data_stride;
+  Ab.weights = A.weights + y * B.weights_stride;
+  Ab.params = A.params + y * B.params_stride;
+  Ab.g_comp = A.g_comp + y * B.comp_stride;
+  Ab.g_sub = A.g_sub + y * B.sub_stride;
+  Ab.g_chan = A.g_chan + y * B.chan_stride;
+  Ab.chan_list = A.chan_list + y * B.list_stride;
+  Ab.num_chan = B.num_good[y];
+  Ab.partials = A.partials + y * B.partials_stride;
+  eval_body<MODE>(Ab, blockIdx.x, gridDim.x);
+}
+
+__global__ void __launch_bounds__(128) k_tables_batched(const PlanConst pc, const double* __restrict__ params,
+                                                        CompTab* __restrict__ g_comp, SubTab* __restrict__ g_sub,
+                                                        ChanTab* __restrict__ g_chan, const int* __restrict__ done) {
+  const int y = blockIdx.y, nc = pc.num_comp;
+  if (done[y]) return;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= pc.num_freq * nc) return;
+  const int i = e / nc, c = e % nc;
+  const double* pr = params + (size_t)y * FB_NUM_PARAMETERS * nc;
+  CompTab ct;
+  make_comp_tab(pc, pr, c, ct);
+  if (i == 0) g_comp[(size_t)y * nc + c] = ct;
+  const size_t ce = (size_t)y * pc.num_freq * nc + e;
+  make_channel_tables(pc, pr, ct, i, c, g_sub + ce * pc.kf, g_chan[ce]);
 }
 
 // Second stage: sums the per-block partial tiles in block order and writes the symmetric

@@ -97,6 +97,7 @@ struct TrfState {
   double cost;
   // decomposition of A, valid for the current outer iteration
   double lam[kMaxN], V[kMaxN * kMaxN], suf[kMaxN];
+  double work[kMaxN * kMaxN];  // scratch copy of A destroyed by the eigen-solver
   int decomposed;
   // trust region
   double Delta, alpha;
@@ -227,33 +228,40 @@ FB_HD inline void trf_load_accepted(TrfState& st, const double* gram) {
   st.decomposed = 0;
 }
 
-// Top of trf.py's outer loop + the first trust-region solve of the inner loop. Returns 1 if
-// a trial point st.x_new is ready to be evaluated, 0 if the fit has finished.
-FB_HD inline int trf_propose(TrfState& st) {
+// Top of trf.py's outer loop (trf.py:465-482). Returns 0 when the fit has finished, 1 when
+// J^T J must be decomposed for a new outer iteration, 2 when the current decomposition is still
+// valid (the inner loop is retrying with a smaller radius).
+FB_HD inline int trf_head(TrfState& st) {
   const int n = st.n;
-  if (!st.decomposed) {
-    // outer-loop head, trf.py:465-482
-    double gn = 0.0;
-    for (int i = 0; i < n; ++i) gn = fmax(gn, fabs(st.g[i]));
-    st.g_norm = gn;
-    if (gn < st.gtol) st.status = 1;
-    if (st.status != -100 || st.nfev == st.max_nfev) {
-      if (st.status == -100) st.status = 0;
-      st.finished = 1;
-      return 0;
-    }
-    double work[kMaxN * kMaxN];
-    for (int i = 0; i < n * n; ++i) work[i] = st.A[i];
-    jacobi_eigh(work, st.V, st.lam, n, n);
-    for (int k = 0; k < n; ++k) {
-      double acc = 0.0;
-      for (int i = 0; i < n; ++i) acc += st.V[i * n + k] * st.g[i];
-      st.suf[k] = acc;
-    }
-    st.decomposed = 1;
-    st.actual = -1.0;
+  if (st.decomposed) return 2;
+  double gn = 0.0;
+  for (int i = 0; i < n; ++i) gn = fmax(gn, fabs(st.g[i]));
+  st.g_norm = gn;
+  if (gn < st.gtol) st.status = 1;
+  if (st.status != -100 || st.nfev == st.max_nfev) {
+    if (st.status == -100) st.status = 0;
+    st.finished = 1;
+    return 0;
   }
-  // inner loop body up to the function evaluation, trf.py:503-513
+  for (int i = 0; i < n * n; ++i) st.work[i] = st.A[i];
+  return 1;
+}
+
+// After s^2, V = eigh(work): s * U^T f = V^T g.
+FB_HD inline void trf_after_decomposition(TrfState& st) {
+  const int n = st.n;
+  for (int k = 0; k < n; ++k) {
+    double acc = 0.0;
+    for (int i = 0; i < n; ++i) acc += st.V[i * n + k] * st.g[i];
+    st.suf[k] = acc;
+  }
+  st.decomposed = 1;
+  st.actual = -1.0;
+}
+
+// Inner-loop body up to the function evaluation, trf.py:503-513: trial step and prediction.
+FB_HD inline void trf_step(TrfState& st) {
+  const int n = st.n;
   solve_lsq_trust_region(st);
   double q = 0.0, l = 0.0;
   for (int i = 0; i < n; ++i) {
@@ -265,6 +273,17 @@ FB_HD inline int trf_propose(TrfState& st) {
   st.predicted = -(0.5 * q + l);
   for (int i = 0; i < n; ++i) st.x_new[i] = st.x[i] + st.p[i];
   st.step_norm = vnorm(st.p, n);
+}
+
+// Returns 1 if a trial point st.x_new is ready to be evaluated, 0 if the fit has finished.
+FB_HD inline int trf_propose(TrfState& st) {
+  const int h = trf_head(st);
+  if (h == 0) return 0;
+  if (h == 1) {
+    jacobi_eigh(st.work, st.V, st.lam, st.n, st.n);
+    trf_after_decomposition(st);
+  }
+  trf_step(st);
   return 1;
 }
 

@@ -96,3 +96,34 @@ def test_multi_gpu_nccl(native_lib):
         capture_output=True, text=True, timeout=600)
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-4000:]
     assert "MULTI_GPU_OK" in proc.stdout
+
+
+def test_device_and_sequential_batched_paths_agree(native_lib, monkeypatch):
+    """The on-device batched solver (one warp per burst) and the host-driven loop make the same
+    decisions: same status / nfev and the same best fit."""
+    from fitburst_b200.analysis.model import SpectrumModeler
+    from fitburst_b200.batch import fit_batched
+    num_freq, num_time, count = 48, 96, 6
+    freqs, times = syn.chime_axes(num_freq, num_time)
+    kwargs = dict(factor_freq_upsample=2, factor_time_upsample=2, num_components=2)
+    model = SpectrumModeler(freqs, times, **kwargs)
+    datas, goods, starts = [], [], []
+    for b in range(count):
+        truth, start = syn.random_burst(b, num_time)
+        truth = syn.truncate_components({k: (v * 2)[:2] if len(v) < 2 else v for k, v in truth.items()}, 2)
+        truth["arrival_time"] = [0.4 * times[-1], 0.6 * times[-1]]
+        model.update_parameters(truth)
+        good = syn.make_good_freq(num_freq, 0.2 if b else 0.0, 30 + b)
+        datas.append(syn.add_noise(model.compute_model(), good, 0.05, 30 + b))
+        goods.append(good)
+        starts.append(syn.config2_start(truth))
+    fixed = ["dm_index", "scattering_index"]
+    out = {}
+    for mode in ("device", "sequential"):
+        monkeypatch.setenv("FITBURST_B200_BATCHED", mode)
+        out[mode] = fit_batched(model, np.stack(datas), np.stack(goods), starts, fixed)
+    for b in range(count):
+        d, s = out["device"][b], out["sequential"][b]
+        assert d["status"] == s["status"] and d["nfev"] == s["nfev"] and d["njev"] == s["njev"], (b, d["status"], s["status"])
+        np.testing.assert_allclose(d["x"], s["x"], rtol=1e-7)
+        np.testing.assert_allclose(d["uncertainties"], s["uncertainties"], rtol=1e-5)
