@@ -39,6 +39,35 @@ def jacobian_flop_per_sample(num_comp, p_c, p_g):
     return num_comp * (38 + 8 * p_c) + 8 * p_g * num_comp + n * (n + 1) + 2 * n + 6
 
 
+def regime_census(freqs, times, params, good, kf, kt, dm_const=4149.377593360996):
+    """Counts, for the scattered branch, how many (channel, component, sample) items fall in the
+    clamp plateau, the exponential tail and the general (rise/peak) regime of fb_core.cuh --
+    the same boundaries as make_channel_tables / eval_sample_fast, restated in numpy. Used only to
+    report the EXECUTED-work model next to the contract's 110 flop per profile evaluation."""
+    res_f = abs(freqs[1] - freqs[0])
+    res_t = abs(times[1] - times[0])
+    nt = len(times)
+    sub = freqs[good][:, None] - res_f / 2 + res_f / (2 * kf) + np.arange(kf)[None, :] * (res_f / kf)
+    counts = {"plateau": 0, "tail": 0, "general": 0}
+    nc = len(params["amplitude"])
+    for c in range(nc):
+        w, t_arr, fref = params["burst_width"][c], params["arrival_time"][c], params["ref_freq"][c]
+        dm, beta = params["dm"][0], params["dm_index"][0]
+        tau0, alpha = params["scattering_timescale"][0], params["scattering_index"][0]
+        delay = dm * dm_const * (sub ** beta - fref ** beta)
+        tau = tau0 * (sub / fref) ** alpha
+        step = res_t / kt
+        u0 = (times - t_arr) - res_t / 2 + step / 2           # first sub-time of every sample
+        u_last = u0 + (kt - 1) * step
+        plateau = (u_last[None, :] - delay.min(axis=1)[:, None]) < -5 * w
+        tail_lo = delay.max(axis=1) + (w * w / tau).max(axis=1) + 6 * np.sqrt(2) * w
+        tail = u0[None, :] >= tail_lo[:, None]
+        counts["plateau"] += int(plateau.sum())
+        counts["tail"] += int((tail & ~plateau).sum())
+        counts["general"] += int((~tail & ~plateau).sum())
+    return counts
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -370,6 +399,11 @@ def run_cuda(args):
     peak = __import__("ctypes").c_double(0.0)
     _lib.check(lib.fb_measure_fp64_peak(peak, stream))
     achieved = flop / (eval_ms * 1e-3) / 1e12
+    census = regime_census(freqs, times, bursts[0][1], bursts[0][2], args.kf, args.kt)
+    # executed-work model: plateau = table look-up (0 flop), tail = one exp + 4 flop per
+    # (sample, sub-frequency), general = the contract's 110 flop per profile evaluation
+    flop_exec = (census["general"] * args.kf * args.kt * FLOP_PER_PE_SCATTERED + census["tail"] * args.kf * 34.0 +
+                 float(num_good) * args.ntime * jacobian_flop_per_sample(args.ncomp, 5, 2))
     roofline = {
         "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
         "frac": achieved / peak.value if peak.value > 0 else None, "traffic": None,
@@ -378,6 +412,15 @@ def run_cuda(args):
         "units_per_launch": {"profile_evaluations": n_pe, "good_channels": num_good},
         "peak_source": "measured live: dependent-free DFMA chains on all SMs (MEASURED_PEAKS.json has no FP64 entry)",
         "hbm_algorithmic_bytes_per_launch": 8.0 * num_good * args.ntime,
+        "executed_model": {
+            "note": ("the kernel replaces most exp+erfcx pairs by closed forms (clamp plateau: table look-up; "
+                     "exponential tail: one exp per sample and sub-frequency), so `frac` above measures speed "
+                     "against the contract's work model, not pipe utilisation; this object counts the work "
+                     "actually required by the regimes"),
+            "sample_component_items": census, "flop_per_launch": flop_exec,
+            "achieved": flop_exec / (eval_ms * 1e-3) / 1e12,
+            "frac": (flop_exec / (eval_ms * 1e-3) / 1e12) / peak.value if peak.value > 0 else None,
+        },
         "evals_per_s": 1e3 / eval_ms,
     }
 

@@ -258,7 +258,8 @@ __device__ __forceinline__ bool eval_sample_fast(const PlanConst& pc, const Comp
 #pragma unroll 4
     for (int a = 0; a < kf; ++a) {  // independent exps: unrolled for instruction-level parallelism
       const SubTab& st = sub[a];
-      const double p = st.tail_c * exp(fma(-u0, st.inv_tau, st.tail_e));
+      const double earg = fma(-u0, st.inv_tau, st.tail_e);
+      const double p = (earg < -746.0) ? 0.0 : st.tail_c * exp(earg);  // exp underflows to exactly 0
       s_p += p;
       s_ps = fma(p, st.sed, s_ps);
     }
@@ -347,7 +348,8 @@ __device__ __forceinline__ void first_derivatives(const ChanTab& ch, const ChanT
   const double arg_erf = (td - w * w * inv_tau) * inv_w * kSqrtHalf;
   const double ws = w * inv_tau;
   const double arg_exp = 0.5 * ws * ws - td * inv_tau - arg_erf * arg_erf;
-  const double g = amp * ch.amp_pbf * exp(arg_exp) * kTwoOverSqrtPi;
+  // exp() is exactly 0 below -745.2: far from the burst (|T| > 38.6 w) skip the call
+  const double g = (arg_exp < -746.0) ? 0.0 : amp * ch.amp_pbf * exp(arg_exp) * kTwoOverSqrtPi;
   *gfac_out = g;
   if (arg_erf_out) *arg_erf_out = arg_erf;
   if (ch.sc_time == 0.0) {  // per-channel Gaussian branch, routines/derivative.py:568,629,695,767

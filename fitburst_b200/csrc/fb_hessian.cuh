@@ -510,7 +510,7 @@ __host__ __device__ inline size_t hess_acc_smem_bytes(int nc, int kf, int num_pa
   return n;
 }
 
-__global__ void __launch_bounds__(kBlock, 2) k_hessian_acc(const HessAccArgs H) {
+__global__ void __launch_bounds__(kBlock, 4) k_hessian_acc(const HessAccArgs H) {
   extern __shared__ double smem_raw[];
   const EvalArgs& A = H.E;
   const PlanConst& pc = A.pc;

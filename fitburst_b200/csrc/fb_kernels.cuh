@@ -6,7 +6,7 @@
 
 namespace fb {
 
-constexpr int kBlock = 256;
+constexpr int kBlock = 128;
 constexpr int kTile = 4;  // register tile edge of the Gram accumulation
 
 enum EvalMode { MODE_MODEL = 0, MODE_GRAM = 1, MODE_JAC = 2, MODE_DERIV = 3, MODE_CHI2 = 4 };
@@ -75,6 +75,7 @@ __device__ __forceinline__ void gram_accumulate(const double* __restrict__ X, in
   if (!active) return;
   const double* xa = X + ti * kTile;
   const double* xb = X + tj * kTile;
+#pragma unroll 2
   for (int s = slice; s < rows; s += nslices) {
     const double* ra = xa + s * stride;
     const double* rb = xb + s * stride;
@@ -582,7 +583,7 @@ __device__ __forceinline__ void eval_body(const EvalArgs& A, const int block_id,
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_eval(const EvalArgs A) {
+__global__ void __launch_bounds__(kBlock, 4) k_eval(const EvalArgs A) {
   eval_body<MODE>(A, blockIdx.x, gridDim.x);
 }
 
@@ -596,7 +597,7 @@ struct BatchArgs {
 };
 
 template <int MODE>
-__global__ void __launch_bounds__(kBlock) k_eval_batched(const EvalArgs A, const BatchArgs B) {
+__global__ void __launch_bounds__(kBlock, 4) k_eval_batched(const EvalArgs A, const BatchArgs B) {
   const int y = blockIdx.y;
   if (B.done[y]) return;
   EvalArgs Ab = A;
