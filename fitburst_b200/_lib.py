@@ -109,6 +109,12 @@ SIGNATURES = {
     "fb_trf_result": (ctypes.c_int, [_P, ctypes.POINTER(FitResult), _D]),
     "fb_fit_batched": (ctypes.c_int, [_P, _I32, _P, _P, _P, ctypes.POINTER(FitOptions), ctypes.POINTER(FitResult), _P]),
     "fb_chisq_grid": (ctypes.c_int, [_P, _P, _D, _I32, _D, _I32, _P, _P]),
+    "fb_pre_channel_moments": (ctypes.c_int, [_P, _P, _I32, _I32, _P, _P]),
+    "fb_pre_remove_baseline": (ctypes.c_int, [_P, _P, _P, _P, _I32, _I32, _P]),
+    "fb_pre_power_sums": (ctypes.c_int, [_P, _I32, _I32, _P, _P]),
+    "fb_pre_zero_channels": (ctypes.c_int, [_P, _P, _I32, _I32, _P]),
+    "fb_pre_downsample_2d": (ctypes.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P]),
+    "fb_pre_window": (ctypes.c_int, [_P, _I32, _I32, _P, _I32, _P, _P]),
     "fb_measure_fp64_peak": (ctypes.c_int, [_D, _P]),
     "fb_launch_count": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int64), _I32]),
 }

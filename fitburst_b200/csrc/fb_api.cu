@@ -14,6 +14,7 @@
 #include "fb_kernels.cuh"
 #include "fb_hessian.cuh"
 #include "fb_batched.cuh"
+#include "fb_preprocess.cuh"
 #define FB_HAVE_HESSIAN 1
 #include "fb_trf.h"
 
@@ -636,6 +637,76 @@ extern "C" int fb_measure_fp64_peak(double* tflops_out, void* stream) {
   cudaEventDestroy(e1);
   cudaFree(d_out);
   *tflops_out = best;
+  return FB_OK;
+}
+
+// ---- pre-fit data preparation (fb_preprocess.cuh) ---------------------------------------------------
+static int pre_check(const void* a, int nf, int nt) {
+  if (!a) return fail(FB_ERR_INVALID, "null argument");
+  if (nf < 1 || nt < 1) return fail(FB_ERR_INVALID, "empty spectrum");
+  return FB_OK;
+}
+
+extern "C" int fb_pre_channel_moments(const double* data_dev, const double* weights_dev, int32_t nf, int32_t nt,
+                                      double* moments_dev, void* stream) {
+  if (!weights_dev || !moments_dev) return fail(FB_ERR_INVALID, "null argument");
+  int rc = pre_check(data_dev, nf, nt);
+  if (rc != FB_OK) return rc;
+  k_pre_moments<<<nf, kPreBlock, 0, (cudaStream_t)stream>>>(data_dev, weights_dev, nt, moments_dev);
+  CUDA_TRY(cudaGetLastError());
+  return FB_OK;
+}
+
+extern "C" int fb_pre_remove_baseline(double* data_dev, const double* weights_dev, const uint8_t* good_dev,
+                                      const double* mean_dev, int32_t nf, int32_t nt, void* stream) {
+  if (!weights_dev || !good_dev || !mean_dev) return fail(FB_ERR_INVALID, "null argument");
+  int rc = pre_check(data_dev, nf, nt);
+  if (rc != FB_OK) return rc;
+  k_pre_baseline<<<nf, kPreBlock, 0, (cudaStream_t)stream>>>(data_dev, weights_dev, good_dev, mean_dev, nt);
+  CUDA_TRY(cudaGetLastError());
+  return FB_OK;
+}
+
+extern "C" int fb_pre_power_sums(const double* data_dev, int32_t nf, int32_t nt, double* sums_dev, void* stream) {
+  if (!sums_dev) return fail(FB_ERR_INVALID, "null argument");
+  int rc = pre_check(data_dev, nf, nt);
+  if (rc != FB_OK) return rc;
+  k_pre_power_sums<<<nf, kPreBlock, 0, (cudaStream_t)stream>>>(data_dev, nt, sums_dev);
+  CUDA_TRY(cudaGetLastError());
+  return FB_OK;
+}
+
+extern "C" int fb_pre_zero_channels(double* data_dev, const uint8_t* keep_dev, int32_t nf, int32_t nt, void* stream) {
+  if (!keep_dev) return fail(FB_ERR_INVALID, "null argument");
+  int rc = pre_check(data_dev, nf, nt);
+  if (rc != FB_OK) return rc;
+  k_pre_zero_channels<<<nf, kPreBlock, 0, (cudaStream_t)stream>>>(data_dev, keep_dev, nt);
+  CUDA_TRY(cudaGetLastError());
+  return FB_OK;
+}
+
+extern "C" int fb_pre_downsample_2d(const double* in_dev, int32_t nf, int32_t nt, int32_t ff, int32_t ft,
+                                    double* out_dev, void* stream) {
+  if (!out_dev) return fail(FB_ERR_INVALID, "null argument");
+  int rc = pre_check(in_dev, nf, nt);
+  if (rc != FB_OK) return rc;
+  if (ff < 1 || ft < 1 || nf % ff != 0 || nt % ft != 0)
+    return fail(FB_ERR_INVALID, "cannot reshape array of size %d x %d by factors %d x %d", nf, nt, ff, ft);
+  const int nfo = nf / ff, nto = nt / ft;
+  const dim3 grid((nto + kPreBlock - 1) / kPreBlock, nfo);
+  k_pre_downsample<<<grid, kPreBlock, 0, (cudaStream_t)stream>>>(in_dev, nt, ff, ft, nto, out_dev);
+  CUDA_TRY(cudaGetLastError());
+  return FB_OK;
+}
+
+extern "C" int fb_pre_window(const double* in_dev, int32_t nf, int32_t nt, const int32_t* start_dev, int32_t width,
+                             double* out_dev, void* stream) {
+  if (!start_dev || !out_dev) return fail(FB_ERR_INVALID, "null argument");
+  int rc = pre_check(in_dev, nf, nt);
+  if (rc != FB_OK) return rc;
+  if (width < 1 || width > nt) return fail(FB_ERR_INVALID, "window width %d out of range", width);
+  k_pre_window<<<nf, kPreBlock, 0, (cudaStream_t)stream>>>(in_dev, nt, start_dev, width, out_dev);
+  CUDA_TRY(cudaGetLastError());
   return FB_OK;
 }
 

@@ -1,0 +1,143 @@
+// Pre-fit data preparation on the device: the per-channel reductions,
+// masking, block-mean down-sampling and de-dispersed windowing of
+// utilities/bases.py:129-336 (ReaderBaseClass.preprocess_data / downsample / window_data).
+// All of it is HBM-bound streaming over a (num_freq, num_time) f64 spectrum: one block per
+// channel row (or per output row), coalesced 8-byte accesses, fixed-order tree reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace fb {
+
+constexpr int kPreBlock = 256;
+
+__device__ __forceinline__ double pre_block_sum(double v, double* red) {
+  const int tid = threadIdx.x;
+  red[tid] = v;
+  __syncthreads();
+  for (int off = kPreBlock / 2; off > 0; off >>= 1) {
+    if (tid < off) red[tid] += red[tid + off];
+    __syncthreads();
+  }
+  const double out = red[0];
+  __syncthreads();
+  return out;
+}
+
+// Per channel: sum(w), sum(d w), min(d), max(d)      (utilities/bases.py:251-264)
+__global__ void __launch_bounds__(kPreBlock) k_pre_moments(const double* __restrict__ data,
+                                                          const double* __restrict__ weights, int nt,
+                                                          double* __restrict__ out) {
+  __shared__ double red[kPreBlock];
+  const int i = blockIdx.x, tid = threadIdx.x;
+  const double* d = data + (size_t)i * nt;
+  const double* w = weights + (size_t)i * nt;
+  double sw = 0.0, sdw = 0.0, mn = INFINITY, mx = -INFINITY;
+  for (int j = tid; j < nt; j += kPreBlock) {
+    const double dv = d[j], wv = w[j];
+    sw += wv;
+    sdw = fma(dv, wv, sdw);
+    mn = fmin(mn, dv);
+    mx = fmax(mx, dv);
+  }
+  const double tsw = pre_block_sum(sw, red);
+  const double tsdw = pre_block_sum(sdw, red);
+  red[tid] = mn;
+  __syncthreads();
+  for (int off = kPreBlock / 2; off > 0; off >>= 1) {
+    if (tid < off) red[tid] = fmin(red[tid], red[tid + off]);
+    __syncthreads();
+  }
+  const double tmn = red[0];
+  __syncthreads();
+  red[tid] = mx;
+  __syncthreads();
+  for (int off = kPreBlock / 2; off > 0; off >>= 1) {
+    if (tid < off) red[tid] = fmax(red[tid], red[tid + off]);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    out[4 * i + 0] = tsw;
+    out[4 * i + 1] = tsdw;
+    out[4 * i + 2] = tmn;
+    out[4 * i + 3] = red[0];
+  }
+}
+
+// Baseline removal (utilities/bases.py:270-273): good channels d <- d / mean - 1, then every
+// sample whose weight is zero is zeroed (all channels).
+__global__ void __launch_bounds__(kPreBlock) k_pre_baseline(double* __restrict__ data,
+                                                           const double* __restrict__ weights,
+                                                           const uint8_t* __restrict__ good,
+                                                           const double* __restrict__ mean, int nt) {
+  const int i = blockIdx.x;
+  double* d = data + (size_t)i * nt;
+  const double* w = weights + (size_t)i * nt;
+  const bool g = good[i] != 0;
+  const double m = mean[i];
+  for (int j = threadIdx.x; j < nt; j += kPreBlock) {
+    double v = d[j];
+    if (g) v = v / m - 1.0;
+    if (w[j] == 0.0) v = 0.0;
+    d[j] = v;
+  }
+}
+
+// Per channel: sum(d^2), sum(d^3)                    (utilities/bases.py:276-279)
+__global__ void __launch_bounds__(kPreBlock) k_pre_power_sums(const double* __restrict__ data, int nt,
+                                                             double* __restrict__ out) {
+  __shared__ double red[kPreBlock];
+  const int i = blockIdx.x;
+  const double* d = data + (size_t)i * nt;
+  double s2 = 0.0, s3 = 0.0;
+  for (int j = threadIdx.x; j < nt; j += kPreBlock) {
+    const double v = d[j], v2 = v * v;
+    s2 += v2;
+    s3 = fma(v2, v, s3);
+  }
+  const double t2 = pre_block_sum(s2, red);
+  const double t3 = pre_block_sum(s3, red);
+  if (threadIdx.x == 0) {
+    out[2 * i + 0] = t2;
+    out[2 * i + 1] = t3;
+  }
+}
+
+// data[i, :] = 0 where keep[i] == 0                  (utilities/bases.py:296, 168)
+__global__ void __launch_bounds__(kPreBlock) k_pre_zero_channels(double* __restrict__ data,
+                                                                const uint8_t* __restrict__ keep, int nt) {
+  const int i = blockIdx.x;
+  if (keep[i]) return;
+  double* d = data + (size_t)i * nt;
+  for (int j = threadIdx.x; j < nt; j += kPreBlock) d[j] = 0.0;
+}
+
+// downsample_2d (routines/manipulate.py:43-72): mean over factor_time (inner), then over
+// factor_freq, of the (nf/ff, ff, nt/ft, ft) reshape. One thread per output sample.
+__global__ void __launch_bounds__(kPreBlock) k_pre_downsample(const double* __restrict__ in, int nt_in, int ff,
+                                                             int ft, int nt_out, double* __restrict__ out) {
+  const int io = blockIdx.y;
+  const int jo = blockIdx.x * kPreBlock + threadIdx.x;
+  if (jo >= nt_out) return;
+  double acc = 0.0;
+  for (int a = 0; a < ff; ++a) {
+    const double* row = in + (size_t)(io * ff + a) * nt_in + (size_t)jo * ft;
+    double s = 0.0;
+    for (int b = 0; b < ft; ++b) s += row[b];
+    acc += s / (double)ft;
+  }
+  out[(size_t)io * nt_out + jo] = acc / (double)ff;
+}
+
+// window_data (utilities/bases.py:300-336): out[i, k] = data[i, start[i] + k], k < width.
+__global__ void __launch_bounds__(kPreBlock) k_pre_window(const double* __restrict__ in, int nt,
+                                                         const int* __restrict__ start, int width,
+                                                         double* __restrict__ out) {
+  const int i = blockIdx.x;
+  const double* src = in + (size_t)i * nt + start[i];
+  double* dst = out + (size_t)i * width;
+  for (int k = threadIdx.x; k < width; k += kPreBlock) dst[k] = src[k];
+}
+
+}  // namespace fb

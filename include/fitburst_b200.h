@@ -221,6 +221,28 @@ int fb_chisq_grid(fb_plan_t plan, const double* data_dev,
                   const double* dm_values_host, int32_t num_dm, const double* sc_values_host,
                   int32_t num_sc, double* chisq_dev, void* stream);
 
+/* ---- pre-fit data preparation (utilities/bases.py:129-336), SURVEY.md section 8f.1 ----------
+ * All arrays are device pointers; spectra are (num_freq, num_time) f64 C order. */
+/* per channel [sum(w), sum(d*w), min(d), max(d)] -> moments_dev (num_freq, 4); bases.py:251-264 */
+int fb_pre_channel_moments(const double* data_dev, const double* weights_dev, int32_t num_freq,
+                           int32_t num_time, double* moments_dev, void* stream);
+/* bases.py:270-273: good channels d <- d / mean - 1, then samples with zero weight are zeroed */
+int fb_pre_remove_baseline(double* data_dev, const double* weights_dev, const uint8_t* good_dev,
+                           const double* mean_dev, int32_t num_freq, int32_t num_time, void* stream);
+/* per channel [sum(d^2), sum(d^3)] -> sums_dev (num_freq, 2); bases.py:276-279 */
+int fb_pre_power_sums(const double* data_dev, int32_t num_freq, int32_t num_time, double* sums_dev,
+                      void* stream);
+/* data[i, :] = 0 where keep_dev[i] == 0; bases.py:296,168 */
+int fb_pre_zero_channels(double* data_dev, const uint8_t* keep_dev, int32_t num_freq, int32_t num_time,
+                         void* stream);
+/* downsample_2d, routines/manipulate.py:43-72; out is (num_freq/factor_freq, num_time/factor_time) */
+int fb_pre_downsample_2d(const double* in_dev, int32_t num_freq, int32_t num_time, int32_t factor_freq,
+                         int32_t factor_time, double* out_dev, void* stream);
+/* window_data, bases.py:300-336: out[i, k] = in[i, start_dev[i] + k] for k < width; the caller
+ * guarantees 0 <= start[i] and start[i] + width <= num_time */
+int fb_pre_window(const double* in_dev, int32_t num_freq, int32_t num_time, const int32_t* start_dev,
+                  int32_t width, double* out_dev, void* stream);
+
 /* Measured FP64 FMA peak of the device (dependent-free DFMA chains on every SM), TFLOP/s.
  * MEASURED_PEAKS.json carries no FP64 figure; bench.py reports this one as the roofline peak. */
 int fb_measure_fp64_peak(double* tflops_out, void* stream);
