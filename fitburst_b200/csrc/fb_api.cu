@@ -50,6 +50,8 @@ struct fb_plan_s {
   size_t partials_cap = 0;
   double* d_gram = nullptr;  // (FB_MAX_FREE+1)^2
   double* h_gram = nullptr;  // pinned
+  double* d_vals = nullptr;  // split evaluation: (spectrum, timediff, timeprof) per (sample, component)
+  size_t vals_cap = 0;
   CompTab* d_comp = nullptr;
   SubTab* d_sub = nullptr;
   ChanTab* d_chan = nullptr;
@@ -199,6 +201,7 @@ extern "C" int fb_plan_destroy(fb_plan_t p) {
   cudaFree(p->d_hess_partials);
   cudaFree(p->d_pairs);
   cudaFree(p->d_comp_list);
+  cudaFree(p->d_vals);
   cudaFree(p->d_desc);
   cudaFree(p->d_comp);
   cudaFree(p->d_sub);
@@ -403,6 +406,48 @@ extern "C" int fb_set_free_parameters(fb_plan_t p, const int32_t* free_mask, int
   return FB_OK;
 }
 
+// Two-kernel evaluation (k_vals + k_gram2), see fb_kernels.cuh "split evaluation".
+static int launch_split_gram(fb_plan_s* p, EvalArgs& A, int ncols, cudaStream_t st, int* grid_out) {
+  int rc = ensure_tables(p, st);
+  if (rc != FB_OK) return rc;
+  const int nc = p->pc.num_comp, kf = p->pc.kf;
+  const int tiles = (p->pc.num_time + kBlock - 1) / kBlock;
+  const long long items = (long long)A.num_chan * tiles;
+  const size_t need_vals = (size_t)items * kBlock * val_stride(nc);
+  if (need_vals > p->vals_cap) {
+    cudaFree(p->d_vals);
+    p->d_vals = nullptr;
+    p->vals_cap = 0;
+    CUDA_TRY(cudaMalloc(&p->d_vals, sizeof(double) * need_vals));
+    p->vals_cap = need_vals;
+  }
+  const size_t smem1 = smem_bytes(nc, kf, 1, false, false, SM_QUEUE);
+  const size_t smem2 = smem_bytes(nc, kf, ncols, false, false, SM_PARK | SM_X);
+  if (smem1 > 227 * 1024 || smem2 > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request exceeds 227 KB");
+  if (smem1 > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_vals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+  if (smem2 > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_gram2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  int occ1 = 1, occ2 = 1;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_vals, kBlock, smem1));
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_gram2, kBlock, smem2));
+  long long grid1 = std::min<long long>(items, (long long)p->sm_count * std::max(1, occ1) * 4);
+  long long grid2 = std::min<long long>(items, (long long)p->sm_count * std::max(1, occ2));
+  const size_t need = (size_t)grid2 * gram_ntiles(ncols) * kTile * kTile;
+  if (need > p->partials_cap) {
+    cudaFree(p->d_partials);
+    p->d_partials = nullptr;
+    p->partials_cap = 0;
+    CUDA_TRY(cudaMalloc(&p->d_partials, sizeof(double) * need));
+    p->partials_cap = need;
+  }
+  A.partials = p->d_partials;
+  k_vals<<<(int)grid1, kBlock, smem1, st>>>(A, p->d_vals);
+  k_gram2<<<(int)grid2, kBlock, smem2, st>>>(A, p->d_vals);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 2;
+  *grid_out = (int)grid2;
+  return FB_OK;
+}
+
 static int normal_equations_async(fb_plan_s* p, const double* data_dev, double* gram_dev, cudaStream_t st) {
   if (!p->have_weights) return fail(FB_ERR_INVALID, "fb_set_weights / fb_load_weights must be called first");
   if (p->n_free < 1) return fail(FB_ERR_INVALID, "no free parameters");
@@ -417,7 +462,14 @@ static int normal_equations_async(fb_plan_s* p, const double* data_dev, double* 
   A.chan_list = p->d_chan_list;
   A.num_chan = p->num_good;
   int grid = 0;
-  int rc = launch_eval<MODE_GRAM>(p, A, ncols, st, &grid);
+  int rc = FB_OK;
+  const char* split_env = getenv("FITBURST_B200_SPLIT");
+  const bool split = !p->pc.scintillation && !(split_env && !strcmp(split_env, "0"));
+  if (split) {
+    rc = launch_split_gram(p, A, ncols, st, &grid);
+  } else {
+    rc = launch_eval<MODE_GRAM>(p, A, ncols, st, &grid);
+  }
   if (rc != FB_OK) return rc;
   k_gram_finalize<<<1, 256, 0, st>>>(p->d_partials, grid, ncols, gram_dev);
   CUDA_TRY(cudaGetLastError());

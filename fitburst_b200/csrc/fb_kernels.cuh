@@ -166,7 +166,12 @@ struct SmemLayout {
 
 __host__ __device__ inline int val_stride(int nc) { return (3 * nc) | 1; }
 
-__host__ __device__ inline size_t smem_bytes(int nc, int kf, int ncols_main, bool scint, bool lean = false) {
+// shared-memory regions a kernel may ask for
+enum SmemRegion { SM_VALS = 1, SM_PARK = 2, SM_X = 4, SM_QUEUE = 8, SM_ALL = 15 };
+
+__host__ __device__ inline size_t smem_bytes(int nc, int kf, int ncols_main, bool scint, bool lean = false,
+                                            int regions = SM_ALL) {
+  if (lean) regions &= ~(SM_VALS | SM_PARK);
   size_t n = 0;
   n += sizeof(CompTab) * nc;
   n += sizeof(ChanTab) * nc;
@@ -174,10 +179,10 @@ __host__ __device__ inline size_t smem_bytes(int nc, int kf, int ncols_main, boo
   n += sizeof(double) * nc;
   n += sizeof(double) * ((nc + 1) * (nc + 1) + nc + 2);
   n += sizeof(double) * gram_ntiles(nc + 1) * kTile * kTile;
-  // lean layout (Hessian accumulate kernel): no per-tile value rows, no parked Gram tiles
-  if (!lean) n += sizeof(double) * (size_t)kBlock * val_stride(nc);
-  if (!lean) n += sizeof(double) * (size_t)kBlock * kTile * kTile;
-  n += sizeof(int) * ((size_t)kBlock * nc + 2);
+  if (regions & SM_VALS) n += sizeof(double) * (size_t)kBlock * val_stride(nc);
+  if (regions & SM_PARK) n += sizeof(double) * (size_t)kBlock * kTile * kTile;
+  if (regions & SM_QUEUE) n += sizeof(int) * ((size_t)kBlock * nc + 2);
+  if (!(regions & SM_X)) return n;
   int stride = gram_stride(ncols_main);
   if (scint) {
     const int s2 = gram_stride(nc + 1);
@@ -189,7 +194,8 @@ __host__ __device__ inline size_t smem_bytes(int nc, int kf, int ncols_main, boo
   return n;
 }
 
-__device__ inline SmemLayout carve(double* base, int nc, int kf, bool lean = false) {
+__device__ inline SmemLayout carve(double* base, int nc, int kf, bool lean = false, int regions = SM_ALL) {
+  if (lean) regions &= ~(SM_VALS | SM_PARK);
   SmemLayout L;
   char* p = reinterpret_cast<char*>(base);
   L.comp = reinterpret_cast<CompTab*>(p);
@@ -205,12 +211,12 @@ __device__ inline SmemLayout carve(double* base, int nc, int kf, bool lean = fal
   L.tilesum = reinterpret_cast<double*>(p);
   p += sizeof(double) * gram_ntiles(nc + 1) * kTile * kTile;
   L.vals = reinterpret_cast<double*>(p);
-  if (!lean) p += sizeof(double) * (size_t)kBlock * val_stride(nc);
+  if (regions & SM_VALS) p += sizeof(double) * (size_t)kBlock * val_stride(nc);
   L.park = reinterpret_cast<double*>(p);
-  if (!lean) p += sizeof(double) * (size_t)kBlock * kTile * kTile;
+  if (regions & SM_PARK) p += sizeof(double) * (size_t)kBlock * kTile * kTile;
   L.queue = reinterpret_cast<int*>(p);
   L.qcount = L.queue + (size_t)kBlock * nc;
-  p += sizeof(int) * ((size_t)kBlock * nc + 2);
+  if (regions & SM_QUEUE) p += sizeof(int) * ((size_t)kBlock * nc + 2);
   L.X = reinterpret_cast<double*>(p);
   return L;
 }
@@ -365,12 +371,13 @@ __device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, 
 // Everything a thread does for one sample of one channel, for every mode.
 template <int MODE>
 __device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayout& L, int i, int j,
-                                               bool valid, double* row, int stride) {
+                                               bool valid, double* row, int stride,
+                                               const double* vrow_in = nullptr) {
   const PlanConst& pc = A.pc;
   const int nc = pc.num_comp, kf = pc.kf, n = A.n_free;
   const double wi = (A.weights != nullptr) ? A.weights[i] : 1.0;
   const double tau0 = global_param(A.params, nc, FB_SCATTERING_TIMESCALE);
-  const double* vrow = L.vals + (size_t)threadIdx.x * val_stride(nc);
+  const double* vrow = vrow_in ? vrow_in : L.vals + (size_t)threadIdx.x * val_stride(nc);
   if (MODE == MODE_GRAM || MODE == MODE_JAC) {
     for (int k = 0; k <= n; ++k) row[k] = 0.0;
     if (MODE == MODE_GRAM)
@@ -627,6 +634,78 @@ __global__ void __launch_bounds__(128) k_tables_batched(const PlanConst pc, cons
   if (i == 0) g_comp[(size_t)y * nc + c] = ct;
   const size_t ce = (size_t)y * pc.num_freq * nc + e;
   make_channel_tables(pc, pr, ct, i, c, g_sub + ce * pc.kf, g_chan[ce]);
+}
+
+// ---- split evaluation ---------------------------------------------------------------------
+// The fused kernel is latency-bound at 16 warps/SM (122 registers, 52 KB shared memory per
+// 128-thread block). Splitting it at the natural seam -- the (spectrum, timediff) pair of every
+// (sample, component) -- gives two kernels that each need far fewer registers and far less
+// shared memory, so twice as many warps hide the FP64 latency; the price is one round trip of
+// 16 B per (sample, component) through HBM, which this path has to spare (the fused kernel
+// uses 1 % of the DRAM bandwidth).
+//   stage 1  k_vals   model side: regime split + general-case queue -> values in global memory
+//   stage 2  k_gram2  derivative side: [J r] rows -> [J r]^T [J r]
+__global__ void __launch_bounds__(kBlock, 6) k_vals(const EvalArgs A, double* __restrict__ gvals) {
+  extern __shared__ double smem_raw[];
+  const PlanConst& pc = A.pc;
+  const int nc = pc.num_comp, kf = pc.kf;
+  SmemLayout L = carve(smem_raw, nc, kf, false, SM_QUEUE);
+  load_comp_tables(A, L);
+  const int tiles = (pc.num_time + kBlock - 1) / kBlock;
+  const int vs = val_stride(nc);
+  const long long total = (long long)A.num_chan * tiles;
+  const long long begin = total * blockIdx.x / gridDim.x, end = total * (blockIdx.x + 1) / gridDim.x;
+  int cur = -1;
+  for (long long item = begin; item < end; ++item) {
+    const int chi = (int)(item / tiles), tile = (int)(item % tiles);
+    const int i = A.chan_list ? A.chan_list[chi] : chi;
+    if (chi != cur) {
+      load_channel_tables(A, L, i);
+      cur = chi;
+    }
+    eval_tile(A, L, i, tile, gvals + (size_t)item * kBlock * vs);
+  }
+}
+
+__global__ void __launch_bounds__(kBlock, 6) k_gram2(const EvalArgs A, const double* __restrict__ gvals) {
+  extern __shared__ double smem_raw[];
+  const PlanConst& pc = A.pc;
+  const int nc = pc.num_comp, kf = pc.kf, tid = threadIdx.x;
+  SmemLayout L = carve(smem_raw, nc, kf, false, SM_PARK | SM_X);
+  load_comp_tables(A, L);
+  const int ncols = A.n_free + 1;
+  const int stride = gram_stride(ncols), side = gram_side(ncols), ntiles = gram_ntiles(ncols);
+  const int nslices = kBlock / ntiles;
+  const int g_tile = tid % ntiles, g_slice = tid / ntiles;
+  const bool g_active = g_slice < nslices;
+  int g_ti = 0, g_tj = 0;
+  tile_coords(g_tile, side, g_ti, g_tj);
+#pragma unroll
+  for (int k = 0; k < kTile * kTile; ++k) L.park[k * kBlock + tid] = 0.0;
+  const int tiles = (pc.num_time + kBlock - 1) / kBlock;
+  const int vs = val_stride(nc);
+  double* row = L.X + (size_t)tid * stride;
+  const long long total = (long long)A.num_chan * tiles;
+  const long long begin = total * blockIdx.x / gridDim.x, end = total * (blockIdx.x + 1) / gridDim.x;
+  int cur = -1;
+  for (long long item = begin; item < end; ++item) {
+    const int chi = (int)(item / tiles), tile = (int)(item % tiles);
+    const int i = A.chan_list ? A.chan_list[chi] : chi;
+    if (chi != cur) {
+      load_channel_tables(A, L, i);
+      cur = chi;
+    }
+    const int j = tile * kBlock + tid;
+    process_sample<MODE_GRAM>(A, L, i, j, j < pc.num_time, row, stride, gvals + ((size_t)item * kBlock + tid) * vs);
+    __syncthreads();
+    gram_accumulate_parked(L, stride, ntiles, nslices, g_ti, g_tj, g_slice, g_active);
+    __syncthreads();
+  }
+  double acc[kTile * kTile];
+#pragma unroll
+  for (int k = 0; k < kTile * kTile; ++k) acc[k] = L.park[k * kBlock + tid];
+  gram_block_reduce(L.X, ntiles, nslices, g_tile, g_slice, g_active, acc,
+                    A.partials + (size_t)blockIdx.x * ntiles * kTile * kTile);
 }
 
 // Second stage: sums the per-block partial tiles in block order and writes the symmetric
