@@ -406,8 +406,36 @@ extern "C" int fb_set_free_parameters(fb_plan_t p, const int32_t* free_mask, int
   return FB_OK;
 }
 
-// Two-kernel evaluation (k_vals + k_gram2), see fb_kernels.cuh "split evaluation".
-static int launch_split_gram(fb_plan_s* p, EvalArgs& A, int ncols, cudaStream_t st, int* grid_out) {
+// Two-kernel evaluation (k_vals + k_gram2 / k_gram2_mma), see fb_kernels.cuh "split evaluation".
+// *mma_warps_out > 0 tells the caller to finalize with k_gram_finalize_mma.
+template <int NB>
+static int launch_gram2_mma(fb_plan_s* p, const EvalArgs& A, int ncols, long long items, cudaStream_t st, int* warps_out) {
+  const int nc = p->pc.num_comp, kf = p->pc.kf;
+  const size_t smem = gram_mma_smem_bytes(nc, kf, ncols);
+  if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request exceeds 227 KB");
+  if (smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(k_gram2_mma<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gram2_mma<NB>, kBlock, smem));
+  const long long grid = std::min<long long>(items, (long long)p->sm_count * std::max(1, occ));
+  const int warps = (int)grid * (kBlock / 32);
+  const size_t need = (size_t)warps * (NB * (NB + 1) / 2) * 64;
+  if (need > p->partials_cap) {
+    cudaFree(p->d_partials);
+    p->d_partials = nullptr;
+    p->partials_cap = 0;
+    CUDA_TRY(cudaMalloc(&p->d_partials, sizeof(double) * need));
+    p->partials_cap = need;
+  }
+  EvalArgs B = A;
+  B.partials = p->d_partials;
+  k_gram2_mma<NB><<<(int)grid, kBlock, smem, st>>>(B, p->d_vals);
+  CUDA_TRY(cudaGetLastError());
+  *warps_out = warps;
+  return FB_OK;
+}
+
+static int launch_split_gram(fb_plan_s* p, EvalArgs& A, int ncols, cudaStream_t st, int* grid_out, int* mma_warps_out) {
   int rc = ensure_tables(p, st);
   if (rc != FB_OK) return rc;
   const int nc = p->pc.num_comp, kf = p->pc.kf;
@@ -422,15 +450,31 @@ static int launch_split_gram(fb_plan_s* p, EvalArgs& A, int ncols, cudaStream_t 
     p->vals_cap = need_vals;
   }
   const size_t smem1 = smem_bytes(nc, kf, 1, false, false, SM_QUEUE);
-  const size_t smem2 = smem_bytes(nc, kf, ncols, false, false, SM_PARK | SM_X);
-  if (smem1 > 227 * 1024 || smem2 > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request exceeds 227 KB");
+  if (smem1 > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request exceeds 227 KB");
   if (smem1 > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_vals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
-  if (smem2 > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_gram2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
-  int occ1 = 1, occ2 = 1;
+  int occ1 = 1;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ1, k_vals, kBlock, smem1));
+  const long long grid1 = std::min<long long>(items, (long long)p->sm_count * std::max(1, occ1) * 4);
+  k_vals<<<(int)grid1, kBlock, smem1, st>>>(A, p->d_vals);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 2;
+  *mma_warps_out = 0;
+  const int nb = (ncols + 7) / 8;
+  const char* mma_env = getenv("FITBURST_B200_DMMA");
+  if (nb <= 4 && !(mma_env && !strcmp(mma_env, "0"))) {
+    switch (nb) {
+      case 1: return launch_gram2_mma<1>(p, A, ncols, items, st, mma_warps_out);
+      case 2: return launch_gram2_mma<2>(p, A, ncols, items, st, mma_warps_out);
+      case 3: return launch_gram2_mma<3>(p, A, ncols, items, st, mma_warps_out);
+      default: return launch_gram2_mma<4>(p, A, ncols, items, st, mma_warps_out);
+    }
+  }
+  const size_t smem2 = smem_bytes(nc, kf, ncols, false, false, SM_PARK | SM_X);
+  if (smem2 > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request exceeds 227 KB");
+  if (smem2 > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_gram2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+  int occ2 = 1;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ2, k_gram2, kBlock, smem2));
-  long long grid1 = std::min<long long>(items, (long long)p->sm_count * std::max(1, occ1) * 4);
-  long long grid2 = std::min<long long>(items, (long long)p->sm_count * std::max(1, occ2));
+  const long long grid2 = std::min<long long>(items, (long long)p->sm_count * std::max(1, occ2));
   const size_t need = (size_t)grid2 * gram_ntiles(ncols) * kTile * kTile;
   if (need > p->partials_cap) {
     cudaFree(p->d_partials);
@@ -440,10 +484,8 @@ static int launch_split_gram(fb_plan_s* p, EvalArgs& A, int ncols, cudaStream_t 
     p->partials_cap = need;
   }
   A.partials = p->d_partials;
-  k_vals<<<(int)grid1, kBlock, smem1, st>>>(A, p->d_vals);
   k_gram2<<<(int)grid2, kBlock, smem2, st>>>(A, p->d_vals);
   CUDA_TRY(cudaGetLastError());
-  p->launches += 2;
   *grid_out = (int)grid2;
   return FB_OK;
 }
@@ -465,13 +507,20 @@ static int normal_equations_async(fb_plan_s* p, const double* data_dev, double* 
   int rc = FB_OK;
   const char* split_env = getenv("FITBURST_B200_SPLIT");
   const bool split = !p->pc.scintillation && !(split_env && !strcmp(split_env, "0"));
+  int mma_warps = 0;
   if (split) {
-    rc = launch_split_gram(p, A, ncols, st, &grid);
+    rc = launch_split_gram(p, A, ncols, st, &grid, &mma_warps);
   } else {
     rc = launch_eval<MODE_GRAM>(p, A, ncols, st, &grid);
   }
   if (rc != FB_OK) return rc;
-  k_gram_finalize<<<1, 256, 0, st>>>(p->d_partials, grid, ncols, gram_dev);
+  if (mma_warps > 0) {
+    const int nb = (ncols + 7) / 8, entries = nb * (nb + 1) / 2 * 64;
+    k_gram_finalize_mma<<<(entries + 7) / 8, 256, 0, st>>>(p->d_partials, mma_warps, ncols, nb, gram_dev);
+  } else {
+    const int entries = gram_ntiles(ncols) * kTile * kTile;
+    k_gram_finalize<<<(entries + 7) / 8, 256, 0, st>>>(p->d_partials, grid, ncols, gram_dev);
+  }
   CUDA_TRY(cudaGetLastError());
   p->launches += 1;
   return FB_OK;

@@ -284,7 +284,7 @@ __device__ inline void load_comp_tables(const EvalArgs& A, const SmemLayout& L) 
 // per LANE, so that the expensive work is spread over the whole block instead of stalling
 // every other warp at the next barrier.
 __device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, int tile,
-                                 double* vals_out = nullptr) {
+                                 double* vals_out = nullptr, int soa = 0) {
   const PlanConst& pc = A.pc;
   const int nc = pc.num_comp, kf = pc.kf, kt = pc.kt, tid = threadIdx.x;
   const int vs = val_stride(nc);
@@ -293,22 +293,25 @@ __device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, 
   const int j = tile * kBlock + tid;
   if (tid == 0) *L.qcount = 0;
   __syncthreads();
+  // value (thread t, slot k) lives at vals[t * ts + k * ss]: per-thread rows in shared memory,
+  // slot-major planes (coalesced) when the values go to global memory
   double* vals = vals_out ? vals_out : L.vals;
-  double* v = vals + (size_t)tid * vs;
+  const int ts = soa ? 1 : vs, ss = soa ? kBlock : 1;
+  double* v = vals + (size_t)tid * ts;
   if (j < pc.num_time) {
     for (int c = 0; c < nc; ++c) {
       SampleComp sc;
       if (eval_sample_fast(pc, L.comp[c], L.chan[c], L.sub + c * kf, j, sc)) {
-        v[3 * c] = sc.spectrum;
-        v[3 * c + 1] = sc.timediff;
-        v[3 * c + 2] = sc.timeprof;
+        v[(3 * c) * ss] = sc.spectrum;
+        v[(3 * c + 1) * ss] = sc.timediff;
+        v[(3 * c + 2) * ss] = sc.timeprof;
       } else if (use_queue) {
         L.queue[atomicAdd(L.qcount, 1)] = (tid << 5) | c;
       } else {
         sc = eval_sample_general(pc, L.comp[c], L.chan[c], L.sub + c * kf, j);
-        v[3 * c] = sc.spectrum;
-        v[3 * c + 1] = sc.timediff;
-        v[3 * c + 2] = sc.timeprof;
+        v[(3 * c) * ss] = sc.spectrum;
+        v[(3 * c + 1) * ss] = sc.timediff;
+        v[(3 * c + 2) * ss] = sc.timeprof;
       }
     }
   }
@@ -358,10 +361,10 @@ __device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, 
         s_ps += __shfl_xor_sync(0xffffffffu, s_ps, off);
       }
       if (active && gl == 0) {
-        double* o = vals + (size_t)t_idx * vs + 3 * c;
+        double* o = vals + (size_t)t_idx * ts + (size_t)(3 * c) * ss;
         o[0] = L.comp[c].amp10 * (s_ps * inv_n);
-        o[1] = s_t * inv_n;
-        o[2] = s_p * inv_n;
+        o[ss] = s_t * inv_n;
+        o[2 * ss] = s_p * inv_n;
       }
     }
   }
@@ -372,16 +375,16 @@ __device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, 
 template <int MODE>
 __device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayout& L, int i, int j,
                                                bool valid, double* row, int stride,
-                                               const double* vrow_in = nullptr) {
+                                               const double* vrow_in = nullptr, int vss = 1, int rs = 1) {
   const PlanConst& pc = A.pc;
   const int nc = pc.num_comp, kf = pc.kf, n = A.n_free;
   const double wi = (A.weights != nullptr) ? A.weights[i] : 1.0;
   const double tau0 = global_param(A.params, nc, FB_SCATTERING_TIMESCALE);
   const double* vrow = vrow_in ? vrow_in : L.vals + (size_t)threadIdx.x * val_stride(nc);
   if (MODE == MODE_GRAM || MODE == MODE_JAC) {
-    for (int k = 0; k <= n; ++k) row[k] = 0.0;
+    for (int k = 0; k <= n; ++k) row[k * rs] = 0.0;
     if (MODE == MODE_GRAM)
-      for (int k = n + 1; k < stride; ++k) row[k] = 0.0;
+      for (int k = n + 1; k < stride; ++k) row[k * rs] = 0.0;
   }
   if (MODE == MODE_CHI2) row[0] = 0.0;
   if (!valid) return;
@@ -391,9 +394,9 @@ __device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayo
     const CompTab& ct = L.comp[c];
     const ChanTab& ch = L.chan[c];
     SampleComp sc;
-    sc.spectrum = vrow[3 * c];
-    sc.timediff = vrow[3 * c + 1];
-    sc.timeprof = vrow[3 * c + 2];
+    sc.spectrum = vrow[(3 * c) * vss];
+    sc.timediff = vrow[(3 * c + 1) * vss];
+    sc.timeprof = vrow[(3 * c + 2) * vss];
     double amp = ch.amp;
     if (pc.scintillation) {  // analysis/model.py:274-277
       amp = L.scint_amp[c];
@@ -427,8 +430,8 @@ __device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayo
         for (int p = 0; p < 9; ++p) {
           const int col = A.col_of[p];
           if (col < 0) continue;
-          if (is_fit_global(p)) row[col] += -d[p] * wi;
-          else row[col + c] = -d[p] * wi;
+          if (is_fit_global(p)) row[col * rs] += -d[p] * wi;
+          else row[(col + c) * rs] = -d[p] * wi;
         }
       }
     }
@@ -442,10 +445,10 @@ __device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayo
     A.d_out[s_idx] = dsum;
   } else {
     const double r = (A.data[s_idx] - msum) * wi;  // analysis/fitter.py:262-264
-    row[n] = r;
+    row[n * rs] = r;
     if (MODE == MODE_JAC) {
       if (A.jac)
-        for (int k = 0; k < n; ++k) A.jac[s_idx * n + k] = row[k];
+        for (int k = 0; k < n; ++k) A.jac[s_idx * n + k] = row[k * rs];
       if (A.resid) A.resid[s_idx] = r;
     }
   }
@@ -663,7 +666,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_vals(const EvalArgs A, double* __
       load_channel_tables(A, L, i);
       cur = chi;
     }
-    eval_tile(A, L, i, tile, gvals + (size_t)item * kBlock * vs);
+    eval_tile(A, L, i, tile, gvals + (size_t)item * kBlock * vs, 1);
   }
 }
 
@@ -696,7 +699,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_gram2(const EvalArgs A, const dou
       cur = chi;
     }
     const int j = tile * kBlock + tid;
-    process_sample<MODE_GRAM>(A, L, i, j, j < pc.num_time, row, stride, gvals + ((size_t)item * kBlock + tid) * vs);
+    process_sample<MODE_GRAM>(A, L, i, j, j < pc.num_time, row, stride, gvals + (size_t)item * kBlock * vs + tid, kBlock);
     __syncthreads();
     gram_accumulate_parked(L, stride, ntiles, nslices, g_ti, g_tj, g_slice, g_active);
     __syncthreads();
@@ -708,24 +711,133 @@ __global__ void __launch_bounds__(kBlock, 6) k_gram2(const EvalArgs A, const dou
                     A.partials + (size_t)blockIdx.x * ntiles * kTile * kTile);
 }
 
-// Second stage: sums the per-block partial tiles in block order and writes the symmetric
-// (ncols x ncols) matrix.
-__global__ void k_gram_finalize(const double* __restrict__ partials, int nblocks, int ncols,
-                                double* __restrict__ gram) {
+// Stage 2 with FP64 tensor cores. ncu on k_gram2 showed the register-tile Gram limited by shared
+// memory (short-scoreboard + MIO-throttle stalls, 8 LDS per 16 FMA, 24 % bank conflicts), not by
+// the FP64 pipe. mma.sync.m8n8k4.f64 needs ONE shared-memory load per lane per 8-column block and
+// 4-sample step -- the A fragment of block m and the B fragment of block n are the same element
+// X[sample l%4][8 blk + l/4] -- i.e. 60x fewer loads. Each warp stages its own 32 rows
+// (column-major, stride 36 = 4 mod 16: conflict-free for the lane-private writes AND the
+// fragment reads), so a tile needs no block barrier at all; the C fragments of the NB(NB+1)/2
+// upper block pairs stay in registers for the whole kernel.
+constexpr int kMmaRowStride = 36;
+
+__device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__host__ __device__ inline size_t gram_mma_smem_bytes(int nc, int kf, int ncols) {
+  const int nb = (ncols + 7) / 8;
+  return smem_bytes(nc, kf, 1, false, false, 0) + sizeof(double) * (size_t)(kBlock / 32) * nb * 8 * kMmaRowStride;
+}
+
+template <int NB>
+__global__ void __launch_bounds__(kBlock, 6) k_gram2_mma(const EvalArgs A, const double* __restrict__ gvals) {
+  extern __shared__ double smem_raw[];
+  const PlanConst& pc = A.pc;
+  const int nc = pc.num_comp, kf = pc.kf, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  SmemLayout L = carve(smem_raw, nc, kf, false, 0);
+  double* xt = smem_raw + smem_bytes(nc, kf, 1, false, false, 0) / sizeof(double) +
+               (size_t)warp * NB * 8 * kMmaRowStride;  // this warp's [NB*8 columns][36] stage
+  load_comp_tables(A, L);
+  const int ncols = A.n_free + 1;
+  constexpr int kPairs = NB * (NB + 1) / 2;
+  double c0[kPairs], c1[kPairs];
+#pragma unroll
+  for (int k = 0; k < kPairs; ++k) c0[k] = c1[k] = 0.0;
+  // padding columns are never written by process_sample: clear them once
+  for (int e = lane; e < NB * 8 * kMmaRowStride; e += 32) xt[e] = 0.0;
+  __syncwarp();
+  const int tiles = (pc.num_time + kBlock - 1) / kBlock;
+  const int vs = val_stride(nc);
+  const long long total = (long long)A.num_chan * tiles;
+  const long long begin = total * blockIdx.x / gridDim.x, end = total * (blockIdx.x + 1) / gridDim.x;
+  int cur = -1;
+  const int fr = lane & 3, fc = lane >> 2;  // fragment element: sample fr of the step, column fc of the block
+  for (long long item = begin; item < end; ++item) {
+    const int chi = (int)(item / tiles), tile = (int)(item % tiles);
+    const int i = A.chan_list ? A.chan_list[chi] : chi;
+    if (chi != cur) {
+      load_channel_tables(A, L, i);
+      cur = chi;
+    }
+    const int j = tile * kBlock + tid;
+    // [J r] row of this lane's sample -> column `lane` of the warp's stage
+    process_sample<MODE_GRAM>(A, L, i, j, j < pc.num_time, xt + lane, ncols, gvals + (size_t)item * kBlock * vs + tid,
+                              kBlock, kMmaRowStride);
+    __syncwarp();
+#pragma unroll
+    for (int step = 0; step < 8; ++step) {
+      double f[NB];
+#pragma unroll
+      for (int b = 0; b < NB; ++b) f[b] = xt[(8 * b + fc) * kMmaRowStride + 4 * step + fr];
+      int k = 0;
+#pragma unroll
+      for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+        for (int bj = bi; bj < NB; ++bj) {
+          dmma8x8x4(c0[k], c1[k], f[bi], f[bj]);
+          ++k;
+        }
+    }
+    __syncwarp();
+  }
+  // C fragment of pair k: rows 8 bi + lane/4, columns 8 bj + 2 (lane%4) + {0, 1}
+  double* out = A.partials + ((size_t)blockIdx.x * (kBlock / 32) + warp) * kPairs * 64;
+#pragma unroll
+  for (int k = 0; k < kPairs; ++k) {
+    out[k * 64 + (lane >> 2) * 8 + (lane & 3) * 2] = c0[k];
+    out[k * 64 + (lane >> 2) * 8 + (lane & 3) * 2 + 1] = c1[k];
+  }
+}
+
+// Sums the per-warp C fragments and writes the symmetric (ncols x ncols) matrix: one warp per
+// matrix entry, lanes stride over the contributing warps, fixed-shape shuffle tree (deterministic).
+__global__ void __launch_bounds__(256) k_gram_finalize_mma(const double* __restrict__ partials, int nwarps,
+                                                          int ncols, int nb, double* __restrict__ gram) {
+  const int pairs = nb * (nb + 1) / 2;
+  const int e = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (e >= pairs * 64) return;
+  double s = 0.0;
+  for (int w = lane; w < nwarps; w += 32) s += partials[(size_t)w * pairs * 64 + e];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) {
+    int k = e / 64, bi = 0;
+    while (k >= nb - bi) {
+      k -= nb - bi;
+      ++bi;
+    }
+    const int bj = bi + k;
+    const int gr = 8 * bi + (e % 64) / 8, gc = 8 * bj + (e % 8);
+    if (gr < ncols && gc < ncols && (bi != bj || gr <= gc)) {
+      gram[gr * ncols + gc] = s;
+      gram[gc * ncols + gr] = s;
+    }
+  }
+}
+
+// Second stage: sums the per-block partial tiles (one warp per entry, lanes stride over the
+// blocks, fixed-shape shuffle tree) and writes the symmetric (ncols x ncols) matrix.
+__global__ void __launch_bounds__(256) k_gram_finalize(const double* __restrict__ partials, int nblocks,
+                                                      int ncols, double* __restrict__ gram) {
   const int side = gram_side(ncols), ntiles = gram_ntiles(ncols);
   constexpr int kk = kTile * kTile;
-  for (int e = threadIdx.x; e < ntiles * kk; e += blockDim.x) {
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * ntiles * kk + e];
+  const int e = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (e >= ntiles * kk) return;
+  double s = 0.0;
+  for (int b = lane; b < nblocks; b += 32) s += partials[(size_t)b * ntiles * kk + e];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) {
     const int t = e / kk, r = (e % kk) / kTile, q = e % kTile;
     int ti, tj;
     tile_coords(t, side, ti, tj);
     const int gr = ti * kTile + r, gc = tj * kTile + q;
-    if (gr < ncols && gc < ncols) {
-      if (ti != tj || gr <= gc) {
-        gram[gr * ncols + gc] = s;
-        gram[gc * ncols + gr] = s;
-      }
+    if (gr < ncols && gc < ncols && (ti != tj || gr <= gc)) {
+      gram[gr * ncols + gc] = s;
+      gram[gc * ncols + gr] = s;
     }
   }
 }
