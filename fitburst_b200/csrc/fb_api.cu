@@ -441,7 +441,8 @@ static int launch_split_gram(fb_plan_s* p, EvalArgs& A, int ncols, cudaStream_t 
   const int nc = p->pc.num_comp, kf = p->pc.kf;
   const int tiles = (p->pc.num_time + kBlock - 1) / kBlock;
   const long long items = (long long)A.num_chan * tiles;
-  const size_t need_vals = (size_t)items * kBlock * val_stride(nc);
+  A.vals_spc = 2;  // the fit needs spectrum + time difference only
+  const size_t need_vals = (size_t)items * kBlock * 2 * nc;
   if (need_vals > p->vals_cap) {
     cudaFree(p->d_vals);
     p->d_vals = nullptr;

@@ -42,6 +42,9 @@ struct EvalArgs {
   int* err_flag;  // set to 1 on a singular scintillation system (routines/ism.py:46)
   // MODE_CHI2: per-block partial sums of ((data - model) w)^2
   double* chi2_partials;
+  // values stored per (sample, component): 3 = spectrum, timediff, timeprof; 2 = without timeprof
+  // (only the caches and the scintillation solve need the mean profile). 0 means 3.
+  int vals_spc;
 };
 
 __host__ __device__ inline bool is_fit_global(int p) {
@@ -297,21 +300,22 @@ __device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, 
   // slot-major planes (coalesced) when the values go to global memory
   double* vals = vals_out ? vals_out : L.vals;
   const int ts = soa ? 1 : vs, ss = soa ? kBlock : 1;
+  const int spc = A.vals_spc == 2 ? 2 : 3;
   double* v = vals + (size_t)tid * ts;
   if (j < pc.num_time) {
     for (int c = 0; c < nc; ++c) {
       SampleComp sc;
       if (eval_sample_fast(pc, L.comp[c], L.chan[c], L.sub + c * kf, j, sc)) {
-        v[(3 * c) * ss] = sc.spectrum;
-        v[(3 * c + 1) * ss] = sc.timediff;
-        v[(3 * c + 2) * ss] = sc.timeprof;
+        v[(spc * c) * ss] = sc.spectrum;
+        v[(spc * c + 1) * ss] = sc.timediff;
+        if (spc == 3) v[(spc * c + 2) * ss] = sc.timeprof;
       } else if (use_queue) {
         L.queue[atomicAdd(L.qcount, 1)] = (tid << 5) | c;
       } else {
         sc = eval_sample_general(pc, L.comp[c], L.chan[c], L.sub + c * kf, j);
-        v[(3 * c) * ss] = sc.spectrum;
-        v[(3 * c + 1) * ss] = sc.timediff;
-        v[(3 * c + 2) * ss] = sc.timeprof;
+        v[(spc * c) * ss] = sc.spectrum;
+        v[(spc * c + 1) * ss] = sc.timediff;
+        if (spc == 3) v[(spc * c + 2) * ss] = sc.timeprof;
       }
     }
   }
@@ -361,10 +365,10 @@ __device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, 
         s_ps += __shfl_xor_sync(0xffffffffu, s_ps, off);
       }
       if (active && gl == 0) {
-        double* o = vals + (size_t)t_idx * ts + (size_t)(3 * c) * ss;
+        double* o = vals + (size_t)t_idx * ts + (size_t)(spc * c) * ss;
         o[0] = L.comp[c].amp10 * (s_ps * inv_n);
         o[ss] = s_t * inv_n;
-        o[2 * ss] = s_p * inv_n;
+        if (spc == 3) o[2 * ss] = s_p * inv_n;
       }
     }
   }
@@ -394,9 +398,10 @@ __device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayo
     const CompTab& ct = L.comp[c];
     const ChanTab& ch = L.chan[c];
     SampleComp sc;
-    sc.spectrum = vrow[(3 * c) * vss];
-    sc.timediff = vrow[(3 * c + 1) * vss];
-    sc.timeprof = vrow[(3 * c + 2) * vss];
+    const int spc = A.vals_spc == 2 ? 2 : 3;
+    sc.spectrum = vrow[(spc * c) * vss];
+    sc.timediff = vrow[(spc * c + 1) * vss];
+    sc.timeprof = spc == 3 ? vrow[(spc * c + 2) * vss] : 0.0;
     double amp = ch.amp;
     if (pc.scintillation) {  // analysis/model.py:274-277
       amp = L.scint_amp[c];
@@ -655,7 +660,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_vals(const EvalArgs A, double* __
   SmemLayout L = carve(smem_raw, nc, kf, false, SM_QUEUE);
   load_comp_tables(A, L);
   const int tiles = (pc.num_time + kBlock - 1) / kBlock;
-  const int vs = val_stride(nc);
+  const int vs = (A.vals_spc == 2 ? 2 : 3) * nc;  // slot planes per item in global memory
   const long long total = (long long)A.num_chan * tiles;
   const long long begin = total * blockIdx.x / gridDim.x, end = total * (blockIdx.x + 1) / gridDim.x;
   int cur = -1;
@@ -686,7 +691,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_gram2(const EvalArgs A, const dou
 #pragma unroll
   for (int k = 0; k < kTile * kTile; ++k) L.park[k * kBlock + tid] = 0.0;
   const int tiles = (pc.num_time + kBlock - 1) / kBlock;
-  const int vs = val_stride(nc);
+  const int vs = (A.vals_spc == 2 ? 2 : 3) * nc;
   double* row = L.X + (size_t)tid * stride;
   const long long total = (long long)A.num_chan * tiles;
   const long long begin = total * blockIdx.x / gridDim.x, end = total * (blockIdx.x + 1) / gridDim.x;
@@ -750,7 +755,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_gram2_mma(const EvalArgs A, const
   for (int e = lane; e < NB * 8 * kMmaRowStride; e += 32) xt[e] = 0.0;
   __syncwarp();
   const int tiles = (pc.num_time + kBlock - 1) / kBlock;
-  const int vs = val_stride(nc);
+  const int vs = (A.vals_spc == 2 ? 2 : 3) * nc;
   const long long total = (long long)A.num_chan * tiles;
   const long long begin = total * blockIdx.x / gridDim.x, end = total * (blockIdx.x + 1) / gridDim.x;
   int cur = -1;
