@@ -56,6 +56,7 @@ struct fb_plan_s {
   SubTab* d_sub = nullptr;
   ChanTab* d_chan = nullptr;
   bool tables_dirty = true;
+  bool last_eval_split = false;
   double* d_hess_partials = nullptr;
   size_t hess_partials_cap = 0;
   HessPair* d_pairs = nullptr;
@@ -81,6 +82,7 @@ struct fb_plan_s {
   bool gram_cache_valid = false;
   std::vector<double> gram_cache, gram_cache_params;
   const double* gram_cache_data = nullptr;
+  bool vals_match_cache = false;  // d_vals holds k_vals output of the cached evaluation
 };
 
 extern "C" const char* fb_last_error(void) { return g_err; }
@@ -509,6 +511,8 @@ static int normal_equations_async(fb_plan_s* p, const double* data_dev, double* 
   const char* split_env = getenv("FITBURST_B200_SPLIT");
   const bool split = !p->pc.scintillation && !(split_env && !strcmp(split_env, "0"));
   int mma_warps = 0;
+  p->last_eval_split = split;
+  p->vals_match_cache = false;
   if (split) {
     rc = launch_split_gram(p, A, ncols, st, &grid, &mma_warps);
   } else {
@@ -545,6 +549,7 @@ extern "C" int fb_normal_equations(fb_plan_t p, const double* data_dev, double* 
   p->gram_cache_params.assign(p->h_params, p->h_params + (size_t)FB_NUM_PARAMETERS * p->desc.num_components);
   p->gram_cache_data = data_dev;
   p->gram_cache_valid = true;
+  p->vals_match_cache = p->last_eval_split;
   return check_err_flag(p, st);
 }
 
@@ -926,15 +931,18 @@ int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, 
   // after a fit that is normally the last trust-region evaluation, still cached.
   int rc = FB_OK;
   const size_t nparam = (size_t)FB_NUM_PARAMETERS * nc;
+  bool reuse_vals = false;
   if (p->gram_cache_valid && p->gram_cache_data == data_dev && p->gram_cache.size() == (size_t)ncols * ncols &&
       p->gram_cache_params.size() == nparam &&
       memcmp(p->gram_cache_params.data(), p->h_params, sizeof(double) * nparam) == 0) {
     gram = p->gram_cache;
+    reuse_vals = p->vals_match_cache;
   } else {
     rc = normal_equations_async(p, data_dev, p->d_gram, st);
     if (rc != FB_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(gram.data(), p->d_gram, sizeof(double) * ncols * ncols, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    reuse_vals = p->last_eval_split;  // k_vals just ran at these parameters
   }
   if (p->num_good > 0 && !p->pc.scintillation) {
     // fast path: register accumulation of the 30 term values per (sample, component)
@@ -968,6 +976,7 @@ int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, 
     H.desc = p->d_desc;
     H.num_pairs = npairs;
     H.comp_list = p->d_comp_list;
+    H.gvals = reuse_vals ? p->d_vals : nullptr;
     for (int c = 0; c <= nc; ++c) H.comp_off[c] = comp_off[c];
     rc = ensure_tables(p, st);
     if (rc != FB_OK) return rc;

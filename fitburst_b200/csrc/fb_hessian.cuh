@@ -499,6 +499,9 @@ struct HessAccArgs {
   unsigned need[FB_MAX_COMPONENTS];  // term values needed per component
   int need_sum_dmidx;
   double* partials;       // [grid][num_pairs]
+  // (spectrum, timediff) planes left in global memory by k_vals at the SAME parameters
+  // (the last trust-region evaluation); nullptr = evaluate the model here
+  const double* gvals;
 };
 
 __host__ __device__ inline size_t hess_acc_smem_bytes(int nc, int kf, int num_pairs) {
@@ -545,7 +548,15 @@ __global__ void __launch_bounds__(kBlock, 4) k_hessian_acc(const HessAccArgs H) 
     // 1. term inputs (spectrum, timediff) of every component + rho for the super-tile
     for (int t = t_lo; t < t_hi; ++t) {
       double* dst = big + (size_t)(t - t_lo) * kBlock * vs;
-      eval_tile(A, L, i, t, dst);
+      if (H.gvals) {
+        const double* g = H.gvals + ((size_t)chi * tiles + t) * kBlock * 2 * nc + tid;
+        for (int c = 0; c < nc; ++c) {
+          dst[(size_t)tid * vs + 3 * c] = g[(size_t)(2 * c) * kBlock];
+          dst[(size_t)tid * vs + 3 * c + 1] = g[(size_t)(2 * c + 1) * kBlock];
+        }
+      } else {
+        eval_tile(A, L, i, t, dst);
+      }
       const int j = t * kBlock + tid, r = (t - t_lo) * kBlock + tid;
       double rho = 0.0, sdm = 0.0;
       if (j < pc.num_time) {
