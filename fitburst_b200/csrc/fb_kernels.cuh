@@ -387,7 +387,15 @@ __device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayo
   const double tau0 = global_param(A.params, nc, FB_SCATTERING_TIMESCALE);
   const double* vrow = vrow_in ? vrow_in : L.vals + (size_t)threadIdx.x * val_stride(nc);
   if (MODE == MODE_GRAM || MODE == MODE_JAC) {
-    for (int k = 0; k <= n; ++k) row[k * rs] = 0.0;
+    if (!valid) {
+      for (int k = 0; k <= n; ++k) row[k * rs] = 0.0;
+    } else {
+      // per-component columns and the residual are assigned below; only the columns that
+      // accumulate over components start from zero
+#pragma unroll
+      for (int p = 0; p < 9; ++p)
+        if (is_fit_global(p) && A.col_of[p] >= 0) row[A.col_of[p] * rs] = 0.0;
+    }
     if (MODE == MODE_GRAM)
       for (int k = n + 1; k < stride; ++k) row[k * rs] = 0.0;
   }
