@@ -332,7 +332,10 @@ __device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, 
     for (int base = warp * gpw; base < qn; base += nwarps * gpw) {
       const int q = base + g;
       const bool active = q < qn;
-      double s_t = 0.0, s_p = 0.0, s_ps = 0.0;
+      // only the SED-weighted profile sum needs the cross-lane reduction: the mean time
+      // difference has the same closed form as in the fast regimes, and the plain profile mean
+      // is wanted only when the caches / the scintillation solve ask for it (spc == 3)
+      double s_p = 0.0, s_ps = 0.0;
       int t_idx = 0, c = 0;
       if (active) {
         const int item = L.queue[q];
@@ -348,8 +351,7 @@ __device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, 
         for (int pe = gl; pe < npe; pe += gs) {
           double t, p;
           eval_subsample(pc, ct, scattered, sub[a], jj * kt + b, t, p);
-          s_t += t;
-          s_p += p;
+          if (spc == 3) s_p += p;
           s_ps = fma(p, sub[a].sed, s_ps);
           b += db;
           a += da;
@@ -360,14 +362,15 @@ __device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, 
         }
       }
       for (int off = gs >> 1; off > 0; off >>= 1) {
-        s_t += __shfl_xor_sync(0xffffffffu, s_t, off);
-        s_p += __shfl_xor_sync(0xffffffffu, s_p, off);
+        if (spc == 3) s_p += __shfl_xor_sync(0xffffffffu, s_p, off);
         s_ps += __shfl_xor_sync(0xffffffffu, s_ps, off);
       }
       if (active && gl == 0) {
+        const CompTab& ct = L.comp[c];
+        const int jj = tile * kBlock + t_idx;
         double* o = vals + (size_t)t_idx * ts + (size_t)(spc * c) * ss;
-        o[0] = L.comp[c].amp10 * (s_ps * inv_n);
-        o[ss] = s_t * inv_n;
+        o[0] = ct.amp10 * (s_ps * inv_n);
+        o[ss] = fma(ct.t_step, (double)(jj * kt) + 0.5 * (double)(kt - 1), ct.t_start) - L.chan[c].mean_delay;
         if (spc == 3) o[2 * ss] = s_p * inv_n;
       }
     }
