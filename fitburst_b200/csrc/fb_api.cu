@@ -1188,7 +1188,7 @@ extern "C" int fb_chisq_grid(fb_plan_t p, const double* data_dev, const double* 
       A.n_free = 0;
       int grid = 0;
       // per-block partials live in the Gram partial buffer
-      const size_t need = (size_t)p->sm_count * 64;
+      const size_t need = (size_t)p->sm_count * 256;
       if (need > p->partials_cap) {
         cudaFree(p->d_partials);
         p->d_partials = nullptr;
@@ -1197,7 +1197,23 @@ extern "C" int fb_chisq_grid(fb_plan_t p, const double* data_dev, const double* 
         p->partials_cap = need;
       }
       A.chi2_partials = p->d_partials;
-      int rc = launch_eval<MODE_CHI2>(p, A, 1, st, &grid);
+      int rc = FB_OK;
+      if (p->pc.scintillation) {
+        rc = launch_eval<MODE_CHI2>(p, A, 1, st, &grid);
+      } else {
+        rc = ensure_tables(p, st);
+        if (rc != FB_OK) return rc;
+        const size_t smem = smem_bytes(nc, p->pc.kf, 1, false, false, SM_VALS | SM_QUEUE);
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_chi2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 1;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_chi2, kBlock, smem));
+        const long long items = (long long)p->num_good * ((p->pc.num_time + kBlock - 1) / kBlock);
+        grid = (int)std::min<long long>(items, (long long)p->sm_count * std::max(1, occ) * 4);
+        if ((size_t)grid > p->partials_cap) return fail(FB_ERR_INVALID, "chi^2 partial buffer too small");
+        k_chi2<<<grid, kBlock, smem, st>>>(A);
+        CUDA_TRY(cudaGetLastError());
+        p->launches += 1;
+      }
       if (rc != FB_OK) return rc;
       k_chi2_finalize<<<1, 32, 0, st>>>(p->d_partials, grid, chisq_dev + (size_t)a * num_sc + b);
       CUDA_TRY(cudaGetLastError());

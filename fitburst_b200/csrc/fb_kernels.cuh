@@ -898,6 +898,49 @@ __global__ void __launch_bounds__(256) k_gram_finalize(const double* __restrict_
   }
 }
 
+// chi^2 only (grid sweeps, BASELINE.json config 4): the model side of the split evaluation with
+// the residual accumulated in place -- no derivative state, so it runs at k_vals' occupancy.
+__global__ void __launch_bounds__(kBlock, 6) k_chi2(const EvalArgs A) {
+  extern __shared__ double smem_raw[];
+  const PlanConst& pc = A.pc;
+  const int nc = pc.num_comp, kf = pc.kf, tid = threadIdx.x;
+  SmemLayout L = carve(smem_raw, nc, kf, false, SM_VALS | SM_QUEUE);
+  load_comp_tables(A, L);
+  const int tiles = (pc.num_time + kBlock - 1) / kBlock;
+  const int vs = val_stride(nc);
+  const long long total = (long long)A.num_chan * tiles;
+  const long long begin = total * blockIdx.x / gridDim.x, end = total * (blockIdx.x + 1) / gridDim.x;
+  int cur = -1;
+  double acc = 0.0;
+  for (long long item = begin; item < end; ++item) {
+    const int chi = (int)(item / tiles), tile = (int)(item % tiles);
+    const int i = A.chan_list ? A.chan_list[chi] : chi;
+    if (chi != cur) {
+      load_channel_tables(A, L, i);
+      cur = chi;
+    }
+    eval_tile(A, L, i, tile);
+    const int j = tile * kBlock + tid;
+    if (j < pc.num_time) {
+      const double* v = L.vals + (size_t)tid * vs;
+      double msum = 0.0;
+      for (int c = 0; c < nc; ++c) msum += v[3 * c];
+      const double r = (A.data[(size_t)i * pc.num_time + j] - msum) * A.weights[i];
+      acc = fma(r, r, acc);
+    }
+  }
+  // deterministic block tree-sum (the value rows are free again)
+  __syncthreads();
+  double* red = L.vals;
+  red[tid] = acc;
+  __syncthreads();
+  for (int off = kBlock / 2; off > 0; off >>= 1) {
+    if (tid < off) red[tid] += red[tid + off];
+    __syncthreads();
+  }
+  if (tid == 0) A.chi2_partials[blockIdx.x] = red[0];
+}
+
 // Sums per-block chi^2 partials in block order into out[0].
 __global__ void k_chi2_finalize(const double* __restrict__ partials, int nblocks, double* __restrict__ out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
