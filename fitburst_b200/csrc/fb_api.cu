@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "fb_kernels.cuh"
+#include "fb_fast.cuh"
 #include "fb_hessian.cuh"
 #include "fb_batched.cuh"
 #include "fb_preprocess.cuh"
@@ -57,6 +58,9 @@ struct fb_plan_s {
   ChanTab* d_chan = nullptr;
   bool tables_dirty = true;
   bool last_eval_split = false;
+  int vals_layout = 2;       // 2: k_vals planes (spectrum, timediff) per tile; 3: k_vals3 rows (spectrum only)
+  double* d_racc = nullptr;  // k_gram3 accumulators summed over blocks
+  int occ_cache[64];         // occupancy of the fast kernels by instantiation (0 = not queried yet)
   double* d_hess_partials = nullptr;
   size_t hess_partials_cap = 0;
   HessPair* d_pairs = nullptr;
@@ -168,6 +172,7 @@ extern "C" int fb_plan_create(const fb_plan_desc* desc, const double* freqs_host
   chk(cudaMalloc(&p->d_good, nf));
   chk(cudaMalloc(&p->d_err, sizeof(int)));
   chk(cudaMalloc(&p->d_gram, gsz));
+  chk(cudaMalloc(&p->d_racc, sizeof(double) * 64 * 16));
   chk(cudaMalloc(&p->d_comp, sizeof(CompTab) * FB_MAX_COMPONENTS));
   chk(cudaMalloc(&p->d_sub, sizeof(SubTab) * (size_t)nf * desc->num_components * kf));
   chk(cudaMalloc(&p->d_chan, sizeof(ChanTab) * (size_t)nf * desc->num_components));
@@ -182,6 +187,7 @@ extern "C" int fb_plan_create(const fb_plan_desc* desc, const double* freqs_host
   pc.freqs = p->d_freqs;
   pc.subfreqs = p->d_subfreqs;
   memset(p->h_params, 0, sizeof(p->h_params));
+  memset(p->occ_cache, 0, sizeof(p->occ_cache));
   for (int k = 0; k < 9; ++k) p->free_mask[k] = 1;
   layout_free(p);
   *plan_out = p;
@@ -204,6 +210,7 @@ extern "C" int fb_plan_destroy(fb_plan_t p) {
   cudaFree(p->d_pairs);
   cudaFree(p->d_comp_list);
   cudaFree(p->d_vals);
+  cudaFree(p->d_racc);
   cudaFree(p->d_desc);
   cudaFree(p->d_comp);
   cudaFree(p->d_sub);
@@ -408,6 +415,176 @@ extern "C" int fb_set_free_parameters(fb_plan_t p, const int32_t* free_mask, int
   return FB_OK;
 }
 
+// ---- fast evaluation (fb_fast.cuh) ---------------------------------------------------------------
+static bool env_off(const char* name) {
+  const char* v = getenv(name);
+  return v && !strcmp(v, "0");
+}
+
+static int ensure_capacity(double** buf, size_t* cap, size_t need) {
+  if (need <= *cap) return FB_OK;
+  cudaFree(*buf);
+  *buf = nullptr;
+  *cap = 0;
+  CUDA_TRY(cudaMalloc(buf, sizeof(double) * need));
+  *cap = need;
+  return FB_OK;
+}
+
+// Reduced-column layout of k_gram3 for the plan's free-parameter set.
+static GramLayout gram3_layout(const fb_plan_s* p) {
+  const int nc = p->desc.num_components;
+  GramLayout G;
+  int r = 0;
+  const bool has_s = p->col_of[FB_AMPLITUDE] >= 0 || p->col_of[FB_SPECTRAL_INDEX] >= 0 ||
+                     p->col_of[FB_SPECTRAL_RUNNING] >= 0;
+  G.rc_S = has_s ? r : -1;
+  r += has_s ? nc : 0;
+  G.rc_t = p->col_of[FB_ARRIVAL_TIME] >= 0 ? r : -1;
+  r += G.rc_t >= 0 ? nc : 0;
+  G.rc_w = p->col_of[FB_BURST_WIDTH] >= 0 ? r : -1;
+  r += G.rc_w >= 0 ? nc : 0;
+  G.rc_dm = p->col_of[FB_DM] >= 0 ? r++ : -1;
+  G.rc_dmidx = p->col_of[FB_DM_INDEX] >= 0 ? r++ : -1;
+  G.rc_tau = p->col_of[FB_SCATTERING_TIMESCALE] >= 0 ? r++ : -1;
+  G.rc_alpha = p->col_of[FB_SCATTERING_INDEX] >= 0 ? r++ : -1;
+  G.rc_res = r++;
+  G.nr = r;
+  return G;
+}
+
+// The fast kernels cover the scattered, unfolded, non-scintillating model with up to 4 components.
+static bool fast_path_ok(const fb_plan_s* p, bool for_gram) {
+  if (env_off("FITBURST_B200_FAST")) return false;
+  const int nc = p->desc.num_components;
+  if (p->pc.scintillation || p->pc.is_folded || nc > 4) return false;
+  if (!(p->h_params[FB_SCATTERING_TIMESCALE * nc] > 0.0)) return false;
+  for (int c = 0; c < nc; ++c) {
+    if (!(p->h_params[FB_BURST_WIDTH * nc + c] > 0.0)) return false;
+    if (!(p->h_params[FB_REF_FREQ * nc + c] > 0.0)) return false;
+  }
+  if (for_gram && gram3_layout(p).nr > 24) return false;
+  return true;
+}
+
+template <int KF, bool CHI2>
+static int launch_vals3_t(fb_plan_s* p, const EvalArgs& A, double* out, cudaStream_t st, int* grid_out) {
+  const int nc = p->pc.num_comp, kf = p->pc.kf;
+  const size_t smem = vals3_smem_bytes(nc, kf);
+  if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request exceeds 227 KB");
+  int& occ = p->occ_cache[(CHI2 ? 8 : 0) + (KF == 0 ? 0 : KF == 1 ? 1 : KF == 2 ? 2 : KF == 4 ? 3 : 4)];
+  if (occ == 0 || KF == 0) {
+    if (smem > 48 * 1024)
+      CUDA_TRY(cudaFuncSetAttribute(k_vals3<KF, CHI2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_vals3<KF, CHI2>, kFastBlock, smem));
+    if (occ < 1) occ = 1;
+  }
+  const int grid = std::min(A.num_chan, p->sm_count * occ);
+  k_vals3<KF, CHI2><<<grid, kFastBlock, smem, st>>>(A, out);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 1;
+  if (grid_out) *grid_out = grid;
+  return FB_OK;
+}
+
+template <bool CHI2>
+static int launch_vals3(fb_plan_s* p, const EvalArgs& A, double* out, cudaStream_t st, int* grid_out) {
+  switch (p->pc.kf) {
+    case 1: return launch_vals3_t<1, CHI2>(p, A, out, st, grid_out);
+    case 2: return launch_vals3_t<2, CHI2>(p, A, out, st, grid_out);
+    case 4: return launch_vals3_t<4, CHI2>(p, A, out, st, grid_out);
+    case 8: return launch_vals3_t<8, CHI2>(p, A, out, st, grid_out);
+    default: return launch_vals3_t<0, CHI2>(p, A, out, st, grid_out);
+  }
+}
+
+template <int NC, int NB>
+static int launch_gram3_t(fb_plan_s* p, const EvalArgs& A, const GramLayout& G, cudaStream_t st, int* grid_out) {
+  const size_t smem = gram3_smem_bytes(NC, NB);
+  int& occ = p->occ_cache[16 + (NC - 1) * 3 + (NB - 1)];
+  if (occ == 0) {
+    if (smem > 48 * 1024)
+      CUDA_TRY(cudaFuncSetAttribute(k_gram3<NC, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gram3<NC, NB>, kFastBlock, smem));
+    if (occ < 1) occ = 1;
+  }
+  const int grid = std::min(A.num_chan, p->sm_count * occ);
+  int rc = ensure_capacity(&p->d_partials, &p->partials_cap, (size_t)grid * g3_nacc(NB) * 64);
+  if (rc != FB_OK) return rc;
+  EvalArgs B = A;
+  B.partials = p->d_partials;
+  k_gram3<NC, NB><<<grid, kFastBlock, smem, st>>>(B, G, p->d_vals);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 1;
+  *grid_out = grid;
+  return FB_OK;
+}
+
+template <int NC>
+static int launch_gram3_nc(fb_plan_s* p, const EvalArgs& A, const GramLayout& G, int nb, cudaStream_t st, int* grid_out) {
+  switch (nb) {
+    case 1: return launch_gram3_t<NC, 1>(p, A, G, st, grid_out);
+    case 2: return launch_gram3_t<NC, 2>(p, A, G, st, grid_out);
+    default: return launch_gram3_t<NC, 3>(p, A, G, st, grid_out);
+  }
+}
+
+// k_vals3 + k_gram3 + reduction + expansion into the full (n+1)^2 matrix at gram_dev.
+static int launch_fast_gram(fb_plan_s* p, EvalArgs& A, int ncols, double* gram_dev, cudaStream_t st) {
+  int rc = ensure_tables(p, st);
+  if (rc != FB_OK) return rc;
+  const int nc = p->pc.num_comp, nt = p->pc.num_time;
+  rc = ensure_capacity(&p->d_vals, &p->vals_cap, (size_t)A.num_chan * nc * nt);
+  if (rc != FB_OK) return rc;
+  rc = launch_vals3<false>(p, A, p->d_vals, st, nullptr);
+  if (rc != FB_OK) return rc;
+  const GramLayout G = gram3_layout(p);
+  const int nb = (G.nr + 7) / 8;
+  int grid = 0;
+  switch (nc) {
+    case 1: rc = launch_gram3_nc<1>(p, A, G, nb, st, &grid); break;
+    case 2: rc = launch_gram3_nc<2>(p, A, G, nb, st, &grid); break;
+    case 3: rc = launch_gram3_nc<3>(p, A, G, nb, st, &grid); break;
+    default: rc = launch_gram3_nc<4>(p, A, G, nb, st, &grid); break;
+  }
+  if (rc != FB_OK) return rc;
+  const int entries = g3_nacc(nb) * 64;
+  k_gram3_reduce<<<(entries + 7) / 8, 256, 0, st>>>(p->d_partials, grid, entries, p->d_racc);
+  CUDA_TRY(cudaGetLastError());
+  ExpandArgs X;
+  memset(&X, 0, sizeof(X));
+  X.ncols = ncols;
+  X.nb = nb;
+  const double ref0 = p->h_params[FB_REF_FREQ * nc];
+  for (int k = 0; k < 9; ++k) {
+    const int col = p->col_of[k];
+    if (col < 0) continue;
+    if (is_fit_global(k)) {
+      X.red[col] = k == FB_DM ? G.rc_dm : k == FB_DM_INDEX ? G.rc_dmidx : k == FB_SCATTERING_TIMESCALE ? G.rc_tau : G.rc_alpha;
+      X.power[col] = 0;
+      X.factor[col] = 1.0;
+      X.shift[col] = 0.0;
+      continue;
+    }
+    for (int c = 0; c < nc; ++c) {
+      const bool spectral = k == FB_AMPLITUDE || k == FB_SPECTRAL_INDEX || k == FB_SPECTRAL_RUNNING;
+      X.red[col + c] = (spectral ? G.rc_S : k == FB_ARRIVAL_TIME ? G.rc_t : G.rc_w) + c;
+      X.power[col + c] = k == FB_SPECTRAL_INDEX ? 1 : k == FB_SPECTRAL_RUNNING ? 2 : 0;
+      X.factor[col + c] = k == FB_AMPLITUDE ? kLn10 : 1.0;
+      // ln(f / ref_c) = ln(f / ref_0) + ln(ref_0 / ref_c)
+      X.shift[col + c] = spectral ? log(ref0 / p->h_params[FB_REF_FREQ * nc + c]) : 0.0;
+    }
+  }
+  X.red[ncols - 1] = G.rc_res;
+  X.power[ncols - 1] = 0;
+  X.factor[ncols - 1] = 1.0;
+  X.shift[ncols - 1] = 0.0;
+  k_gram3_expand<<<(ncols * ncols + 255) / 256, 256, 0, st>>>(p->d_racc, X, gram_dev);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 2;
+  return FB_OK;
+}
+
 // Two-kernel evaluation (k_vals + k_gram2 / k_gram2_mma), see fb_kernels.cuh "split evaluation".
 // *mma_warps_out > 0 tells the caller to finalize with k_gram_finalize_mma.
 template <int NB>
@@ -513,6 +690,11 @@ static int normal_equations_async(fb_plan_s* p, const double* data_dev, double* 
   int mma_warps = 0;
   p->last_eval_split = split;
   p->vals_match_cache = false;
+  if (split && fast_path_ok(p, true)) {
+    p->vals_layout = 3;
+    return launch_fast_gram(p, A, ncols, gram_dev, st);
+  }
+  p->vals_layout = 2;
   if (split) {
     rc = launch_split_gram(p, A, ncols, st, &grid, &mma_warps);
   } else {
@@ -977,6 +1159,7 @@ int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, 
     H.num_pairs = npairs;
     H.comp_list = p->d_comp_list;
     H.gvals = reuse_vals ? p->d_vals : nullptr;
+    H.gvals_layout = p->vals_layout;
     for (int c = 0; c <= nc; ++c) H.comp_off[c] = comp_off[c];
     rc = ensure_tables(p, st);
     if (rc != FB_OK) return rc;

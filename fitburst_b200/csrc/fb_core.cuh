@@ -74,7 +74,10 @@ struct ChanTab {
   double ref_freq;
   int scattered;      // any(sc_time(f_ia) > 0) over the sub-frequencies, analysis/model.py:339
   int fast_ok;        // regime fast paths usable (scattered, not folded, finite tables)
+  int pad_[2];        // sizeof % 16 == 0: the fast kernels stage the tables with 16-byte cp.async
 };
+static_assert(sizeof(ChanTab) % 16 == 0 && sizeof(SubTab) % 16 == 0 && sizeof(CompTab) % 16 == 0,
+              "tables are staged in 16-byte chunks");
 
 __host__ __device__ inline double global_param(const double* params, int nc, int p) {
   return params[p * nc];  // element 0 is used for all components, analysis/model.py:155-159

@@ -1,0 +1,527 @@
+// fitburst_b200 fast evaluation: warp-granular kernels for the common case of the fit
+// (scattered branch, not folded, no per-channel scintillation amplitudes).
+//
+// The block-granular kernels of fb_kernels.cuh treat every sample alike and pay for their
+// generality in instruction issue (ncu, config 2: k_vals 5.4e8 warp instructions of which ~40 %
+// are the exp of the exponential tail and ~35 % loop / queue / addressing overhead; k_gram2_mma
+// 2.5e8 of which ~20 % is the run-time column scatter). Here
+//
+//   k_vals3   a block owns one channel at a time, its warps take 32-sample tiles from a shared
+//             counter. Per (tile, component) the three regimes of the scattered profile
+//             (fb_core.cuh: clamp plateau / rise / exponential tail) are decided WARP-wide:
+//             * a tile wholly in the tail needs no exp per sample at all: with
+//               u0(j0 + lane) = u0(j0) + lane kt step the kf geometric series factorise into
+//               B[a] = exp(tail_e[a] - u0(j0) / tau[a])        (one exp per lane per tile, all
+//                                                                components at once)
+//               R[a][lane] = 10^A sed[a] tail_c[a] exp(-lane kt step / tau[a])   (per channel)
+//               and the spectrum value is the kf-term dot product sum_a B[a] R[a][lane];
+//             * a tile wholly on the plateau stores a table constant;
+//             * in the one or two mixed tiles per (channel, component) the samples that need
+//               the general exp + erfcx sub-grid are evaluated one after the other by the whole
+//               warp (one sub-sample per lane, shuffle reduction).
+//             Only the spectrum value goes to global memory: the mean time difference is a
+//             closed form of the sample index (fb_core.cuh: eval_sample_fast) and is recomputed
+//             by its consumers.
+//   k_gram3   derivative side on the FP64 tensor cores over the REDUCED column set. The
+//             amplitude / spectral_index / spectral_running columns of a component are the
+//             spectrum times per-channel factors (ln 10, L, L^2 with L = ln(f / ref_freq),
+//             routines/derivative.py:454-530,880-936), and the weight is per channel too
+//             (analysis/fitter.py:506-542), so per sample only [S_c, dt_c, dw_c, globals, r] are
+//             staged (14 instead of 18 columns at config 2: 2 instead of 3 column blocks, 24
+//             instead of 48 DMMA per 32 samples); at the end of a channel the C fragments are
+//             folded into the accumulators of w^2 L^p (p = 0..4) and cleared, and
+//             k_gram3_expand rebuilds the full [J r]^T [J r].
+#pragma once
+#include "fb_kernels.cuh"
+
+namespace fb {
+
+constexpr int kFastBlock = 256;
+constexpr int kFastWarps = kFastBlock / 32;
+constexpr unsigned kFullMask = 0xffffffffu;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gmem_src) : "memory");
+}
+
+// ---- model side ---------------------------------------------------------------------------
+__host__ __device__ inline int vals3_bw_stride(int nck) { return (nck + 31) & ~31; }
+
+__host__ __device__ inline size_t vals3_smem_bytes(int nc, int kf) {
+  size_t n = 0;
+  n += sizeof(CompTab) * nc;
+  n += 2 * (sizeof(ChanTab) * nc + sizeof(SubTab) * nc * kf);  // double-buffered channel tables
+  n += sizeof(double) * (size_t)nc * kf * 32;                 // R
+  n += sizeof(double) * (size_t)kFastWarps * vals3_bw_stride(nc * kf);  // B per warp
+  n += sizeof(double) * kFastWarps;                           // chi^2 block reduction
+  n += 16;                                                    // tile counter
+  return n;
+}
+
+// Spectrum value of component c for the 32 samples of warp tile `wt` (one per lane).
+template <int KF>
+__device__ __forceinline__ double vals3_component(const PlanConst& pc, const CompTab& ct, const ChanTab& ch,
+                                                  const SubTab* __restrict__ sb, const double* __restrict__ r_lane,
+                                                  const double* __restrict__ bw, int j0, int lane, bool valid,
+                                                  unsigned vmask) {
+  const int kf = KF > 0 ? KF : pc.kf, kt = pc.kt, n = pc.ntk;
+  const int npe = kf * kt;
+  const int j = j0 + lane;
+  const int m0 = j * kt;
+  const double u0 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, m0, n);
+  const double u_last = linspace_at(ct.t_start, ct.t_step, ct.t_stop, m0 + kt - 1, n);
+  const bool fast = ch.fast_ok != 0;
+  const bool plateau = fast && (u_last - ch.min_delay) < ct.neg5w;
+  const bool tail = fast && !plateau && u0 >= ch.tail_lo;
+  const unsigned tm = __ballot_sync(kFullMask, tail && valid);
+  if (tm == vmask) {
+    double s = 0.0;
+#pragma unroll
+    for (int a = 0; a < kf; ++a) s = fma(bw[a], r_lane[a * 32], s);
+    return s;
+  }
+  const unsigned gm = __ballot_sync(kFullMask, valid && !plateau && !tail);
+  double val = 0.0;
+  if (plateau) {
+    val = ch.plateau_ps;
+  } else if (tail) {
+    double s_ps = 0.0;
+#pragma unroll 4
+    for (int a = 0; a < kf; ++a) {
+      const SubTab& st = sb[a];
+      const double earg = fma(-u0, st.inv_tau, st.tail_e);
+      const double p = (earg < -746.0) ? 0.0 : st.tail_c * fb_exp(earg);
+      s_ps = fma(p, st.sed, s_ps);
+    }
+    val = ct.amp10 * s_ps;
+  }
+  if (gm == 0u) return val;
+  if (npe >= 16) {
+    // rise / peak region: the whole warp evaluates the sub-grid of one sample at a time
+    const double inv_n = 1.0 / (double)npe;
+    unsigned rem = gm;
+    while (rem) {
+      const int s = __ffs(rem) - 1;
+      rem &= rem - 1;
+      const int jj = j0 + s;
+      double s_ps = 0.0;
+      for (int pe = lane; pe < npe; pe += 32) {
+        const int b = pe / kf, a = pe - b * kf;
+        double t, p;
+        eval_subsample(pc, ct, ch.scattered, sb[a], jj * kt + b, t, p);
+        s_ps = fma(p, sb[a].sed, s_ps);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) s_ps += __shfl_xor_sync(kFullMask, s_ps, off);
+      if (lane == s) val = ct.amp10 * (s_ps * inv_n);
+    }
+  } else if ((gm >> lane) & 1u) {
+    val = eval_sample_general(pc, ct, ch, sb, j).spectrum;
+  }
+  return val;
+}
+
+// CHI2 = false: stores the spectrum values, gvals[(chi * nc + c) * num_time + j].
+// CHI2 = true : accumulates sum(((data - model) w)^2) into chi2_partials[blockIdx.x] instead.
+template <int KF, bool CHI2>
+__global__ void __launch_bounds__(kFastBlock, 3) k_vals3(const EvalArgs A, double* __restrict__ gvals) {
+  extern __shared__ __align__(16) unsigned char fast_smem[];
+  const PlanConst& pc = A.pc;
+  const int nc = pc.num_comp, kf = KF > 0 ? KF : pc.kf, kt = pc.kt, nt = pc.num_time;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nck = nc * kf;
+  char* sp = reinterpret_cast<char*>(fast_smem);
+  CompTab* comp = reinterpret_cast<CompTab*>(sp);
+  sp += sizeof(CompTab) * nc;
+  const size_t tab_bytes = sizeof(ChanTab) * nc + sizeof(SubTab) * nck;
+  char* tabs = sp;  // [2][ChanTab nc | SubTab nc*kf]
+  sp += 2 * tab_bytes;
+  double* R = reinterpret_cast<double*>(sp);
+  sp += sizeof(double) * (size_t)nck * 32;
+  const int bws = vals3_bw_stride(nck);
+  double* bw = reinterpret_cast<double*>(sp) + (size_t)warp * bws;
+  sp += sizeof(double) * (size_t)kFastWarps * bws;
+  double* red = reinterpret_cast<double*>(sp);
+  sp += sizeof(double) * kFastWarps;
+  int* next = reinterpret_cast<int*>(sp);
+
+  {
+    const double* src = reinterpret_cast<const double*>(A.g_comp);
+    double* dst = reinterpret_cast<double*>(comp);
+    for (int e = tid; e < nc * (int)(sizeof(CompTab) / sizeof(double)); e += kFastBlock) dst[e] = src[e];
+  }
+  const int wtiles = (nt + 31) / 32;
+  const int chan_chunks = (int)(sizeof(ChanTab) * nc / 16), sub_chunks = (int)(sizeof(SubTab) * nck / 16);
+  auto prefetch_tables = [&](int chi, int buf) {
+    if (chi < A.num_chan) {
+      const int i = A.chan_list ? A.chan_list[chi] : chi;
+      char* dst = tabs + (size_t)buf * tab_bytes;
+      const char* src_c = reinterpret_cast<const char*>(A.g_chan + (size_t)i * nc);
+      const char* src_s = reinterpret_cast<const char*>(A.g_sub + (size_t)i * nck);
+      for (int e = tid; e < chan_chunks; e += kFastBlock) cp_async16(dst + 16 * e, src_c + 16 * e);
+      for (int e = tid; e < sub_chunks; e += kFastBlock)
+        cp_async16(dst + sizeof(ChanTab) * nc + 16 * e, src_s + 16 * e);
+    }
+    cp_async_commit();
+  };
+  double chi2_acc = 0.0;
+  prefetch_tables(blockIdx.x, 0);
+  int buf = 0;
+  for (int chi = blockIdx.x; chi < A.num_chan; chi += gridDim.x, buf ^= 1) {
+    const int i = A.chan_list ? A.chan_list[chi] : chi;
+    cp_async_wait<0>();
+    __syncthreads();  // tables of this channel landed; every warp is done with the previous one
+    prefetch_tables(chi + gridDim.x, buf ^ 1);
+    const ChanTab* chan = reinterpret_cast<const ChanTab*>(tabs + (size_t)buf * tab_bytes);
+    const SubTab* sub = reinterpret_cast<const SubTab*>(tabs + (size_t)buf * tab_bytes + sizeof(ChanTab) * nc);
+    if (tid == 0) *next = 0;
+    for (int e = tid; e < nck * 32; e += kFastBlock) {
+      const int l = e & 31, ca = e >> 5, c = ca / kf;
+      const SubTab& st = sub[ca];
+      const double decay = fb_exp(-((double)(l * kt) * comp[c].t_step) * st.inv_tau);
+      R[e] = ((comp[c].amp10 * st.tail_c) * st.sed) * decay;
+    }
+    __syncthreads();
+    const double wi = CHI2 ? A.weights[i] : 0.0;
+    for (;;) {
+      int wt = 0;
+      if (lane == 0) wt = atomicAdd(next, 1);
+      wt = __shfl_sync(kFullMask, wt, 0);
+      if (wt >= wtiles) break;
+      const int j0 = wt * 32, j = j0 + lane;
+      const bool valid = j < nt;
+      const unsigned vmask = __ballot_sync(kFullMask, valid);
+      // tail base factors of every (component, sub-frequency) of this tile, one per lane
+      for (int e = lane; e < nck; e += 32) {
+        const CompTab& ct = comp[e / kf];
+        const double u0b = linspace_at(ct.t_start, ct.t_step, ct.t_stop, j0 * kt, pc.ntk);
+        const double earg = fma(-u0b, sub[e].inv_tau, sub[e].tail_e);
+        bw[e] = (earg < -746.0) ? 0.0 : fb_exp(earg);
+      }
+      __syncwarp();
+      double msum = 0.0;
+      for (int c = 0; c < nc; ++c) {
+        const double v = vals3_component<KF>(pc, comp[c], chan[c], sub + c * kf, R + (size_t)c * kf * 32 + lane,
+                                             bw + c * kf, j0, lane, valid, vmask);
+        if (CHI2) msum += v;
+        else if (valid) gvals[((size_t)chi * nc + c) * nt + j] = v;
+      }
+      if (CHI2 && valid) {
+        const double r = (A.data[(size_t)i * nt + j] - msum) * wi;
+        chi2_acc = fma(r, r, chi2_acc);
+      }
+      __syncwarp();
+    }
+  }
+  cp_async_wait<0>();
+  if (CHI2) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) chi2_acc += __shfl_xor_sync(kFullMask, chi2_acc, off);
+    __syncthreads();
+    if (lane == 0) red[warp] = chi2_acc;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int w = 0; w < kFastWarps; ++w) s += red[w];
+      A.chi2_partials[blockIdx.x] = s;
+    }
+  }
+}
+
+// ---- derivative side ------------------------------------------------------------------------
+// Reduced column layout (first column of every group, -1 = not fitted); built on the host.
+struct GramLayout {
+  int rc_S, rc_t, rc_w;                    // per-component groups: nc columns each
+  int rc_dm, rc_dmidx, rc_tau, rc_alpha;   // global parameters: one column each (summed over components)
+  int rc_res;                              // residual column = nr - 1
+  int nr;                                  // number of reduced columns
+};
+
+// Per (channel, component) constants of the scattered-branch first derivatives
+// (routines/derivative.py:14-152,454-936 evaluated at the channel centre).
+struct GTab {
+  double inv_tau, ws, k2, h, ws2, g0, a_w, a_tau, a_alpha, lf, d_dm, d_dmidx, mean_delay;
+};
+
+__host__ __device__ constexpr int g3_pairs(int nb) { return nb * (nb + 1) / 2; }
+// powers of L kept for the block pair (bi, bj): the spectrum columns live in block 0
+__host__ __device__ constexpr int g3_npow(int bi, int bj) { return bi == 0 ? (bj == 0 ? 5 : 3) : 1; }
+__host__ __device__ constexpr int g3_acc_offset(int nb, int bi, int bj) {
+  int off = 0;
+  for (int i = 0; i < nb; ++i)
+    for (int j = i; j < nb; ++j) {
+      if (i == bi && j == bj) return off;
+      off += g3_npow(i, j);
+    }
+  return off;
+}
+__host__ __device__ constexpr int g3_nacc(int nb) { return g3_acc_offset(nb, nb, nb); }
+
+__host__ __device__ inline size_t gram3_smem_bytes(int nc, int nb) {
+  size_t stage = sizeof(double) * (size_t)kFastWarps * nb * 8 * kMmaRowStride;
+  const size_t red = sizeof(double) * (size_t)kFastWarps * g3_nacc(nb) * 64;
+  if (red > stage) stage = red;  // the stage doubles as the block-reduction buffer
+  return sizeof(CompTab) * nc + 2 * sizeof(ChanTab) * nc + sizeof(GTab) * nc + stage;
+}
+
+template <int NC, int NB>
+__global__ void __launch_bounds__(kFastBlock, 3) k_gram3(const EvalArgs A, const GramLayout G,
+                                                         const double* __restrict__ gvals) {
+  extern __shared__ __align__(16) unsigned char fast_smem[];
+  const PlanConst& pc = A.pc;
+  const int kt = pc.kt, nt = pc.num_time;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  char* sp = reinterpret_cast<char*>(fast_smem);
+  CompTab* comp = reinterpret_cast<CompTab*>(sp);
+  sp += sizeof(CompTab) * NC;
+  char* tabs = sp;  // [2][ChanTab NC]
+  sp += 2 * sizeof(ChanTab) * NC;
+  GTab* gt = reinterpret_cast<GTab*>(sp);
+  sp += sizeof(GTab) * NC;
+  double* stage_all = reinterpret_cast<double*>(sp);
+  double* xt = stage_all + (size_t)warp * NB * 8 * kMmaRowStride;  // this warp's [NB*8 columns][36]
+
+  {
+    const double* src = reinterpret_cast<const double*>(A.g_comp);
+    double* dst = reinterpret_cast<double*>(comp);
+    for (int e = tid; e < NC * (int)(sizeof(CompTab) / sizeof(double)); e += kFastBlock) dst[e] = src[e];
+  }
+  for (int e = lane; e < NB * 8 * kMmaRowStride; e += 32) xt[e] = 0.0;  // padding columns stay zero
+
+  constexpr int kPairs = g3_pairs(NB), kAcc = g3_nacc(NB);
+  double c0[kPairs], c1[kPairs], acc0[kAcc], acc1[kAcc];
+#pragma unroll
+  for (int k = 0; k < kPairs; ++k) c0[k] = c1[k] = 0.0;
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) acc0[k] = acc1[k] = 0.0;
+
+  const int wtiles = (nt + 31) / 32;
+  const int chan_chunks = (int)(sizeof(ChanTab) * NC / 16);
+  auto prefetch_tables = [&](int chi, int buf) {
+    if (chi < A.num_chan && tid < chan_chunks) {
+      const int i = A.chan_list ? A.chan_list[chi] : chi;
+      cp_async16(tabs + (size_t)buf * sizeof(ChanTab) * NC + 16 * tid,
+                 reinterpret_cast<const char*>(A.g_chan + (size_t)i * NC) + 16 * tid);
+    }
+    cp_async_commit();
+  };
+  const double tau0 = global_param(A.params, NC, FB_SCATTERING_TIMESCALE);
+  const double inv_tau0 = 1.0 / tau0;
+  const double kt_mid = 0.5 * (double)(kt - 1);
+  const int fr = lane & 3, fc = lane >> 2;  // fragment element: sample fr of the step, column fc of the block
+  prefetch_tables(blockIdx.x, 0);
+  int buf = 0;
+  for (int chi = blockIdx.x; chi < A.num_chan; chi += gridDim.x, buf ^= 1) {
+    const int i = A.chan_list ? A.chan_list[chi] : chi;
+    cp_async_wait<0>();
+    __syncthreads();
+    prefetch_tables(chi + gridDim.x, buf ^ 1);
+    const ChanTab* chan = reinterpret_cast<const ChanTab*>(tabs + (size_t)buf * sizeof(ChanTab) * NC);
+    if (tid < NC) {
+      const ChanTab& ch = chan[tid];
+      const ChanTab& ch0 = chan[0];
+      const CompTab& ct = comp[tid];
+      GTab t;
+      t.inv_tau = ch.inv_tau;
+      t.ws = ct.w * ch.inv_tau;
+      t.k2 = t.ws * kSqrtHalf;
+      t.ws2 = t.ws * t.ws;
+      t.h = 0.5 * t.ws2;
+      t.g0 = ch.amp * ch.amp_pbf * kTwoOverSqrtPi;
+      t.a_w = ch.dap_w * ch.inv_apbf + t.ws * ch.inv_tau;
+      // LSFitter.compute_jacobian passes component 0 to the global derivative functions, which
+      // look deriv_amplitude_pbf up with it (analysis/fitter.py:213-223, routines/derivative.py:847,916)
+      t.a_tau = ch0.dap_tau * ch.inv_apbf;
+      t.a_alpha = ch0.dap_alpha * ch.inv_apbf;
+      t.lf = ch.logf;
+      t.d_dm = ch.d_dm;
+      t.d_dmidx = ch.d_dmidx;
+      t.mean_delay = ch.mean_delay;
+      gt[tid] = t;
+    }
+    __syncthreads();
+    bool std_ok = true;  // every component on the scattered branch at this channel
+#pragma unroll
+    for (int c = 0; c < NC; ++c) std_ok = std_ok && (chan[c].sc_time != 0.0);
+
+    const double* srow = gvals + (size_t)chi * NC * nt;
+    const double* drow = A.data + (size_t)i * nt;
+    for (int wt = warp; wt < wtiles; wt += kFastWarps) {
+      const int j = wt * 32 + lane;
+      const bool valid = j < nt;
+      double m[NC], dval = 0.0;
+      if (valid) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) m[c] = __ldg(srow + (size_t)c * nt + j);
+        dval = __ldg(drow + j);
+      } else {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) m[c] = 0.0;
+      }
+      double msum = 0.0, s_dm = 0.0, s_dmidx = 0.0, s_tau = 0.0, s_alpha = 0.0;
+      double* row = xt + lane;
+      const double tj = (double)(j * kt) + kt_mid;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) {
+        const CompTab& ct = comp[c];
+        const GTab& t = gt[c];
+        const double td = fma(ct.t_step, tj, ct.t_start) - t.mean_delay;
+        const double mc = m[c];
+        double d_t, d_w, d_tau, d_alpha, d_dm, d_dmidx;
+        if (std_ok) {
+          const double k1 = ct.inv_w * kSqrtHalf;
+          const double arg_erf = (td - ct.w * ct.w * t.inv_tau) * ct.inv_w * kSqrtHalf;
+          const double arg_exp = t.h - td * t.inv_tau - arg_erf * arg_erf;
+          const double g = (arg_exp < -746.0) ? 0.0 : t.g0 * fb_exp(arg_exp);
+          const double gs = g * k1;
+          const double mt = mc * t.inv_tau;
+          d_t = mt - gs;
+          d_w = mc * t.a_w - gs * (td * ct.inv_w + t.ws);
+          const double u = td * t.inv_tau - t.ws2;
+          const double gtt = g * t.k2;
+          d_tau = mc * (t.a_tau + u * inv_tau0) + gtt * inv_tau0;
+          d_alpha = mc * (t.a_alpha + t.lf * u) + gtt * t.lf;
+          d_dm = -t.d_dm * d_t;
+          d_dmidx = -t.d_dmidx * d_t;
+        } else {
+          double d[9], gfac;
+          first_derivatives(chan[c], chan[c], ct, tau0, chan[c].amp, mc, td, d, &gfac);
+          d[FB_SCATTERING_TIMESCALE] += mc * (chan[0].dap_tau - chan[c].dap_tau) * chan[c].inv_apbf;
+          d[FB_SCATTERING_INDEX] += mc * (chan[0].dap_alpha - chan[c].dap_alpha) * chan[c].inv_apbf;
+          d_t = d[FB_ARRIVAL_TIME];
+          d_w = d[FB_BURST_WIDTH];
+          d_tau = d[FB_SCATTERING_TIMESCALE];
+          d_alpha = d[FB_SCATTERING_INDEX];
+          d_dm = d[FB_DM];
+          d_dmidx = d[FB_DM_INDEX];
+        }
+        msum += mc;
+        s_dm += d_dm;
+        s_dmidx += d_dmidx;
+        s_tau += d_tau;
+        s_alpha += d_alpha;
+        if (G.rc_S >= 0) row[(G.rc_S + c) * kMmaRowStride] = -mc;
+        if (G.rc_t >= 0) row[(G.rc_t + c) * kMmaRowStride] = valid ? -d_t : 0.0;
+        if (G.rc_w >= 0) row[(G.rc_w + c) * kMmaRowStride] = valid ? -d_w : 0.0;
+      }
+      if (G.rc_dm >= 0) row[G.rc_dm * kMmaRowStride] = valid ? -s_dm : 0.0;
+      if (G.rc_dmidx >= 0) row[G.rc_dmidx * kMmaRowStride] = valid ? -s_dmidx : 0.0;
+      if (G.rc_tau >= 0) row[G.rc_tau * kMmaRowStride] = valid ? -s_tau : 0.0;
+      if (G.rc_alpha >= 0) row[G.rc_alpha * kMmaRowStride] = valid ? -s_alpha : 0.0;
+      row[G.rc_res * kMmaRowStride] = valid ? dval - msum : 0.0;  // analysis/fitter.py:262-264 (weight at the flush)
+      __syncwarp();
+#pragma unroll
+      for (int step = 0; step < 8; ++step) {
+        double f[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) f[b] = xt[(8 * b + fc) * kMmaRowStride + 4 * step + fr];
+        int k = 0;
+#pragma unroll
+        for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+          for (int bj = bi; bj < NB; ++bj) {
+            dmma8x8x4(c0[k], c1[k], f[bi], f[bj]);
+            ++k;
+          }
+      }
+      __syncwarp();
+    }
+    // channel flush: acc[p] += w^2 L^p C, C = 0 (L of component 0; k_gram3_expand shifts it
+    // for components with a different reference frequency)
+    {
+      const double wi = A.weights[i];
+      const double lf0 = chan[0].logf;
+      double sp_[5];
+      sp_[0] = wi * wi;
+#pragma unroll
+      for (int p = 1; p < 5; ++p) sp_[p] = sp_[p - 1] * lf0;
+      int k = 0;
+#pragma unroll
+      for (int bi = 0; bi < NB; ++bi)
+#pragma unroll
+        for (int bj = bi; bj < NB; ++bj) {
+          const int off = g3_acc_offset(NB, bi, bj);
+#pragma unroll
+          for (int p = 0; p < g3_npow(bi, bj); ++p) {
+            acc0[off + p] = fma(sp_[p], c0[k], acc0[off + p]);
+            acc1[off + p] = fma(sp_[p], c1[k], acc1[off + p]);
+          }
+          c0[k] = c1[k] = 0.0;
+          ++k;
+        }
+    }
+  }
+  cp_async_wait<0>();
+  // block reduction in warp order (deterministic); fragment element of accumulator k:
+  // row lane/4, columns 2 (lane%4) + {0, 1} of its 8x8 block
+  __syncthreads();
+  double* red = stage_all;  // [warp][kAcc][64]
+#pragma unroll
+  for (int k = 0; k < kAcc; ++k) {
+    red[((size_t)warp * kAcc + k) * 64 + (lane >> 2) * 8 + (lane & 3) * 2] = acc0[k];
+    red[((size_t)warp * kAcc + k) * 64 + (lane >> 2) * 8 + (lane & 3) * 2 + 1] = acc1[k];
+  }
+  __syncthreads();
+  for (int e = tid; e < kAcc * 64; e += kFastBlock) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kFastWarps; ++w) s += red[(size_t)w * kAcc * 64 + e];
+    A.partials[(size_t)blockIdx.x * kAcc * 64 + e] = s;
+  }
+}
+
+// Sums the per-block accumulators: one warp per entry, fixed-shape tree (deterministic).
+__global__ void __launch_bounds__(256) k_gram3_reduce(const double* __restrict__ partials, int nblocks, int entries,
+                                                      double* __restrict__ out) {
+  const int e = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (e >= entries) return;
+  double s = 0.0;
+  for (int b = lane; b < nblocks; b += 32) s += partials[(size_t)b * entries + e];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(kFullMask, s, off);
+  if (lane == 0) out[e] = s;
+}
+
+// Full column k of [J r] = factor * (L + shift)^power * reduced column `red` (per channel).
+struct ExpandArgs {
+  int ncols, nb;
+  int red[FB_MAX_FREE + 1];
+  int power[FB_MAX_FREE + 1];
+  double factor[FB_MAX_FREE + 1];
+  double shift[FB_MAX_FREE + 1];
+};
+
+__device__ inline double g3_binom(int n, int k) {
+  return (k == 0 || k == n) ? 1.0 : (n == 2 ? 2.0 : (double)n);  // n <= 2 here (n = 3, 4 never occur)
+}
+
+__global__ void __launch_bounds__(256) k_gram3_expand(const double* __restrict__ racc, const ExpandArgs X,
+                                                      double* __restrict__ gram) {
+  const int n = X.ncols;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
+    int k = e / n, l = e % n;
+    if (X.red[k] > X.red[l]) {
+      const int t = k;
+      k = l;
+      l = t;
+    }
+    const int rk = X.red[k], rl = X.red[l];
+    const int bi = rk >> 3, bj = rl >> 3;
+    const int off = g3_acc_offset(X.nb, bi, bj);
+    const double* base = racc + (size_t)off * 64 + (rk & 7) * 8 + (rl & 7);
+    double s = 0.0;
+    for (int a = 0; a <= X.power[k]; ++a) {
+      double ca = g3_binom(X.power[k], a);
+      for (int q = 0; q < X.power[k] - a; ++q) ca *= X.shift[k];
+      for (int b = 0; b <= X.power[l]; ++b) {
+        double cb = g3_binom(X.power[l], b);
+        for (int q = 0; q < X.power[l] - b; ++q) cb *= X.shift[l];
+        s += ca * cb * base[(size_t)(a + b) * 64];
+      }
+    }
+    gram[e] = X.factor[k] * X.factor[l] * s;
+  }
+}
+
+}  // namespace fb

@@ -502,6 +502,7 @@ struct HessAccArgs {
   // (spectrum, timediff) planes left in global memory by k_vals at the SAME parameters
   // (the last trust-region evaluation); nullptr = evaluate the model here
   const double* gvals;
+  int gvals_layout;  // 2: k_vals tile planes (spectrum, timediff); 3: k_vals3 rows (spectrum only)
 };
 
 __host__ __device__ inline size_t hess_acc_smem_bytes(int nc, int kf, int num_pairs) {
@@ -548,7 +549,17 @@ __global__ void __launch_bounds__(kBlock, 4) k_hessian_acc(const HessAccArgs H) 
     // 1. term inputs (spectrum, timediff) of every component + rho for the super-tile
     for (int t = t_lo; t < t_hi; ++t) {
       double* dst = big + (size_t)(t - t_lo) * kBlock * vs;
-      if (H.gvals) {
+      if (H.gvals && H.gvals_layout == 3) {
+        const int jv = t * kBlock + tid;
+        if (jv < pc.num_time) {
+          const double tj = (double)(jv * pc.kt) + 0.5 * (double)(pc.kt - 1);
+          for (int c = 0; c < nc; ++c) {
+            dst[(size_t)tid * vs + 3 * c] = H.gvals[((size_t)chi * nc + c) * pc.num_time + jv];
+            // closed form of the mean time difference, fb_core.cuh: eval_sample_fast
+            dst[(size_t)tid * vs + 3 * c + 1] = fma(L.comp[c].t_step, tj, L.comp[c].t_start) - L.chan[c].mean_delay;
+          }
+        }
+      } else if (H.gvals) {
         const double* g = H.gvals + ((size_t)chi * tiles + t) * kBlock * 2 * nc + tid;
         for (int c = 0; c < nc; ++c) {
           dst[(size_t)tid * vs + 3 * c] = g[(size_t)(2 * c) * kBlock];
