@@ -467,34 +467,33 @@ static bool fast_path_ok(const fb_plan_s* p, bool for_gram) {
   return true;
 }
 
-template <int KF, bool CHI2>
+template <int KF>
 static int launch_vals3_t(fb_plan_s* p, const EvalArgs& A, double* out, cudaStream_t st, int* grid_out) {
   const int nc = p->pc.num_comp, kf = p->pc.kf;
   const size_t smem = vals3_smem_bytes(nc, kf);
   if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request exceeds 227 KB");
-  int& occ = p->occ_cache[(CHI2 ? 8 : 0) + (KF == 0 ? 0 : KF == 1 ? 1 : KF == 2 ? 2 : KF == 4 ? 3 : 4)];
+  int& occ = p->occ_cache[KF == 0 ? 0 : KF == 1 ? 1 : KF == 2 ? 2 : KF == 4 ? 3 : 4];
   if (occ == 0 || KF == 0) {
     if (smem > 48 * 1024)
-      CUDA_TRY(cudaFuncSetAttribute(k_vals3<KF, CHI2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_vals3<KF, CHI2>, kFastBlock, smem));
+      CUDA_TRY(cudaFuncSetAttribute(k_vals3<KF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_vals3<KF>, kFastBlock, smem));
     if (occ < 1) occ = 1;
   }
   const int grid = std::min(A.num_chan, p->sm_count * occ);
-  k_vals3<KF, CHI2><<<grid, kFastBlock, smem, st>>>(A, out);
+  k_vals3<KF><<<grid, kFastBlock, smem, st>>>(A, out);
   CUDA_TRY(cudaGetLastError());
   p->launches += 1;
   if (grid_out) *grid_out = grid;
   return FB_OK;
 }
 
-template <bool CHI2>
 static int launch_vals3(fb_plan_s* p, const EvalArgs& A, double* out, cudaStream_t st, int* grid_out) {
   switch (p->pc.kf) {
-    case 1: return launch_vals3_t<1, CHI2>(p, A, out, st, grid_out);
-    case 2: return launch_vals3_t<2, CHI2>(p, A, out, st, grid_out);
-    case 4: return launch_vals3_t<4, CHI2>(p, A, out, st, grid_out);
-    case 8: return launch_vals3_t<8, CHI2>(p, A, out, st, grid_out);
-    default: return launch_vals3_t<0, CHI2>(p, A, out, st, grid_out);
+    case 1: return launch_vals3_t<1>(p, A, out, st, grid_out);
+    case 2: return launch_vals3_t<2>(p, A, out, st, grid_out);
+    case 4: return launch_vals3_t<4>(p, A, out, st, grid_out);
+    case 8: return launch_vals3_t<8>(p, A, out, st, grid_out);
+    default: return launch_vals3_t<0>(p, A, out, st, grid_out);
   }
 }
 
@@ -536,7 +535,7 @@ static int launch_fast_gram(fb_plan_s* p, EvalArgs& A, int ncols, double* gram_d
   const int nc = p->pc.num_comp, nt = p->pc.num_time;
   rc = ensure_capacity(&p->d_vals, &p->vals_cap, (size_t)A.num_chan * nc * nt);
   if (rc != FB_OK) return rc;
-  rc = launch_vals3<false>(p, A, p->d_vals, st, nullptr);
+  rc = launch_vals3(p, A, p->d_vals, st, nullptr);
   if (rc != FB_OK) return rc;
   const GramLayout G = gram3_layout(p);
   const int nb = (G.nr + 7) / 8;
@@ -1163,6 +1162,46 @@ int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, 
     for (int c = 0; c <= nc; ++c) H.comp_off[c] = comp_off[c];
     rc = ensure_tables(p, st);
     if (rc != FB_OK) return rc;
+    if (fast_path_ok(p, false)) {
+      // warp-granular contraction over the spectrum rows of k_vals3
+      if (!(reuse_vals && p->vals_layout == 3)) {
+        rc = ensure_capacity(&p->d_vals, &p->vals_cap, (size_t)p->num_good * nc * p->pc.num_time);
+        if (rc == FB_OK) rc = launch_vals3(p, H.E, p->d_vals, st, nullptr);
+        if (rc != FB_OK) return rc;
+        p->vals_layout = 3;
+        p->vals_match_cache = false;
+      }
+      H.gvals = p->d_vals;
+      H.gvals_layout = 3;
+      const size_t smem3 = hess3_smem_bytes(nc, npairs);
+      if (smem3 > 227 * 1024) return fail(FB_ERR_INVALID, "Hessian shared-memory request %zu B exceeds 227 KB", smem3);
+      auto kern = nc == 1 ? k_hess3<1> : nc == 2 ? k_hess3<2> : nc == 3 ? k_hess3<3> : k_hess3<4>;
+      int& occ3 = p->occ_cache[40 + nc];
+      if (occ3 == 0 || smem3 > 48 * 1024) {
+        if (smem3 > 48 * 1024)
+          CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem3));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ3, kern, kFastBlock, smem3));
+        if (occ3 < 1) occ3 = 1;
+      }
+      const int grid3 = std::min(p->num_good, p->sm_count * occ3);
+      const size_t need3 = (size_t)grid3 * npairs;
+      if (need3 > p->hess_partials_cap) {
+        cudaFree(p->d_hess_partials);
+        p->d_hess_partials = nullptr;
+        p->hess_partials_cap = 0;
+        CUDA_TRY(cudaMalloc(&p->d_hess_partials, sizeof(double) * need3));
+        p->hess_partials_cap = need3;
+      }
+      H.partials = p->d_hess_partials;
+      kern<<<grid3, kFastBlock, smem3, st>>>(H);
+      CUDA_TRY(cudaGetLastError());
+      p->launches += 1;
+      double* d_out3 = p->d_gram;  // reuse: npairs <= (n+1)^2
+      k_hess_finalize<<<(npairs + 3) / 4, 128, 0, st>>>(p->d_hess_partials, grid3, npairs, d_out3);
+      CUDA_TRY(cudaGetLastError());
+      p->launches += 1;
+      CUDA_TRY(cudaMemcpyAsync(S.data(), d_out3, sizeof(double) * npairs, cudaMemcpyDeviceToHost, st));
+    } else {
     const size_t smem = hess_acc_smem_bytes(nc, p->pc.kf, npairs);
     if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "Hessian shared-memory request %zu B exceeds 227 KB", smem);
     if (smem > 48 * 1024)
@@ -1188,10 +1227,11 @@ int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, 
     p->launches += 1;
     double* d_out = p->d_gram;  // reuse: npairs <= (n+1)^2
     CUDA_TRY(cudaStreamSynchronize(st));
-    k_hess_finalize<<<(npairs + 127) / 128, 128, 0, st>>>(p->d_hess_partials, (int)grid, npairs, d_out);
+    k_hess_finalize<<<(npairs + 3) / 4, 128, 0, st>>>(p->d_hess_partials, (int)grid, npairs, d_out);
     CUDA_TRY(cudaGetLastError());
     p->launches += 1;
     CUDA_TRY(cudaMemcpyAsync(S.data(), d_out, sizeof(double) * npairs, cudaMemcpyDeviceToHost, st));
+    }
   } else if (p->num_good > 0) {
     HessArgs H;
     memset(&H, 0, sizeof(H));
@@ -1209,7 +1249,7 @@ int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, 
     if (rc != FB_OK) return rc;
     double* d_out = p->d_gram;  // reuse: npairs <= (n+1)^2
     CUDA_TRY(cudaStreamSynchronize(st));
-    k_hess_finalize<<<(npairs + 127) / 128, 128, 0, st>>>(p->d_hess_partials, grid, npairs, d_out);
+    k_hess_finalize<<<(npairs + 3) / 4, 128, 0, st>>>(p->d_hess_partials, grid, npairs, d_out);
     CUDA_TRY(cudaGetLastError());
     p->launches += 1;
     CUDA_TRY(cudaMemcpyAsync(S.data(), d_out, sizeof(double) * npairs, cudaMemcpyDeviceToHost, st));
@@ -1356,6 +1396,10 @@ extern "C" int fb_chisq_grid(fb_plan_t p, const double* data_dev, const double* 
     CUDA_TRY(cudaMemsetAsync(chisq_dev, 0, sizeof(double) * (size_t)num_dm * num_sc, st));
     return FB_OK;
   }
+  // fast kernels (fb_fast.cuh) whenever the grid point is on the scattered branch
+  bool fast_grid = !env_off("FITBURST_B200_FAST") && !p->pc.scintillation && !p->pc.is_folded && nc <= 4;
+  for (int c = 0; c < nc; ++c)
+    fast_grid = fast_grid && p->h_params[FB_BURST_WIDTH * nc + c] > 0.0 && p->h_params[FB_REF_FREQ * nc + c] > 0.0;
   for (int a = 0; a < num_dm; ++a)
     for (int b = 0; b < num_sc; ++b) {
       // the whole sweep is enqueued without a host round trip: the grid point is written into
@@ -1383,6 +1427,20 @@ extern "C" int fb_chisq_grid(fb_plan_t p, const double* data_dev, const double* 
       int rc = FB_OK;
       if (p->pc.scintillation) {
         rc = launch_eval<MODE_CHI2>(p, A, 1, st, &grid);
+      } else if (fast_grid && sc_values_host[b] > 0.0) {
+        rc = ensure_tables(p, st);
+        if (rc != FB_OK) return rc;
+        rc = ensure_capacity(&p->d_vals, &p->vals_cap, (size_t)p->num_good * nc * p->pc.num_time);
+        if (rc == FB_OK) rc = ensure_capacity(&p->d_partials, &p->partials_cap, (size_t)p->num_good);
+        if (rc != FB_OK) return rc;
+        A.chi2_partials = p->d_partials;
+        rc = launch_vals3(p, A, p->d_vals, st, nullptr);
+        if (rc != FB_OK) return rc;
+        k_chi2_vals<<<p->num_good, 256, 0, st>>>(A, p->d_vals);
+        CUDA_TRY(cudaGetLastError());
+        p->launches += 1;
+        grid = p->num_good;
+        p->vals_match_cache = false;
       } else {
         rc = ensure_tables(p, st);
         if (rc != FB_OK) return rc;
@@ -1398,7 +1456,7 @@ extern "C" int fb_chisq_grid(fb_plan_t p, const double* data_dev, const double* 
         p->launches += 1;
       }
       if (rc != FB_OK) return rc;
-      k_chi2_finalize<<<1, 32, 0, st>>>(p->d_partials, grid, chisq_dev + (size_t)a * num_sc + b);
+      k_chi2_finalize<<<1, 256, 0, st>>>(p->d_partials, grid, chisq_dev + (size_t)a * num_sc + b);
       CUDA_TRY(cudaGetLastError());
       p->launches += 1;
     }

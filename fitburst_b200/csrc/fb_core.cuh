@@ -138,11 +138,13 @@ __device__ __forceinline__ double fb_exp(double x) {
 //   -6 < arg < 0   2 exp(ratio (ratio/2 - z)) - exp(-z^2/2) erfcx(-arg)     [erfcx(-y) = 2e^{y^2} - erfcx(y)]
 //   arg <= -6      2 exp(ratio (ratio/2 - z))                               [erfc(6)/2 = 1.1e-17 < ulp/2]
 __device__ __forceinline__ double emg_shape(double z, double ratio) {
+  // one exp + erfcx on |arg| for both signs (lanes of a warp straddle arg = 0 near the peak:
+  // separate code per sign would execute both), the second exp only where arg < 0
   const double arg = (ratio - z) * kSqrtHalf;
-  if (arg >= 0.0) return fb_exp(-0.5 * z * z) * erfcx(arg);
-  const double tail = 2.0 * fb_exp(ratio * (0.5 * ratio - z));
-  if (arg <= kTailArg) return tail;
-  return tail - fb_exp(-0.5 * z * z) * erfcx(-arg);
+  if (arg <= kTailArg) return 2.0 * fb_exp(ratio * (0.5 * ratio - z));
+  const double e = fb_exp(-0.5 * z * z) * erfcx(fabs(arg));
+  if (arg >= 0.0) return e;
+  return 2.0 * fb_exp(ratio * (0.5 * ratio - z)) - e;
 }
 
 __device__ inline void make_comp_tab(const PlanConst& pc, const double* params, int c, CompTab& ct) {
@@ -382,7 +384,8 @@ __device__ __forceinline__ SampleComp eval_sample_component(const PlanConst& pc,
 // returns the shared factor amp * amp_pbf * exp(arg_exp) * 2/sqrt(pi) for the second derivatives.
 __device__ __forceinline__ void first_derivatives(const ChanTab& ch, const ChanTab& cho, const CompTab& ct,
                                                   double tau0, double amp, double m, double td, double* d,
-                                                  double* gfac_out, double* arg_erf_out = nullptr) {
+                                                  double* gfac_out, double* arg_erf_out = nullptr,
+                                                  bool force_far = false) {
   const double lf = ch.logf, w = ct.w, inv_w = ct.inv_w;
   d[FB_AMPLITUDE] = kLn10 * m;
   d[FB_SPECTRAL_INDEX] = lf * m;
@@ -393,7 +396,8 @@ __device__ __forceinline__ void first_derivatives(const ChanTab& ch, const ChanT
   const double ws = w * inv_tau;
   const double arg_exp = 0.5 * ws * ws - td * inv_tau - arg_erf * arg_erf;
   // exp() is exactly 0 below -745.2: far from the burst (|T| > 38.6 w) skip the call
-  const double g = (arg_exp < -746.0) ? 0.0 : amp * ch.amp_pbf * fb_exp(arg_exp) * kTwoOverSqrtPi;
+  // force_far: the G = 0 limit whatever td is (node evaluation of the far-sample polynomials)
+  const double g = (force_far || arg_exp < -746.0) ? 0.0 : amp * ch.amp_pbf * fb_exp(arg_exp) * kTwoOverSqrtPi;
   *gfac_out = g;
   if (arg_erf_out) *arg_erf_out = arg_erf;
   if (ch.sc_time == 0.0) {  // per-channel Gaussian branch, routines/derivative.py:568,629,695,767

@@ -46,46 +46,92 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 
 // ---- model side ---------------------------------------------------------------------------
+constexpr int kValsQueue = 1024;  // general-case (sample, component) items queued per channel
+
 __host__ __device__ inline int vals3_bw_stride(int nck) { return (nck + 31) & ~31; }
 
 __host__ __device__ inline size_t vals3_smem_bytes(int nc, int kf) {
   size_t n = 0;
   n += sizeof(CompTab) * nc;
   n += 2 * (sizeof(ChanTab) * nc + sizeof(SubTab) * nc * kf);  // double-buffered channel tables
-  n += sizeof(double) * (size_t)nc * kf * 32;                 // R
+  n += sizeof(double) * (size_t)nc * kf * 33;                 // R, D
   n += sizeof(double) * (size_t)kFastWarps * vals3_bw_stride(nc * kf);  // B per warp
-  n += sizeof(double) * kFastWarps;                           // chi^2 block reduction
-  n += 16;                                                    // tile counter
+  n += sizeof(int) * (kValsQueue + 4 + 2 * FB_MAX_COMPONENTS);  // queue, counter, regime boundaries
   return n;
 }
 
-// Spectrum value of component c for the 32 samples of warp tile `wt` (one per lane).
+// General case of one (sample jj, component): the whole warp evaluates the kf x kt sub-grid, one
+// sub-sample per lane (analysis/model.py:208-247); every lane returns the spectrum value.
+template <int KF>
+__device__ __forceinline__ double vals3_general_warp(const PlanConst& pc, const CompTab& ct, const ChanTab& ch,
+                                                     const SubTab* __restrict__ sb, int jj, int lane) {
+  const int kf = KF > 0 ? KF : pc.kf, kt = pc.kt;
+  const int npe = kf * kt;
+  double s_ps = 0.0;
+  for (int pe = lane; pe < npe; pe += 32) {
+    const int b = pe / kf, a = pe - b * kf;
+    double t, p;
+    eval_subsample(pc, ct, ch.scattered, sb[a], jj * kt + b, t, p);
+    s_ps = fma(p, sb[a].sed, s_ps);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s_ps += __shfl_xor_sync(kFullMask, s_ps, off);
+  return ct.amp10 * (s_ps * (1.0 / (double)npe));
+}
+
+// First sample that is NOT on the clamp plateau (jp) and first sample in the pure exponential
+// tail (jt) of one (channel, component): closed-form guess, then fixed up with the very
+// predicates of eval_sample_fast so that the classification is identical to the per-sample one.
+__device__ inline void vals3_boundaries(const PlanConst& pc, const CompTab& ct, const ChanTab& ch, int& jp, int& jt) {
+  const int nt = pc.num_time, kt = pc.kt, n = pc.ntk;
+  if (!ch.fast_ok) {
+    jp = 0;
+    jt = nt;
+    return;
+  }
+  auto plateau = [&](int j) {
+    return (linspace_at(ct.t_start, ct.t_step, ct.t_stop, j * kt + kt - 1, n) - ch.min_delay) < ct.neg5w;
+  };
+  auto tail = [&](int j) { return linspace_at(ct.t_start, ct.t_step, ct.t_stop, j * kt, n) >= ch.tail_lo; };
+  const double span = ct.t_step * (double)kt;
+  double g = ceil((ct.neg5w + ch.min_delay - ct.t_start) / span);
+  jp = (int)fmin(fmax(g, 0.0), (double)nt);
+  while (jp > 0 && !plateau(jp - 1)) --jp;
+  while (jp < nt && plateau(jp)) ++jp;
+  g = ceil((ch.tail_lo - ct.t_start) / span);
+  jt = (int)fmin(fmax(g, 0.0), (double)nt);
+  while (jt > 0 && tail(jt - 1)) --jt;
+  while (jt < nt && !tail(jt)) ++jt;
+}
+
+// Spectrum value of component c for the 32 samples of one warp tile (one per lane). Samples in
+// the rise region are pushed on the block's queue (*deferred = true for that lane) unless the
+// queue is full or the sub-grid is too small to share, in which case they are done here.
 template <int KF>
 __device__ __forceinline__ double vals3_component(const PlanConst& pc, const CompTab& ct, const ChanTab& ch,
                                                   const SubTab* __restrict__ sb, const double* __restrict__ r_lane,
-                                                  const double* __restrict__ bw, int j0, int lane, bool valid,
-                                                  unsigned vmask) {
-  const int kf = KF > 0 ? KF : pc.kf, kt = pc.kt, n = pc.ntk;
-  const int npe = kf * kt;
-  const int j = j0 + lane;
-  const int m0 = j * kt;
-  const double u0 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, m0, n);
-  const double u_last = linspace_at(ct.t_start, ct.t_step, ct.t_stop, m0 + kt - 1, n);
-  const bool fast = ch.fast_ok != 0;
-  const bool plateau = fast && (u_last - ch.min_delay) < ct.neg5w;
-  const bool tail = fast && !plateau && u0 >= ch.tail_lo;
-  const unsigned tm = __ballot_sync(kFullMask, tail && valid);
-  if (tm == vmask) {
+                                                  const double* __restrict__ bw, int c, int jp, int jt, int j0,
+                                                  int lane, bool valid, int* __restrict__ queue,
+                                                  int* __restrict__ qcount, bool* deferred) {
+  const int kf = KF > 0 ? KF : pc.kf, kt = pc.kt;
+  *deferred = false;
+  if (j0 >= jt && j0 >= jp) {  // whole tile in the exponential tail
     double s = 0.0;
 #pragma unroll
     for (int a = 0; a < kf; ++a) s = fma(bw[a], r_lane[a * 32], s);
     return s;
   }
-  const unsigned gm = __ballot_sync(kFullMask, valid && !plateau && !tail);
+  if (j0 + 32 <= jp) return ch.plateau_ps;  // whole tile on the clamp plateau
+  const int j = j0 + lane;
+  const bool plateau = j < jp;
+  const bool tail = !plateau && j >= jt;
+  const bool general = valid && !plateau && !tail;
+  const unsigned gm = __ballot_sync(kFullMask, general);
   double val = 0.0;
   if (plateau) {
     val = ch.plateau_ps;
   } else if (tail) {
+    const double u0 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, j * kt, pc.ntk);
     double s_ps = 0.0;
 #pragma unroll 4
     for (int a = 0; a < kf; ++a) {
@@ -97,34 +143,34 @@ __device__ __forceinline__ double vals3_component(const PlanConst& pc, const Com
     val = ct.amp10 * s_ps;
   }
   if (gm == 0u) return val;
-  if (npe >= 16) {
-    // rise / peak region: the whole warp evaluates the sub-grid of one sample at a time
-    const double inv_n = 1.0 / (double)npe;
-    unsigned rem = gm;
-    while (rem) {
-      const int s = __ffs(rem) - 1;
-      rem &= rem - 1;
-      const int jj = j0 + s;
-      double s_ps = 0.0;
-      for (int pe = lane; pe < npe; pe += 32) {
-        const int b = pe / kf, a = pe - b * kf;
-        double t, p;
-        eval_subsample(pc, ct, ch.scattered, sb[a], jj * kt + b, t, p);
-        s_ps = fma(p, sb[a].sed, s_ps);
-      }
-#pragma unroll
-      for (int off = 16; off > 0; off >>= 1) s_ps += __shfl_xor_sync(kFullMask, s_ps, off);
-      if (lane == s) val = ct.amp10 * (s_ps * inv_n);
+  if (kf * kt < 16) {
+    if (general) val = eval_sample_general(pc, ct, ch, sb, j).spectrum;
+    return val;
+  }
+  if (ch.fast_ok) {
+    const int cnt = __popc(gm);
+    int base = 0;
+    if (lane == 0) base = atomicAdd(qcount, cnt);
+    base = __shfl_sync(kFullMask, base, 0);
+    if (base + cnt <= kValsQueue) {
+      if (general) queue[base + __popc(gm & ((1u << lane) - 1u))] = (c << 27) | j;
+      *deferred = general;
+      return val;
     }
-  } else if ((gm >> lane) & 1u) {
-    val = eval_sample_general(pc, ct, ch, sb, j).spectrum;
+  }
+  unsigned rem = gm;
+  while (rem) {
+    const int s = __ffs(rem) - 1;
+    rem &= rem - 1;
+    const double v = vals3_general_warp<KF>(pc, ct, ch, sb, j0 + s, lane);
+    if (lane == s) val = v;
   }
   return val;
 }
 
-// CHI2 = false: stores the spectrum values, gvals[(chi * nc + c) * num_time + j].
-// CHI2 = true : accumulates sum(((data - model) w)^2) into chi2_partials[blockIdx.x] instead.
-template <int KF, bool CHI2>
+// Stores the spectrum value of every (good channel, component, sample):
+// gvals[(chi * nc + c) * num_time + j].
+template <int KF>
 __global__ void __launch_bounds__(kFastBlock, 3) k_vals3(const EvalArgs A, double* __restrict__ gvals) {
   extern __shared__ __align__(16) unsigned char fast_smem[];
   const PlanConst& pc = A.pc;
@@ -139,12 +185,14 @@ __global__ void __launch_bounds__(kFastBlock, 3) k_vals3(const EvalArgs A, doubl
   sp += 2 * tab_bytes;
   double* R = reinterpret_cast<double*>(sp);
   sp += sizeof(double) * (size_t)nck * 32;
+  double* D = reinterpret_cast<double*>(sp);  // tile-to-tile decay exp(-32 kt step / tau)
+  sp += sizeof(double) * (size_t)nck;
   const int bws = vals3_bw_stride(nck);
   double* bw = reinterpret_cast<double*>(sp) + (size_t)warp * bws;
   sp += sizeof(double) * (size_t)kFastWarps * bws;
-  double* red = reinterpret_cast<double*>(sp);
-  sp += sizeof(double) * kFastWarps;
-  int* next = reinterpret_cast<int*>(sp);
+  int* queue = reinterpret_cast<int*>(sp);
+  int* qcount = queue + kValsQueue;
+  int* bounds = qcount + 1;  // [nc][2]: jp, jt
 
   {
     const double* src = reinterpret_cast<const double*>(A.g_comp);
@@ -152,6 +200,7 @@ __global__ void __launch_bounds__(kFastBlock, 3) k_vals3(const EvalArgs A, doubl
     for (int e = tid; e < nc * (int)(sizeof(CompTab) / sizeof(double)); e += kFastBlock) dst[e] = src[e];
   }
   const int wtiles = (nt + 31) / 32;
+  const int tpw = (wtiles + kFastWarps - 1) / kFastWarps;  // contiguous tiles per warp
   const int chan_chunks = (int)(sizeof(ChanTab) * nc / 16), sub_chunks = (int)(sizeof(SubTab) * nck / 16);
   auto prefetch_tables = [&](int chi, int buf) {
     if (chi < A.num_chan) {
@@ -165,67 +214,98 @@ __global__ void __launch_bounds__(kFastBlock, 3) k_vals3(const EvalArgs A, doubl
     }
     cp_async_commit();
   };
-  double chi2_acc = 0.0;
   prefetch_tables(blockIdx.x, 0);
   int buf = 0;
   for (int chi = blockIdx.x; chi < A.num_chan; chi += gridDim.x, buf ^= 1) {
-    const int i = A.chan_list ? A.chan_list[chi] : chi;
     cp_async_wait<0>();
     __syncthreads();  // tables of this channel landed; every warp is done with the previous one
     prefetch_tables(chi + gridDim.x, buf ^ 1);
     const ChanTab* chan = reinterpret_cast<const ChanTab*>(tabs + (size_t)buf * tab_bytes);
     const SubTab* sub = reinterpret_cast<const SubTab*>(tabs + (size_t)buf * tab_bytes + sizeof(ChanTab) * nc);
-    if (tid == 0) *next = 0;
+    if (tid == 0) *qcount = 0;
+    if (tid >= 32 && tid < 32 + nc) {
+      int jp, jt;
+      vals3_boundaries(pc, comp[tid - 32], chan[tid - 32], jp, jt);
+      bounds[2 * (tid - 32)] = jp;
+      bounds[2 * (tid - 32) + 1] = jt;
+    }
     for (int e = tid; e < nck * 32; e += kFastBlock) {
       const int l = e & 31, ca = e >> 5, c = ca / kf;
       const SubTab& st = sub[ca];
       const double decay = fb_exp(-((double)(l * kt) * comp[c].t_step) * st.inv_tau);
       R[e] = ((comp[c].amp10 * st.tail_c) * st.sed) * decay;
     }
+    for (int e = tid; e < nck; e += kFastBlock)
+      D[e] = fb_exp(-((double)(32 * kt) * comp[e / kf].t_step) * sub[e].inv_tau);
     __syncthreads();
-    const double wi = CHI2 ? A.weights[i] : 0.0;
-    for (;;) {
-      int wt = 0;
-      if (lane == 0) wt = atomicAdd(next, 1);
-      wt = __shfl_sync(kFullMask, wt, 0);
-      if (wt >= wtiles) break;
+    double* out = gvals + (size_t)chi * nc * nt;
+    // phase A: closed-form regimes tile by tile (uniform cost), rise-region samples queued
+    const int wt_lo = warp * tpw, wt_hi = min(wtiles, wt_lo + tpw);
+    for (int wt = wt_lo; wt < wt_hi; ++wt) {
       const int j0 = wt * 32, j = j0 + lane;
       const bool valid = j < nt;
-      const unsigned vmask = __ballot_sync(kFullMask, valid);
-      // tail base factors of every (component, sub-frequency) of this tile, one per lane
+      // tail base factors B of every (component, sub-frequency) at the first sample of the tile:
+      // one exp per lane every 8th tile, the decay recurrence in between
+      // (a factor that overflowed ahead of the burst is recomputed: inf * decay would stay inf)
+      const bool refresh = ((wt - wt_lo) & 7) == 0;
       for (int e = lane; e < nck; e += 32) {
-        const CompTab& ct = comp[e / kf];
-        const double u0b = linspace_at(ct.t_start, ct.t_step, ct.t_stop, j0 * kt, pc.ntk);
-        const double earg = fma(-u0b, sub[e].inv_tau, sub[e].tail_e);
-        bw[e] = (earg < -746.0) ? 0.0 : fb_exp(earg);
+        const double prev = bw[e];
+        if (refresh || !(prev < 1e290)) {
+          const CompTab& ct = comp[e / kf];
+          const double u0b = linspace_at(ct.t_start, ct.t_step, ct.t_stop, j0 * kt, pc.ntk);
+          const double earg = fma(-u0b, sub[e].inv_tau, sub[e].tail_e);
+          bw[e] = (earg < -746.0) ? 0.0 : fb_exp(earg);
+        } else {
+          bw[e] = prev * D[e];
+        }
       }
       __syncwarp();
-      double msum = 0.0;
       for (int c = 0; c < nc; ++c) {
+        bool deferred;
         const double v = vals3_component<KF>(pc, comp[c], chan[c], sub + c * kf, R + (size_t)c * kf * 32 + lane,
-                                             bw + c * kf, j0, lane, valid, vmask);
-        if (CHI2) msum += v;
-        else if (valid) gvals[((size_t)chi * nc + c) * nt + j] = v;
-      }
-      if (CHI2 && valid) {
-        const double r = (A.data[(size_t)i * nt + j] - msum) * wi;
-        chi2_acc = fma(r, r, chi2_acc);
+                                             bw + c * kf, c, bounds[2 * c], bounds[2 * c + 1], j0, lane, valid,
+                                             queue, qcount, &deferred);
+        if (valid && !deferred) out[(size_t)c * nt + j] = v;
       }
       __syncwarp();
+    }
+    __syncthreads();
+    // phase B: the queued rise-region samples, one per warp pass (uniform cost)
+    const int qn = min(*qcount, kValsQueue);
+    for (int q = warp; q < qn; q += kFastWarps) {
+      const int item = queue[q];
+      const int c = item >> 27, jj = item & ((1 << 27) - 1);
+      const double v = vals3_general_warp<KF>(pc, comp[c], chan[c], sub + c * kf, jj, lane);
+      if (lane == 0) out[(size_t)c * nt + jj] = v;
     }
   }
   cp_async_wait<0>();
-  if (CHI2) {
+}
+
+// chi^2 of the stored spectrum values against the data (grid sweeps, BASELINE.json config 4):
+// one block per good channel row, fixed-order reduction.
+__global__ void __launch_bounds__(256) k_chi2_vals(const EvalArgs A, const double* __restrict__ gvals) {
+  __shared__ double red[8];
+  const int chi = blockIdx.x, tid = threadIdx.x, nc = A.pc.num_comp, nt = A.pc.num_time;
+  const int i = A.chan_list ? A.chan_list[chi] : chi;
+  const double wi = A.weights[i];
+  const double* v = gvals + (size_t)chi * nc * nt;
+  const double* d = A.data + (size_t)i * nt;
+  double acc = 0.0;
+  for (int j = tid; j < nt; j += 256) {
+    double m = 0.0;
+    for (int c = 0; c < nc; ++c) m += v[(size_t)c * nt + j];
+    const double r = (d[j] - m) * wi;
+    acc = fma(r, r, acc);
+  }
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) chi2_acc += __shfl_xor_sync(kFullMask, chi2_acc, off);
-    __syncthreads();
-    if (lane == 0) red[warp] = chi2_acc;
-    __syncthreads();
-    if (tid == 0) {
-      double s = 0.0;
-      for (int w = 0; w < kFastWarps; ++w) s += red[w];
-      A.chi2_partials[blockIdx.x] = s;
-    }
+  for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(kFullMask, acc, off);
+  if ((tid & 31) == 0) red[tid >> 5] = acc;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += red[w];
+    A.chi2_partials[chi] = s;
   }
 }
 
@@ -262,7 +342,8 @@ __host__ __device__ inline size_t gram3_smem_bytes(int nc, int nb) {
   size_t stage = sizeof(double) * (size_t)kFastWarps * nb * 8 * kMmaRowStride;
   const size_t red = sizeof(double) * (size_t)kFastWarps * g3_nacc(nb) * 64;
   if (red > stage) stage = red;  // the stage doubles as the block-reduction buffer
-  return sizeof(CompTab) * nc + 2 * sizeof(ChanTab) * nc + sizeof(GTab) * nc + stage;
+  const size_t pref = sizeof(double) * 2 * (size_t)(nc + 1) * kFastBlock;  // double-buffered value + data prefetch
+  return sizeof(CompTab) * nc + 2 * sizeof(ChanTab) * nc + sizeof(GTab) * nc + stage + pref;
 }
 
 template <int NC, int NB>
@@ -281,6 +362,15 @@ __global__ void __launch_bounds__(kFastBlock, 3) k_gram3(const EvalArgs A, const
   sp += sizeof(GTab) * NC;
   double* stage_all = reinterpret_cast<double*>(sp);
   double* xt = stage_all + (size_t)warp * NB * 8 * kMmaRowStride;  // this warp's [NB*8 columns][36]
+  {
+    size_t stage = sizeof(double) * (size_t)kFastWarps * NB * 8 * kMmaRowStride;
+    const size_t red_bytes = sizeof(double) * (size_t)kFastWarps * g3_nacc(NB) * 64;
+    if (red_bytes > stage) stage = red_bytes;
+    sp += stage;
+  }
+  // [2][NC + 1][32] per warp: every lane copies and later reads only its own elements, so
+  // cp.async.wait_group is the only synchronisation the prefetch needs
+  double* pref = reinterpret_cast<double*>(sp) + (size_t)warp * 2 * (NC + 1) * 32 + lane;
 
   {
     const double* src = reinterpret_cast<const double*>(A.g_comp);
@@ -347,17 +437,29 @@ __global__ void __launch_bounds__(kFastBlock, 3) k_gram3(const EvalArgs A, const
 
     const double* srow = gvals + (size_t)chi * NC * nt;
     const double* drow = A.data + (size_t)i * nt;
-    for (int wt = warp; wt < wtiles; wt += kFastWarps) {
+    auto prefetch_tile = [&](int wt, int pb) {
+      const int j = wt * 32 + lane;
+      if (wt < wtiles && j < nt) {
+        double* dst = pref + (size_t)pb * (NC + 1) * 32;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) cp_async8(dst + c * 32, srow + (size_t)c * nt + j);
+        cp_async8(dst + NC * 32, drow + j);
+      }
+      cp_async_commit();
+    };
+    prefetch_tile(warp, 0);
+    int pb = 0;
+    for (int wt = warp; wt < wtiles; wt += kFastWarps, pb ^= 1) {
       const int j = wt * 32 + lane;
       const bool valid = j < nt;
+      prefetch_tile(wt + kFastWarps, pb ^ 1);
+      cp_async_wait<1>();
       double m[NC], dval = 0.0;
-      if (valid) {
+      {
+        const double* src = pref + (size_t)pb * (NC + 1) * 32;
 #pragma unroll
-        for (int c = 0; c < NC; ++c) m[c] = __ldg(srow + (size_t)c * nt + j);
-        dval = __ldg(drow + j);
-      } else {
-#pragma unroll
-        for (int c = 0; c < NC; ++c) m[c] = 0.0;
+        for (int c = 0; c < NC; ++c) m[c] = valid ? src[c * 32] : 0.0;
+        if (valid) dval = src[NC * 32];
       }
       double msum = 0.0, s_dm = 0.0, s_dmidx = 0.0, s_tau = 0.0, s_alpha = 0.0;
       double* row = xt + lane;
@@ -371,17 +473,16 @@ __global__ void __launch_bounds__(kFastBlock, 3) k_gram3(const EvalArgs A, const
         double d_t, d_w, d_tau, d_alpha, d_dm, d_dmidx;
         if (std_ok) {
           const double k1 = ct.inv_w * kSqrtHalf;
-          const double arg_erf = (td - ct.w * ct.w * t.inv_tau) * ct.inv_w * kSqrtHalf;
-          const double arg_exp = t.h - td * t.inv_tau - arg_erf * arg_erf;
+          const double arg_erf = fma(td, k1, -t.k2);
+          const double arg_exp = fma(-arg_erf, arg_erf, fma(-td, t.inv_tau, t.h));
           const double g = (arg_exp < -746.0) ? 0.0 : t.g0 * fb_exp(arg_exp);
           const double gs = g * k1;
-          const double mt = mc * t.inv_tau;
-          d_t = mt - gs;
-          d_w = mc * t.a_w - gs * (td * ct.inv_w + t.ws);
-          const double u = td * t.inv_tau - t.ws2;
+          d_t = fma(mc, t.inv_tau, -gs);
+          d_w = fma(mc, t.a_w, -gs * fma(td, ct.inv_w, t.ws));
+          const double u = fma(td, t.inv_tau, -t.ws2);
           const double gtt = g * t.k2;
-          d_tau = mc * (t.a_tau + u * inv_tau0) + gtt * inv_tau0;
-          d_alpha = mc * (t.a_alpha + t.lf * u) + gtt * t.lf;
+          d_tau = fma(mc, fma(u, inv_tau0, t.a_tau), gtt * inv_tau0);
+          d_alpha = fma(mc, fma(t.lf, u, t.a_alpha), gtt * t.lf);
           d_dm = -t.d_dm * d_t;
           d_dmidx = -t.d_dmidx * d_t;
         } else {

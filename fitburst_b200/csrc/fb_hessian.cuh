@@ -7,6 +7,7 @@
 // is flagged "quirk" with its line.
 #pragma once
 #include "fb_kernels.cuh"
+#include "fb_fast.cuh"
 
 namespace fb {
 
@@ -185,10 +186,10 @@ __device__ __forceinline__ double d2_term(int pa, int pb, const D2Ctx& c) {
 
 __device__ __forceinline__ void make_d2ctx(const EvalArgs& A, const ChanTab& ch, const CompTab& ct, double amp,
                                            double m, double td, double sum_dmidx, double apbf_outer,
-                                           D2Ctx& c) {
+                                           D2Ctx& c, bool force_far = false) {
   const int nc = A.pc.num_comp;
   c.tau0 = global_param(A.params, nc, FB_SCATTERING_TIMESCALE);
-  first_derivatives(ch, ch, ct, c.tau0, amp, m, td, c.d1, &c.G, &c.arg_erf);
+  first_derivatives(ch, ch, ct, c.tau0, amp, m, td, c.d1, &c.G, &c.arg_erf, force_far);
   const double w = ct.w;
   c.M = m;
   c.T = td;
@@ -505,15 +506,39 @@ struct HessAccArgs {
   int gvals_layout;  // 2: k_vals tile planes (spectrum, timediff); 3: k_vals3 rows (spectrum only)
 };
 
+// Term value `idx` (0..8 first derivatives, 9..29 second derivatives in FB_TERM order).
+__device__ inline double hess_term_value(int idx, const D2Ctx& c) {
+  if (idx < 9) return c.d1[idx];
+  constexpr int8_t pa[21] = {FB_ARRIVAL_TIME, FB_ARRIVAL_TIME, FB_ARRIVAL_TIME, FB_ARRIVAL_TIME, FB_ARRIVAL_TIME,
+                             FB_ARRIVAL_TIME, FB_BURST_WIDTH, FB_BURST_WIDTH, FB_BURST_WIDTH, FB_BURST_WIDTH,
+                             FB_BURST_WIDTH, FB_DM, FB_DM, FB_DM, FB_DM, FB_DM_INDEX, FB_DM_INDEX, FB_DM_INDEX,
+                             FB_SCATTERING_TIMESCALE, FB_SCATTERING_TIMESCALE, FB_SCATTERING_INDEX};
+  constexpr int8_t pb[21] = {FB_ARRIVAL_TIME, FB_BURST_WIDTH, FB_DM, FB_DM_INDEX, FB_SCATTERING_TIMESCALE,
+                             FB_SCATTERING_INDEX, FB_BURST_WIDTH, FB_DM, FB_DM_INDEX, FB_SCATTERING_TIMESCALE,
+                             FB_SCATTERING_INDEX, FB_DM, FB_DM_INDEX, FB_SCATTERING_TIMESCALE, FB_SCATTERING_INDEX,
+                             FB_DM_INDEX, FB_SCATTERING_TIMESCALE, FB_SCATTERING_INDEX, FB_SCATTERING_TIMESCALE,
+                             FB_SCATTERING_INDEX, FB_SCATTERING_INDEX};
+  return d2_term(pa[idx - 9], pb[idx - 9], c);
+}
+
 __host__ __device__ inline size_t hess_acc_smem_bytes(int nc, int kf, int num_pairs) {
   size_t n = smem_bytes(nc, kf, 1, false, true);
   n += sizeof(double) * (size_t)kHessSuper * kBlock * val_stride(nc);  // term inputs of the super-tile
   n += sizeof(double) * (size_t)kHessSuper * kBlock * 2;               // rho, sum_dmidx
   n += sizeof(double) * ((size_t)(kBlock / 32) * 32 + 32);             // column partials, totals
   n += sizeof(double) * (size_t)num_pairs;
+  n += sizeof(double) * ((size_t)3 * nc * kBlock + 3 * nc + 3 * kNumTerms);  // far-sample moments, node values
   return n;
 }
 
+// Far from the burst the shared factor G of the scattered-branch derivatives is exactly zero
+// (first_derivatives: exp underflow cut at arg_exp < -746, |T| > 38.6 w), and every one of the 30
+// term values is then the spectrum M times a polynomial of degree <= 2 in the time difference T
+// with per-(channel, component) coefficients (see d2_term with G = 0). For those samples -- ~94 %
+// at config 2 -- only the three moments sum(rho M x^p), x = T mapped to [-1, 1] over the channel,
+// are accumulated, and at the end of the channel the term polynomials are evaluated at the three
+// nodes x = -1, 0, 1 with the SAME device functions (M = 1, G = 0) and contracted with the
+// Lagrange weights of the moments: exact for quadratics, no per-term algebra to keep in sync.
 __global__ void __launch_bounds__(kBlock, 4) k_hessian_acc(const HessAccArgs H) {
   extern __shared__ double smem_raw[];
   const EvalArgs& A = H.E;
@@ -527,20 +552,79 @@ __global__ void __launch_bounds__(kBlock, 4) k_hessian_acc(const HessAccArgs H) 
   double* part = sdm_s + (size_t)kHessSuper * kBlock;  // [8][32]
   double* total = part + (kBlock / 32) * 32;           // [32]
   double* pacc = total + 32;                           // [num_pairs]
+  double* mu_s = pacc + H.num_pairs;                   // [nc * 3][kBlock] per-thread moment slots
+  double* lam_s = mu_s + (size_t)3 * nc * kBlock;      // [nc * 3] Lagrange-weighted sums
+  double* node_s = lam_s + 3 * nc;                     // [3][kNumTerms] term values at the nodes
   double* stage = L.X;                                 // [kFlushChunk][kBlock + 1] (X region >= 32 KB)
   const int npairs = H.num_pairs;
   for (int e = tid; e < npairs; e += kBlock) pacc[e] = 0.0;
+  for (int e = tid; e < 3 * nc * kBlock; e += kBlock) mu_s[e] = 0.0;
   load_comp_tables(A, L);
   const int tiles = (pc.num_time + kBlock - 1) / kBlock;
   const int supers = (tiles + kHessSuper - 1) / kHessSuper;
   const double tau0 = global_param(A.params, nc, FB_SCATTERING_TIMESCALE);
+  const double kt_mid = 0.5 * (double)(pc.kt - 1);
+  const double tj_last = (double)((pc.num_time - 1) * pc.kt) + kt_mid;
+  const bool shortcut = !H.need_sum_dmidx && pc.num_time > 2;
   const long long total_items = (long long)A.num_chan * supers;
   const long long begin = total_items * blockIdx.x / gridDim.x, end = total_items * (blockIdx.x + 1) / gridDim.x;
+
+  // contracts the moments of the channel whose tables are in shared memory; block-uniform
+  auto flush_moments = [&]() {
+    __syncthreads();
+    if (tid < 3 * nc) {
+      double s = 0.0;
+      for (int t = 0; t < kBlock; ++t) s += mu_s[(size_t)tid * kBlock + t];
+      lam_s[tid] = s;
+    }
+    __syncthreads();
+    for (int e = tid; e < 3 * nc * kBlock; e += kBlock) mu_s[e] = 0.0;
+    for (int c = 0; c < nc; ++c) {
+      const double m0 = lam_s[3 * c], m1 = lam_s[3 * c + 1], m2 = lam_s[3 * c + 2];
+      if (m0 == 0.0 && m1 == 0.0 && m2 == 0.0) continue;  // block-uniform
+      const unsigned need = H.need[c];
+      if (tid < 3 * kNumTerms) {
+        const int q = tid / kNumTerms, idx = tid % kNumTerms;
+        double v = 0.0;
+        if (need & (1u << idx)) {
+          const CompTab& ct = L.comp[c];
+          const ChanTab& ch = L.chan[c];
+          const double t_lo = fma(ct.t_step, kt_mid, ct.t_start) - ch.mean_delay;
+          const double t_hi = fma(ct.t_step, tj_last, ct.t_start) - ch.mean_delay;
+          const double t_node = q == 0 ? t_lo : (q == 2 ? t_hi : 0.5 * (t_lo + t_hi));
+          D2Ctx ctx;
+          make_d2ctx(A, ch, ct, ch.amp, 1.0, t_node, 0.0, L.chan[0].amp_pbf, ctx, true);
+          v = hess_term_value(idx, ctx);
+        }
+        node_s[tid] = v;
+      }
+      __syncthreads();
+      if (tid < kNumTerms) {
+        // Lagrange weights of the nodes -1, 0, 1 applied to the moments
+        const double l_lo = 0.5 * (m2 - m1), l_mid = m0 - m2, l_hi = 0.5 * (m2 + m1);
+        total[tid] = node_s[tid] * l_lo + node_s[kNumTerms + tid] * l_mid + node_s[2 * kNumTerms + tid] * l_hi;
+      }
+      __syncthreads();
+      {
+        const double lf = L.chan[c].logf;
+        const int lo = H.comp_off[c], cnt = H.comp_off[c + 1] - lo;
+        for (int p = tid; p < cnt; p += kBlock) {
+          const int pair = H.comp_list[lo + p];
+          const HessDesc d = H.desc[pair];
+          const double factor = d.code == 0 ? 1.0 : (d.code == 1 ? kLn10 : (d.code == 2 ? lf : lf * lf));
+          pacc[pair] += factor * total[d.idx];
+        }
+      }
+      __syncthreads();
+    }
+  };
+
   int cur = -1;
   for (long long item = begin; item < end; ++item) {
     const int chi = (int)(item / supers), sup = (int)(item % supers);
     const int i = A.chan_list ? A.chan_list[chi] : chi;
     if (chi != cur) {
+      if (cur >= 0 && shortcut) flush_moments();
       load_channel_tables(A, L, i);
       cur = chi;
     }
@@ -552,7 +636,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_hessian_acc(const HessAccArgs H) 
       if (H.gvals && H.gvals_layout == 3) {
         const int jv = t * kBlock + tid;
         if (jv < pc.num_time) {
-          const double tj = (double)(jv * pc.kt) + 0.5 * (double)(pc.kt - 1);
+          const double tj = (double)(jv * pc.kt) + kt_mid;
           for (int c = 0; c < nc; ++c) {
             dst[(size_t)tid * vs + 3 * c] = H.gvals[((size_t)chi * nc + c) * pc.num_time + jv];
             // closed form of the mean time difference, fb_core.cuh: eval_sample_fast
@@ -593,16 +677,46 @@ __global__ void __launch_bounds__(kBlock, 4) k_hessian_acc(const HessAccArgs H) 
 #pragma unroll
       for (int k = 0; k < kNumTerms; ++k) acc[k] = 0.0;
       const unsigned need = H.need[c];
+      const CompTab& ct = L.comp[c];
+      const ChanTab& ch = L.chan[c];
+      const bool gate = shortcut && ch.sc_time != 0.0;
+      // T -> x in [-1, 1] over the channel
+      const double tc_lo = fma(ct.t_step, kt_mid, ct.t_start) - ch.mean_delay;
+      const double tc_hi = fma(ct.t_step, tj_last, ct.t_start) - ch.mean_delay;
+      const double tc_mid = 0.5 * (tc_lo + tc_hi), inv_half = 2.0 / (tc_hi - tc_lo);
+      double mu0 = 0.0, mu1 = 0.0, mu2 = 0.0;
+      int any_full = 0;
       for (int t = t_lo; t < t_hi; ++t) {
         const int j = t * kBlock + tid, r = (t - t_lo) * kBlock + tid;
         if (j < pc.num_time) {
           const double* vrow = big + (size_t)r * vs;
-          D2Ctx ctx;
-          make_d2ctx(A, L.chan[c], L.comp[c], L.chan[c].amp, vrow[3 * c], vrow[3 * c + 1], sdm_s[r],
-                     L.chan[0].amp_pbf, ctx);
-          accumulate_terms(ctx, rho_s[r], need, acc);
+          const double m = vrow[3 * c], td = vrow[3 * c + 1];
+          bool far = false;
+          if (gate) {  // the very expressions of first_derivatives
+            const double arg_erf = (td - ct.w * ct.w * ch.inv_tau) * ct.inv_w * kSqrtHalf;
+            const double ws = ct.w * ch.inv_tau;
+            const double arg_exp = 0.5 * ws * ws - td * ch.inv_tau - arg_erf * arg_erf;
+            far = arg_exp < -746.0;
+          }
+          if (far) {
+            const double x = (td - tc_mid) * inv_half, rm = rho_s[r] * m;
+            mu0 += rm;
+            mu1 = fma(rm, x, mu1);
+            mu2 = fma(rm * x, x, mu2);
+          } else {
+            D2Ctx ctx;
+            make_d2ctx(A, ch, ct, ch.amp, m, td, sdm_s[r], L.chan[0].amp_pbf, ctx);
+            accumulate_terms(ctx, rho_s[r], need, acc);
+            any_full = 1;
+          }
         }
       }
+      if (gate) {
+        mu_s[(size_t)(3 * c) * kBlock + tid] += mu0;
+        mu_s[(size_t)(3 * c + 1) * kBlock + tid] += mu1;
+        mu_s[(size_t)(3 * c + 2) * kBlock + tid] += mu2;
+      }
+      if (!__syncthreads_or(any_full)) continue;  // nothing but far samples in this super-tile
       // flush: column sums of the needed accumulators (fixed order), then the pair updates
       for (int k0 = 0; k0 < kNumTerms; k0 += kFlushChunk) {
 #pragma unroll
@@ -639,17 +753,311 @@ __global__ void __launch_bounds__(kBlock, 4) k_hessian_acc(const HessAccArgs H) 
       __syncthreads();
     }
   }
+  if (cur >= 0 && shortcut) flush_moments();
   __syncthreads();
   for (int e = tid; e < npairs; e += kBlock) H.partials[(size_t)blockIdx.x * npairs + e] = pacc[e];
 }
 
-__global__ void k_hess_finalize(const double* __restrict__ partials, int nblocks, int npairs,
-                                double* __restrict__ out) {
-  for (int pi = blockIdx.x * blockDim.x + threadIdx.x; pi < npairs; pi += gridDim.x * blockDim.x) {
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * npairs + pi];
-    out[pi] = s;
+// ---- warp-granular Hessian contraction for the fast path (fb_fast.cuh conventions) ------------
+// Same far-sample polynomial shortcut as k_hessian_acc, organised like k_gram3: a block owns one
+// channel at a time and reads the spectrum rows k_vals3 left in global memory.
+//   phase A  every warp streams 32-sample tiles; samples OUTSIDE the near range [j_lo, j_hi) of a
+//            component (where the shared factor G is exactly zero) only feed the three moments
+//            sum(rho M x^p), held in registers for the whole channel;
+//   phase B  the near range of each component (a few dozen samples around the burst) is walked
+//            by the whole block with the full 30-term evaluation, then one block flush;
+//   end      the moments are contracted with the term polynomials at the nodes x = -1, 0, 1.
+constexpr int kHess3Chunk = 15;
+
+__host__ __device__ inline size_t hess3_smem_bytes(int nc, int num_pairs) {
+  size_t n = sizeof(CompTab) * nc + 2 * sizeof(ChanTab) * nc;
+  n += sizeof(double) * (size_t)kHess3Chunk * (kFastBlock + 1);         // flush stage
+  n += sizeof(double) * ((size_t)nc * kFastWarps * 16 + (size_t)nc * 32);  // column partials, totals
+  n += sizeof(double) * (size_t)num_pairs;
+  n += sizeof(double) * ((size_t)kFastWarps * 3 * nc);                  // per-warp moments
+  n += sizeof(double) * 2 * nc;                                         // x mapping per component
+  n += sizeof(int) * (3 * nc + 4 + kFastBlock);                         // ranges, offsets, item component
+  return n;
+}
+
+// Near range of one (channel, component): samples whose arg_exp (first_derivatives) is >= -746.
+// arg_exp is a concave quadratic of the time difference, so the set is an interval; the guess
+// from its roots is fixed up with the exact predicate.
+__device__ inline void hess3_near_range(const PlanConst& pc, const CompTab& ct, const ChanTab& ch, int& j_lo,
+                                        int& j_hi) {
+  const int nt = pc.num_time;
+  if (ch.sc_time == 0.0) {  // Gaussian branch: no shortcut
+    j_lo = 0;
+    j_hi = nt;
+    return;
   }
+  const double kt_mid = 0.5 * (double)(pc.kt - 1);
+  auto far = [&](int j) {
+    const double td = fma(ct.t_step, (double)(j * pc.kt) + kt_mid, ct.t_start) - ch.mean_delay;
+    const double arg_erf = (td - ct.w * ct.w * ch.inv_tau) * ct.inv_w * kSqrtHalf;
+    const double ws = ct.w * ch.inv_tau;
+    const double arg_exp = 0.5 * ws * ws - td * ch.inv_tau - arg_erf * arg_erf;
+    return arg_exp < -746.0;
+  };
+  // arg_exp = -td^2 / (2 w^2): near where |td| <= w sqrt(2 * 746)
+  const double half = ct.w * sqrt(2.0 * 746.0);
+  const double span = ct.t_step * (double)pc.kt;
+  const double t0 = fma(ct.t_step, kt_mid, ct.t_start) - ch.mean_delay;  // td of sample 0
+  double g = floor((-half - t0) / span);
+  j_lo = (int)fmin(fmax(g, 0.0), (double)nt);
+  g = ceil((half - t0) / span) + 1.0;
+  j_hi = (int)fmin(fmax(g, 0.0), (double)nt);
+  if (!(j_lo <= j_hi)) {  // NaN tables: no shortcut
+    j_lo = 0;
+    j_hi = nt;
+    return;
+  }
+  if (j_lo == j_hi) {  // guess says "no near sample": make sure by probing the closest one
+    const int jc = min(max((int)((0.0 - t0) / span), 0), nt - 1);
+    if (far(jc)) return;
+    j_lo = jc;
+    j_hi = jc + 1;
+  }
+  while (j_lo > 0 && !far(j_lo - 1)) --j_lo;
+  while (j_lo < j_hi && far(j_lo)) ++j_lo;
+  while (j_hi < nt && !far(j_hi)) ++j_hi;
+  while (j_hi > j_lo && far(j_hi - 1)) --j_hi;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(kFastBlock, 2) k_hess3(const HessAccArgs H) {
+  extern __shared__ __align__(16) unsigned char fast_smem[];
+  const EvalArgs& A = H.E;
+  const PlanConst& pc = A.pc;
+  const int nt = pc.num_time, kt = pc.kt;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int npairs = H.num_pairs;
+  char* sp = reinterpret_cast<char*>(fast_smem);
+  CompTab* comp = reinterpret_cast<CompTab*>(sp);
+  sp += sizeof(CompTab) * NC;
+  char* tabs = sp;
+  sp += 2 * sizeof(ChanTab) * NC;
+  double* stage = reinterpret_cast<double*>(sp);             // [kHess3Chunk][kFastBlock + 1]
+  double* part = stage + (size_t)kHess3Chunk * (kFastBlock + 1);  // [NC][warps][16]
+  double* total = part + NC * kFastWarps * 16;               // [NC][32]
+  double* pacc = total + NC * 32;
+  double* musum = pacc + npairs;                             // [warps][3 NC]
+  double* xmap = musum + kFastWarps * 3 * NC;                // [NC][2]: x = tj * xmap[0] + xmap[1]
+  int* range = reinterpret_cast<int*>(xmap + 2 * NC);        // [NC][2]
+  int* offs = range + 2 * NC;                                // [NC + 1] item offsets of the near ranges
+  int* compid = offs + NC + 4;                               // [kFastBlock] component of each thread's item
+
+  {
+    const double* src = reinterpret_cast<const double*>(A.g_comp);
+    double* dst = reinterpret_cast<double*>(comp);
+    for (int e = tid; e < NC * (int)(sizeof(CompTab) / sizeof(double)); e += kFastBlock) dst[e] = src[e];
+  }
+  for (int e = tid; e < npairs; e += kFastBlock) pacc[e] = 0.0;
+  const int wtiles = (nt + 31) / 32;
+  const int chan_chunks = (int)(sizeof(ChanTab) * NC / 16);
+  auto prefetch_tables = [&](int chi, int buf) {
+    if (chi < A.num_chan && tid < chan_chunks) {
+      const int i = A.chan_list ? A.chan_list[chi] : chi;
+      cp_async16(tabs + (size_t)buf * sizeof(ChanTab) * NC + 16 * tid,
+                 reinterpret_cast<const char*>(A.g_chan + (size_t)i * NC) + 16 * tid);
+    }
+    cp_async_commit();
+  };
+  const double tau0 = global_param(A.params, NC, FB_SCATTERING_TIMESCALE);
+  const double kt_mid = 0.5 * (double)(kt - 1);
+  const double tj_last = (double)((nt - 1) * kt) + kt_mid;
+  const bool shortcut = !H.need_sum_dmidx && nt > 2;
+
+  prefetch_tables(blockIdx.x, 0);
+  int buf = 0;
+  for (int chi = blockIdx.x; chi < A.num_chan; chi += gridDim.x, buf ^= 1) {
+    const int i = A.chan_list ? A.chan_list[chi] : chi;
+    cp_async_wait<0>();
+    __syncthreads();
+    prefetch_tables(chi + gridDim.x, buf ^ 1);
+    const ChanTab* chan = reinterpret_cast<const ChanTab*>(tabs + (size_t)buf * sizeof(ChanTab) * NC);
+    if (tid < NC) {
+      const CompTab& ct = comp[tid];
+      const ChanTab& ch = chan[tid];
+      int j_lo = 0, j_hi = nt;
+      if (shortcut) hess3_near_range(pc, ct, ch, j_lo, j_hi);
+      range[2 * tid] = j_lo;
+      range[2 * tid + 1] = j_hi;
+      const double tc_lo = fma(ct.t_step, kt_mid, ct.t_start) - ch.mean_delay;
+      const double tc_hi = fma(ct.t_step, tj_last, ct.t_start) - ch.mean_delay;
+      const double tc_mid = 0.5 * (tc_lo + tc_hi), inv_half = 2.0 / (tc_hi - tc_lo);
+      xmap[2 * tid] = ct.t_step * inv_half;
+      xmap[2 * tid + 1] = (ct.t_start - ch.mean_delay - tc_mid) * inv_half;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int o = 0;
+      for (int c = 0; c < NC; ++c) {
+        offs[c] = o;
+        o += range[2 * c + 1] - range[2 * c];
+      }
+      offs[NC] = o;
+    }
+    const double wi = A.weights[i];
+    const double w2 = wi * wi;
+    const double* srow = H.gvals + (size_t)chi * NC * nt;
+    const double* drow = A.data + (size_t)i * nt;
+
+    // phase A: far samples -> moments
+    {
+      double mu[NC][3];
+#pragma unroll
+      for (int c = 0; c < NC; ++c) mu[c][0] = mu[c][1] = mu[c][2] = 0.0;
+      for (int wt = warp; wt < wtiles; wt += kFastWarps) {
+        const int j = wt * 32 + lane;
+        if (j < nt) {
+          double m[NC], msum = 0.0;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            m[c] = __ldg(srow + (size_t)c * nt + j);
+            msum += m[c];
+          }
+          const double rho = (__ldg(drow + j) - msum) * w2;
+          const double tj = (double)(j * kt) + kt_mid;
+#pragma unroll
+          for (int c = 0; c < NC; ++c) {
+            if (j < range[2 * c] || j >= range[2 * c + 1]) {
+              const double x = fma(tj, xmap[2 * c], xmap[2 * c + 1]), rm = rho * m[c];
+              mu[c][0] += rm;
+              mu[c][1] = fma(rm, x, mu[c][1]);
+              mu[c][2] = fma(rm * x, x, mu[c][2]);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {
+          double v = mu[c][p];
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(kFullMask, v, off);
+          if (lane == 0) musum[warp * 3 * NC + 3 * c + p] = v;
+        }
+    }
+    __syncthreads();
+
+    // phase B: one item per thread -- the near samples of every component with the full term
+    // evaluation, plus 3 node items per component that contract the far-sample moments
+    const int n_near = offs[NC];
+    const int n_items = n_near + (shortcut ? 3 * NC : 0);
+    for (int base = 0; base < n_items; base += kFastBlock) {
+      const int e = base + tid;
+      double acc[kNumTerms];
+#pragma unroll
+      for (int k = 0; k < kNumTerms; ++k) acc[k] = 0.0;
+      int my_c = -1;
+      if (e < n_near) {
+        int c = 0;
+#pragma unroll
+        for (int cc = 1; cc < NC; ++cc)
+          if (e >= offs[cc]) c = cc;
+        const int j = range[2 * c] + (e - offs[c]);
+        double msum = 0.0, mc = 0.0, sdm = 0.0;
+        const double tj = (double)(j * kt) + kt_mid;
+#pragma unroll
+        for (int cc = 0; cc < NC; ++cc) {
+          const double mv = __ldg(srow + (size_t)cc * nt + j);
+          msum += mv;
+          if (cc == c) mc = mv;
+          if (H.need_sum_dmidx) {
+            double d[9], g;
+            first_derivatives(chan[cc], chan[cc], comp[cc], tau0, chan[cc].amp, mv,
+                              fma(comp[cc].t_step, tj, comp[cc].t_start) - chan[cc].mean_delay, d, &g);
+            sdm += d[FB_DM_INDEX];
+          }
+        }
+        const double rho = (__ldg(drow + j) - msum) * w2;
+        const double td = fma(comp[c].t_step, tj, comp[c].t_start) - chan[c].mean_delay;
+        D2Ctx ctx;
+        make_d2ctx(A, chan[c], comp[c], chan[c].amp, mc, td, sdm, chan[0].amp_pbf, ctx);
+        accumulate_terms(ctx, rho, H.need[c], acc);
+        my_c = c;
+      } else if (e < n_items) {
+        const int c = (e - n_near) / 3, q = (e - n_near) % 3;
+        double m0 = 0.0, m1 = 0.0, m2 = 0.0;
+        for (int wv = 0; wv < kFastWarps; ++wv) {
+          m0 += musum[wv * 3 * NC + 3 * c];
+          m1 += musum[wv * 3 * NC + 3 * c + 1];
+          m2 += musum[wv * 3 * NC + 3 * c + 2];
+        }
+        // Lagrange weights of the nodes x = -1, 0, 1 applied to the moments
+        const double lam = q == 0 ? 0.5 * (m2 - m1) : (q == 1 ? m0 - m2 : 0.5 * (m2 + m1));
+        if (lam != 0.0) {
+          const CompTab& ct = comp[c];
+          const ChanTab& ch = chan[c];
+          const double t_lo = fma(ct.t_step, kt_mid, ct.t_start) - ch.mean_delay;
+          const double t_hi = fma(ct.t_step, tj_last, ct.t_start) - ch.mean_delay;
+          const double t_node = q == 0 ? t_lo : (q == 2 ? t_hi : 0.5 * (t_lo + t_hi));
+          D2Ctx ctx;
+          make_d2ctx(A, ch, ct, ch.amp, 1.0, t_node, 0.0, chan[0].amp_pbf, ctx, true);
+          accumulate_terms(ctx, lam, H.need[c], acc);
+          my_c = c;
+        }
+      }
+      compid[tid] = my_c;
+      // flush: per-component column sums in fixed order
+      for (int k0 = 0; k0 < kNumTerms; k0 += kHess3Chunk) {
+#pragma unroll
+        for (int k = 0; k < kHess3Chunk; ++k) stage[k * (kFastBlock + 1) + tid] = acc[k0 + k];
+        __syncthreads();
+        if (lane < kHess3Chunk) {
+          const double* col = stage + lane * (kFastBlock + 1) + warp * 32;
+          const int* cid = compid + warp * 32;
+          double sum[NC];
+#pragma unroll
+          for (int c = 0; c < NC; ++c) sum[c] = 0.0;
+          for (int r = 0; r < 32; ++r) {
+            const double v = col[r];
+            const int id = cid[r];
+#pragma unroll
+            for (int c = 0; c < NC; ++c) sum[c] += (id == c) ? v : 0.0;
+          }
+#pragma unroll
+          for (int c = 0; c < NC; ++c) part[(c * kFastWarps + warp) * 16 + lane] = sum[c];
+        }
+        __syncthreads();
+        if (tid < kHess3Chunk * NC) {
+          const int c = tid / kHess3Chunk, k = tid % kHess3Chunk;
+          double sum = 0.0;
+          for (int wv = 0; wv < kFastWarps; ++wv) sum += part[(c * kFastWarps + wv) * 16 + k];
+          total[c * 32 + k0 + k] = sum;
+        }
+        __syncthreads();
+      }
+      for (int c = 0; c < NC; ++c) {
+        const double lf = chan[c].logf;
+        const int lo = H.comp_off[c], cnt = H.comp_off[c + 1] - lo;
+        for (int p = tid; p < cnt; p += kFastBlock) {
+          const int pair = H.comp_list[lo + p];
+          const HessDesc d = H.desc[pair];
+          const double factor = d.code == 0 ? 1.0 : (d.code == 1 ? kLn10 : (d.code == 2 ? lf : lf * lf));
+          pacc[pair] += factor * total[c * 32 + d.idx];
+        }
+        __syncthreads();
+      }
+    }
+  }
+  cp_async_wait<0>();
+  __syncthreads();
+  for (int e = tid; e < npairs; e += kFastBlock) H.partials[(size_t)blockIdx.x * npairs + e] = pacc[e];
+}
+
+// One warp per pair: lanes stride over the blocks, fixed-shape shuffle tree (deterministic).
+__global__ void __launch_bounds__(128) k_hess_finalize(const double* __restrict__ partials, int nblocks, int npairs,
+                                                      double* __restrict__ out) {
+  const int pi = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (pi >= npairs) return;
+  double s = 0.0;
+  for (int b = lane; b < nblocks; b += 32) s += partials[(size_t)b * npairs + pi];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) out[pi] = s;
 }
 
 }  // namespace fb

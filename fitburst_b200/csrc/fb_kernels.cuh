@@ -941,13 +941,21 @@ __global__ void __launch_bounds__(kBlock, 6) k_chi2(const EvalArgs A) {
   if (tid == 0) A.chi2_partials[blockIdx.x] = red[0];
 }
 
-// Sums per-block chi^2 partials in block order into out[0].
-__global__ void k_chi2_finalize(const double* __restrict__ partials, int nblocks, double* __restrict__ out) {
-  if (threadIdx.x == 0 && blockIdx.x == 0) {
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += partials[b];
-    out[0] = s;
+// Sums per-block chi^2 partials into out[0]: strided per-thread sums, then a fixed-shape tree
+// (deterministic). Launch with one block of 256 threads.
+__global__ void __launch_bounds__(256) k_chi2_finalize(const double* __restrict__ partials, int nblocks,
+                                                      double* __restrict__ out) {
+  __shared__ double red[256];
+  const int tid = threadIdx.x;
+  double s = 0.0;
+  for (int b = tid; b < nblocks; b += 256) s += partials[b];
+  red[tid] = s;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if (tid < off) red[tid] += red[tid + off];
+    __syncthreads();
   }
+  if (tid == 0) out[0] = red[0];
 }
 
 // Overrides the global dm / scattering_timescale rows of a parameter block (chi^2 grid sweep).
