@@ -60,6 +60,7 @@ struct fb_plan_s {
   bool last_eval_split = false;
   int vals_layout = 2;       // 2: k_vals planes (spectrum, timediff) per tile; 3: k_vals3 rows (spectrum only)
   double* d_racc = nullptr;  // k_gram3 accumulators summed over blocks
+  double* d_far = nullptr;   // k_gram3 far-tile matrix (upper triangle) summed over blocks
   int occ_cache[64];         // occupancy of the fast kernels by instantiation (0 = not queried yet)
   double* d_hess_partials = nullptr;
   size_t hess_partials_cap = 0;
@@ -173,6 +174,7 @@ extern "C" int fb_plan_create(const fb_plan_desc* desc, const double* freqs_host
   chk(cudaMalloc(&p->d_err, sizeof(int)));
   chk(cudaMalloc(&p->d_gram, gsz));
   chk(cudaMalloc(&p->d_racc, sizeof(double) * 64 * 16));
+  chk(cudaMalloc(&p->d_far, sizeof(double) * (FB_MAX_FREE + 1) * (FB_MAX_FREE + 2) / 2));
   chk(cudaMalloc(&p->d_comp, sizeof(CompTab) * FB_MAX_COMPONENTS));
   chk(cudaMalloc(&p->d_sub, sizeof(SubTab) * (size_t)nf * desc->num_components * kf));
   chk(cudaMalloc(&p->d_chan, sizeof(ChanTab) * (size_t)nf * desc->num_components));
@@ -211,6 +213,7 @@ extern "C" int fb_plan_destroy(fb_plan_t p) {
   cudaFree(p->d_comp_list);
   cudaFree(p->d_vals);
   cudaFree(p->d_racc);
+  cudaFree(p->d_far);
   cudaFree(p->d_desc);
   cudaFree(p->d_comp);
   cudaFree(p->d_sub);
@@ -498,21 +501,25 @@ static int launch_vals3(fb_plan_s* p, const EvalArgs& A, double* out, cudaStream
 }
 
 template <int NC, int NB>
-static int launch_gram3_t(fb_plan_s* p, const EvalArgs& A, const GramLayout& G, cudaStream_t st, int* grid_out) {
-  const size_t smem = gram3_smem_bytes(NC, NB);
+static int launch_gram3_t(fb_plan_s* p, const EvalArgs& A, const GramLayout& G, const FarLayout& F, cudaStream_t st,
+                          int* grid_out) {
+  const size_t smem = gram3_smem_bytes(NC, NB, F.ncols);
+  if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request exceeds 227 KB");
   int& occ = p->occ_cache[16 + (NC - 1) * 3 + (NB - 1)];
-  if (occ == 0) {
+  if (occ == 0 || smem > 48 * 1024) {
     if (smem > 48 * 1024)
       CUDA_TRY(cudaFuncSetAttribute(k_gram3<NC, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gram3<NC, NB>, kFastBlock, smem));
     if (occ < 1) occ = 1;
   }
   const int grid = std::min(A.num_chan, p->sm_count * occ);
-  int rc = ensure_capacity(&p->d_partials, &p->partials_cap, (size_t)grid * g3_nacc(NB) * 64);
+  const int nent = F.ncols * (F.ncols + 1) / 2;
+  const size_t near_sz = (size_t)grid * g3_nacc(NB) * 64;
+  int rc = ensure_capacity(&p->d_partials, &p->partials_cap, near_sz + (size_t)grid * nent);
   if (rc != FB_OK) return rc;
   EvalArgs B = A;
   B.partials = p->d_partials;
-  k_gram3<NC, NB><<<grid, kFastBlock, smem, st>>>(B, G, p->d_vals);
+  k_gram3<NC, NB><<<grid, kFastBlock, smem, st>>>(B, G, F, p->d_vals, p->d_partials + near_sz);
   CUDA_TRY(cudaGetLastError());
   p->launches += 1;
   *grid_out = grid;
@@ -520,11 +527,12 @@ static int launch_gram3_t(fb_plan_s* p, const EvalArgs& A, const GramLayout& G, 
 }
 
 template <int NC>
-static int launch_gram3_nc(fb_plan_s* p, const EvalArgs& A, const GramLayout& G, int nb, cudaStream_t st, int* grid_out) {
+static int launch_gram3_nc(fb_plan_s* p, const EvalArgs& A, const GramLayout& G, const FarLayout& F, int nb,
+                           cudaStream_t st, int* grid_out) {
   switch (nb) {
-    case 1: return launch_gram3_t<NC, 1>(p, A, G, st, grid_out);
-    case 2: return launch_gram3_t<NC, 2>(p, A, G, st, grid_out);
-    default: return launch_gram3_t<NC, 3>(p, A, G, st, grid_out);
+    case 1: return launch_gram3_t<NC, 1>(p, A, G, F, st, grid_out);
+    case 2: return launch_gram3_t<NC, 2>(p, A, G, F, st, grid_out);
+    default: return launch_gram3_t<NC, 3>(p, A, G, F, st, grid_out);
   }
 }
 
@@ -539,17 +547,43 @@ static int launch_fast_gram(fb_plan_s* p, EvalArgs& A, int ncols, double* gram_d
   if (rc != FB_OK) return rc;
   const GramLayout G = gram3_layout(p);
   const int nb = (G.nr + 7) / 8;
+  // far-tile path: full-column descriptors (2 nc + 1 basis values must fit one 8-column block)
+  FarLayout F;
+  memset(&F, 0, sizeof(F));
+  F.ncols = ncols;
+  const int nent = ncols * (ncols + 1) / 2;
+  F.enabled = (2 * nc + 1 <= 8 && nent <= 2 * kFastBlock && !env_off("FITBURST_B200_FAR")) ? 1 : 0;
+  for (int k = 0; k < 9; ++k) {
+    const int col = p->col_of[k];
+    if (col < 0) continue;
+    if (is_fit_global(k)) {
+      F.param[col] = (int8_t)k;
+      F.comp[col] = -1;
+    } else {
+      for (int c = 0; c < nc; ++c) {
+        F.param[col + c] = (int8_t)k;
+        F.comp[col + c] = (int8_t)c;
+      }
+    }
+  }
+  F.param[ncols - 1] = 9;
+  F.comp[ncols - 1] = -1;
   int grid = 0;
   switch (nc) {
-    case 1: rc = launch_gram3_nc<1>(p, A, G, nb, st, &grid); break;
-    case 2: rc = launch_gram3_nc<2>(p, A, G, nb, st, &grid); break;
-    case 3: rc = launch_gram3_nc<3>(p, A, G, nb, st, &grid); break;
-    default: rc = launch_gram3_nc<4>(p, A, G, nb, st, &grid); break;
+    case 1: rc = launch_gram3_nc<1>(p, A, G, F, nb, st, &grid); break;
+    case 2: rc = launch_gram3_nc<2>(p, A, G, F, nb, st, &grid); break;
+    case 3: rc = launch_gram3_nc<3>(p, A, G, F, nb, st, &grid); break;
+    default: rc = launch_gram3_nc<4>(p, A, G, F, nb, st, &grid); break;
   }
   if (rc != FB_OK) return rc;
   const int entries = g3_nacc(nb) * 64;
   k_gram3_reduce<<<(entries + 7) / 8, 256, 0, st>>>(p->d_partials, grid, entries, p->d_racc);
   CUDA_TRY(cudaGetLastError());
+  if (F.enabled) {
+    k_gram3_reduce<<<(nent + 7) / 8, 256, 0, st>>>(p->d_partials + (size_t)grid * entries, grid, nent, p->d_far);
+    CUDA_TRY(cudaGetLastError());
+    p->launches += 1;
+  }
   ExpandArgs X;
   memset(&X, 0, sizeof(X));
   X.ncols = ncols;
@@ -578,7 +612,7 @@ static int launch_fast_gram(fb_plan_s* p, EvalArgs& A, int ncols, double* gram_d
   X.power[ncols - 1] = 0;
   X.factor[ncols - 1] = 1.0;
   X.shift[ncols - 1] = 0.0;
-  k_gram3_expand<<<(ncols * ncols + 255) / 256, 256, 0, st>>>(p->d_racc, X, gram_dev);
+  k_gram3_expand<<<(ncols * ncols + 255) / 256, 256, 0, st>>>(p->d_racc, X, F.enabled ? p->d_far : nullptr, gram_dev);
   CUDA_TRY(cudaGetLastError());
   p->launches += 2;
   return FB_OK;

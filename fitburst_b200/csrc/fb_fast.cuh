@@ -36,7 +36,19 @@
 
 namespace fb {
 
-constexpr int kFastBlock = 256;
+#ifndef FB_FAST_BLOCK
+#define FB_FAST_BLOCK 128  // measured: 128-thread blocks beat 256 (0.71 -> 0.60 ms per evaluation) and 64
+#endif
+#ifndef FB_V3_MINB
+#define FB_V3_MINB 5
+#endif
+#ifndef FB_G3_MINB
+#define FB_G3_MINB 4
+#endif
+#ifndef FB_H3_MINB
+#define FB_H3_MINB 4
+#endif
+constexpr int kFastBlock = FB_FAST_BLOCK;
 constexpr int kFastWarps = kFastBlock / 32;
 constexpr unsigned kFullMask = 0xffffffffu;
 
@@ -171,7 +183,7 @@ __device__ __forceinline__ double vals3_component(const PlanConst& pc, const Com
 // Stores the spectrum value of every (good channel, component, sample):
 // gvals[(chi * nc + c) * num_time + j].
 template <int KF>
-__global__ void __launch_bounds__(kFastBlock, 3) k_vals3(const EvalArgs A, double* __restrict__ gvals) {
+__global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs A, double* __restrict__ gvals) {
   extern __shared__ __align__(16) unsigned char fast_smem[];
   const PlanConst& pc = A.pc;
   const int nc = pc.num_comp, kf = KF > 0 ? KF : pc.kf, kt = pc.kt, nt = pc.num_time;
@@ -338,17 +350,83 @@ __host__ __device__ constexpr int g3_acc_offset(int nb, int bi, int bj) {
 }
 __host__ __device__ constexpr int g3_nacc(int nb) { return g3_acc_offset(nb, nb, nb); }
 
-__host__ __device__ inline size_t gram3_smem_bytes(int nc, int nb) {
+// Near range of one (channel, component): samples whose arg_exp (first_derivatives) is >= -746.
+// arg_exp is a concave quadratic of the time difference, so the set is an interval; the guess
+// from its roots is fixed up with the exact predicate.
+__device__ inline void near_range(const PlanConst& pc, const CompTab& ct, const ChanTab& ch, int& j_lo,
+                                        int& j_hi) {
+  const int nt = pc.num_time;
+  if (ch.sc_time == 0.0) {  // Gaussian branch: no shortcut
+    j_lo = 0;
+    j_hi = nt;
+    return;
+  }
+  const double kt_mid = 0.5 * (double)(pc.kt - 1);
+  auto far = [&](int j) {
+    const double td = fma(ct.t_step, (double)(j * pc.kt) + kt_mid, ct.t_start) - ch.mean_delay;
+    const double arg_erf = (td - ct.w * ct.w * ch.inv_tau) * ct.inv_w * kSqrtHalf;
+    const double ws = ct.w * ch.inv_tau;
+    const double arg_exp = 0.5 * ws * ws - td * ch.inv_tau - arg_erf * arg_erf;
+    return arg_exp < -746.0;
+  };
+  // arg_exp = -td^2 / (2 w^2): near where |td| <= w sqrt(2 * 746)
+  const double half = ct.w * sqrt(2.0 * 746.0);
+  const double span = ct.t_step * (double)pc.kt;
+  const double t0 = fma(ct.t_step, kt_mid, ct.t_start) - ch.mean_delay;  // td of sample 0
+  double g = floor((-half - t0) / span);
+  j_lo = (int)fmin(fmax(g, 0.0), (double)nt);
+  g = ceil((half - t0) / span) + 1.0;
+  j_hi = (int)fmin(fmax(g, 0.0), (double)nt);
+  if (!(j_lo <= j_hi)) {  // NaN tables: no shortcut
+    j_lo = 0;
+    j_hi = nt;
+    return;
+  }
+  if (j_lo == j_hi) {  // guess says "no near sample": make sure by probing the closest one
+    const int jc = min(max((int)((0.0 - t0) / span), 0), nt - 1);
+    if (far(jc)) return;
+    j_lo = jc;
+    j_hi = jc + 1;
+  }
+  while (j_lo > 0 && !far(j_lo - 1)) --j_lo;
+  while (j_lo < j_hi && far(j_lo)) ++j_lo;
+  while (j_hi < nt && !far(j_hi)) ++j_hi;
+  while (j_hi > j_lo && far(j_hi - 1)) --j_hi;
+}
+
+
+// Far tiles (every sample outside the near range of every component: the shared factor G of
+// the first derivatives is exactly zero there): each column of [J r] is a per-channel linear
+// combination of the 2 NC + 1 basis values b = [M_c, M_c xi ..., r], xi = sample position mapped
+// to [-1, 1] (d/dtau and d/dalpha are M times a polynomial of degree 1 in the time difference).
+// Such a tile contributes through ONE 8x8 block B = sum b b^T (8 DMMA per 32 samples instead of
+// 24, a dozen flops per sample instead of ~100), and at the end of the channel the block adds
+// T B T^T to its full-matrix accumulators, T = (n+1) x 8 per-channel coefficients.
+struct FarLayout {
+  int enabled;
+  int ncols;                          // n + 1
+  int8_t param[FB_MAX_FREE + 1];      // fb_parameter of full column k, 9 = residual
+  int8_t comp[FB_MAX_FREE + 1];       // component of column k (-1: global / residual)
+};
+
+__host__ __device__ inline size_t gram3_far_smem_bytes(int ncols) {
+  // T [ncols][8], U [8][ncols], per-warp B [warps][64], B [64], ranges
+  return sizeof(double) * ((size_t)16 * ncols + (size_t)kFastWarps * 64 + 64) + sizeof(int) * 2 * FB_MAX_COMPONENTS;
+}
+
+__host__ __device__ inline size_t gram3_smem_bytes(int nc, int nb, int ncols) {
   size_t stage = sizeof(double) * (size_t)kFastWarps * nb * 8 * kMmaRowStride;
   const size_t red = sizeof(double) * (size_t)kFastWarps * g3_nacc(nb) * 64;
   if (red > stage) stage = red;  // the stage doubles as the block-reduction buffer
   const size_t pref = sizeof(double) * 2 * (size_t)(nc + 1) * kFastBlock;  // double-buffered value + data prefetch
-  return sizeof(CompTab) * nc + 2 * sizeof(ChanTab) * nc + sizeof(GTab) * nc + stage + pref;
+  return sizeof(CompTab) * nc + 2 * sizeof(ChanTab) * nc + sizeof(GTab) * nc + stage + pref +
+         gram3_far_smem_bytes(ncols);
 }
 
 template <int NC, int NB>
-__global__ void __launch_bounds__(kFastBlock, 3) k_gram3(const EvalArgs A, const GramLayout G,
-                                                         const double* __restrict__ gvals) {
+__global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs A, const GramLayout G, const FarLayout F,
+                                                         const double* __restrict__ gvals,
+                                                         double* __restrict__ far_partials) {
   extern __shared__ __align__(16) unsigned char fast_smem[];
   const PlanConst& pc = A.pc;
   const int kt = pc.kt, nt = pc.num_time;
@@ -371,6 +449,15 @@ __global__ void __launch_bounds__(kFastBlock, 3) k_gram3(const EvalArgs A, const
   // [2][NC + 1][32] per warp: every lane copies and later reads only its own elements, so
   // cp.async.wait_group is the only synchronisation the prefetch needs
   double* pref = reinterpret_cast<double*>(sp) + (size_t)warp * 2 * (NC + 1) * 32 + lane;
+  sp += sizeof(double) * 2 * (size_t)(NC + 1) * kFastBlock;
+  const int ncols = F.ncols;
+  double* Tm = reinterpret_cast<double*>(sp);       // [ncols][8]
+  double* Um = Tm + (size_t)8 * ncols;              // [8][ncols]
+  double* Bw = Um + (size_t)8 * ncols;              // [warps][64]
+  double* Bs = Bw + kFastWarps * 64;                // [64]
+  int* range = reinterpret_cast<int*>(Bs + 64);     // [NC][2] near range of every component
+  constexpr bool kFarFits = 2 * NC + 1 <= 8;
+  const bool far_on = kFarFits && F.enabled && nt > 2;
 
   {
     const double* src = reinterpret_cast<const double*>(A.g_comp);
@@ -385,6 +472,25 @@ __global__ void __launch_bounds__(kFastBlock, 3) k_gram3(const EvalArgs A, const
   for (int k = 0; k < kPairs; ++k) c0[k] = c1[k] = 0.0;
 #pragma unroll
   for (int k = 0; k < kAcc; ++k) acc0[k] = acc1[k] = 0.0;
+  double cf0 = 0.0, cf1 = 0.0;  // far-tile block B of the current channel
+  // full-matrix accumulators of the far tiles: thread e owns upper-triangle entries e and e + 256
+  const int nent = ncols * (ncols + 1) / 2;
+  double gacc[2] = {0.0, 0.0};
+  int ek[2] = {0, 0}, el[2] = {0, 0};
+  if (far_on) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      int e = tid + s * kFastBlock, k = 0;
+      if (e < nent) {
+        while (e >= ncols - k) {
+          e -= ncols - k;
+          ++k;
+        }
+        ek[s] = k;
+        el[s] = k + e;
+      }
+    }
+  }
 
   const int wtiles = (nt + 31) / 32;
   const int chan_chunks = (int)(sizeof(ChanTab) * NC / 16);
@@ -399,6 +505,9 @@ __global__ void __launch_bounds__(kFastBlock, 3) k_gram3(const EvalArgs A, const
   const double tau0 = global_param(A.params, NC, FB_SCATTERING_TIMESCALE);
   const double inv_tau0 = 1.0 / tau0;
   const double kt_mid = 0.5 * (double)(kt - 1);
+  // xi = (tj - tj_mid) / tj_half over the samples of a channel
+  const double tj_half = 0.5 * (double)((nt - 1) * kt), tj_mid = kt_mid + tj_half;
+  const double xi_s = 1.0 / tj_half, xi_o = -tj_mid / tj_half;
   const int fr = lane & 3, fc = lane >> 2;  // fragment element: sample fr of the step, column fc of the block
   prefetch_tables(blockIdx.x, 0);
   int buf = 0;
@@ -408,6 +517,9 @@ __global__ void __launch_bounds__(kFastBlock, 3) k_gram3(const EvalArgs A, const
     __syncthreads();
     prefetch_tables(chi + gridDim.x, buf ^ 1);
     const ChanTab* chan = reinterpret_cast<const ChanTab*>(tabs + (size_t)buf * sizeof(ChanTab) * NC);
+    bool std_ok = true;  // every component on the scattered branch at this channel
+#pragma unroll
+    for (int c = 0; c < NC; ++c) std_ok = std_ok && (chan[c].sc_time != 0.0);
     if (tid < NC) {
       const ChanTab& ch = chan[tid];
       const ChanTab& ch0 = chan[0];
@@ -429,11 +541,44 @@ __global__ void __launch_bounds__(kFastBlock, 3) k_gram3(const EvalArgs A, const
       t.d_dmidx = ch.d_dmidx;
       t.mean_delay = ch.mean_delay;
       gt[tid] = t;
+      int j_lo = 0, j_hi = nt;
+      if (far_on && std_ok) near_range(pc, ct, ch, j_lo, j_hi);
+      range[2 * tid] = j_lo;
+      range[2 * tid + 1] = j_hi;
     }
     __syncthreads();
-    bool std_ok = true;  // every component on the scattered branch at this channel
-#pragma unroll
-    for (int c = 0; c < NC; ++c) std_ok = std_ok && (chan[c].sc_time != 0.0);
+    const double wi = A.weights[i];
+    if (far_on) {
+      // T[k][a]: coefficient of basis value a in full column k (weight included)
+      for (int e = tid; e < ncols * 8; e += kFastBlock) {
+        const int k = e >> 3, a = e & 7, prm = F.param[k], cc = F.comp[k];
+        const int ca = a >> 1;            // component the basis value belongs to (a < 2 NC)
+        const bool lin = (a & 1) != 0;    // M_c xi rather than M_c
+        double v = 0.0;
+        if (a < 2 * NC) {
+          const GTab& t = gt[ca];
+          const CompTab& ct = comp[ca];
+          // time difference of component ca: td = p + q xi
+          const double q = ct.t_step * tj_half;
+          const double p = fma(ct.t_step, tj_mid, ct.t_start) - t.mean_delay;
+          const double u0 = p * t.inv_tau - t.ws2, u1 = q * t.inv_tau;  // u = u0 + u1 xi
+          if (cc == ca && !lin) {
+            if (prm == FB_AMPLITUDE) v = -kLn10;
+            else if (prm == FB_SPECTRAL_INDEX) v = -t.lf;
+            else if (prm == FB_SPECTRAL_RUNNING) v = -t.lf * t.lf;
+            else if (prm == FB_ARRIVAL_TIME) v = -t.inv_tau;
+            else if (prm == FB_BURST_WIDTH) v = -t.a_w;
+          }
+          if (prm == FB_DM && !lin) v = t.d_dm * t.inv_tau;
+          if (prm == FB_DM_INDEX && !lin) v = t.d_dmidx * t.inv_tau;
+          if (prm == FB_SCATTERING_TIMESCALE) v = lin ? -u1 * inv_tau0 : -(t.a_tau + u0 * inv_tau0);
+          if (prm == FB_SCATTERING_INDEX) v = lin ? -t.lf * u1 : -(t.a_alpha + t.lf * u0);
+        } else if (a == 2 * NC && prm == 9) {
+          v = 1.0;
+        }
+        Tm[e] = v * wi;
+      }
+    }
 
     const double* srow = gvals + (size_t)chi * NC * nt;
     const double* drow = A.data + (size_t)i * nt;
@@ -450,7 +595,7 @@ __global__ void __launch_bounds__(kFastBlock, 3) k_gram3(const EvalArgs A, const
     prefetch_tile(warp, 0);
     int pb = 0;
     for (int wt = warp; wt < wtiles; wt += kFastWarps, pb ^= 1) {
-      const int j = wt * 32 + lane;
+      const int j0 = wt * 32, j = j0 + lane;
       const bool valid = j < nt;
       prefetch_tile(wt + kFastWarps, pb ^ 1);
       cp_async_wait<1>();
@@ -461,9 +606,33 @@ __global__ void __launch_bounds__(kFastBlock, 3) k_gram3(const EvalArgs A, const
         for (int c = 0; c < NC; ++c) m[c] = valid ? src[c * 32] : 0.0;
         if (valid) dval = src[NC * 32];
       }
-      double msum = 0.0, s_dm = 0.0, s_dmidx = 0.0, s_tau = 0.0, s_alpha = 0.0;
       double* row = xt + lane;
       const double tj = (double)(j * kt) + kt_mid;
+      bool far_tile = far_on;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) far_tile = far_tile && (j0 + 32 <= range[2 * c] || j0 >= range[2 * c + 1]);
+      if (far_tile) {
+        const double xi = fma(tj, xi_s, xi_o);
+        double msum = 0.0;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          msum += m[c];
+          row[(2 * c) * kMmaRowStride] = m[c];
+          row[(2 * c + 1) * kMmaRowStride] = m[c] * xi;
+        }
+        row[(2 * NC) * kMmaRowStride] = valid ? dval - msum : 0.0;
+#pragma unroll
+        for (int a = 2 * NC + 1; a < 8; ++a) row[a * kMmaRowStride] = 0.0;
+        __syncwarp();
+#pragma unroll
+        for (int step = 0; step < 8; ++step) {
+          const double f = xt[fc * kMmaRowStride + 4 * step + fr];
+          dmma8x8x4(cf0, cf1, f, f);
+        }
+        __syncwarp();
+        continue;
+      }
+      double msum = 0.0, s_dm = 0.0, s_dmidx = 0.0, s_tau = 0.0, s_alpha = 0.0;
 #pragma unroll
       for (int c = 0; c < NC; ++c) {
         const CompTab& ct = comp[c];
@@ -511,6 +680,8 @@ __global__ void __launch_bounds__(kFastBlock, 3) k_gram3(const EvalArgs A, const
       if (G.rc_tau >= 0) row[G.rc_tau * kMmaRowStride] = valid ? -s_tau : 0.0;
       if (G.rc_alpha >= 0) row[G.rc_alpha * kMmaRowStride] = valid ? -s_alpha : 0.0;
       row[G.rc_res * kMmaRowStride] = valid ? dval - msum : 0.0;  // analysis/fitter.py:262-264 (weight at the flush)
+      // columns the far path may have used beyond the reduced set
+      for (int a = G.nr; a < 8; ++a) row[a * kMmaRowStride] = 0.0;
       __syncwarp();
 #pragma unroll
       for (int step = 0; step < 8; ++step) {
@@ -531,7 +702,6 @@ __global__ void __launch_bounds__(kFastBlock, 3) k_gram3(const EvalArgs A, const
     // channel flush: acc[p] += w^2 L^p C, C = 0 (L of component 0; k_gram3_expand shifts it
     // for components with a different reference frequency)
     {
-      const double wi = A.weights[i];
       const double lf0 = chan[0].logf;
       double sp_[5];
       sp_[0] = wi * wi;
@@ -552,8 +722,44 @@ __global__ void __launch_bounds__(kFastBlock, 3) k_gram3(const EvalArgs A, const
           ++k;
         }
     }
+    if (far_on) {
+      // far tiles of the channel: B summed over the warps (warp order), U = B T^T, G += T U
+      Bw[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2] = cf0;
+      Bw[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2 + 1] = cf1;
+      cf0 = cf1 = 0.0;
+      __syncthreads();
+      if (tid < 64) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kFastWarps; ++w) s += Bw[w * 64 + tid];
+        Bs[tid] = s;
+      }
+      __syncthreads();
+      for (int e = tid; e < 8 * ncols; e += kFastBlock) {
+        const int a = e / ncols, l = e - a * ncols;
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) s = fma(Bs[a * 8 + b], Tm[l * 8 + b], s);
+        Um[e] = s;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        if (tid + s2 * kFastBlock < nent) {
+          double s = 0.0;
+#pragma unroll
+          for (int a = 0; a < 8; ++a) s = fma(Tm[ek[s2] * 8 + a], Um[a * ncols + el[s2]], s);
+          gacc[s2] += s;
+        }
+      }
+    }
   }
   cp_async_wait<0>();
+  if (far_on) {
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2)
+      if (tid + s2 * kFastBlock < nent) far_partials[(size_t)blockIdx.x * nent + tid + s2 * kFastBlock] = gacc[s2];
+  }
   // block reduction in warp order (deterministic); fragment element of accumulator k:
   // row lane/4, columns 2 (lane%4) + {0, 1} of its 8x8 block
   __syncthreads();
@@ -598,10 +804,15 @@ __device__ inline double g3_binom(int n, int k) {
 }
 
 __global__ void __launch_bounds__(256) k_gram3_expand(const double* __restrict__ racc, const ExpandArgs X,
-                                                      double* __restrict__ gram) {
+                                                      const double* __restrict__ far, double* __restrict__ gram) {
   const int n = X.ncols;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
     int k = e / n, l = e % n;
+    double far_part = 0.0;
+    if (far) {  // upper-triangle entry (min, max) of the far-tile matrix
+      const int a = k < l ? k : l, b = k < l ? l : k;
+      far_part = far[a * n - a * (a - 1) / 2 + (b - a)];
+    }
     if (X.red[k] > X.red[l]) {
       const int t = k;
       k = l;
@@ -621,7 +832,7 @@ __global__ void __launch_bounds__(256) k_gram3_expand(const double* __restrict__
         s += ca * cb * base[(size_t)(a + b) * 64];
       }
     }
-    gram[e] = X.factor[k] * X.factor[l] * s;
+    gram[e] = X.factor[k] * X.factor[l] * s + far_part;
   }
 }
 

@@ -780,52 +780,8 @@ __host__ __device__ inline size_t hess3_smem_bytes(int nc, int num_pairs) {
   return n;
 }
 
-// Near range of one (channel, component): samples whose arg_exp (first_derivatives) is >= -746.
-// arg_exp is a concave quadratic of the time difference, so the set is an interval; the guess
-// from its roots is fixed up with the exact predicate.
-__device__ inline void hess3_near_range(const PlanConst& pc, const CompTab& ct, const ChanTab& ch, int& j_lo,
-                                        int& j_hi) {
-  const int nt = pc.num_time;
-  if (ch.sc_time == 0.0) {  // Gaussian branch: no shortcut
-    j_lo = 0;
-    j_hi = nt;
-    return;
-  }
-  const double kt_mid = 0.5 * (double)(pc.kt - 1);
-  auto far = [&](int j) {
-    const double td = fma(ct.t_step, (double)(j * pc.kt) + kt_mid, ct.t_start) - ch.mean_delay;
-    const double arg_erf = (td - ct.w * ct.w * ch.inv_tau) * ct.inv_w * kSqrtHalf;
-    const double ws = ct.w * ch.inv_tau;
-    const double arg_exp = 0.5 * ws * ws - td * ch.inv_tau - arg_erf * arg_erf;
-    return arg_exp < -746.0;
-  };
-  // arg_exp = -td^2 / (2 w^2): near where |td| <= w sqrt(2 * 746)
-  const double half = ct.w * sqrt(2.0 * 746.0);
-  const double span = ct.t_step * (double)pc.kt;
-  const double t0 = fma(ct.t_step, kt_mid, ct.t_start) - ch.mean_delay;  // td of sample 0
-  double g = floor((-half - t0) / span);
-  j_lo = (int)fmin(fmax(g, 0.0), (double)nt);
-  g = ceil((half - t0) / span) + 1.0;
-  j_hi = (int)fmin(fmax(g, 0.0), (double)nt);
-  if (!(j_lo <= j_hi)) {  // NaN tables: no shortcut
-    j_lo = 0;
-    j_hi = nt;
-    return;
-  }
-  if (j_lo == j_hi) {  // guess says "no near sample": make sure by probing the closest one
-    const int jc = min(max((int)((0.0 - t0) / span), 0), nt - 1);
-    if (far(jc)) return;
-    j_lo = jc;
-    j_hi = jc + 1;
-  }
-  while (j_lo > 0 && !far(j_lo - 1)) --j_lo;
-  while (j_lo < j_hi && far(j_lo)) ++j_lo;
-  while (j_hi < nt && !far(j_hi)) ++j_hi;
-  while (j_hi > j_lo && far(j_hi - 1)) --j_hi;
-}
-
 template <int NC>
-__global__ void __launch_bounds__(kFastBlock, 2) k_hess3(const HessAccArgs H) {
+__global__ void __launch_bounds__(kFastBlock, FB_H3_MINB) k_hess3(const HessAccArgs H) {
   extern __shared__ __align__(16) unsigned char fast_smem[];
   const EvalArgs& A = H.E;
   const PlanConst& pc = A.pc;
@@ -880,7 +836,7 @@ __global__ void __launch_bounds__(kFastBlock, 2) k_hess3(const HessAccArgs H) {
       const CompTab& ct = comp[tid];
       const ChanTab& ch = chan[tid];
       int j_lo = 0, j_hi = nt;
-      if (shortcut) hess3_near_range(pc, ct, ch, j_lo, j_hi);
+      if (shortcut) near_range(pc, ct, ch, j_lo, j_hi);
       range[2 * tid] = j_lo;
       range[2 * tid + 1] = j_hi;
       const double tc_lo = fma(ct.t_step, kt_mid, ct.t_start) - ch.mean_delay;
