@@ -79,3 +79,74 @@ def fit_batched(model, data, good_freq, start_parameters, fixed_parameters, weig
         }
         out.append(item)
     return out
+
+
+def pinned_like(array) -> np.ndarray:
+    """Copy of `array` in page-locked host memory (what fit_stream wants its spectra in: the
+    host->device copy of a pageable array is staged by the driver and cannot overlap a fit)."""
+    tensor = torch.from_numpy(np.ascontiguousarray(array, dtype=np.float64)).pin_memory()
+    return tensor.numpy()
+
+
+def fit_stream(model, bursts, fixed_parameters, weighted_fit=True, weight_range=None, exact_jacobian=True):
+    """
+    Fits a sequence of bursts of the model's shape one after the other, overlapping the
+    host->device copy of burst k+1 (second CUDA stream, double-buffered device spectra) with the
+    fit of burst k -- the multi-file caller of LSFitter (the loop of
+    pipelines/fitburst_pipeline.py:494-532 over many inputs) without the per-burst upload stall.
+
+    bursts: iterable of (data, good_freq, start_parameters); data is a (Nf, Nt) float64 host array
+    (page-locked for the overlap to happen, see pinned_like) or a device tensor.
+    Yields one dict per burst, in order: {"results": OptimizeResult without the lazy `fun` / `jac`
+    members, "fit_statistics": ..., "success": ...}. The device copy of a spectrum is recycled two
+    bursts later, so nothing that needs it is handed out.
+    """
+    import contextlib
+    import io
+
+    from .analysis.fitter import LSFitter
+
+    device = model._device
+    shape = (model.num_freq, model.num_time)
+    main = torch.cuda.current_stream(device)
+    copier = torch.cuda.Stream(device=device)
+    buffers = [torch.empty(shape, dtype=torch.float64, device=device) for _ in range(2)]
+    ready = [torch.cuda.Event() for _ in range(2)]
+    free = [torch.cuda.Event() for _ in range(2)]
+    iterator = iter(bursts)
+
+    def upload(slot, item):
+        data = item[0]
+        if isinstance(data, torch.Tensor) and data.is_cuda:
+            return data.to(dtype=torch.float64).contiguous(), None
+        source = data if isinstance(data, torch.Tensor) else torch.from_numpy(
+            np.ascontiguousarray(data, dtype=np.float64))
+        with torch.cuda.stream(copier):
+            copier.wait_event(free[slot])  # the fit that used this buffer two bursts ago is done
+            buffers[slot].copy_(source, non_blocking=True)
+            ready[slot].record(copier)
+        return buffers[slot], ready[slot]
+
+    for event in free:
+        event.record(main)
+    slot = 0
+    item = next(iterator, None)
+    staged = upload(slot, item) if item is not None else None
+    while item is not None:
+        following = next(iterator, None)
+        staged_next = upload(slot ^ 1, following) if following is not None else None
+        data_dev, event = staged
+        if event is not None:
+            main.wait_event(event)
+        model.update_parameters(item[2])
+        with contextlib.redirect_stdout(io.StringIO()):
+            fitter = LSFitter(data_dev, model, item[1], weighted_fit=weighted_fit, weight_range=weight_range)
+            fitter.fix_parameter(list(fixed_parameters))
+            fitter.fit(exact_jacobian=exact_jacobian)
+        free[slot].record(main)
+        results = getattr(fitter, "results", None)
+        if results is not None and hasattr(results, "_lazy"):
+            object.__setattr__(results, "_lazy", {})
+        yield {"results": results, "fit_statistics": fitter.fit_statistics, "success": fitter.success}
+        item, staged, slot = following, staged_next, slot ^ 1
+    copier.synchronize()

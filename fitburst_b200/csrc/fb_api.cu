@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <new>
 #include <vector>
@@ -882,7 +883,20 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
   accepted = gram;
   S.nfev = 1;
   S.njev = 1;
-  while (trf_propose(S)) {
+  // FITBURST_B200_TIMING=1: host-side breakdown of the loop on stderr
+  const bool timing = getenv("FITBURST_B200_TIMING") != nullptr;
+  using clk = std::chrono::steady_clock;
+  double t_host = 0.0, t_eval = 0.0;
+  auto t_prev = clk::now();
+  auto lap = [&](double& acc) {
+    const auto now = clk::now();
+    acc += std::chrono::duration<double, std::micro>(now - t_prev).count();
+    t_prev = now;
+  };
+  for (;;) {
+    const bool more = trf_propose(S);
+    if (timing) lap(t_host);
+    if (!more) break;
     unpack_free(p, S.x_new);
     rc = fb_set_parameters(p, p->h_params, stream);
     if (rc == FB_OK) rc = fb_normal_equations(p, data_dev, gram.data(), stream);
@@ -890,10 +904,14 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
       delete stt;
       return rc;
     }
+    if (timing) lap(t_eval);
     const int njev_before = S.njev;
     trf_update(S, gram.data());
     if (S.njev != njev_before) accepted = gram;
+    if (timing) lap(t_host);
   }
+  if (timing)
+    fprintf(stderr, "fb_fit: nfev %d, host TRF %.1f us, evaluations (launch + wait) %.1f us\n", S.nfev, t_host, t_eval);
   result->status = S.status;
   result->nfev = S.nfev;
   result->njev = S.njev;

@@ -808,6 +808,11 @@ __global__ void __launch_bounds__(256) k_gram3_expand(const double* __restrict__
   const int n = X.ncols;
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
     int k = e / n, l = e % n;
+    if (k > l) {  // entries (k, l) and (l, k) go through the same arithmetic: exactly symmetric output
+      const int t = k;
+      k = l;
+      l = t;
+    }
     double far_part = 0.0;
     if (far) {  // upper-triangle entry (min, max) of the far-tile matrix
       const int a = k < l ? k : l, b = k < l ? l : k;

@@ -1,0 +1,197 @@
+"""
+GPU tests of the warp-granular fast kernels (fb_fast.cuh: k_vals3, k_gram3 with its far-tile
+path, k_hess3 with the far-sample moments) at window lengths where their special cases actually
+occur -- whole tiles in the exponential tail, far tiles, near ranges -- against the numpy oracle
+and against the general kernels (FITBURST_B200_FAST=0) on identical inputs.
+"""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+from fitburst_b200 import synthetic as syn
+from tests.helpers import model_pair, rel_to_max
+
+pytestmark = pytest.mark.gpu
+
+
+@contextlib.contextmanager
+def general_kernels():
+    """Routes the evaluation through the block-granular kernels of fb_kernels.cuh."""
+    os.environ["FITBURST_B200_FAST"] = "0"
+    try:
+        yield
+    finally:
+        del os.environ["FITBURST_B200_FAST"]
+
+
+def _case(num_freq=12, num_time=1024, num_comp=3, kf=8, kt=4, ref_freqs=None, dm=0.0, dm_inc=0.0, widths=None):
+    freqs, times = syn.chime_axes(num_freq, num_time)
+    truth = syn.truncate_components(syn.config2_truth(num_time), min(num_comp, 3))
+    if num_comp == 4:  # a fourth component late in the window
+        for key, value in (("amplitude", -0.2), ("arrival_time", 0.75 * times[-1]), ("burst_width", 1.0e-3),
+                           ("dm", 0.0), ("dm_index", -2.0), ("ref_freq", 600.0), ("scattering_timescale", 2.0e-3),
+                           ("scattering_index", -4.0), ("spectral_index", 0.5), ("spectral_running", -1.0)):
+            truth[key] = list(truth[key]) + [value]
+    truth["dm"] = [dm] * num_comp
+    if ref_freqs is not None:
+        truth["ref_freq"] = list(ref_freqs)
+    if widths is not None:
+        truth["burst_width"] = list(widths)
+    kwargs = dict(dm_incoherent=dm_inc, factor_freq_upsample=kf, factor_time_upsample=kt, num_components=num_comp)
+    return freqs, times, truth, kwargs
+
+
+def _fitters(case, fixed, seed=3):
+    from fitburst_b200.analysis.fitter import LSFitter
+    from oracle.fitburst_oracle import OracleFitter
+    freqs, times, truth, kwargs = _case(**case)
+    cuda, oracle = model_pair(freqs, times, kwargs, truth)
+    good = syn.make_good_freq(len(freqs), 0.25, seed)
+    data = syn.add_noise(oracle.compute_model(), good, 0.1, seed)
+    start = syn.config2_start(truth)
+    cuda.update_parameters(start)
+    oracle.update_parameters(start)
+    with contextlib.redirect_stdout(io.StringIO()):
+        fc = LSFitter(data, cuda, good)
+        fo = OracleFitter(data, oracle, good)
+        fc.fix_parameter(list(fixed))
+        fo.fix_parameter(list(fixed))
+    return fc, fo
+
+
+def _gram(fitter, native_lib):
+    from fitburst_b200 import _lib
+    plan, n = fitter._prepare()
+    fitter.model._push_parameters()
+    gram = np.zeros((n + 1, n + 1))
+    _lib.check(native_lib.fb_normal_equations(plan, fitter._data_on_device().data_ptr(), _lib.dptr(gram),
+                                             fitter._stream()))
+    return gram
+
+
+GRAM_CASES = {
+    "config2_columns": (dict(), ["dm_index", "scattering_index"]),
+    "all_nine_free": (dict(), []),
+    "reference_frequencies_differ": (dict(ref_freqs=[600.0, 500.0, 720.0]), ["dm_index", "scattering_index"]),
+    "one_component": (dict(num_comp=1), ["dm_index", "scattering_index"]),
+    "two_components_dm_offset": (dict(num_comp=2, dm=0.2), ["scattering_index"]),
+    "four_components": (dict(num_comp=4), ["dm_index", "scattering_index"]),
+    "generic_upsampling": (dict(kf=3, kt=2), ["dm_index", "scattering_index"]),
+    "no_upsampling": (dict(kf=1, kt=1), ["dm_index"]),
+    "ragged_window": (dict(num_time=1000), ["dm_index", "scattering_index"]),
+    "incoherent_dm": (dict(dm_inc=30.0, dm=0.05, kf=4, kt=2), ["dm_index", "scattering_index"]),
+    "only_shapes_free": (dict(), ["amplitude", "spectral_index", "spectral_running", "dm_index", "scattering_index"]),
+    "wide_bursts_no_far_tiles": (dict(num_time=512, widths=[6e-3, 8e-3, 5e-3]), ["dm_index", "scattering_index"]),
+}
+
+
+@pytest.mark.parametrize("name", list(GRAM_CASES))
+def test_normal_equations_fast_vs_oracle_and_general(name, native_lib):
+    case, fixed = GRAM_CASES[name]
+    fc, fo = _fitters(case, fixed)
+    x0 = fo.get_fit_parameters_list()
+    fast = _gram(fc, native_lib)
+    with general_kernels():
+        general = _gram(fc, native_lib)
+    resid = fo.compute_residuals(x0)  # also refreshes the caches the oracle Jacobian reads
+    full = np.concatenate([fo.compute_jacobian(x0), resid[:, None]], axis=1)
+    want = full.T @ full
+    scale = np.sqrt(np.outer(np.diag(want), np.diag(want)))
+    assert np.max(np.abs(fast - want) / scale) < 1e-9, "fast kernels vs oracle"
+    assert np.max(np.abs(fast - general) / scale) < 1e-11, "fast vs general kernels"
+    assert np.array_equal(fast, fast.T)
+
+
+@pytest.mark.parametrize("case,fixed", [
+    (dict(num_freq=8), ["dm_index", "scattering_index"]),
+    (dict(num_freq=6, num_comp=2, kf=2, kt=2), ["dm_index"]),
+    (dict(num_freq=6, num_comp=2, kf=2, kt=2), []),  # dm_index free: no far-sample shortcut
+    (dict(num_freq=6, ref_freqs=[600.0, 500.0, 720.0], kf=2, kt=2), ["dm_index", "scattering_index"]),
+])
+def test_hessian_fast_vs_oracle_and_general(case, fixed, native_lib):
+    from oracle import hessian_oracle
+    fc, fo = _fitters(case, fixed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        fast, labels = fc.compute_hessian(fc.data, fc.fit_parameters)
+        with general_kernels():
+            general, _ = fc.compute_hessian(fc.data, fc.fit_parameters)
+    want, want_labels = hessian_oracle.compute_hessian(fo, fo.data)
+    assert labels == want_labels
+    scale = np.sqrt(np.outer(np.abs(np.diag(want)), np.abs(np.diag(want))))
+    assert np.max(np.abs(fast - want) / scale) < 1e-8, "fast Hessian vs oracle"
+    assert np.max(np.abs(fast - general) / scale) < 1e-10, "fast vs general Hessian"
+
+
+def test_fit_trajectory_long_window(native_lib):
+    """A fit at a window length with far tiles: same trajectory as scipy on the oracle."""
+    fc, fo = _fitters(dict(num_freq=24, num_time=768), ["dm_index", "scattering_index"])
+    with contextlib.redirect_stdout(io.StringIO()):
+        fc.fit()
+        fo.fit(with_statistics=False)
+    assert fc.results.status == fo.results.status
+    assert fc.results.nfev == fo.results.nfev and fc.results.njev == fo.results.njev
+    np.testing.assert_allclose(fc.results.x, fo.results.x, rtol=1e-6)
+
+
+def test_chisq_grid_fast_vs_general(native_lib):
+    from fitburst_b200.batch import chisq_grid
+    fc, _ = _fitters(dict(num_freq=16, num_time=512), ["dm_index", "scattering_index"])
+    dm_values = np.linspace(-0.05, 0.05, 3)
+    sc_values = np.logspace(-3.5, -2.0, 3)
+    fast = chisq_grid(fc, dm_values, sc_values)
+    with general_kernels():
+        general = chisq_grid(fc, dm_values, sc_values)
+    np.testing.assert_allclose(fast, general, rtol=1e-12)
+
+
+def test_fit_stream_matches_individual_fits(native_lib):
+    from fitburst_b200.analysis.fitter import LSFitter
+    from fitburst_b200.batch import fit_stream, pinned_like
+    freqs, times, truth, kwargs = _case(num_freq=16, num_time=256, kf=2, kt=2)
+    cuda, oracle = model_pair(freqs, times, kwargs, truth)
+    clean = oracle.compute_model()
+    start = syn.config2_start(truth)
+    bursts = []
+    for seed in range(5):
+        good = syn.make_good_freq(len(freqs), 0.2, seed)
+        bursts.append((pinned_like(syn.add_noise(clean, good, 0.1, seed)), good, start))
+    fixed = ["dm_index", "scattering_index"]
+    streamed = list(fit_stream(cuda, bursts, fixed))
+    assert len(streamed) == len(bursts)
+    for (data, good, begin), out in zip(bursts, streamed):
+        cuda.update_parameters(begin)
+        with contextlib.redirect_stdout(io.StringIO()):
+            single = LSFitter(data, cuda, good)
+            single.fix_parameter(fixed)
+            single.fit()
+        assert out["results"].status == single.results.status and out["results"].nfev == single.results.nfev
+        np.testing.assert_array_equal(out["results"].x, single.results.x)
+        assert out["fit_statistics"]["bestfit_uncertainties"] == single.fit_statistics["bestfit_uncertainties"]
+
+
+def test_full_size_fast_vs_general(native_lib):
+    """Config-2 size: the fast and the general kernels agree on [J r]^T [J r] and on the Hessian."""
+    from fitburst_b200.analysis.fitter import LSFitter
+    from fitburst_b200.analysis.model import SpectrumModeler
+    freqs, times = syn.chime_axes(16384, 1024)
+    truth = syn.config2_truth(1024)
+    model = SpectrumModeler(freqs, times, factor_freq_upsample=8, factor_time_upsample=4, num_components=3)
+    model.update_parameters(truth)
+    good = syn.make_good_freq(16384, 0.35, 5)
+    data = syn.add_noise(model.compute_model(), good, 0.1, 5)
+    model.update_parameters(syn.config2_start(truth))
+    with contextlib.redirect_stdout(io.StringIO()):
+        fitter = LSFitter(data, model, good)
+        fitter.fix_parameter(["dm_index", "scattering_index"])
+        fast = _gram(fitter, native_lib)
+        h_fast, _ = fitter.compute_hessian(fitter.data, fitter.fit_parameters)
+        with general_kernels():
+            general = _gram(fitter, native_lib)
+            h_general, _ = fitter.compute_hessian(fitter.data, fitter.fit_parameters)
+    scale = np.sqrt(np.outer(np.diag(general), np.diag(general)))
+    assert np.max(np.abs(fast - general) / scale) < 1e-11
+    hs = np.sqrt(np.outer(np.abs(np.diag(h_general)), np.abs(np.diag(h_general))))
+    assert np.max(np.abs(h_fast - h_general) / hs) < 1e-9
