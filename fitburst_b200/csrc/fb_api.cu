@@ -58,10 +58,12 @@ struct fb_plan_s {
   SubTab* d_sub = nullptr;
   ChanTab* d_chan = nullptr;
   bool tables_dirty = true;
+  bool tables_full = false;  // the current tables cover every channel (not only the good ones)
   bool last_eval_split = false;
   int vals_layout = 2;       // 2: k_vals planes (spectrum, timediff) per tile; 3: k_vals3 rows (spectrum only)
   double* d_racc = nullptr;  // k_gram3 accumulators summed over blocks
   double* d_far = nullptr;   // k_gram3 far-tile matrix (upper triangle) summed over blocks
+  unsigned* d_counter = nullptr;  // k_gram3_finish: blocks done (self-resetting)
   int occ_cache[64];         // occupancy of the fast kernels by instantiation (0 = not queried yet)
   double* d_hess_partials = nullptr;
   size_t hess_partials_cap = 0;
@@ -182,7 +184,9 @@ extern "C" int fb_plan_create(const fb_plan_desc* desc, const double* freqs_host
   chk(cudaMallocHost(&p->h_gram, gsz));
   if (e == cudaSuccess) chk(cudaMemcpy(p->d_freqs, freqs_host, sizeof(double) * nf, cudaMemcpyHostToDevice));
   if (e == cudaSuccess) chk(cudaMemcpy(p->d_subfreqs, sub.data(), sizeof(double) * nf * kf, cudaMemcpyHostToDevice));
+  chk(cudaMalloc(&p->d_counter, sizeof(unsigned)));
   if (e == cudaSuccess) chk(cudaMemset(p->d_err, 0, sizeof(int)));
+  if (e == cudaSuccess) chk(cudaMemset(p->d_counter, 0, sizeof(unsigned)));
   if (e != cudaSuccess) {
     fb_plan_destroy(p);
     return fail(FB_ERR_CUDA, "plan allocation failed: %s", cudaGetErrorString(e));
@@ -215,6 +219,7 @@ extern "C" int fb_plan_destroy(fb_plan_t p) {
   cudaFree(p->d_vals);
   cudaFree(p->d_racc);
   cudaFree(p->d_far);
+  cudaFree(p->d_counter);
   cudaFree(p->d_desc);
   cudaFree(p->d_comp);
   cudaFree(p->d_sub);
@@ -234,14 +239,37 @@ extern "C" int fb_set_parameters(fb_plan_t p, const double* params_host, void* s
   return FB_OK;
 }
 
-// Rebuilds the per-channel tables when the parameters changed since the last build.
-static int ensure_tables(fb_plan_s* p, cudaStream_t st) {
-  if (!p->tables_dirty) return FB_OK;
-  const int total = p->desc.num_freq * p->desc.num_components;
-  k_tables<<<(total + 127) / 128, 128, 0, st>>>(p->pc, p->d_params, p->d_comp, p->d_sub, p->d_chan);
+// Rebuilds the per-channel tables when the parameters changed since the last build. The fit only
+// ever reads the tables of the good channels (good_only); everything else needs all of them.
+template <int KF>
+static void launch_tables_group(fb_plan_s* p, const int* list, int count, cudaStream_t st) {
+  const long long threads = (long long)count * p->desc.num_components * KF;
+  k_tables_group<KF><<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(p->pc, p->d_params, p->d_comp, p->d_sub,
+                                                                        p->d_chan, list, count);
+}
+
+static int ensure_tables(fb_plan_s* p, cudaStream_t st, bool good_only = false) {
+  const bool list_ok = good_only && p->have_weights && p->num_good > 0;
+  if (!p->tables_dirty && (p->tables_full || list_ok)) return FB_OK;
+  const int* list = list_ok ? p->d_chan_list : nullptr;
+  const int count = list_ok ? p->num_good : p->desc.num_freq;
+  switch (p->pc.kf) {
+    case 1: launch_tables_group<1>(p, list, count, st); break;
+    case 2: launch_tables_group<2>(p, list, count, st); break;
+    case 4: launch_tables_group<4>(p, list, count, st); break;
+    case 8: launch_tables_group<8>(p, list, count, st); break;
+    case 16: launch_tables_group<16>(p, list, count, st); break;
+    case 32: launch_tables_group<32>(p, list, count, st); break;
+    default: {
+      const int total = p->desc.num_freq * p->desc.num_components;
+      k_tables<<<(total + 127) / 128, 128, 0, st>>>(p->pc, p->d_params, p->d_comp, p->d_sub, p->d_chan);
+      list = nullptr;
+    }
+  }
   CUDA_TRY(cudaGetLastError());
   p->launches += 1;
   p->tables_dirty = false;
+  p->tables_full = list == nullptr;
   return FB_OK;
 }
 
@@ -274,7 +302,7 @@ static EvalArgs base_args(fb_plan_s* p) {
 template <int MODE>
 static int launch_eval(fb_plan_s* p, const EvalArgs& A, int ncols_main, cudaStream_t st, int* grid_out) {
   {
-    const int rc_t = ensure_tables(p, st);
+    const int rc_t = ensure_tables(p, st, A.chan_list != nullptr && A.chan_list == p->d_chan_list);
     if (rc_t != FB_OK) return rc_t;
   }
   const size_t smem = smem_bytes(p->pc.num_comp, p->pc.kf, ncols_main, p->pc.scintillation != 0);
@@ -355,6 +383,7 @@ static int rebuild_channel_list(fb_plan_s* p, cudaStream_t st) {
   CUDA_TRY(cudaStreamSynchronize(st));
   p->have_weights = true;
   p->gram_cache_valid = false;
+  if (!p->tables_full) p->tables_dirty = true;  // tables built for the previous channel list
   return FB_OK;
 }
 
@@ -539,7 +568,7 @@ static int launch_gram3_nc(fb_plan_s* p, const EvalArgs& A, const GramLayout& G,
 
 // k_vals3 + k_gram3 + reduction + expansion into the full (n+1)^2 matrix at gram_dev.
 static int launch_fast_gram(fb_plan_s* p, EvalArgs& A, int ncols, double* gram_dev, cudaStream_t st) {
-  int rc = ensure_tables(p, st);
+  int rc = ensure_tables(p, st, true);
   if (rc != FB_OK) return rc;
   const int nc = p->pc.num_comp, nt = p->pc.num_time;
   rc = ensure_capacity(&p->d_vals, &p->vals_cap, (size_t)A.num_chan * nc * nt);
@@ -578,13 +607,6 @@ static int launch_fast_gram(fb_plan_s* p, EvalArgs& A, int ncols, double* gram_d
   }
   if (rc != FB_OK) return rc;
   const int entries = g3_nacc(nb) * 64;
-  k_gram3_reduce<<<(entries + 7) / 8, 256, 0, st>>>(p->d_partials, grid, entries, p->d_racc);
-  CUDA_TRY(cudaGetLastError());
-  if (F.enabled) {
-    k_gram3_reduce<<<(nent + 7) / 8, 256, 0, st>>>(p->d_partials + (size_t)grid * entries, grid, nent, p->d_far);
-    CUDA_TRY(cudaGetLastError());
-    p->launches += 1;
-  }
   ExpandArgs X;
   memset(&X, 0, sizeof(X));
   X.ncols = ncols;
@@ -613,9 +635,11 @@ static int launch_fast_gram(fb_plan_s* p, EvalArgs& A, int ncols, double* gram_d
   X.power[ncols - 1] = 0;
   X.factor[ncols - 1] = 1.0;
   X.shift[ncols - 1] = 0.0;
-  k_gram3_expand<<<(ncols * ncols + 255) / 256, 256, 0, st>>>(p->d_racc, X, F.enabled ? p->d_far : nullptr, gram_dev);
+  const int far_entries = F.enabled ? nent : 0;
+  k_gram3_finish<<<(entries + far_entries + 7) / 8, 256, 0, st>>>(p->d_partials, grid, entries, far_entries, p->d_racc,
+                                                                 p->d_far, X, p->d_counter, gram_dev);
   CUDA_TRY(cudaGetLastError());
-  p->launches += 2;
+  p->launches += 1;
   return FB_OK;
 }
 
@@ -649,7 +673,7 @@ static int launch_gram2_mma(fb_plan_s* p, const EvalArgs& A, int ncols, long lon
 }
 
 static int launch_split_gram(fb_plan_s* p, EvalArgs& A, int ncols, cudaStream_t st, int* grid_out, int* mma_warps_out) {
-  int rc = ensure_tables(p, st);
+  int rc = ensure_tables(p, st, true);
   if (rc != FB_OK) return rc;
   const int nc = p->pc.num_comp, kf = p->pc.kf;
   const int tiles = (p->pc.num_time + kBlock - 1) / kBlock;
@@ -1062,7 +1086,7 @@ extern "C" int fb_launch_count(fb_plan_t p, int64_t* count_out, int32_t reset) {
 template <bool MAP>
 static int launch_hessian(fb_plan_s* p, HessArgs& H, cudaStream_t st, int* grid_out) {
   {
-    const int rc_t = ensure_tables(p, st);
+    const int rc_t = ensure_tables(p, st, H.E.chan_list != nullptr && H.E.chan_list == p->d_chan_list);
     if (rc_t != FB_OK) return rc_t;
   }
   const size_t smem = hess_smem_bytes(p->pc.num_comp, p->pc.kf, MAP ? 0 : H.num_pairs);
@@ -1212,7 +1236,7 @@ int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, 
     H.gvals = reuse_vals ? p->d_vals : nullptr;
     H.gvals_layout = p->vals_layout;
     for (int c = 0; c <= nc; ++c) H.comp_off[c] = comp_off[c];
-    rc = ensure_tables(p, st);
+    rc = ensure_tables(p, st, true);
     if (rc != FB_OK) return rc;
     if (fast_path_ok(p, false)) {
       // warp-granular contraction over the spectrum rows of k_vals3
@@ -1480,7 +1504,7 @@ extern "C" int fb_chisq_grid(fb_plan_t p, const double* data_dev, const double* 
       if (p->pc.scintillation) {
         rc = launch_eval<MODE_CHI2>(p, A, 1, st, &grid);
       } else if (fast_grid && sc_values_host[b] > 0.0) {
-        rc = ensure_tables(p, st);
+        rc = ensure_tables(p, st, true);
         if (rc != FB_OK) return rc;
         rc = ensure_capacity(&p->d_vals, &p->vals_cap, (size_t)p->num_good * nc * p->pc.num_time);
         if (rc == FB_OK) rc = ensure_capacity(&p->d_partials, &p->partials_cap, (size_t)p->num_good);
@@ -1494,7 +1518,7 @@ extern "C" int fb_chisq_grid(fb_plan_t p, const double* data_dev, const double* 
         grid = p->num_good;
         p->vals_match_cache = false;
       } else {
-        rc = ensure_tables(p, st);
+        rc = ensure_tables(p, st, true);
         if (rc != FB_OK) return rc;
         const size_t smem = smem_bytes(nc, p->pc.kf, 1, false, false, SM_VALS | SM_QUEUE);
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_chi2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -167,11 +167,11 @@ __device__ inline void make_comp_tab(const PlanConst& pc, const double* params, 
   ct.ref_freq = params[FB_REF_FREQ * nc + c];
 }
 
-// All tables of one (channel, component): kf SubTab entries + the ChanTab. One thread.
-__device__ inline void make_channel_tables(const PlanConst& pc, const double* params, const CompTab& ct,
-                                           int i, int c, SubTab* sub, ChanTab& ch) {
+// Table entry of one (channel, component, sub-frequency a) and its plateau profile value.
+__device__ inline void make_sub_tab(const PlanConst& pc, const double* params, const CompTab& ct, int i, int c, int a,
+                                    double fref_b, double fc_b, SubTab& st, double& plateau_p,
+                                    double& sc_time_out) {
   const int nc = pc.num_comp, kf = pc.kf, kt = pc.kt;
-  const double fc = pc.freqs[i];
   const double dm = global_param(params, nc, FB_DM);
   const double beta = global_param(params, nc, FB_DM_INDEX);
   const double tau0 = global_param(params, nc, FB_SCATTERING_TIMESCALE);
@@ -179,68 +179,104 @@ __device__ inline void make_channel_tables(const PlanConst& pc, const double* pa
   const double sp_idx = params[FB_SPECTRAL_INDEX * nc + c];
   const double sp_run = params[FB_SPECTRAL_RUNNING * nc + c];
   const double fref = ct.ref_freq;
-  const double fref_b = pow(fref, beta);
-  const double fc_b = pow(fc, beta);
   const double w = ct.w;
+  const double f = pc.subfreqs[(size_t)i * kf + a];
+  // routines/ism.py:78: dm_value * dm_const * (freq1 ** dm_idx - freq2 ** dm_idx)
+  double delay = ((pc.dm_incoherent + dm) * pc.dm_const) * (pow(f, beta) - fref_b);
+  delay -= (pc.dm_incoherent * pc.dm_const) * (fc_b - fref_b);
+  st.delay = delay;
+  const double fr = f / fref;
+  const double sc_time = tau0 * pow(fr, alpha);  // analysis/model.py:336
+  sc_time_out = sc_time;
+  st.ratio = w / sc_time;
+  st.amp_term = pc.normalize_pbf ? kSqrtHalfPi * st.ratio : tau0 / sc_time;
+  const double lf = log(fr);
+  st.sed = exp(sp_idx * lf + sp_run * (lf * lf));
+  st.inv_tau = 1.0 / sc_time;
+  st.tail_e = 0.5 * st.ratio * st.ratio + delay * st.inv_tau;
+  double geom = 0.0;
+  for (int b = 0; b < kt; ++b) geom += exp(-(double)b * ct.t_step * st.inv_tau);
+  st.tail_c = 2.0 * st.amp_term * geom / ((double)kt * (double)kf);
+  if (pc.is_folded) {
+    // analysis/model.py:327-331 on the delay-corrected labels of this sub-frequency row.
+    const int n = pc.ntk;
+    const double t0 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, 0, n) - delay;
+    const double t1 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, 1, n) - delay;
+    const double tl = linspace_at(ct.t_start, ct.t_step, ct.t_stop, n - 1, n) - delay;
+    const double res = t1 - t0;
+    st.fold_start = tl + res;
+    st.fold_stop = tl + res * (double)n;
+    st.fold_step = (n > 1) ? (st.fold_stop - st.fold_start) / (double)(n - 1) : 0.0;
+  } else {
+    st.fold_start = st.fold_step = st.fold_stop = 0.0;
+  }
+  plateau_p = st.amp_term * emg_shape(ct.neg5w * ct.inv_w, st.ratio);
+}
 
-  int scattered = 0;
-  double min_delay = INFINITY, max_delay = -INFINITY, sum_delay = 0.0, max_wr = 0.0;
-  double plat_p = 0.0, plat_ps = 0.0;
-  const double z_clamp = ct.neg5w * ct.inv_w;
-  for (int a = 0; a < kf; ++a) {
-    SubTab st;
-    const double f = pc.subfreqs[(size_t)i * kf + a];
-    // routines/ism.py:78: dm_value * dm_const * (freq1 ** dm_idx - freq2 ** dm_idx)
-    double delay = ((pc.dm_incoherent + dm) * pc.dm_const) * (pow(f, beta) - fref_b);
-    delay -= (pc.dm_incoherent * pc.dm_const) * (fc_b - fref_b);
-    st.delay = delay;
-    const double fr = f / fref;
-    const double sc_time = tau0 * pow(fr, alpha);  // analysis/model.py:336
-    if (sc_time > 0.0) scattered = 1;
-    st.ratio = w / sc_time;
-    st.amp_term = pc.normalize_pbf ? kSqrtHalfPi * st.ratio : tau0 / sc_time;
-    const double lf = log(fr);
-    st.sed = exp(sp_idx * lf + sp_run * (lf * lf));
-    st.inv_tau = 1.0 / sc_time;
-    st.tail_e = 0.5 * st.ratio * st.ratio + delay * st.inv_tau;
-    double geom = 0.0;
-    for (int b = 0; b < kt; ++b) geom += exp(-(double)b * ct.t_step * st.inv_tau);
-    st.tail_c = 2.0 * st.amp_term * geom / ((double)kt * (double)kf);
-    if (pc.is_folded) {
-      // analysis/model.py:327-331 on the delay-corrected labels of this sub-frequency row.
-      const int n = pc.ntk;
-      const double t0 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, 0, n) - delay;
-      const double t1 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, 1, n) - delay;
-      const double tl = linspace_at(ct.t_start, ct.t_step, ct.t_stop, n - 1, n) - delay;
-      const double res = t1 - t0;
-      st.fold_start = tl + res;
-      st.fold_stop = tl + res * (double)n;
-      st.fold_step = (n > 1) ? (st.fold_stop - st.fold_start) / (double)(n - 1) : 0.0;
-    } else {
-      st.fold_start = st.fold_step = st.fold_stop = 0.0;
-    }
-    sub[a] = st;
+// Sub-frequency summary of one (channel, component) accumulated in sub-frequency order.
+struct SubSummary {
+  double min_delay, max_delay, sum_delay, max_wr, plat_p, plat_ps;
+  int scattered;
+  __device__ void init() {
+    min_delay = INFINITY;
+    max_delay = -INFINITY;
+    sum_delay = max_wr = plat_p = plat_ps = 0.0;
+    scattered = 0;
+  }
+  __device__ void add(double delay, double ratio, double sed, double w, double p) {
     min_delay = fmin(min_delay, delay);
     max_delay = fmax(max_delay, delay);
     sum_delay += delay;
-    max_wr = fmax(max_wr, w * st.ratio);
-    const double p = st.amp_term * emg_shape(z_clamp, st.ratio);
+    max_wr = fmax(max_wr, w * ratio);
     plat_p += p;
-    plat_ps += p * st.sed;
+    plat_ps += p * sed;
   }
+};
+
+// The ChanTab of one (channel, component) from the sub-frequency summary.
+// The four powers every (channel, component) needs once: ref_freq ** dm_index, f ** dm_index,
+// (f / ref_freq) ** sc_index and (f / ref_freq) ** -sc_index at the channel centre.
+struct ChanPowers {
+  double fref_b, fc_b, fr_alpha, fr_nalpha;
+};
+
+__device__ inline ChanPowers make_chan_powers(const PlanConst& pc, const double* params, const CompTab& ct, int i) {
+  const int nc = pc.num_comp;
+  const double beta = global_param(params, nc, FB_DM_INDEX), alpha = global_param(params, nc, FB_SCATTERING_INDEX);
+  const double fc = pc.freqs[i], fr = fc / ct.ref_freq;
+  ChanPowers cp;
+  cp.fref_b = pow(ct.ref_freq, beta);
+  cp.fc_b = pow(fc, beta);
+  cp.fr_alpha = pow(fr, alpha);
+  cp.fr_nalpha = pow(fr, -alpha);
+  return cp;
+}
+
+__device__ inline void finish_chan_tab(const PlanConst& pc, const double* params, const CompTab& ct, int i, int c,
+                                       const SubSummary& sm, const ChanPowers& cp, ChanTab& ch) {
+  const int nc = pc.num_comp, kf = pc.kf;
+  const double fc = pc.freqs[i];
+  const double dm = global_param(params, nc, FB_DM);
+  const double beta = global_param(params, nc, FB_DM_INDEX);
+  const double tau0 = global_param(params, nc, FB_SCATTERING_TIMESCALE);
+  const double sp_idx = params[FB_SPECTRAL_INDEX * nc + c];
+  const double sp_run = params[FB_SPECTRAL_RUNNING * nc + c];
+  const double fref = ct.ref_freq;
+  const double fref_b = cp.fref_b, fc_b = cp.fc_b;
+  const double w = ct.w;
   const double fr = fc / fref;
   const double lf = log(fr);
   ch.amp = exp(sp_idx * lf + sp_run * (lf * lf)) * ct.amp10;
-  ch.min_delay = min_delay;
-  ch.mean_delay = sum_delay / (double)kf;
+  ch.min_delay = sm.min_delay;
+  ch.mean_delay = sm.sum_delay / (double)kf;
   // pure tail for every sub-sample:  (T/w - ratio)/sqrt(2) >= 6  <=  T >= w*ratio + 6 sqrt(2) w
-  ch.tail_lo = max_delay + max_wr + (6.0 * kSqrt2 + 1e-6) * w;
-  ch.plateau_p = plat_p / (double)kf;
-  ch.plateau_ps = ct.amp10 * (plat_ps / (double)kf);
+  ch.tail_lo = sm.max_delay + sm.max_wr + (6.0 * kSqrt2 + 1e-6) * w;
+  ch.plateau_p = sm.plat_p / (double)kf;
+  ch.plateau_ps = ct.amp10 * (sm.plat_ps / (double)kf);
   ch.logf = lf;
-  ch.sc_time = tau0 * pow(fr, alpha);
+  ch.sc_time = tau0 * cp.fr_alpha;
   ch.inv_tau = 1.0 / ch.sc_time;
-  double amp_pbf = pow(fr, -alpha);
+  double amp_pbf = cp.fr_nalpha;
   if (pc.normalize_pbf) amp_pbf *= kSqrtHalfPi * w / tau0;
   ch.amp_pbf = amp_pbf;
   ch.inv_apbf = 1.0 / amp_pbf;
@@ -252,8 +288,8 @@ __device__ inline void make_channel_tables(const PlanConst& pc, const double* pa
   } else {
     ch.dap_w = 0.0;
     ch.dap_tau = 0.0;
-    ch.dap_alpha = -lf * pow(fr, -alpha);
-    ch.d2ap_alpha = lf * lf * pow(fr, -alpha);
+    ch.dap_alpha = -lf * cp.fr_nalpha;
+    ch.d2ap_alpha = lf * lf * cp.fr_nalpha;
   }
   ch.d_dm = -pc.dm_const * (fc_b - fref_b);
   ch.q1 = log(fc) * fc_b - log(fref) * fref_b;
@@ -262,9 +298,27 @@ __device__ inline void make_channel_tables(const PlanConst& pc, const double* pa
   ch.fpow = fc_b;
   ch.refpow = fref_b;
   ch.ref_freq = fref;
-  ch.scattered = scattered;
-  ch.fast_ok = scattered && !pc.is_folded && isfinite(ch.tail_lo) && isfinite(ch.plateau_ps) &&
-               isfinite(min_delay) && w > 0.0 && tau0 > 0.0;
+  ch.scattered = sm.scattered;
+  ch.fast_ok = sm.scattered && !pc.is_folded && isfinite(ch.tail_lo) && isfinite(ch.plateau_ps) &&
+               isfinite(sm.min_delay) && w > 0.0 && tau0 > 0.0;
+  ch.pad_[0] = ch.pad_[1] = 0;
+}
+
+// All tables of one (channel, component): kf SubTab entries + the ChanTab. One thread.
+__device__ inline void make_channel_tables(const PlanConst& pc, const double* params, const CompTab& ct,
+                                           int i, int c, SubTab* sub, ChanTab& ch) {
+  SubSummary sm;
+  sm.init();
+  const ChanPowers cp = make_chan_powers(pc, params, ct, i);
+  for (int a = 0; a < pc.kf; ++a) {
+    SubTab st;
+    double p, sc_time;
+    make_sub_tab(pc, params, ct, i, c, a, cp.fref_b, cp.fc_b, st, p, sc_time);
+    sub[a] = st;
+    if (sc_time > 0.0) sm.scattered = 1;  // analysis/model.py:339 any(sc_time > 0)
+    sm.add(st.delay, st.ratio, st.sed, ct.w, p);
+  }
+  finish_chan_tab(pc, params, ct, i, c, sm, cp, ch);
 }
 
 // Per-sample, per-component result: the three cached maps of analysis/model.py:212-256.

@@ -30,7 +30,7 @@
 //             staged (14 instead of 18 columns at config 2: 2 instead of 3 column blocks, 24
 //             instead of 48 DMMA per 32 samples); at the end of a channel the C fragments are
 //             folded into the accumulators of w^2 L^p (p = 0..4) and cleared, and
-//             k_gram3_expand rebuilds the full [J r]^T [J r].
+//             k_gram3_finish rebuilds the full [J r]^T [J r].
 #pragma once
 #include "fb_kernels.cuh"
 
@@ -699,7 +699,7 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
       }
       __syncwarp();
     }
-    // channel flush: acc[p] += w^2 L^p C, C = 0 (L of component 0; k_gram3_expand shifts it
+    // channel flush: acc[p] += w^2 L^p C, C = 0 (L of component 0; k_gram3_finish shifts it
     // for components with a different reference frequency)
     {
       const double lf0 = chan[0].logf;
@@ -778,18 +778,6 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
   }
 }
 
-// Sums the per-block accumulators: one warp per entry, fixed-shape tree (deterministic).
-__global__ void __launch_bounds__(256) k_gram3_reduce(const double* __restrict__ partials, int nblocks, int entries,
-                                                      double* __restrict__ out) {
-  const int e = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (e >= entries) return;
-  double s = 0.0;
-  for (int b = lane; b < nblocks; b += 32) s += partials[(size_t)b * entries + e];
-#pragma unroll
-  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(kFullMask, s, off);
-  if (lane == 0) out[e] = s;
-}
-
 // Full column k of [J r] = factor * (L + shift)^power * reduced column `red` (per channel).
 struct ExpandArgs {
   int ncols, nb;
@@ -803,29 +791,53 @@ __device__ inline double g3_binom(int n, int k) {
   return (k == 0 || k == n) ? 1.0 : (n == 2 ? 2.0 : (double)n);  // n <= 2 here (n = 3, 4 never occur)
 }
 
-__global__ void __launch_bounds__(256) k_gram3_expand(const double* __restrict__ racc, const ExpandArgs X,
-                                                      const double* __restrict__ far, double* __restrict__ gram) {
+// One launch finishes an evaluation: every warp sums one accumulator entry over the blocks of
+// k_gram3 (near accumulators first, then the far-tile matrix; fixed-shape tree, deterministic);
+// the last block to finish expands the reduced accumulators into the full symmetric
+// (n+1) x (n+1) matrix [J r]^T [J r] and adds the far-tile matrix.
+__global__ void __launch_bounds__(256) k_gram3_finish(const double* __restrict__ partials, int nblocks,
+                                                      int near_entries, int far_entries, double* __restrict__ racc,
+                                                      double* __restrict__ far, const ExpandArgs X,
+                                                      unsigned* __restrict__ counter, double* __restrict__ gram) {
+  __shared__ bool last;
+  const int e = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (e < near_entries + far_entries) {
+    const bool is_far = e >= near_entries;
+    const double* src = is_far ? partials + (size_t)nblocks * near_entries + (e - near_entries) : partials + e;
+    const int stride = is_far ? far_entries : near_entries;
+    double s = 0.0;
+    for (int b = lane; b < nblocks; b += 32) s += src[(size_t)b * stride];
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(kFullMask, s, off);
+    if (lane == 0) {
+      if (is_far) far[e - near_entries] = s;
+      else racc[e] = s;
+    }
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x == 0) *counter = 0u;  // ready for the next evaluation
   const int n = X.ncols;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n * n; e += gridDim.x * blockDim.x) {
-    int k = e / n, l = e % n;
+  for (int o = threadIdx.x; o < n * n; o += blockDim.x) {
+    int k = o / n, l = o % n;
     if (k > l) {  // entries (k, l) and (l, k) go through the same arithmetic: exactly symmetric output
       const int t = k;
       k = l;
       l = t;
     }
     double far_part = 0.0;
-    if (far) {  // upper-triangle entry (min, max) of the far-tile matrix
-      const int a = k < l ? k : l, b = k < l ? l : k;
-      far_part = far[a * n - a * (a - 1) / 2 + (b - a)];
-    }
+    if (far_entries > 0) far_part = __ldcg(far + (k * n - k * (k - 1) / 2 + (l - k)));
     if (X.red[k] > X.red[l]) {
       const int t = k;
       k = l;
       l = t;
     }
     const int rk = X.red[k], rl = X.red[l];
-    const int bi = rk >> 3, bj = rl >> 3;
-    const int off = g3_acc_offset(X.nb, bi, bj);
+    const int off = g3_acc_offset(X.nb, rk >> 3, rl >> 3);
     const double* base = racc + (size_t)off * 64 + (rk & 7) * 8 + (rl & 7);
     double s = 0.0;
     for (int a = 0; a <= X.power[k]; ++a) {
@@ -834,10 +846,10 @@ __global__ void __launch_bounds__(256) k_gram3_expand(const double* __restrict__
       for (int b = 0; b <= X.power[l]; ++b) {
         double cb = g3_binom(X.power[l], b);
         for (int q = 0; q < X.power[l] - b; ++q) cb *= X.shift[l];
-        s += ca * cb * base[(size_t)(a + b) * 64];
+        s += ca * cb * __ldcg(base + (size_t)(a + b) * 64);
       }
     }
-    gram[e] = X.factor[k] * X.factor[l] * s + far_part;
+    gram[o] = X.factor[k] * X.factor[l] * s + far_part;
   }
 }
 

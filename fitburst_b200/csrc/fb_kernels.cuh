@@ -252,6 +252,68 @@ __global__ void __launch_bounds__(128) k_tables(const PlanConst pc, const double
   make_channel_tables(pc, params, ct, i, c, g_sub + (size_t)e * pc.kf, g_chan[e]);
 }
 
+// Same tables with one thread per (channel, component, SUB-FREQUENCY): k_tables above is a
+// latency-bound chain of ~8 transcendental calls per sub-frequency per thread (49 k threads at
+// config 2, 50 us); spreading the sub-frequencies over the lanes of a KF-wide group gives 8x the
+// parallelism, and the group leader reads the per-lane results back in sub-frequency order, so
+// every sum is formed exactly like in the serial loop. Visits only the listed channels.
+template <int KF>
+__global__ void __launch_bounds__(128) k_tables_group(const PlanConst pc, const double* __restrict__ params,
+                                                      CompTab* __restrict__ g_comp, SubTab* __restrict__ g_sub,
+                                                      ChanTab* __restrict__ g_chan, const int* __restrict__ chan_list,
+                                                      int num_chan) {
+  const int nc = pc.num_comp;
+  const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int a = (int)(gid % KF), lane = threadIdx.x & 31;
+  long long item = gid / KF;
+  const bool active = item < (long long)num_chan * nc;
+  if (!active) item = 0;  // keeps the lane in the shuffles below
+  const int chi = (int)(item / nc), c = (int)(item % nc);
+  const int i = chan_list ? chan_list[chi] : chi;
+  CompTab ct;
+  make_comp_tab(pc, params, c, ct);
+  if (active && chi == 0 && a == 0) g_comp[c] = ct;
+  const int base = lane & ~(KF - 1);
+  // the four channel-level powers, one per lane of the group (same pow calls as make_chan_powers)
+  ChanPowers cp;
+  {
+    const double beta = global_param(params, nc, FB_DM_INDEX), alpha = global_param(params, nc, FB_SCATTERING_INDEX);
+    const double fc = pc.freqs[i], fr = fc / ct.ref_freq;
+    double vals[4];
+#pragma unroll
+    for (int round = 0; round < (4 + KF - 1) / KF; ++round) {
+      const int q = round * KF + a;  // which power this lane computes in this round
+      const double x = q == 0 ? ct.ref_freq : (q == 1 ? fc : fr);
+      const double y = q <= 1 ? beta : (q == 2 ? alpha : -alpha);
+      const double v = pow(x, y);
+#pragma unroll
+      for (int k = 0; k < KF; ++k)
+        if (round * KF + k < 4) vals[round * KF + k] = __shfl_sync(0xffffffffu, v, base + k);
+    }
+    cp.fref_b = vals[0];
+    cp.fc_b = vals[1];
+    cp.fr_alpha = vals[2];
+    cp.fr_nalpha = vals[3];
+  }
+  SubTab st;
+  double p, sc_time;
+  make_sub_tab(pc, params, ct, i, c, a, cp.fref_b, cp.fc_b, st, p, sc_time);
+  if (active) g_sub[((size_t)i * nc + c) * KF + a] = st;
+  SubSummary sm;
+  sm.init();
+#pragma unroll
+  for (int k = 0; k < KF; ++k) {
+    const double delay = __shfl_sync(0xffffffffu, st.delay, base + k);
+    const double ratio = __shfl_sync(0xffffffffu, st.ratio, base + k);
+    const double sed = __shfl_sync(0xffffffffu, st.sed, base + k);
+    const double pk = __shfl_sync(0xffffffffu, p, base + k);
+    const double sck = __shfl_sync(0xffffffffu, sc_time, base + k);
+    if (sck > 0.0) sm.scattered = 1;
+    sm.add(delay, ratio, sed, ct.w, pk);
+  }
+  if (active && a == 0) finish_chan_tab(pc, params, ct, i, c, sm, cp, g_chan[(size_t)i * nc + c]);
+}
+
 // Stages one channel's tables from global memory (L2-resident, written by k_tables).
 __device__ inline void load_channel_tables(const EvalArgs& A, const SmemLayout& L, int i) {
   const PlanConst& pc = A.pc;
