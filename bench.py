@@ -68,6 +68,33 @@ def regime_census(freqs, times, params, good, kf, kt, dm_const=4149.377593360996
     return counts
 
 
+def ncu_profile_summary():
+    """Per-kernel figures of the committed `ncu --set full` capture of this same command
+    (profiles/r1_fast_ncu_full_summary.csv): DRAM bytes per launch and pipe utilisation."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r1_fast_ncu_full_summary.csv")
+    if not os.path.exists(path):
+        return {}
+    rows = list(csv.reader(open(path)))
+    head = rows[0]
+    col = {name: head.index(name) for name in head}
+    kernels, total = {}, 0.0
+    for row in rows[2:]:
+        name = row[col["Kernel Name"]].split("(")[0].replace("void ", "")
+        dram = (float(row[col["dram__bytes_read.sum"]]) + float(row[col["dram__bytes_write.sum"]])) * 1e6
+        kernels[name] = {
+            "us_per_launch_under_ncu": float(row[col["gpu__time_duration.sum"]]),
+            "dram_bytes_per_launch": dram,
+            "issue_active_pct": float(row[col["smsp__issue_active.avg.pct_of_peak_sustained_active"]]),
+            "fp64_pipe_active_pct": float(row[col["sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"]]),
+            "dmma_pipe_pct": float(row[col["sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active"]]),
+            "registers": int(row[col["launch__registers_per_thread"]]),
+        }
+        total += dram
+    return {"kernels": kernels, "dram_bytes_per_evaluation": total,
+            "source": "profiles/r1_fast_ncu_full_summary.csv (ncu --set full --clock-control none, one launch each)"}
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -273,6 +300,9 @@ def run_cuda(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # rank 0 prints exactly one line on stdout: keep NCCL's version banner out of it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.load_library()
 
@@ -396,7 +426,7 @@ def run_cuda(args):
         pass
     ms_step_e = max(float(t[0]), float(t[1])) / args.steps
     e2e_value = world * 1e3 / ms_step_e
-    assert last["stream"]["results"].status == last["e2e"][0].results.status
+    assert last["stream"]["results"].status > 0, "streamed fit did not converge"
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
@@ -432,27 +462,26 @@ def run_cuda(args):
     _lib.check(lib.fb_measure_fp64_peak(peak, stream))
     achieved = flop / (eval_ms * 1e-3) / 1e12
     census = regime_census(freqs, times, bursts[0][1], bursts[0][2], args.kf, args.kt)
-    # executed-work model: plateau = table look-up (0 flop), tail = one exp + 4 flop per
-    # (sample, sub-frequency), general = the contract's 110 flop per profile evaluation
-    flop_exec = (census["general"] * args.kf * args.kt * FLOP_PER_PE_SCATTERED + census["tail"] * args.kf * 34.0 +
-                 float(num_good) * args.ntime * jacobian_flop_per_sample(args.ncomp, 5, 2))
+    prof = ncu_profile_summary()
     roofline = {
         "bound": "fp64", "achieved": achieved, "peak": peak.value, "unit": "TFLOP/s",
-        "frac": achieved / peak.value if peak.value > 0 else None, "traffic": None,
-        "kernel": "fb::k_tables + k_vals3 + k_gram3 (+ reduce / expand): one model + analytic Jacobian + [J r]^T[J r] evaluation",
+        "frac": achieved / peak.value if peak.value > 0 else None,
+        "traffic": prof.get("dram_bytes_per_evaluation"),
+        "kernel": "one evaluation = k_tables_group + k_vals3 + k_gram3 + k_gram3_finish "
+                  "(model, analytic Jacobian, [J r]^T[J r]); dominant kernels k_vals3 and k_gram3",
         "ms_per_launch": eval_ms, "algorithmic_flop_per_launch": flop,
         "units_per_launch": {"profile_evaluations": n_pe, "good_channels": num_good},
         "peak_source": "measured live: dependent-free DFMA chains on all SMs (MEASURED_PEAKS.json has no FP64 entry)",
         "hbm_algorithmic_bytes_per_launch": 8.0 * num_good * args.ntime,
-        "executed_model": {
-            "note": ("the kernel replaces most exp+erfcx pairs by closed forms (clamp plateau: table look-up; "
-                     "exponential tail: one exp per sample and sub-frequency), so `frac` above measures speed "
-                     "against the contract's work model, not pipe utilisation; this object counts the work "
-                     "actually required by the regimes"),
-            "sample_component_items": census, "flop_per_launch": flop_exec,
-            "achieved": flop_exec / (eval_ms * 1e-3) / 1e12,
-            "frac": (flop_exec / (eval_ms * 1e-3) / 1e12) / peak.value if peak.value > 0 else None,
-        },
+        "note": ("`achieved` follows the contract work model of SURVEY.md 8d (110 flop per profile evaluation, 628 "
+                 "per sample for the Jacobian / normal equations). The kernels do not execute that work literally: "
+                 "clamp-plateau and exponential-tail tiles are closed forms, far tiles contract an 8-column basis "
+                 "block, so frac > 1 measures speed against the contract, not pipe utilisation. Measured "
+                 "utilisation (ncu) is in `ncu`, the regime census in `regimes`."),
+        "regimes": {"sample_component_items": census,
+                    "general_profile_evaluations": census["general"] * args.kf * args.kt},
+        "ncu": prof.get("kernels"),
+        "ncu_source": prof.get("source"),
         "evals_per_s": 1e3 / eval_ms,
     }
 
