@@ -299,6 +299,10 @@ def run_cuda(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa_bound = False
+    if world > 1 and not os.environ.get("FITBURST_B200_NO_BIND"):
+        from fitburst_b200.distributed import bind_to_gpu_numa
+        numa_bound = bind_to_gpu_numa(local_rank)
     if world > 1:
         # rank 0 prints exactly one line on stdout: keep NCCL's version banner out of it
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):

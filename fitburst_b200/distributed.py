@@ -202,3 +202,21 @@ def grid_argmin(local_chisq: np.ndarray, local_rows: list, num_cols: int, group=
     pairs = [p for p in pairs if p[1] >= 0]
     chisq, flat = min(pairs, key=lambda p: (p[0], p[1]))
     return chisq, flat
+
+
+def bind_to_gpu_numa(device_index: int) -> bool:
+    """
+    Binds the calling process to the CPUs NVML reports as closest to GPU `device_index` (same
+    NUMA node / PCIe root), so that page-locked staging buffers allocated afterwards are
+    node-local and host->device copies of different ranks do not share an inter-socket link.
+    One process per GPU launched by torchrun is not bound by default. Returns False when NVML is
+    unavailable (nothing is changed then).
+    """
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        handle = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        return True
+    except Exception:  # noqa: BLE001 - best effort, never fatal
+        return False

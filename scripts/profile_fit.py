@@ -30,4 +30,4 @@ pr = cProfile.Profile(); pr.enable()
 for r in range(N): one(r % 2)
 torch.cuda.synchronize(); pr.disable()
 print(f"{1e3 * (time.perf_counter() - t0) / N:.2f} ms per fit (under cProfile)")
-s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("tottime").print_stats(22); print(s.getvalue()[:6000])
+s = io.StringIO(); pstats.Stats(pr, stream=s).sort_stats("cumtime").print_stats(45); print(s.getvalue()[:9000])

@@ -120,9 +120,12 @@ def test_hessian_fast_vs_oracle_and_general(case, fixed, native_lib):
             general, _ = fc.compute_hessian(fc.data, fc.fit_parameters)
     want, want_labels = hessian_oracle.compute_hessian(fo, fo.data)
     assert labels == want_labels
+    # entries are compared against the geometric mean of their diagonal entries; the reference's
+    # quirky dm x dm_index term can exceed that scale by nine orders of magnitude, so its own
+    # rounding floor (1e-12 relative) is allowed for as well
     scale = np.sqrt(np.outer(np.abs(np.diag(want)), np.abs(np.diag(want))))
-    assert np.max(np.abs(fast - want) / scale) < 1e-8, "fast Hessian vs oracle"
-    assert np.max(np.abs(fast - general) / scale) < 1e-10, "fast vs general Hessian"
+    assert np.all(np.abs(fast - want) <= 1e-8 * scale + 1e-12 * np.abs(want)), "fast Hessian vs oracle"
+    assert np.all(np.abs(fast - general) <= 1e-10 * scale + 1e-12 * np.abs(want)), "fast vs general Hessian"
 
 
 def test_fit_trajectory_long_window(native_lib):
