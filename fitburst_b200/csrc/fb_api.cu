@@ -1074,6 +1074,19 @@ extern "C" int fb_pre_window(const double* in_dev, int32_t nf, int32_t nt, const
   return FB_OK;
 }
 
+extern "C" int fb_pre_time_series(const double* in_dev, int32_t nf, int32_t nt, double* scratch_dev, double* out_dev,
+                                  void* stream) {
+  if (!scratch_dev || !out_dev) return fail(FB_ERR_INVALID, "null argument");
+  int rc = pre_check(in_dev, nf, nt);
+  if (rc != FB_OK) return rc;
+  const int chunks = (nf + kPreRowChunk - 1) / kPreRowChunk, tiles = (nt + kPreBlock - 1) / kPreBlock;
+  k_pre_colsum_partial<<<dim3(tiles, chunks), kPreBlock, 0, (cudaStream_t)stream>>>(in_dev, nf, nt, scratch_dev);
+  CUDA_TRY(cudaGetLastError());
+  k_pre_colmean_final<<<tiles, kPreBlock, 0, (cudaStream_t)stream>>>(scratch_dev, chunks, nf, nt, out_dev);
+  CUDA_TRY(cudaGetLastError());
+  return FB_OK;
+}
+
 extern "C" int fb_launch_count(fb_plan_t p, int64_t* count_out, int32_t reset) {
   if (!p || !count_out) return fail(FB_ERR_INVALID, "null argument");
   *count_out = p->launches;

@@ -140,4 +140,28 @@ __global__ void __launch_bounds__(kPreBlock) k_pre_window(const double* __restri
   for (int k = threadIdx.x; k < width; k += kPreBlock) dst[k] = src[k];
 }
 
+// Band-averaged time series, FindPeak.find_peak: data.mean(axis=0) (analysis/peak_finder.py:80).
+// Stage 1: block (column tile, row chunk) adds its rows in row order, threads along the columns
+// (coalesced); stage 2 adds the chunk partials in chunk order and divides: fixed order, deterministic.
+constexpr int kPreRowChunk = 64;
+
+__global__ void __launch_bounds__(kPreBlock) k_pre_colsum_partial(const double* __restrict__ data, int nf, int nt,
+                                                                 double* __restrict__ partial) {
+  const int j = blockIdx.x * kPreBlock + threadIdx.x;
+  if (j >= nt) return;
+  const int r0 = blockIdx.y * kPreRowChunk, r1 = min(nf, r0 + kPreRowChunk);
+  double s = 0.0;
+  for (int i = r0; i < r1; ++i) s += data[(size_t)i * nt + j];
+  partial[(size_t)blockIdx.y * nt + j] = s;
+}
+
+__global__ void __launch_bounds__(kPreBlock) k_pre_colmean_final(const double* __restrict__ partial, int chunks,
+                                                                int nf, int nt, double* __restrict__ out) {
+  const int j = blockIdx.x * kPreBlock + threadIdx.x;
+  if (j >= nt) return;
+  double s = 0.0;
+  for (int c = 0; c < chunks; ++c) s += partial[(size_t)c * nt + j];
+  out[j] = s / (double)nf;
+}
+
 }  // namespace fb

@@ -243,6 +243,12 @@ int fb_pre_downsample_2d(const double* in_dev, int32_t num_freq, int32_t num_tim
 int fb_pre_window(const double* in_dev, int32_t num_freq, int32_t num_time, const int32_t* start_dev,
                   int32_t width, double* out_dev, void* stream);
 
+/* band-averaged time series out_dev[j] = mean_i in_dev[i, j] (FindPeak.find_peak,
+ * analysis/peak_finder.py:80 `self.data.mean(axis=0)`); scratch_dev holds
+ * ceil(num_freq / 64) * num_time doubles */
+int fb_pre_time_series(const double* in_dev, int32_t num_freq, int32_t num_time, double* scratch_dev,
+                       double* out_dev, void* stream);
+
 /* Measured FP64 FMA peak of the device (dependent-free DFMA chains on every SM), TFLOP/s.
  * MEASURED_PEAKS.json carries no FP64 figure; bench.py reports this one as the roofline peak. */
 int fb_measure_fp64_peak(double* tflops_out, void* stream);

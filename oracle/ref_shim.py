@@ -28,6 +28,10 @@ def import_reference():
     """Returns the imported reference package `fitburst` (stubs matplotlib/pytz)."""
     if not reference_available():
         raise ImportError(f"reference tree not found at {REFERENCE_ROOT}")
+    try:  # pandas (imported by the reference's peak finder) must see the REAL absence of pytz
+        import pandas  # noqa: F401
+    except Exception:  # noqa: BLE001
+        pass
     for name in ("pytz", "matplotlib", "matplotlib.pyplot", "matplotlib.gridspec"):
         if name not in sys.modules:
             try:

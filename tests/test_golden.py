@@ -12,7 +12,8 @@ import pytest
 
 from tests.helpers import assert_close, rel_to_max
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not os.path.basename(p).startswith("pipeline_"))  # those belong to tests/test_pipeline.py
 NAMES = [os.path.splitext(os.path.basename(p))[0] for p in GOLDEN]
 
 
