@@ -60,6 +60,14 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 // ---- model side ---------------------------------------------------------------------------
 constexpr int kValsQueue = 1024;  // general-case (sample, component) items queued per channel
 
+// Per (channel, component) constants of the sub-frequency expansion (see make_tay_tab).
+struct TayTab {
+  double d_bar, rho_bar, dz_max;
+  double c0, c1z, c1r, c2zz, c2zr, c2rr, c3rrr;
+  int ok, pad_;
+};
+
+
 __host__ __device__ inline int vals3_bw_stride(int nck) { return (nck + 31) & ~31; }
 
 __host__ __device__ inline size_t vals3_smem_bytes(int nc, int kf) {
@@ -69,6 +77,7 @@ __host__ __device__ inline size_t vals3_smem_bytes(int nc, int kf) {
   n += sizeof(double) * (size_t)nc * kf * 33;                 // R, D
   n += sizeof(double) * (size_t)kFastWarps * vals3_bw_stride(nc * kf);  // B per warp
   n += sizeof(int) * (kValsQueue + 4 + 2 * FB_MAX_COMPONENTS);  // queue, counter, regime boundaries
+  n += sizeof(TayTab) * nc + 16;
   return n;
 }
 
@@ -89,6 +98,81 @@ __device__ __forceinline__ double vals3_general_warp(const PlanConst& pc, const 
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) s_ps += __shfl_xor_sync(kFullMask, s_ps, off);
   return ct.amp10 * (s_ps * (1.0 / (double)npe));
+}
+
+// Rise-region samples, sub-frequency direction by expansion. Within one channel the kf
+// sub-frequencies of a component differ only slightly in delay (d_a) and in ratio = w / tau_a
+// (rho_a), so the sum over the sub-frequencies of one sub-time
+//     sum_a c_a E((T - d_a) / w, rho_a),   E(z, r) = exp(-z^2 / 2) erfcx((r - z) / sqrt 2),
+// c_a = amp_term_a sed_a, is expanded about the channel means (second order in the delay, third
+// in the ratio): ONE exp + erfcx per sub-time instead of kf, all derivatives of E follow from the
+// same two values (erfcx' = 2 u erfcx - 2/sqrt(pi)). The expansion is used only where its
+// truncation error is bounded below 5e-13 relative (the bound uses |d^n E / E| <= (rho + 8.5)^n on
+// the rise region) and where no sub-frequency of the sub-time is clamped
+// (analysis/model.py:340); everything else takes the exact sub-grid.
+__device__ inline void make_tay_tab(const PlanConst& pc, const CompTab& ct, const ChanTab& ch,
+                                    const SubTab* __restrict__ sb, int kf, TayTab& t) {
+  double d_bar = 0.0, rho_bar = 0.0;
+  for (int a = 0; a < kf; ++a) {
+    d_bar += sb[a].delay;
+    rho_bar += sb[a].ratio;
+  }
+  d_bar /= (double)kf;
+  rho_bar /= (double)kf;
+  double c0 = 0.0, c1z = 0.0, c1r = 0.0, c2zz = 0.0, c2zr = 0.0, c2rr = 0.0, c3rrr = 0.0, dz_max = 0.0, dr_max = 0.0;
+  for (int a = 0; a < kf; ++a) {
+    const double c = sb[a].amp_term * sb[a].sed;
+    const double dz = -(sb[a].delay - d_bar) * ct.inv_w, dr = sb[a].ratio - rho_bar;
+    c0 += c;
+    c1z = fma(c, dz, c1z);
+    c1r = fma(c, dr, c1r);
+    c2zz = fma(c * dz, dz, c2zz);
+    c2zr = fma(c * dz, dr, c2zr);
+    c2rr = fma(c * dr, dr, c2rr);
+    c3rrr = fma(c * dr * dr, dr, c3rrr);
+    dz_max = fmax(dz_max, fabs(dz));
+    dr_max = fmax(dr_max, fabs(dr));
+  }
+  t.d_bar = d_bar;
+  t.rho_bar = rho_bar;
+  t.dz_max = dz_max;
+  t.c0 = c0;
+  t.c1z = c1z;
+  t.c1r = c1r;
+  t.c2zz = 0.5 * c2zz;
+  t.c2zr = c2zr;
+  t.c2rr = 0.5 * c2rr;
+  t.c3rrr = c3rrr * (1.0 / 6.0);
+  const double s = fabs(rho_bar) + 8.5;
+  const double bound = (s * s) * (s * s) * (1.0 / 24.0) * (dr_max * dr_max) * (dr_max * dr_max) +
+                       s * s * s * (1.0 / 6.0) * dz_max * dz_max * dz_max + s * s * s * 0.5 * dz_max * dr_max * dr_max;
+  t.ok = ch.fast_ok && !pc.is_folded && bound < 5e-13 && rho_bar > 0.0;
+  t.pad_ = 0;
+}
+
+// sum_a c_a E(z - dz_a, rho_a) by the expansion about (z, rho_bar); z = (T - d_bar) / w unclamped.
+__device__ __forceinline__ double tay_eval(const TayTab& t, double z) {
+  const double h = kSqrtHalf;
+  const double u = (t.rho_bar - z) * h;
+  const double g = fb_exp(-0.5 * z * z);
+  const double x0 = erfcx(u);
+  const double x1 = fma(2.0 * u, x0, -kTwoOverSqrtPi);
+  const double x2 = 2.0 * fma(u, x1, x0);
+  const double x3 = fma(2.0 * u, x2, 4.0 * x1);
+  const double e_z = -z * x0 - h * x1;
+  const double e_r = h * x1;
+  const double e_zz = fma(z * z - 1.0, x0, fma(2.0 * z * h, x1, 0.5 * x2));
+  const double e_zr = -z * h * x1 - 0.5 * x2;
+  const double e_rr = 0.5 * x2;
+  const double e_rrr = 0.5 * h * x3;
+  double s = t.c0 * x0;
+  s = fma(t.c1z, e_z, s);
+  s = fma(t.c1r, e_r, s);
+  s = fma(t.c2zz, e_zz, s);
+  s = fma(t.c2zr, e_zr, s);
+  s = fma(t.c2rr, e_rr, s);
+  s = fma(t.c3rrr, e_rrr, s);
+  return g * s;
 }
 
 // First sample that is NOT on the clamp plateau (jp) and first sample in the pure exponential
@@ -128,10 +212,18 @@ __device__ __forceinline__ double vals3_component(const PlanConst& pc, const Com
   const int kf = KF > 0 ? KF : pc.kf, kt = pc.kt;
   *deferred = false;
   if (j0 >= jt && j0 >= jp) {  // whole tile in the exponential tail
-    double s = 0.0;
+    // four interleaved partial sums: the kf-long dependent FMA chain was the critical path of a tile
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int a = 0;
 #pragma unroll
-    for (int a = 0; a < kf; ++a) s = fma(bw[a], r_lane[a * 32], s);
-    return s;
+    for (; a + 3 < kf; a += 4) {
+      s0 = fma(bw[a], r_lane[a * 32], s0);
+      s1 = fma(bw[a + 1], r_lane[(a + 1) * 32], s1);
+      s2 = fma(bw[a + 2], r_lane[(a + 2) * 32], s2);
+      s3 = fma(bw[a + 3], r_lane[(a + 3) * 32], s3);
+    }
+    for (; a < kf; ++a) s0 = fma(bw[a], r_lane[a * 32], s0);
+    return (s0 + s1) + (s2 + s3);
   }
   if (j0 + 32 <= jp) return ch.plateau_ps;  // whole tile on the clamp plateau
   const int j = j0 + lane;
@@ -205,6 +297,7 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
   int* queue = reinterpret_cast<int*>(sp);
   int* qcount = queue + kValsQueue;
   int* bounds = qcount + 1;  // [nc][2]: jp, jt
+  TayTab* tay = reinterpret_cast<TayTab*>((reinterpret_cast<uintptr_t>(bounds + 2 * FB_MAX_COMPONENTS + 2) + 15) & ~(uintptr_t)15);
 
   {
     const double* src = reinterpret_cast<const double*>(A.g_comp);
@@ -241,6 +334,7 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
       bounds[2 * (tid - 32)] = jp;
       bounds[2 * (tid - 32) + 1] = jt;
     }
+    if (tid >= 64 && tid < 64 + nc) make_tay_tab(pc, comp[tid - 64], chan[tid - 64], sub + (tid - 64) * kf, kf, tay[tid - 64]);
     for (int e = tid; e < nck * 32; e += kFastBlock) {
       const int l = e & 31, ca = e >> 5, c = ca / kf;
       const SubTab& st = sub[ca];
@@ -282,13 +376,47 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
       __syncwarp();
     }
     __syncthreads();
-    // phase B: the queued rise-region samples, one per warp pass (uniform cost)
+    // phase B: the queued rise-region samples. A group of lanes (one per sub-time) evaluates an
+    // item by the sub-frequency expansion; items it does not cover (a clamped sub-time, a
+    // component whose expansion bound is too large) take the exact sub-grid, one per warp pass.
     const int qn = min(*qcount, kValsQueue);
-    for (int q = warp; q < qn; q += kFastWarps) {
-      const int item = queue[q];
-      const int c = item >> 27, jj = item & ((1 << 27) - 1);
-      const double v = vals3_general_warp<KF>(pc, comp[c], chan[c], sub + c * kf, jj, lane);
-      if (lane == 0) out[(size_t)c * nt + jj] = v;
+    int lpi = 1;  // lanes per item: power of two >= kt
+    while (lpi < kt && lpi < 32) lpi <<= 1;
+    const int ipw = 32 / lpi;
+    const double inv_n = 1.0 / (double)(kf * kt);
+    for (int base = warp * ipw; base < qn; base += kFastWarps * ipw) {
+      const int q = base + lane / lpi, b = lane % lpi;
+      bool have = q < qn, expanded = false;
+      int c = 0, jj = 0;
+      double v = 0.0;
+      if (have) {
+        const int item = queue[q];
+        c = item >> 27;
+        jj = item & ((1 << 27) - 1);
+        const TayTab& t = tay[c];
+        expanded = t.ok && kt <= 32;
+        if (expanded && b < kt) {
+          const CompTab& ct = comp[c];
+          const double z = (linspace_at(ct.t_start, ct.t_step, ct.t_stop, jj * kt + b, pc.ntk) - t.d_bar) * ct.inv_w;
+          if (z - t.dz_max >= -5.0) v = tay_eval(t, z);  // no sub-frequency clamped at -5 w
+          else expanded = false;
+        }
+      }
+      // an item is expanded only if every one of its sub-times is
+      const unsigned fail = __ballot_sync(kFullMask, have && !expanded);
+      for (int off = lpi >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(kFullMask, v, off);
+      const unsigned group = (lpi == 32 ? kFullMask : ((1u << lpi) - 1u)) << (lane / lpi * lpi);
+      const bool item_fail = (fail & group) != 0u;
+      if (have && !item_fail && b == 0) out[(size_t)c * nt + jj] = comp[c].amp10 * (v * inv_n);
+      // exact sub-grid for the rest, whole warp per item
+      unsigned todo = __ballot_sync(kFullMask, have && item_fail && b == 0);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int c2 = __shfl_sync(kFullMask, c, src), j2 = __shfl_sync(kFullMask, jj, src);
+        const double v2 = vals3_general_warp<KF>(pc, comp[c2], chan[c2], sub + c2 * kf, j2, lane);
+        if (lane == 0) out[(size_t)c2 * nt + j2] = v2;
+      }
     }
   }
   cp_async_wait<0>();
