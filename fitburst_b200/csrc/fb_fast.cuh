@@ -63,7 +63,7 @@ constexpr int kValsQueue = 1024;  // general-case (sample, component) items queu
 // Per (channel, component) constants of the sub-frequency expansion (see make_tay_tab).
 struct TayTab {
   double d_bar, rho_bar, dz_max;
-  double c0, c1z, c1r, c2zz, c2zr, c2rr, c3rrr;
+  double c0, c1z, c1r, c2zz, c2zr, c2rr, c3zzz, c3zzr, c3zrr, c3rrr;
   int ok, pad_;
 };
 
@@ -104,11 +104,11 @@ __device__ __forceinline__ double vals3_general_warp(const PlanConst& pc, const 
 // sub-frequencies of a component differ only slightly in delay (d_a) and in ratio = w / tau_a
 // (rho_a), so the sum over the sub-frequencies of one sub-time
 //     sum_a c_a E((T - d_a) / w, rho_a),   E(z, r) = exp(-z^2 / 2) erfcx((r - z) / sqrt 2),
-// c_a = amp_term_a sed_a, is expanded about the channel means (second order in the delay, third
-// in the ratio): ONE exp + erfcx per sub-time instead of kf, all derivatives of E follow from the
-// same two values (erfcx' = 2 u erfcx - 2/sqrt(pi)). The expansion is used only where its
-// truncation error is bounded below 5e-13 relative (the bound uses |d^n E / E| <= (rho + 8.5)^n on
-// the rise region) and where no sub-frequency of the sub-time is clamped
+// c_a = amp_term_a sed_a, is expanded to third order about the channel means: ONE exp + erfcx per
+// sub-time instead of kf, all derivatives of E follow from the same two values
+// (erfcx' = 2 u erfcx - 2/sqrt(pi)). The expansion is used only where its truncation error is
+// bounded below 5e-13 relative (fourth-order remainder with |d^n E / E| <= (rho + 8.5)^n on the
+// rise region; measured worst case 1.3e-13) and where no sub-frequency of the sub-time is clamped
 // (analysis/model.py:340); everything else takes the exact sub-grid.
 __device__ inline void make_tay_tab(const PlanConst& pc, const CompTab& ct, const ChanTab& ch,
                                     const SubTab* __restrict__ sb, int kf, TayTab& t) {
@@ -119,7 +119,8 @@ __device__ inline void make_tay_tab(const PlanConst& pc, const CompTab& ct, cons
   }
   d_bar /= (double)kf;
   rho_bar /= (double)kf;
-  double c0 = 0.0, c1z = 0.0, c1r = 0.0, c2zz = 0.0, c2zr = 0.0, c2rr = 0.0, c3rrr = 0.0, dz_max = 0.0, dr_max = 0.0;
+  double c0 = 0.0, c1z = 0.0, c1r = 0.0, c2zz = 0.0, c2zr = 0.0, c2rr = 0.0, dz_max = 0.0, dr_max = 0.0;
+  double c3zzz = 0.0, c3zzr = 0.0, c3zrr = 0.0, c3rrr = 0.0;
   for (int a = 0; a < kf; ++a) {
     const double c = sb[a].amp_term * sb[a].sed;
     const double dz = -(sb[a].delay - d_bar) * ct.inv_w, dr = sb[a].ratio - rho_bar;
@@ -129,6 +130,9 @@ __device__ inline void make_tay_tab(const PlanConst& pc, const CompTab& ct, cons
     c2zz = fma(c * dz, dz, c2zz);
     c2zr = fma(c * dz, dr, c2zr);
     c2rr = fma(c * dr, dr, c2rr);
+    c3zzz = fma(c * dz * dz, dz, c3zzz);
+    c3zzr = fma(c * dz * dz, dr, c3zzr);
+    c3zrr = fma(c * dz * dr, dr, c3zrr);
     c3rrr = fma(c * dr * dr, dr, c3rrr);
     dz_max = fmax(dz_max, fabs(dz));
     dr_max = fmax(dr_max, fabs(dr));
@@ -142,10 +146,12 @@ __device__ inline void make_tay_tab(const PlanConst& pc, const CompTab& ct, cons
   t.c2zz = 0.5 * c2zz;
   t.c2zr = c2zr;
   t.c2rr = 0.5 * c2rr;
+  t.c3zzz = c3zzz * (1.0 / 6.0);
+  t.c3zzr = 0.5 * c3zzr;
+  t.c3zrr = 0.5 * c3zrr;
   t.c3rrr = c3rrr * (1.0 / 6.0);
-  const double s = fabs(rho_bar) + 8.5;
-  const double bound = (s * s) * (s * s) * (1.0 / 24.0) * (dr_max * dr_max) * (dr_max * dr_max) +
-                       s * s * s * (1.0 / 6.0) * dz_max * dz_max * dz_max + s * s * s * 0.5 * dz_max * dr_max * dr_max;
+  const double s = fabs(rho_bar) + 8.5, d = dz_max + dr_max;
+  const double bound = (s * s) * (s * s) * (1.0 / 24.0) * (d * d) * (d * d);
   t.ok = ch.fast_ok && !pc.is_folded && bound < 5e-13 && rho_bar > 0.0;
   t.pad_ = 0;
 }
@@ -165,12 +171,18 @@ __device__ __forceinline__ double tay_eval(const TayTab& t, double z) {
   const double e_zr = -z * h * x1 - 0.5 * x2;
   const double e_rr = 0.5 * x2;
   const double e_rrr = 0.5 * h * x3;
+  const double e_zzz = fma(3.0 * z - z * z * z, x0, fma(h * (3.0 - 3.0 * z * z), x1, -1.5 * z * x2 - 0.5 * h * x3));
+  const double e_zzr = h * fma(z * z - 1.0, x1, fma(2.0 * z * h, x2, 0.5 * x3));
+  const double e_zrr = -0.5 * z * x2 - 0.5 * h * x3;
   double s = t.c0 * x0;
   s = fma(t.c1z, e_z, s);
   s = fma(t.c1r, e_r, s);
   s = fma(t.c2zz, e_zz, s);
   s = fma(t.c2zr, e_zr, s);
   s = fma(t.c2rr, e_rr, s);
+  s = fma(t.c3zzz, e_zzz, s);
+  s = fma(t.c3zzr, e_zzr, s);
+  s = fma(t.c3zrr, e_zrr, s);
   s = fma(t.c3rrr, e_rrr, s);
   return g * s;
 }
