@@ -352,12 +352,35 @@ static int check_err_flag(fb_plan_s* p, cudaStream_t st) {
   return FB_OK;
 }
 
+static bool fast_path_ok(const fb_plan_s* p, bool for_gram);
+static int launch_vals3(fb_plan_s* p, const EvalArgs& A, double* out, cudaStream_t st, int* grid_out);
+static int ensure_capacity(double** buf, size_t* cap, size_t need);
+
 extern "C" int fb_model_eval(fb_plan_t p, const double* data_dev, double* model_dev,
                              double* amplitude_dev, double* spectrum_dev, double* timediff_dev,
                              double* timeprof_dev, void* stream) {
   if (!p || !model_dev) return fail(FB_ERR_INVALID, "null argument");
   if (p->pc.scintillation && !data_dev)
     return fail(FB_ERR_INVALID, "ERROR: scintillation modelling is desired by data are missing!");
+  if (!amplitude_dev && !spectrum_dev && !timediff_dev && !timeprof_dev && fast_path_ok(p, false)) {
+    // model only, scattered branch: the warp-granular k_vals3 over every channel + component sum
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nf = p->desc.num_freq, nc = p->desc.num_components, nt = p->desc.num_time;
+    int rc = ensure_tables(p, st);
+    if (rc == FB_OK) rc = ensure_capacity(&p->d_vals, &p->vals_cap, (size_t)nf * nc * nt);
+    if (rc != FB_OK) return rc;
+    EvalArgs A = base_args(p);
+    p->vals_match_cache = false;
+    p->last_eval_split = false;
+    rc = launch_vals3(p, A, p->d_vals, st, nullptr);
+    if (rc != FB_OK) return rc;
+    const long long total = (long long)nf * nt;
+    k_model_from_vals<<<(unsigned)std::min<long long>((total + 255) / 256, 148LL * 32), 256, 0, st>>>(p->d_vals, nc, nt,
+                                                                                                      total, model_dev);
+    CUDA_TRY(cudaGetLastError());
+    p->launches += 1;
+    return FB_OK;
+  }
   EvalArgs A = base_args(p);
   A.data = data_dev;
   A.model = model_dev;

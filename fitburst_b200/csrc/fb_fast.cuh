@@ -434,6 +434,20 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
   cp_async_wait<0>();
 }
 
+// Model spectrum from the stored rows: model[i, j] = sum_c gvals[(i * nc + c) * nt + j], components
+// added in order like spectrum_per_component.sum(axis=2) (analysis/model.py:279).
+__global__ void __launch_bounds__(256) k_model_from_vals(const double* __restrict__ gvals, int nc, int nt,
+                                                         long long total, double* __restrict__ model) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long i = e / nt;
+    const int j = (int)(e - i * nt);
+    const double* v = gvals + (size_t)i * nc * nt + j;
+    double m = 0.0;
+    for (int c = 0; c < nc; ++c) m += v[(size_t)c * nt];
+    model[e] = m;
+  }
+}
+
 // chi^2 of the stored spectrum values against the data (grid sweeps, BASELINE.json config 4):
 // one block per good channel row, fixed-order reduction.
 __global__ void __launch_bounds__(256) k_chi2_vals(const EvalArgs A, const double* __restrict__ gvals) {

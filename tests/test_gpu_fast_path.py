@@ -198,3 +198,27 @@ def test_full_size_fast_vs_general(native_lib):
     assert np.max(np.abs(fast - general) / scale) < 1e-11
     hs = np.sqrt(np.outer(np.abs(np.diag(h_general)), np.abs(np.diag(h_general))))
     assert np.max(np.abs(h_fast - h_general) / hs) < 1e-9
+
+
+MODEL_REGIMES = {
+    # (dm offset, scattering time at ref_freq, widths): the sub-frequency expansion of the rise
+    # region is taken or refused by its truncation bound; either way the model must hold 1e-10
+    "expansion_config2": (0.0, 2e-3, None),
+    "expansion_small_dm_offset": (0.02, 2e-3, None),
+    "exact_large_dm_offset": (0.5, 2e-3, None),
+    "exact_weak_scattering": (0.0, 2e-4, None),
+    "expansion_strong_scattering": (0.01, 2e-2, None),
+    "mixed_wide_and_narrow": (0.005, 1e-3, [3e-3, 4e-4, 1e-3]),
+}
+
+
+@pytest.mark.parametrize("name", list(MODEL_REGIMES))
+def test_model_rise_region_regimes(name, native_lib):
+    from tests.helpers import assert_close
+    dm, tau, widths = MODEL_REGIMES[name]
+    freqs, times, truth, kwargs = _case(num_freq=40, num_time=512, dm=dm, widths=widths)
+    truth["scattering_timescale"] = [tau] * 3
+    cuda, oracle = model_pair(freqs, times, kwargs, truth)
+    got, want = cuda.compute_model(), oracle.compute_model()
+    assert_close(got, want, 1e-10, name)
+    assert rel_to_max(got, want) < 2e-12
