@@ -319,9 +319,11 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
   const int wtiles = (nt + 31) / 32;
   const int tpw = (wtiles + kFastWarps - 1) / kFastWarps;  // contiguous tiles per warp
   const int chan_chunks = (int)(sizeof(ChanTab) * nc / 16), sub_chunks = (int)(sizeof(SubTab) * nck / 16);
-  auto prefetch_tables = [&](int chi, int buf) {
-    if (chi < A.num_chan) {
-      const int i = A.chan_list ? A.chan_list[chi] : chi;
+  // channel numbers are read two iterations ahead: chan_list[] -> table address is a dependent
+  // global-load chain that would otherwise sit in front of every table prefetch
+  auto channel_of = [&](int chi) { return chi < A.num_chan ? (A.chan_list ? __ldg(A.chan_list + chi) : chi) : -1; };
+  auto prefetch_tables = [&](int i, int buf) {
+    if (i >= 0) {
       char* dst = tabs + (size_t)buf * tab_bytes;
       const char* src_c = reinterpret_cast<const char*>(A.g_chan + (size_t)i * nc);
       const char* src_s = reinterpret_cast<const char*>(A.g_sub + (size_t)i * nck);
@@ -331,12 +333,15 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
     }
     cp_async_commit();
   };
-  prefetch_tables(blockIdx.x, 0);
+  int i_next = channel_of(blockIdx.x + gridDim.x);
+  prefetch_tables(channel_of(blockIdx.x), 0);
   int buf = 0;
   for (int chi = blockIdx.x; chi < A.num_chan; chi += gridDim.x, buf ^= 1) {
+    const int i_after = channel_of(chi + 2 * gridDim.x);
     cp_async_wait<0>();
     __syncthreads();  // tables of this channel landed; every warp is done with the previous one
-    prefetch_tables(chi + gridDim.x, buf ^ 1);
+    prefetch_tables(i_next, buf ^ 1);
+    i_next = i_after;
     const ChanTab* chan = reinterpret_cast<const ChanTab*>(tabs + (size_t)buf * tab_bytes);
     const SubTab* sub = reinterpret_cast<const SubTab*>(tabs + (size_t)buf * tab_bytes + sizeof(ChanTab) * nc);
     if (tid == 0) *qcount = 0;
@@ -648,9 +653,11 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
 
   const int wtiles = (nt + 31) / 32;
   const int chan_chunks = (int)(sizeof(ChanTab) * NC / 16);
-  auto prefetch_tables = [&](int chi, int buf) {
-    if (chi < A.num_chan && tid < chan_chunks) {
-      const int i = A.chan_list ? A.chan_list[chi] : chi;
+  // channel number and weight are read ahead of their use (chan_list[] -> weights[] / table address
+  // are dependent global-load chains: ncu showed them exposed once per channel)
+  auto channel_of = [&](int chi) { return chi < A.num_chan ? (A.chan_list ? __ldg(A.chan_list + chi) : chi) : -1; };
+  auto prefetch_tables = [&](int i, int buf) {
+    if (i >= 0 && tid < chan_chunks) {
       cp_async16(tabs + (size_t)buf * sizeof(ChanTab) * NC + 16 * tid,
                  reinterpret_cast<const char*>(A.g_chan + (size_t)i * NC) + 16 * tid);
     }
@@ -663,13 +670,34 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
   const double tj_half = 0.5 * (double)((nt - 1) * kt), tj_mid = kt_mid + tj_half;
   const double xi_s = 1.0 / tj_half, xi_o = -tj_mid / tj_half;
   const int fr = lane & 3, fc = lane >> 2;  // fragment element: sample fr of the step, column fc of the block
-  prefetch_tables(blockIdx.x, 0);
+  int i_cur = channel_of(blockIdx.x), i_next = channel_of(blockIdx.x + gridDim.x);
+  double w_cur = i_cur >= 0 ? __ldg(A.weights + i_cur) : 0.0;
+  prefetch_tables(i_cur, 0);
   int buf = 0;
   for (int chi = blockIdx.x; chi < A.num_chan; chi += gridDim.x, buf ^= 1) {
-    const int i = A.chan_list ? A.chan_list[chi] : chi;
+    const int i = i_cur;
+    const double wi = w_cur;
+    const int i_after = channel_of(chi + 2 * gridDim.x);
+    const double w_next = i_next >= 0 ? __ldg(A.weights + i_next) : 0.0;
+    const double* srow = gvals + (size_t)chi * NC * nt;
+    const double* drow = A.data + (size_t)i * nt;
+    auto prefetch_tile = [&](int wt, int pb) {
+      const int j = wt * 32 + lane;
+      if (wt < wtiles && j < nt) {
+        double* dst = pref + (size_t)pb * (NC + 1) * 32;
+#pragma unroll
+        for (int c = 0; c < NC; ++c) cp_async8(dst + c * 32, srow + (size_t)c * nt + j);
+        cp_async8(dst + NC * 32, drow + j);
+      }
+      cp_async_commit();
+    };
     cp_async_wait<0>();
     __syncthreads();
-    prefetch_tables(chi + gridDim.x, buf ^ 1);
+    prefetch_tables(i_next, buf ^ 1);
+    prefetch_tile(warp, 0);  // the first tile's rows travel while the channel constants are built
+    i_cur = i_next;
+    i_next = i_after;
+    w_cur = w_next;
     const ChanTab* chan = reinterpret_cast<const ChanTab*>(tabs + (size_t)buf * sizeof(ChanTab) * NC);
     bool std_ok = true;  // every component on the scattered branch at this channel
 #pragma unroll
@@ -701,7 +729,6 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
       range[2 * tid + 1] = j_hi;
     }
     __syncthreads();
-    const double wi = A.weights[i];
     if (far_on) {
       // T[k][a]: coefficient of basis value a in full column k (weight included)
       for (int e = tid; e < ncols * 8; e += kFastBlock) {
@@ -734,19 +761,6 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
       }
     }
 
-    const double* srow = gvals + (size_t)chi * NC * nt;
-    const double* drow = A.data + (size_t)i * nt;
-    auto prefetch_tile = [&](int wt, int pb) {
-      const int j = wt * 32 + lane;
-      if (wt < wtiles && j < nt) {
-        double* dst = pref + (size_t)pb * (NC + 1) * 32;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) cp_async8(dst + c * 32, srow + (size_t)c * nt + j);
-        cp_async8(dst + NC * 32, drow + j);
-      }
-      cp_async_commit();
-    };
-    prefetch_tile(warp, 0);
     int pb = 0;
     for (int wt = warp; wt < wtiles; wt += kFastWarps, pb ^= 1) {
       const int j0 = wt * 32, j = j0 + lane;
