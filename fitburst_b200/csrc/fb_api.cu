@@ -567,7 +567,7 @@ static int launch_gram3_t(fb_plan_s* p, const EvalArgs& A, const GramLayout& G, 
   }
   const int grid = std::min(A.num_chan, p->sm_count * occ);
   const int nent = F.ncols * (F.ncols + 1) / 2;
-  const size_t near_sz = (size_t)grid * g3_nacc(NB) * 64;
+  const size_t near_sz = (size_t)grid * kFastWarps * g3_nacc(NB) * 64;  // one accumulator set per warp
   int rc = ensure_capacity(&p->d_partials, &p->partials_cap, near_sz + (size_t)grid * nent);
   if (rc != FB_OK) return rc;
   EvalArgs B = A;
@@ -659,8 +659,8 @@ static int launch_fast_gram(fb_plan_s* p, EvalArgs& A, int ncols, double* gram_d
   X.factor[ncols - 1] = 1.0;
   X.shift[ncols - 1] = 0.0;
   const int far_entries = F.enabled ? nent : 0;
-  k_gram3_finish<<<(entries + far_entries + 7) / 8, 256, 0, st>>>(p->d_partials, grid, entries, far_entries, p->d_racc,
-                                                                 p->d_far, X, p->d_counter, gram_dev);
+  k_gram3_finish<<<(entries + far_entries + 7) / 8, 256, 0, st>>>(p->d_partials, grid, kFastWarps, entries, far_entries,
+                                                                 p->d_racc, p->d_far, X, p->d_counter, gram_dev);
   CUDA_TRY(cudaGetLastError());
   p->launches += 1;
   return FB_OK;

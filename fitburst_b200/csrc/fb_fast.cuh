@@ -573,11 +573,16 @@ __host__ __device__ inline size_t gram3_far_smem_bytes(int ncols) {
   return sizeof(double) * ((size_t)16 * ncols + (size_t)kFastWarps * 64 + 64) + sizeof(int) * 2 * FB_MAX_COMPONENTS;
 }
 
+// Tiles of spectrum rows + data in flight per warp: with one tile ahead the kernel was bound by
+// memory latency (16 KB in flight per SM, 2.2 TB/s: an ablation with all arithmetic removed still
+// took 165 of 230 us); three tiles ahead, across channel boundaries, lift that bound.
+constexpr int kG3Depth = 3, kG3Ring = kG3Depth + 1;
+
 __host__ __device__ inline size_t gram3_smem_bytes(int nc, int nb, int ncols) {
   size_t stage = sizeof(double) * (size_t)kFastWarps * nb * 8 * kMmaRowStride;
   const size_t red = sizeof(double) * (size_t)kFastWarps * g3_nacc(nb) * 64;
   if (red > stage) stage = red;  // the stage doubles as the block-reduction buffer
-  const size_t pref = sizeof(double) * 2 * (size_t)(nc + 1) * kFastBlock;  // double-buffered value + data prefetch
+  const size_t pref = sizeof(double) * kG3Ring * (size_t)(nc + 1) * kFastBlock;  // ring of prefetched tiles
   return sizeof(CompTab) * nc + 2 * sizeof(ChanTab) * nc + sizeof(GTab) * nc + stage + pref +
          gram3_far_smem_bytes(ncols);
 }
@@ -605,10 +610,10 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
     if (red_bytes > stage) stage = red_bytes;
     sp += stage;
   }
-  // [2][NC + 1][32] per warp: every lane copies and later reads only its own elements, so
+  // [kG3Ring][NC + 1][32] per warp: every lane copies and later reads only its own elements, so
   // cp.async.wait_group is the only synchronisation the prefetch needs
-  double* pref = reinterpret_cast<double*>(sp) + (size_t)warp * 2 * (NC + 1) * 32 + lane;
-  sp += sizeof(double) * 2 * (size_t)(NC + 1) * kFastBlock;
+  double* pref = reinterpret_cast<double*>(sp) + (size_t)warp * kG3Ring * (NC + 1) * 32 + lane;
+  sp += sizeof(double) * kG3Ring * (size_t)(NC + 1) * kFastBlock;
   const int ncols = F.ncols;
   double* Tm = reinterpret_cast<double*>(sp);       // [ncols][8]
   double* Um = Tm + (size_t)8 * ncols;              // [8][ncols]
@@ -626,11 +631,15 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
   for (int e = lane; e < NB * 8 * kMmaRowStride; e += 32) xt[e] = 0.0;  // padding columns stay zero
 
   constexpr int kPairs = g3_pairs(NB), kAcc = g3_nacc(NB);
-  double c0[kPairs], c1[kPairs], acc0[kAcc], acc1[kAcc];
+  double c0[kPairs], c1[kPairs];
 #pragma unroll
   for (int k = 0; k < kPairs; ++k) c0[k] = c1[k] = 0.0;
+  // power accumulators of this warp live in its slice of the partial buffer (L2-resident, touched
+  // once per channel, every lane only its own two elements of each 8x8 block): keeping them in
+  // registers cost 36 registers and a fifth block per SM
+  double* accw = A.partials + ((size_t)blockIdx.x * kFastWarps + warp) * kAcc * 64 + (lane >> 2) * 8 + (lane & 3) * 2;
 #pragma unroll
-  for (int k = 0; k < kAcc; ++k) acc0[k] = acc1[k] = 0.0;
+  for (int k = 0; k < kAcc; ++k) *reinterpret_cast<double2*>(accw + k * 64) = make_double2(0.0, 0.0);
   double cf0 = 0.0, cf1 = 0.0;  // far-tile block B of the current channel
   // full-matrix accumulators of the far tiles: thread e owns upper-triangle entries e and e + 256
   const int nent = ncols * (ncols + 1) / 2;
@@ -673,28 +682,34 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
   int i_cur = channel_of(blockIdx.x), i_next = channel_of(blockIdx.x + gridDim.x);
   double w_cur = i_cur >= 0 ? __ldg(A.weights + i_cur) : 0.0;
   prefetch_tables(i_cur, 0);
+  // tiles of this warp within a channel: wt = warp + k * kFastWarps, k < nk
+  const int nk = wtiles > warp ? (wtiles - warp + kFastWarps - 1) / kFastWarps : 0;
+  unsigned q_issue = 0, q_use = 0;  // ring positions (one cp.async group per issued tile, even if empty)
+  auto issue_tile = [&](int chi_t, int i_t, int k) {
+    const int j = (warp + k * kFastWarps) * 32 + lane;
+    if (i_t >= 0 && k < nk && j < nt) {
+      double* dst = pref + (size_t)(q_issue % kG3Ring) * (NC + 1) * 32;
+      const double* srow_t = gvals + (size_t)chi_t * NC * nt;
+#pragma unroll
+      for (int c = 0; c < NC; ++c) cp_async8(dst + c * 32, srow_t + (size_t)c * nt + j);
+      cp_async8(dst + NC * 32, A.data + (size_t)i_t * nt + j);
+    }
+    cp_async_commit();
+    ++q_issue;
+  };
+  for (int k = 0; k < kG3Depth; ++k) issue_tile(blockIdx.x, i_cur, k);
   int buf = 0;
   for (int chi = blockIdx.x; chi < A.num_chan; chi += gridDim.x, buf ^= 1) {
     const int i = i_cur;
     const double wi = w_cur;
     const int i_after = channel_of(chi + 2 * gridDim.x);
     const double w_next = i_next >= 0 ? __ldg(A.weights + i_next) : 0.0;
-    const double* srow = gvals + (size_t)chi * NC * nt;
-    const double* drow = A.data + (size_t)i * nt;
-    auto prefetch_tile = [&](int wt, int pb) {
-      const int j = wt * 32 + lane;
-      if (wt < wtiles && j < nt) {
-        double* dst = pref + (size_t)pb * (NC + 1) * 32;
-#pragma unroll
-        for (int c = 0; c < NC; ++c) cp_async8(dst + c * 32, srow + (size_t)c * nt + j);
-        cp_async8(dst + NC * 32, drow + j);
-      }
-      cp_async_commit();
-    };
-    cp_async_wait<0>();
+    // the table group of this channel is older than the nk tile groups committed since
+    if (nk >= kG3Depth) cp_async_wait<kG3Depth>();
+    else cp_async_wait<0>();
     __syncthreads();
     prefetch_tables(i_next, buf ^ 1);
-    prefetch_tile(warp, 0);  // the first tile's rows travel while the channel constants are built
+    const int i_ahead = i_next, chi_ahead = chi + gridDim.x;  // where the look-ahead continues
     i_cur = i_next;
     i_next = i_after;
     w_cur = w_next;
@@ -761,15 +776,18 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
       }
     }
 
-    int pb = 0;
-    for (int wt = warp; wt < wtiles; wt += kFastWarps, pb ^= 1) {
+    for (int k = 0; k < nk; ++k) {
+      const int wt = warp + k * kFastWarps;
       const int j0 = wt * 32, j = j0 + lane;
       const bool valid = j < nt;
-      prefetch_tile(wt + kFastWarps, pb ^ 1);
-      cp_async_wait<1>();
+      // look-ahead: tile k + depth of this channel, or the first tiles of the block's next channel
+      if (k + kG3Depth < nk) issue_tile(chi, i, k + kG3Depth);
+      else issue_tile(chi_ahead, i_ahead, k + kG3Depth - nk);
+      cp_async_wait<kG3Depth>();
       double m[NC], dval = 0.0;
       {
-        const double* src = pref + (size_t)pb * (NC + 1) * 32;
+        const double* src = pref + (size_t)(q_use % kG3Ring) * (NC + 1) * 32;
+        ++q_use;
 #pragma unroll
         for (int c = 0; c < NC; ++c) m[c] = valid ? src[c * 32] : 0.0;
         if (valid) dval = src[NC * 32];
@@ -883,8 +901,10 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
           const int off = g3_acc_offset(NB, bi, bj);
 #pragma unroll
           for (int p = 0; p < g3_npow(bi, bj); ++p) {
-            acc0[off + p] = fma(sp_[p], c0[k], acc0[off + p]);
-            acc1[off + p] = fma(sp_[p], c1[k], acc1[off + p]);
+            double2 v = *reinterpret_cast<double2*>(accw + (off + p) * 64);
+            v.x = fma(sp_[p], c0[k], v.x);
+            v.y = fma(sp_[p], c1[k], v.y);
+            *reinterpret_cast<double2*>(accw + (off + p) * 64) = v;
           }
           c0[k] = c1[k] = 0.0;
           ++k;
@@ -928,22 +948,6 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
     for (int s2 = 0; s2 < 2; ++s2)
       if (tid + s2 * kFastBlock < nent) far_partials[(size_t)blockIdx.x * nent + tid + s2 * kFastBlock] = gacc[s2];
   }
-  // block reduction in warp order (deterministic); fragment element of accumulator k:
-  // row lane/4, columns 2 (lane%4) + {0, 1} of its 8x8 block
-  __syncthreads();
-  double* red = stage_all;  // [warp][kAcc][64]
-#pragma unroll
-  for (int k = 0; k < kAcc; ++k) {
-    red[((size_t)warp * kAcc + k) * 64 + (lane >> 2) * 8 + (lane & 3) * 2] = acc0[k];
-    red[((size_t)warp * kAcc + k) * 64 + (lane >> 2) * 8 + (lane & 3) * 2 + 1] = acc1[k];
-  }
-  __syncthreads();
-  for (int e = tid; e < kAcc * 64; e += kFastBlock) {
-    double s = 0.0;
-#pragma unroll
-    for (int w = 0; w < kFastWarps; ++w) s += red[(size_t)w * kAcc * 64 + e];
-    A.partials[(size_t)blockIdx.x * kAcc * 64 + e] = s;
-  }
 }
 
 // Full column k of [J r] = factor * (L + shift)^power * reduced column `red` (per channel).
@@ -964,17 +968,21 @@ __device__ inline double g3_binom(int n, int k) {
 // the last block to finish expands the reduced accumulators into the full symmetric
 // (n+1) x (n+1) matrix [J r]^T [J r] and adds the far-tile matrix.
 __global__ void __launch_bounds__(256) k_gram3_finish(const double* __restrict__ partials, int nblocks,
-                                                      int near_entries, int far_entries, double* __restrict__ racc,
+                                                      int warps_per_block, int near_entries, int far_entries,
+                                                      double* __restrict__ racc,
                                                       double* __restrict__ far, const ExpandArgs X,
                                                       unsigned* __restrict__ counter, double* __restrict__ gram) {
   __shared__ bool last;
   const int e = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (e < near_entries + far_entries) {
+    // near accumulators: one set per warp of k_gram3; far matrix: one per block
     const bool is_far = e >= near_entries;
-    const double* src = is_far ? partials + (size_t)nblocks * near_entries + (e - near_entries) : partials + e;
+    const size_t near_sets = (size_t)nblocks * warps_per_block;
+    const double* src = is_far ? partials + near_sets * near_entries + (e - near_entries) : partials + e;
     const int stride = is_far ? far_entries : near_entries;
+    const int count = is_far ? nblocks : (int)near_sets;
     double s = 0.0;
-    for (int b = lane; b < nblocks; b += 32) s += src[(size_t)b * stride];
+    for (int b = lane; b < count; b += 32) s += src[(size_t)b * stride];
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(kFullMask, s, off);
     if (lane == 0) {
