@@ -948,6 +948,11 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
     rc = fb_set_parameters(p, p->h_params, stream);
     if (rc == FB_OK) rc = fb_normal_equations(p, data_dev, gram.data(), stream);
     if (rc != FB_OK) {
+      if (getenv("FITBURST_B200_DEBUG")) {  // the trial point an evaluation failed at
+        fprintf(stderr, "fb_fit: evaluation %d failed (%s) at parameters", S.nfev + 1, fb_last_error());
+        for (int k = 0; k < FB_NUM_PARAMETERS * p->desc.num_components; ++k) fprintf(stderr, " %.17g", p->h_params[k]);
+        fprintf(stderr, "\n");
+      }
       delete stt;
       return rc;
     }

@@ -265,10 +265,22 @@ __device__ __forceinline__ double vals3_component(const PlanConst& pc, const Com
   }
   if (ch.fast_ok) {
     const int cnt = __popc(gm);
-    int base = 0;
-    if (lane == 0) base = atomicAdd(qcount, cnt);
+    // all-or-nothing reservation: a refused request must not move the counter, or the slots it
+    // skipped would be read back as items (uninitialised shared memory) in phase B
+    int base = -1;
+    if (lane == 0) {
+      int seen = *reinterpret_cast<volatile int*>(qcount);
+      while (seen + cnt <= kValsQueue) {
+        const int prev = atomicCAS(qcount, seen, seen + cnt);
+        if (prev == seen) {
+          base = seen;
+          break;
+        }
+        seen = prev;
+      }
+    }
     base = __shfl_sync(kFullMask, base, 0);
-    if (base + cnt <= kValsQueue) {
+    if (base >= 0) {
       if (general) queue[base + __popc(gm & ((1u << lane) - 1u))] = (c << 27) | j;
       *deferred = general;
       return val;
