@@ -150,3 +150,37 @@ def fit_stream(model, bursts, fixed_parameters, weighted_fit=True, weight_range=
         yield {"results": results, "fit_statistics": fitter.fit_statistics, "success": fitter.success}
         item, staged, slot = following, staged_next, slot ^ 1
     copier.synchronize()
+
+
+def fit_bursts(freqs, times, bursts, fixed_parameters, model_kwargs=None, weighted_fit=True, weight_range=None,
+               device=None):
+    """
+    Fits independent bursts that share the axes but not the number of components (BASELINE.json
+    config 3: "1-3 components, random DM/scattering"). The reference would build one
+    SpectrumModeler(num_components=k) per burst (pipelines/fitburst_pipeline.py:413-424); here the
+    bursts are grouped by component count, every group shares one modeler (one plan, one set of
+    device tables) and runs through fit_stream, so uploads overlap fits inside a group.
+
+    bursts: sequence of (data, good_freq, start_parameters); the component count of a burst is
+    len(start_parameters["amplitude"]). Returns one fit_stream() dict per burst, in input order,
+    with the extra key "num_components".
+    """
+    from .analysis.model import SpectrumModeler
+
+    model_kwargs = dict(model_kwargs or {})
+    model_kwargs.pop("num_components", None)
+    if device is not None:
+        model_kwargs["device"] = device
+    groups = {}
+    for index, item in enumerate(bursts):
+        groups.setdefault(len(item[2]["amplitude"]), []).append(index)
+    out = [None] * len(bursts)
+    for num_components in sorted(groups):
+        members = groups[num_components]
+        model = SpectrumModeler(freqs, times, num_components=num_components, **model_kwargs)
+        stream = fit_stream(model, (bursts[i] for i in members), fixed_parameters, weighted_fit=weighted_fit,
+                            weight_range=weight_range)
+        for index, result in zip(members, stream):
+            result["num_components"] = num_components
+            out[index] = result
+    return out

@@ -127,3 +127,34 @@ def test_device_and_sequential_batched_paths_agree(native_lib, monkeypatch):
         assert d["status"] == s["status"] and d["nfev"] == s["nfev"] and d["njev"] == s["njev"], (b, d["status"], s["status"])
         np.testing.assert_allclose(d["x"], s["x"], rtol=1e-7)
         np.testing.assert_allclose(d["uncertainties"], s["uncertainties"], rtol=1e-5)
+
+
+def test_fit_bursts_groups_by_component_count(native_lib):
+    """Config-3 driver: bursts with 1-3 components each, grouped by count; every burst ends where
+    its own LSFitter fit ends."""
+    import contextlib, io
+    from fitburst_b200 import synthetic as syn
+    from fitburst_b200.analysis.fitter import LSFitter
+    from fitburst_b200.analysis.model import SpectrumModeler
+    from fitburst_b200.batch import fit_bursts
+    freqs, times = syn.chime_axes(24, 256)
+    kwargs = dict(factor_freq_upsample=2, factor_time_upsample=2)
+    bursts = []
+    for index in range(6):
+        truth, start = syn.random_burst(index, 256)
+        model = SpectrumModeler(freqs, times, num_components=len(truth["amplitude"]), **kwargs)
+        model.update_parameters(truth)
+        good = syn.make_good_freq(len(freqs), 0.2, index)
+        bursts.append((syn.add_noise(model.compute_model(), good, 0.05, index), good, start))
+    fixed = ["dm_index", "scattering_index"]
+    out = fit_bursts(freqs, times, bursts, fixed, kwargs)
+    assert [o["num_components"] for o in out] == [1, 2, 3, 1, 2, 3]
+    for (data, good, start), got in zip(bursts, out):
+        model = SpectrumModeler(freqs, times, num_components=len(start["amplitude"]), **kwargs)
+        model.update_parameters(start)
+        with contextlib.redirect_stdout(io.StringIO()):
+            single = LSFitter(data, model, good)
+            single.fix_parameter(fixed)
+            single.fit()
+        assert got["results"].status == single.results.status and got["results"].nfev == single.results.nfev
+        np.testing.assert_array_equal(got["results"].x, single.results.x)
