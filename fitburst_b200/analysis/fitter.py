@@ -8,7 +8,9 @@ J^T r and J^T J without ever materialising the Jacobian; the exact Hessian and t
 uncertainties come from a second fused pass. Same attributes, methods, print-outs, error
 convention ("fit() never raises") and fit_statistics keys as the reference.
 """
+import contextlib
 import ctypes
+import threading
 import traceback
 import weakref
 
@@ -17,6 +19,27 @@ import torch
 from scipy.optimize import OptimizeResult, least_squares
 
 from .. import _lib
+
+_thread_state = threading.local()
+
+
+@contextlib.contextmanager
+def quiet():
+    """Silences the reference's progress print-outs of LSFitter for the calling THREAD only
+    (contextlib.redirect_stdout swaps sys.stdout for the whole process, which concurrent fits on
+    several threads must not do)."""
+    previous = getattr(_thread_state, "quiet", False)
+    _thread_state.quiet = True
+    try:
+        yield
+    finally:
+        _thread_state.quiet = previous
+
+
+def _say(*args, **kwargs):
+    if not getattr(_thread_state, "quiet", False):
+        print(*args, **kwargs)
+
 
 _TERMINATION_MESSAGES = {  # scipy/optimize/_lsq/least_squares.py TERMINATION_MESSAGES
     -1: "Improper input parameters status returned from `leastsq`",
@@ -129,7 +152,7 @@ class LSFitter:
         Computes the exact chi-squared Hessian at the model's current state
         (analysis/fitter.py:81-178). Returns (hessian, labels).
         """
-        print("INFO: computing hessian matrix with best-fit parameters.")
+        _say("INFO: computing hessian matrix with best-fit parameters.")
         plan, num_free = self._prepare()
         self.model._push_parameters()
         data_dev = self._data_on_device() if data is self.data else self.model._to_device(data)
@@ -199,18 +222,18 @@ class LSFitter:
             self.results = results
 
             if self.results.success:
-                print("INFO: fit successful!")
+                _say("INFO: fit successful!")
             else:
-                print("INFO: fit didn't work!")
+                _say("INFO: fit didn't work!")
 
             self._compute_fit_statistics(self.data, results)
 
             if self.success:
-                print("INFO: derived uncertainties and fit statistics")
+                _say("INFO: derived uncertainties and fit statistics")
 
         except Exception as exc:
-            print("ERROR: solver encountered a failure! Debug!")
-            print(traceback.format_exc())
+            _say("ERROR: solver encountered a failure! Debug!")
+            _say(traceback.format_exc())
 
     def _fit_native(self, parameter_list):
         """The trust-region loop of fb_fit() wrapped into a scipy-style OptimizeResult."""
@@ -281,10 +304,10 @@ class LSFitter:
         Updates 'fit_parameters' attributes to remove parameters that will
         be held fixed during least-squares fitting (analysis/fitter.py:324-351).
         """
-        print("INFO: removing the following parameters:", ", ".join(parameter_list))
+        _say("INFO: removing the following parameters:", ", ".join(parameter_list))
         for current_parameter in parameter_list:
             self.fit_parameters.remove(current_parameter)
-        print("INFO: new list of fit parameters:", ", ".join(self.fit_parameters))
+        _say("INFO: new list of fit parameters:", ", ".join(self.fit_parameters))
 
     def get_fit_parameters_list(self) -> list:
         """Values of the fit parameters in packing order (analysis/fitter.py:353-384)."""
@@ -360,7 +383,7 @@ class LSFitter:
             uncertainties = [float(x) for x in np.sqrt(np.diag(covariance)).tolist()]
 
             if np.any(np.isnan(uncertainties)):
-                print("WARNING: one or more NaNs in exact uncertainties, replacing with approximates...")
+                _say("WARNING: one or more NaNs in exact uncertainties, replacing with approximates...")
                 uncertainties = [float(x) for x in np.sqrt(np.diag(covariance_approx)).tolist()]
 
             self.covariance_approx = covariance_approx
@@ -374,8 +397,8 @@ class LSFitter:
             self.fit_statistics["bestfit_covariance"] = None  # like analysis/fitter.py:499
 
         except Exception as exc:
-            print(f"ERROR: {exc}; designating fit as unsuccessful...")
-            print(traceback.format_exc())
+            _say(f"ERROR: {exc}; designating fit as unsuccessful...")
+            _say(traceback.format_exc())
             self.success = False
 
     def _set_weights(self) -> None:

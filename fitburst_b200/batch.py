@@ -88,23 +88,49 @@ def pinned_like(array) -> np.ndarray:
     return tensor.numpy()
 
 
-def fit_stream(model, bursts, fixed_parameters, weighted_fit=True, weight_range=None, exact_jacobian=True):
+def _strip_lazy(results):
+    if results is not None and hasattr(results, "_lazy"):
+        object.__setattr__(results, "_lazy", {})
+    return results
+
+
+def _clone_model(model):
+    """A second SpectrumModeler with the configuration of `model` (own plan, own device tables)."""
+    from .analysis.model import SpectrumModeler
+    return SpectrumModeler(model.freqs, model.times, dm_incoherent=model.dm_incoherent,
+                           factor_freq_upsample=model.factor_freq_upsample,
+                           factor_time_upsample=model.factor_time_upsample,
+                           num_components=int(model.num_components), is_dedispersed=model.is_dedispersed,
+                           is_folded=model.is_folded, scintillation=model.scintillation, verbose=False,
+                           device=model._device)
+
+
+def fit_stream(model, bursts, fixed_parameters, weighted_fit=True, weight_range=None, exact_jacobian=True,
+               workers=1):
     """
-    Fits a sequence of bursts of the model's shape one after the other, overlapping the
-    host->device copy of burst k+1 (second CUDA stream, double-buffered device spectra) with the
-    fit of burst k -- the multi-file caller of LSFitter (the loop of
+    Fits a sequence of bursts of the model's shape, overlapping the host->device copy of the next
+    burst(s) with the fit of the current one -- the multi-file caller of LSFitter (the loop of
     pipelines/fitburst_pipeline.py:494-532 over many inputs) without the per-burst upload stall.
 
     bursts: iterable of (data, good_freq, start_parameters); data is a (Nf, Nt) float64 host array
     (page-locked for the overlap to happen, see pinned_like) or a device tensor.
     Yields one dict per burst, in order: {"results": OptimizeResult without the lazy `fun` / `jac`
-    members, "fit_statistics": ..., "success": ...}. The device copy of a spectrum is recycled two
-    bursts later, so nothing that needs it is handed out.
-    """
-    import contextlib
-    import io
+    members, "fit_statistics": ..., "success": ...}. The device copy of a spectrum is recycled, so
+    nothing that needs it is handed out.
 
-    from .analysis.fitter import LSFitter
+    workers = 1: one fit at a time on the current stream, uploads on a second stream (double-
+    buffered). workers > 1: that many fits in flight, each on its own host thread, CUDA stream,
+    device buffer and clone of `model` (the C calls release the GIL). A single fit leaves the GPU
+    idle about a quarter of the time -- trust-region steps on the host between evaluations, the
+    statistics, the read-backs -- and a second / third fit fills those gaps; the per-burst
+    results are identical to workers = 1 (every fit is still one sequential, deterministic
+    computation). `model` itself is left untouched in that mode.
+    """
+    if workers > 1:
+        yield from _fit_stream_concurrent(model, bursts, fixed_parameters, weighted_fit, weight_range,
+                                          exact_jacobian, int(workers))
+        return
+    from .analysis import fitter as fitter_module
 
     device = model._device
     shape = (model.num_freq, model.num_time)
@@ -139,21 +165,131 @@ def fit_stream(model, bursts, fixed_parameters, weighted_fit=True, weight_range=
         if event is not None:
             main.wait_event(event)
         model.update_parameters(item[2])
-        with contextlib.redirect_stdout(io.StringIO()):
-            fitter = LSFitter(data_dev, model, item[1], weighted_fit=weighted_fit, weight_range=weight_range)
+        with fitter_module.quiet():
+            fitter = fitter_module.LSFitter(data_dev, model, item[1], weighted_fit=weighted_fit,
+                                            weight_range=weight_range)
             fitter.fix_parameter(list(fixed_parameters))
             fitter.fit(exact_jacobian=exact_jacobian)
         free[slot].record(main)
-        results = getattr(fitter, "results", None)
-        if results is not None and hasattr(results, "_lazy"):
-            object.__setattr__(results, "_lazy", {})
-        yield {"results": results, "fit_statistics": fitter.fit_statistics, "success": fitter.success}
+        yield {"results": _strip_lazy(getattr(fitter, "results", None)), "fit_statistics": fitter.fit_statistics,
+               "success": fitter.success}
         item, staged, slot = following, staged_next, slot ^ 1
     copier.synchronize()
 
 
+def _fit_stream_concurrent(model, bursts, fixed_parameters, weighted_fit, weight_range, exact_jacobian, workers):
+    """fit_stream with `workers` fits in flight (see there). Bursts are taken from the iterator
+    in order under a lock, at most 2 * workers ahead of the consumer; results come out in order."""
+    import threading
+
+    from .analysis import fitter as fitter_module
+
+    device = model._device
+    shape = (model.num_freq, model.num_time)
+    caller_stream = torch.cuda.current_stream(device)
+    device_index = device.index if device.index is not None else torch.cuda.current_device()
+    iterator = iter(bursts)
+    cond = threading.Condition()
+    state = {"taken": 0, "yielded": 0, "exhausted": False, "stop": False, "error": None, "alive": workers}
+    done = {}
+
+    def take():
+        with cond:
+            while not state["stop"] and not state["exhausted"] and state["taken"] - state["yielded"] >= 2 * workers:
+                cond.wait()
+            if state["stop"] or state["exhausted"]:
+                return None
+            try:
+                item = next(iterator)
+            except StopIteration:
+                state["exhausted"] = True
+                cond.notify_all()
+                return None
+            index = state["taken"]
+            state["taken"] += 1
+            return index, item
+
+    def work(worker_index):
+        try:
+            torch.cuda.set_device(device_index)
+            clone = clones[worker_index]
+            stream = torch.cuda.Stream(device=device)
+            buffer = None
+            with torch.cuda.stream(stream), fitter_module.quiet():
+                while True:
+                    taken = take()
+                    if taken is None:
+                        break
+                    index, (data, good_freq, start) = taken
+                    if isinstance(data, torch.Tensor) and data.is_cuda:
+                        stream.wait_stream(caller_stream)  # whatever produced the tensor
+                        data_dev = data.to(dtype=torch.float64).contiguous()
+                    else:
+                        source = data if isinstance(data, torch.Tensor) else torch.from_numpy(
+                            np.ascontiguousarray(data, dtype=np.float64))
+                        if buffer is None:
+                            buffer = torch.empty(shape, dtype=torch.float64, device=device)
+                        buffer.copy_(source, non_blocking=True)  # ordered after this worker's previous fit
+                        data_dev = buffer
+                    clone.update_parameters(start)
+                    fitter = fitter_module.LSFitter(data_dev, clone, good_freq, weighted_fit=weighted_fit,
+                                                    weight_range=weight_range)
+                    fitter.fix_parameter(list(fixed_parameters))
+                    fitter.fit(exact_jacobian=exact_jacobian)
+                    out = {"results": _strip_lazy(getattr(fitter, "results", None)),
+                           "fit_statistics": fitter.fit_statistics, "success": fitter.success}
+                    del fitter
+                    with cond:
+                        done[index] = out
+                        cond.notify_all()
+                stream.synchronize()
+        except BaseException as exc:  # noqa: BLE001 - handed to the consumer
+            with cond:
+                state["error"] = exc
+                state["stop"] = True
+                cond.notify_all()
+        finally:
+            with cond:
+                state["alive"] -= 1
+                cond.notify_all()
+
+    # the clones (plans, device tables, scratch) are kept on `model` between calls: creating and
+    # freeing ~0.4 GB of device memory per worker per call would stall every stream (cudaFree)
+    key = (model.num_freq, model.num_time, int(model.num_components), int(model.factor_freq_upsample),
+           int(model.factor_time_upsample), bool(model.is_folded), bool(model.scintillation),
+           float(model.dm_incoherent), id(model.freqs), id(model.times))
+    if model.__dict__.get("_stream_clones_key") != key:
+        model.__dict__["_stream_clones"] = []
+        model.__dict__["_stream_clones_key"] = key
+    clones = model.__dict__["_stream_clones"]
+    while len(clones) < workers:
+        clones.append(_clone_model(model))
+    threads = [threading.Thread(target=work, args=(k,), name=f"fit_stream-{k}", daemon=True) for k in range(workers)]
+    for thread in threads:
+        thread.start()
+    try:
+        while True:
+            with cond:
+                while state["yielded"] not in done and state["error"] is None and state["alive"] > 0:
+                    cond.wait()
+                if state["error"] is not None:
+                    raise state["error"]
+                if state["yielded"] not in done:
+                    break  # all workers finished and nothing is pending
+                out = done.pop(state["yielded"])
+                state["yielded"] += 1
+                cond.notify_all()
+            yield out
+    finally:
+        with cond:
+            state["stop"] = True
+            cond.notify_all()
+        for thread in threads:
+            thread.join()
+
+
 def fit_bursts(freqs, times, bursts, fixed_parameters, model_kwargs=None, weighted_fit=True, weight_range=None,
-               device=None):
+               device=None, workers=1):
     """
     Fits independent bursts that share the axes but not the number of components (BASELINE.json
     config 3: "1-3 components, random DM/scattering"). The reference would build one
@@ -179,7 +315,7 @@ def fit_bursts(freqs, times, bursts, fixed_parameters, model_kwargs=None, weight
         members = groups[num_components]
         model = SpectrumModeler(freqs, times, num_components=num_components, **model_kwargs)
         stream = fit_stream(model, (bursts[i] for i in members), fixed_parameters, weighted_fit=weighted_fit,
-                            weight_range=weight_range)
+                            weight_range=weight_range, workers=workers)
         for index, result in zip(members, stream):
             result["num_components"] = num_components
             out[index] = result

@@ -175,6 +175,35 @@ def test_fit_stream_matches_individual_fits(native_lib):
         assert out["fit_statistics"]["bestfit_uncertainties"] == single.fit_statistics["bestfit_uncertainties"]
 
 
+def test_fit_stream_concurrent_workers_identical(native_lib):
+    """Several fits in flight (threads, streams, model clones): same per-burst results, in order."""
+    from fitburst_b200.batch import fit_stream
+    freqs, times, truth, kwargs = _case(num_freq=32, num_time=256, kf=2, kt=2)
+    cuda, oracle = model_pair(freqs, times, kwargs, truth)
+    clean = oracle.compute_model()
+    bursts = []
+    for seed in range(9):
+        good = syn.make_good_freq(len(freqs), 0.2, seed)
+        start = syn.config2_start(truth)
+        start["dm"] = [0.01 + 0.002 * seed] * 3
+        bursts.append((syn.add_noise(clean, good, 0.1, seed), good, start))
+    fixed = ["dm_index", "scattering_index"]
+    serial = list(fit_stream(cuda, bursts, fixed))
+    threaded = list(fit_stream(cuda, bursts, fixed, workers=3))
+    assert len(threaded) == len(serial) == len(bursts)
+    for a, b in zip(serial, threaded):
+        assert a["results"].status == b["results"].status and a["results"].nfev == b["results"].nfev
+        np.testing.assert_array_equal(a["results"].x, b["results"].x)
+        assert a["fit_statistics"]["bestfit_uncertainties"] == b["fit_statistics"]["bestfit_uncertainties"]
+    # device-resident inputs and an early stop of the consumer
+    import torch
+    resident = [(torch.from_numpy(d).cuda(), g, s) for d, g, s in bursts]
+    stream = fit_stream(cuda, resident, fixed, workers=2)
+    first = next(stream)
+    stream.close()
+    np.testing.assert_array_equal(first["results"].x, serial[0]["results"].x)
+
+
 def test_full_size_fast_vs_general(native_lib):
     """Config-2 size: the fast and the general kernels agree on [J r]^T [J r] and on the Hessian."""
     from fitburst_b200.analysis.fitter import LSFitter
