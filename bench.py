@@ -6,10 +6,14 @@ Benchmark of the fitburst hot path on B200 (contract: see the task brief and DES
 A "step" is ONE complete LSFitter fit of one synthetic CHIME-shaped burst at BASELINE.json
 config 2 (16384 channels x 1024 samples, 3 scattered components with running power law, 8x
 frequency / 4x time up-sampling, 17 free parameters, ~35 % flagged channels): trust-region loop
-+ exact Hessian + uncertainties. `value` = fits/s with the spectrum already resident in HBM;
-`e2e` = fits/s through LSFitter(data_host, ...).fit() with the host->device copy of the spectrum
-and the device->host read of the results inside the timed region. With --gpus N every rank fits
-its own bursts (config 3 sharding, no data-path collective): weak scaling.
++ exact Hessian + uncertainties. The K timed steps are submitted together through the public
+batch call fitburst_b200.batch.fit_stream(workers=W) -- W fits in flight per GPU on their own
+streams, each fit still one sequential LSFitter.fit() -- and the clock stops when the last
+result is back. `value` = fits/s with the spectra already resident in HBM; `e2e` = the same
+call on page-locked HOST spectra (the 134 MB upload of every step and the read-back of its
+results inside the timed region); `single_fit_latency_ms` / `e2e.single_call` = one fit at a
+time. With --gpus N every rank fits its own bursts (config 3 sharding, no data-path
+collective): weak scaling.
 
 The `roofline` object describes the dominant kernel (the fused model + Jacobian + normal-equation
 pass), timed alone with CUDA events; `cpu_baseline` is the numpy oracle (a port of the
@@ -98,8 +102,10 @@ def ncu_profile_summary():
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--workers", type=int, default=0,
+                    help="fits in flight per GPU in fit_stream (0 = min(4, host cores / (2 * ranks)))")
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--nfreq", type=int, default=16384)
     ap.add_argument("--ntime", type=int, default=1024)
@@ -277,8 +283,8 @@ def workload_config(args):
                      "up-sampling, single LSFitter fit (17 free parameters) incl. exact Hessian"),
         "num_freq": args.nfreq, "num_time": args.ntime, "num_components": args.ncomp,
         "factor_freq_upsample": args.kf, "factor_time_upsample": args.kt, "free_parameters": 17,
-        "flagged_channel_fraction": 0.35, "sharding": "one independent burst per GPU per step",
-        "l2_note": "134 MB spectrum per fit > 126 MB L2; a different burst buffer is fitted on consecutive steps",
+        "flagged_channel_fraction": 0.35, "sharding": "independent bursts, every GPU fits its own (no data-path collective)",
+        "l2_note": "134 MB spectrum per fit > 126 MB L2; two different bursts alternate between steps and several fits are in flight",
     }
 
 
@@ -376,61 +382,81 @@ def run_cuda(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0]), float(t[1])
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    plan = model._ensure_plan()
-    launches = __import__("ctypes").c_int64(0)
-    lib.fb_launch_count(plan, launches, 1)
+    from fitburst_b200 import batch as fb_batch
+
+    workers = args.workers if args.workers > 0 else max(1, min(4, (os.cpu_count() or 2) // (2 * world)))
+    device_data = [f._data_on_device() for f in resident]
+    dev_bursts = [(device_data[k], bursts[k][2], bursts[k][1]) for k in range(2)]
+    host_bursts = [(host_data[k], bursts[k][2], bursts[k][1]) for k in range(2)]
+
+    def all_plans():
+        return [model._ensure_plan()] + [slot["clone"]._ensure_plan() for slot in model.__dict__.get("_stream_slots", [])]
+
+    def launch_total(reset):
+        total = 0
+        for plan_k in all_plans():
+            count = __import__("ctypes").c_int64(0)
+            lib.fb_launch_count(plan_k, count, 1 if reset else 0)
+            total += count.value
+        return total
+
     last = {}
 
+    def run_batch(source, count):
+        """`count` independent fits through the public batch call: submitted together, `workers`
+        of them in flight, every result consumed."""
+        for out in fb_batch.fit_stream(model, (source[s % 2] for s in range(count)), FIXED, workers=workers):
+            last["stream"] = out
+            assert out["results"] is not None and out["results"].status > 0, "streamed fit did not converge"
+
+    def timed_batch(source, steps, warmup):
+        """Warm-up fits, then EXACTLY `steps` fits inside barrier + synchronize brackets (the
+        pipeline fills and drains inside the timed region). Returns ms (max over ranks)."""
+        import gc
+        run_batch(source, max(warmup, 2 * workers))
+        gc.collect()
+        barrier()
+        t0 = time.perf_counter()
+        run_batch(source, steps)
+        torch.cuda.synchronize()  # every stream of the device
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        t = torch.tensor([wall_ms], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+
+    # (1) value: spectra resident in HBM
+    run_batch(dev_bursts, 2 * workers)  # creates the worker clones before launches are counted
+    launch_total(True)
+    ms_value = timed_batch(dev_bursts, args.steps, args.warmup)
+    counted = launch_total(True)
+    gpu_launches = int(round(counted * args.steps / (args.steps + max(args.warmup, 2 * workers))))
+    ms_step = ms_value / args.steps
+    value = world * 1e3 / ms_step
+
+    # (2) e2e: the same call with HOST spectra (page-locked): every step uploads its own 134 MB
+    # spectrum and reads its results back inside the timed region
+    ms_e2e = timed_batch(host_bursts, args.steps, args.warmup)
+    ms_step_e = ms_e2e / args.steps
+    e2e_value = world * 1e3 / ms_step_e
+
+    # (3) latency view: one fit at a time, resident (a) and through LSFitter(host_array).fit() (b)
     def step_resident(s):
         last["fitter"] = one_fit_resident(resident[s % 2], bursts[s % 2][1])
 
-    ms_dev, ms_wall = timed(step_resident, args.steps, args.warmup)
-    lib.fb_launch_count(plan, launches, 1)
-    # launches were counted over warmup + timed steps: keep the timed share
-    gpu_launches = int(round(launches.value * args.steps / max(1, args.steps + args.warmup)))
-    ms_step = max(ms_dev, ms_wall) / args.steps  # host-driven loop: wall and device agree; take the larger
-    value = world * 1e3 / ms_step
+    lat_steps = max(4, min(args.steps, 12))
+    ms_dev, ms_wall = timed(step_resident, lat_steps, 3)
+    ms_single = max(ms_dev, ms_wall) / lat_steps
 
     def step_e2e(s):
         last["e2e"] = one_fit_e2e(s % 2)
 
-    # (a) one LSFitter(host_array, ...).fit() per step: upload, then fit
-    ms_dev_1, ms_wall_1 = timed(step_e2e, args.steps, args.warmup)
-    ms_step_1 = max(ms_dev_1, ms_wall_1) / args.steps
-
-    # (b) the same bursts through fitburst_b200.batch.fit_stream(): the pinned-host -> device copy
-    # of burst k+1 runs on a second stream while burst k is fitted. Every timed step contains one
-    # complete fit and one complete 134 MB upload (the copy issued during the last timed fit is
-    # waited for before the clock stops).
-    from fitburst_b200 import batch as fb_batch
-
-    def host_bursts(total):
-        for s in range(total):
-            yield host_data[s % 2], bursts[s % 2][2], bursts[s % 2][1]
-
-    stream = fb_batch.fit_stream(model, host_bursts(args.warmup + args.steps + 1), FIXED)
-    for _ in range(args.warmup):
-        next(stream)
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    ev0.record()
-    for _ in range(args.steps):
-        last["stream"] = next(stream)
-    torch.cuda.synchronize()  # includes the copy stream
-    ev1.record()
-    barrier()
-    wall_ms = (time.perf_counter() - t0) * 1e3
-    t = torch.tensor([ev0.elapsed_time(ev1), wall_ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    for _ in stream:  # drain the look-ahead burst
-        pass
-    ms_step_e = max(float(t[0]), float(t[1])) / args.steps
-    e2e_value = world * 1e3 / ms_step_e
-    assert last["stream"]["results"].status > 0, "streamed fit did not converge"
+    ms_dev_1, ms_wall_1 = timed(step_e2e, lat_steps, 3)
+    ms_step_1 = max(ms_dev_1, ms_wall_1) / lat_steps
     sampler.stop_flag.set()
     sampler.join(timeout=2)
 
@@ -498,9 +524,13 @@ def run_cuda(args):
             "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_step_e,
-                    "api": "fitburst_b200.batch.fit_stream (upload of burst k+1 overlaps the fit of burst k)",
+                    "api": f"fitburst_b200.batch.fit_stream(workers={workers}) on page-locked host spectra: "
+                           "uploads and fits of different bursts overlap",
                     "single_call": {"value": world * 1e3 / ms_step_1, "ms_per_step": ms_step_1,
-                                    "api": "LSFitter(host_array, ...).fit(), upload then fit"}},
+                                    "api": "LSFitter(host_array, ...).fit(), upload then fit, one at a time"}},
+            "api": f"fitburst_b200.batch.fit_stream(workers={workers}) on device-resident spectra",
+            "fits_in_flight": workers,
+            "single_fit_latency_ms": ms_single,
             "gpu_launches": gpu_launches, "clocks": sampler.summary(), "roofline": roofline,
             "fit": {"status": int(res.status), "nfev": nfev, "njev": int(res.njev),
                     "chisq_final_reduced": fitter.fit_statistics.get("chisq_final_reduced"),

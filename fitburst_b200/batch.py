@@ -212,9 +212,8 @@ def _fit_stream_concurrent(model, bursts, fixed_parameters, weighted_fit, weight
     def work(worker_index):
         try:
             torch.cuda.set_device(device_index)
-            clone = clones[worker_index]
-            stream = torch.cuda.Stream(device=device)
-            buffer = None
+            slot = slots[worker_index]
+            clone, stream, buffer = slot["clone"], slot["stream"], slot["buffer"]
             with torch.cuda.stream(stream), fitter_module.quiet():
                 while True:
                     taken = take()
@@ -228,7 +227,7 @@ def _fit_stream_concurrent(model, bursts, fixed_parameters, weighted_fit, weight
                         source = data if isinstance(data, torch.Tensor) else torch.from_numpy(
                             np.ascontiguousarray(data, dtype=np.float64))
                         if buffer is None:
-                            buffer = torch.empty(shape, dtype=torch.float64, device=device)
+                            buffer = slot["buffer"] = torch.empty(shape, dtype=torch.float64, device=device)
                         buffer.copy_(source, non_blocking=True)  # ordered after this worker's previous fit
                         data_dev = buffer
                     clone.update_parameters(start)
@@ -253,17 +252,19 @@ def _fit_stream_concurrent(model, bursts, fixed_parameters, weighted_fit, weight
                 state["alive"] -= 1
                 cond.notify_all()
 
-    # the clones (plans, device tables, scratch) are kept on `model` between calls: creating and
-    # freeing ~0.4 GB of device memory per worker per call would stall every stream (cudaFree)
+    # worker contexts (model clone with its plan / device tables / scratch, CUDA stream, upload
+    # buffer) are kept on `model` between calls: re-creating ~0.5 GB of device memory per worker
+    # per call costs tens of milliseconds and stalls every stream (cudaMalloc / cudaFree; torch's
+    # caching allocator does not hand a block cached for one stream to another)
     key = (model.num_freq, model.num_time, int(model.num_components), int(model.factor_freq_upsample),
            int(model.factor_time_upsample), bool(model.is_folded), bool(model.scintillation),
            float(model.dm_incoherent), id(model.freqs), id(model.times))
-    if model.__dict__.get("_stream_clones_key") != key:
-        model.__dict__["_stream_clones"] = []
-        model.__dict__["_stream_clones_key"] = key
-    clones = model.__dict__["_stream_clones"]
-    while len(clones) < workers:
-        clones.append(_clone_model(model))
+    if model.__dict__.get("_stream_slots_key") != key:
+        model.__dict__["_stream_slots"] = []
+        model.__dict__["_stream_slots_key"] = key
+    slots = model.__dict__["_stream_slots"]
+    while len(slots) < workers:
+        slots.append({"clone": _clone_model(model), "stream": torch.cuda.Stream(device=device), "buffer": None})
     threads = [threading.Thread(target=work, args=(k,), name=f"fit_stream-{k}", daemon=True) for k in range(workers)]
     for thread in threads:
         thread.start()
