@@ -58,7 +58,7 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 }
 
 // ---- model side ---------------------------------------------------------------------------
-constexpr int kValsQueue = 1024;  // general-case (sample, component) items queued per channel
+constexpr int kValsQueue = 256;  // rise-region (sample, component) items queued per warp and channel
 
 // Per (channel, component) constants of the sub-frequency expansion (see make_tay_tab).
 struct TayTab {
@@ -76,7 +76,7 @@ __host__ __device__ inline size_t vals3_smem_bytes(int nc, int kf) {
   n += 2 * (sizeof(ChanTab) * nc + sizeof(SubTab) * nc * kf);  // double-buffered channel tables
   n += sizeof(double) * (size_t)nc * kf * 33;                 // R, D
   n += sizeof(double) * (size_t)kFastWarps * vals3_bw_stride(nc * kf);  // B per warp
-  n += sizeof(int) * (kValsQueue + 4 + 2 * FB_MAX_COMPONENTS);  // queue, counter, regime boundaries
+  n += sizeof(int) * (kFastWarps * kValsQueue + 4 + 2 * FB_MAX_COMPONENTS);  // per-warp queues, regime boundaries
   n += sizeof(TayTab) * nc + 16;
   return n;
 }
@@ -220,7 +220,7 @@ __device__ __forceinline__ double vals3_component(const PlanConst& pc, const Com
                                                   const SubTab* __restrict__ sb, const double* __restrict__ r_lane,
                                                   const double* __restrict__ bw, int c, int jp, int jt, int j0,
                                                   int lane, bool valid, int* __restrict__ queue,
-                                                  int* __restrict__ qcount, bool* deferred) {
+                                                  int& qcount, bool* deferred) {
   const int kf = KF > 0 ? KF : pc.kf, kt = pc.kt;
   *deferred = false;
   if (j0 >= jt && j0 >= jp) {  // whole tile in the exponential tail
@@ -264,24 +264,13 @@ __device__ __forceinline__ double vals3_component(const PlanConst& pc, const Com
     return val;
   }
   if (ch.fast_ok) {
+    // the queue is private to the warp (its own tiles feed it, it alone drains it after its
+    // tiles): the counter is a warp-uniform register, a request that does not fit is refused
+    // whole and its samples are evaluated in place
     const int cnt = __popc(gm);
-    // all-or-nothing reservation: a refused request must not move the counter, or the slots it
-    // skipped would be read back as items (uninitialised shared memory) in phase B
-    int base = -1;
-    if (lane == 0) {
-      int seen = *reinterpret_cast<volatile int*>(qcount);
-      while (seen + cnt <= kValsQueue) {
-        const int prev = atomicCAS(qcount, seen, seen + cnt);
-        if (prev == seen) {
-          base = seen;
-          break;
-        }
-        seen = prev;
-      }
-    }
-    base = __shfl_sync(kFullMask, base, 0);
-    if (base >= 0) {
-      if (general) queue[base + __popc(gm & ((1u << lane) - 1u))] = (c << 27) | j;
+    if (qcount + cnt <= kValsQueue) {
+      if (general) queue[qcount + __popc(gm & ((1u << lane) - 1u))] = (c << 27) | j;
+      qcount += cnt;
       *deferred = general;
       return val;
     }
@@ -318,9 +307,8 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
   const int bws = vals3_bw_stride(nck);
   double* bw = reinterpret_cast<double*>(sp) + (size_t)warp * bws;
   sp += sizeof(double) * (size_t)kFastWarps * bws;
-  int* queue = reinterpret_cast<int*>(sp);
-  int* qcount = queue + kValsQueue;
-  int* bounds = qcount + 1;  // [nc][2]: jp, jt
+  int* queue = reinterpret_cast<int*>(sp) + warp * kValsQueue;  // this warp's rise-region items
+  int* bounds = reinterpret_cast<int*>(sp) + kFastWarps * kValsQueue + 1;  // [nc][2]: jp, jt
   TayTab* tay = reinterpret_cast<TayTab*>((reinterpret_cast<uintptr_t>(bounds + 2 * FB_MAX_COMPONENTS + 2) + 15) & ~(uintptr_t)15);
 
   {
@@ -329,7 +317,8 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
     for (int e = tid; e < nc * (int)(sizeof(CompTab) / sizeof(double)); e += kFastBlock) dst[e] = src[e];
   }
   const int wtiles = (nt + 31) / 32;
-  const int tpw = (wtiles + kFastWarps - 1) / kFastWarps;  // contiguous tiles per warp
+  // tiles of a warp: wt = warp + k * kFastWarps (interleaved: the few expensive tiles around the
+  // burst spread over the warps; with contiguous ranges one or two warps held the block)
   const int chan_chunks = (int)(sizeof(ChanTab) * nc / 16), sub_chunks = (int)(sizeof(SubTab) * nck / 16);
   // channel numbers are read two iterations ahead: chan_list[] -> table address is a dependent
   // global-load chain that would otherwise sit in front of every table prefetch
@@ -356,7 +345,7 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
     i_next = i_after;
     const ChanTab* chan = reinterpret_cast<const ChanTab*>(tabs + (size_t)buf * tab_bytes);
     const SubTab* sub = reinterpret_cast<const SubTab*>(tabs + (size_t)buf * tab_bytes + sizeof(ChanTab) * nc);
-    if (tid == 0) *qcount = 0;
+    int qcount = 0;
     if (tid >= 32 && tid < 32 + nc) {
       int jp, jt;
       vals3_boundaries(pc, comp[tid - 32], chan[tid - 32], jp, jt);
@@ -371,18 +360,18 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
       R[e] = ((comp[c].amp10 * st.tail_c) * st.sed) * decay;
     }
     for (int e = tid; e < nck; e += kFastBlock)
-      D[e] = fb_exp(-((double)(32 * kt) * comp[e / kf].t_step) * sub[e].inv_tau);
+      D[e] = fb_exp(-((double)(32 * kFastWarps * kt) * comp[e / kf].t_step) * sub[e].inv_tau);
     __syncthreads();
     double* out = gvals + (size_t)chi * nc * nt;
     // phase A: closed-form regimes tile by tile (uniform cost), rise-region samples queued
-    const int wt_lo = warp * tpw, wt_hi = min(wtiles, wt_lo + tpw);
-    for (int wt = wt_lo; wt < wt_hi; ++wt) {
+    for (int wt = warp, k = 0; wt < wtiles; wt += kFastWarps, ++k) {
       const int j0 = wt * 32, j = j0 + lane;
       const bool valid = j < nt;
       // tail base factors B of every (component, sub-frequency) at the first sample of the tile:
-      // one exp per lane every 8th tile, the decay recurrence in between
-      // (a factor that overflowed ahead of the burst is recomputed: inf * decay would stay inf)
-      const bool refresh = ((wt - wt_lo) & 7) == 0;
+      // one exp per lane every 8th tile of the warp, the decay recurrence (over kFastWarps tiles)
+      // in between (a factor that overflowed ahead of the burst is recomputed: inf * decay would
+      // stay inf)
+      const bool refresh = (k & 7) == 0;
       for (int e = lane; e < nck; e += 32) {
         const double prev = bw[e];
         if (refresh || !(prev < 1e290)) {
@@ -404,16 +393,17 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
       }
       __syncwarp();
     }
-    __syncthreads();
-    // phase B: the queued rise-region samples. A group of lanes (one per sub-time) evaluates an
-    // item by the sub-frequency expansion; items it does not cover (a clamped sub-time, a
-    // component whose expansion bound is too large) take the exact sub-grid, one per warp pass.
-    const int qn = min(*qcount, kValsQueue);
+    __syncwarp();
+    // phase B: the rise-region samples this warp queued. A group of lanes (one per sub-time)
+    // evaluates an item by the sub-frequency expansion; items it does not cover (a clamped
+    // sub-time, a component whose expansion bound is too large) take the exact sub-grid, one per
+    // warp pass. No block barrier between the phases: the queue is the warp's own.
+    const int qn = qcount;
     int lpi = 1;  // lanes per item: power of two >= kt
     while (lpi < kt && lpi < 32) lpi <<= 1;
     const int ipw = 32 / lpi;
     const double inv_n = 1.0 / (double)(kf * kt);
-    for (int base = warp * ipw; base < qn; base += kFastWarps * ipw) {
+    for (int base = 0; base < qn; base += ipw) {
       const int q = base + lane / lpi, b = lane % lpi;
       bool have = q < qn, expanded = false;
       int c = 0, jj = 0;
