@@ -571,8 +571,8 @@ struct FarLayout {
 };
 
 __host__ __device__ inline size_t gram3_far_smem_bytes(int ncols) {
-  // T [ncols][8], U [8][ncols], per-warp B [warps][64], B [64], ranges
-  return sizeof(double) * ((size_t)16 * ncols + (size_t)kFastWarps * 64 + 64) + sizeof(int) * 2 * FB_MAX_COMPONENTS;
+  // T [2][ncols][8] (this channel's and the previous one's), U [8][ncols], per-warp B [warps][64], ranges
+  return sizeof(double) * ((size_t)24 * ncols + (size_t)kFastWarps * 64 + 64) + sizeof(int) * 2 * FB_MAX_COMPONENTS;
 }
 
 // Tiles of spectrum rows + data in flight per warp: with one tile ahead the kernel was bound by
@@ -617,8 +617,8 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
   double* pref = reinterpret_cast<double*>(sp) + (size_t)warp * kG3Ring * (NC + 1) * 32 + lane;
   sp += sizeof(double) * kG3Ring * (size_t)(NC + 1) * kFastBlock;
   const int ncols = F.ncols;
-  double* Tm = reinterpret_cast<double*>(sp);       // [ncols][8]
-  double* Um = Tm + (size_t)8 * ncols;              // [8][ncols]
+  double* Tm2 = reinterpret_cast<double*>(sp);      // [2][ncols][8], indexed by the channel parity `buf`
+  double* Um = Tm2 + (size_t)16 * ncols;            // [8][ncols]
   double* Bw = Um + (size_t)8 * ncols;              // [warps][64]
   double* Bs = Bw + kFastWarps * 64;                // [64]
   int* range = reinterpret_cast<int*>(Bs + 64);     // [NC][2] near range of every component
@@ -700,6 +700,18 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
     ++q_issue;
   };
   for (int k = 0; k < kG3Depth; ++k) issue_tile(blockIdx.x, i_cur, k);
+  bool have_prev = false;  // a previous channel of this block left far-tile blocks to contract
+  auto far_accumulate = [&](const double* Tm) {
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      if (tid + s2 * kFastBlock < nent) {
+        double s = 0.0;
+#pragma unroll
+        for (int a = 0; a < 8; ++a) s = fma(Tm[ek[s2] * 8 + a], Um[a * ncols + el[s2]], s);
+        gacc[s2] += s;
+      }
+    }
+  };
   int buf = 0;
   for (int chi = blockIdx.x; chi < A.num_chan; chi += gridDim.x, buf ^= 1) {
     const int i = i_cur;
@@ -716,6 +728,8 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
     i_next = i_after;
     w_cur = w_next;
     const ChanTab* chan = reinterpret_cast<const ChanTab*>(tabs + (size_t)buf * sizeof(ChanTab) * NC);
+    double* Tm_cur = Tm2 + (size_t)buf * 8 * ncols;
+    const double* Tm_prev = Tm2 + (size_t)(buf ^ 1) * 8 * ncols;
     bool std_ok = true;  // every component on the scattered branch at this channel
 #pragma unroll
     for (int c = 0; c < NC; ++c) std_ok = std_ok && (chan[c].sc_time != 0.0);
@@ -744,9 +758,26 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
       if (far_on && std_ok) near_range(pc, ct, ch, j_lo, j_hi);
       range[2 * tid] = j_lo;
       range[2 * tid + 1] = j_hi;
+    } else if (far_on && have_prev) {
+      // far tiles of the PREVIOUS channel (its B blocks are complete: every warp passed the
+      // barrier above), done by the threads that would otherwise wait for the serial setup of
+      // this one: B summed over the warps in warp order, U = B T^T
+      for (int e = tid - NC; e < 8 * ncols; e += kFastBlock - NC) {
+        const int a = e / ncols, l = e - a * ncols;
+        double s = 0.0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          double bsum = 0.0;
+#pragma unroll
+          for (int w = 0; w < kFastWarps; ++w) bsum += Bw[w * 64 + a * 8 + b];
+          s = fma(bsum, Tm_prev[l * 8 + b], s);
+        }
+        Um[e] = s;
+      }
     }
     __syncthreads();
     if (far_on) {
+      if (have_prev) far_accumulate(Tm_prev);  // G += T U of the previous channel
       // T[k][a]: coefficient of basis value a in full column k (weight included)
       for (int e = tid; e < ncols * 8; e += kFastBlock) {
         const int k = e >> 3, a = e & 7, prm = F.param[k], cc = F.comp[k];
@@ -774,7 +805,7 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
         } else if (a == 2 * NC && prm == 9) {
           v = 1.0;
         }
-        Tm[e] = v * wi;
+        Tm_cur[e] = v * wi;
       }
     }
 
@@ -913,36 +944,32 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
         }
     }
     if (far_on) {
-      // far tiles of the channel: B summed over the warps (warp order), U = B T^T, G += T U
+      // far tiles of the channel: every warp parks its block B; the contraction G += T (sum B) T^T
+      // happens at the top of the block's next channel (or after the loop), inside barriers that
+      // are there anyway -- three block barriers per channel less than flushing here
       Bw[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2] = cf0;
       Bw[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2 + 1] = cf1;
       cf0 = cf1 = 0.0;
-      __syncthreads();
-      if (tid < 64) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < kFastWarps; ++w) s += Bw[w * 64 + tid];
-        Bs[tid] = s;
-      }
-      __syncthreads();
-      for (int e = tid; e < 8 * ncols; e += kFastBlock) {
-        const int a = e / ncols, l = e - a * ncols;
-        double s = 0.0;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) s = fma(Bs[a * 8 + b], Tm[l * 8 + b], s);
-        Um[e] = s;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int s2 = 0; s2 < 2; ++s2) {
-        if (tid + s2 * kFastBlock < nent) {
-          double s = 0.0;
-#pragma unroll
-          for (int a = 0; a < 8; ++a) s = fma(Tm[ek[s2] * 8 + a], Um[a * ncols + el[s2]], s);
-          gacc[s2] += s;
-        }
-      }
+      have_prev = true;
     }
+  }
+  if (far_on && have_prev) {  // far tiles of the block's last channel (buf was flipped by the loop)
+    const double* Tm_last = Tm2 + (size_t)(buf ^ 1) * 8 * ncols;
+    __syncthreads();
+    for (int e = tid; e < 8 * ncols; e += kFastBlock) {
+      const int a = e / ncols, l = e - a * ncols;
+      double s = 0.0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        double bsum = 0.0;
+#pragma unroll
+        for (int w = 0; w < kFastWarps; ++w) bsum += Bw[w * 64 + a * 8 + b];
+        s = fma(bsum, Tm_last[l * 8 + b], s);
+      }
+      Um[e] = s;
+    }
+    __syncthreads();
+    far_accumulate(Tm_last);
   }
   cp_async_wait<0>();
   if (far_on) {
