@@ -309,10 +309,12 @@ def run_cuda(args):
     if world > 1 and not os.environ.get("FITBURST_B200_NO_BIND"):
         from fitburst_b200.distributed import bind_to_gpu_numa
         numa_bound = bind_to_gpu_numa(local_rank)
+    # rank 0 prints exactly ONE line on stdout: everything else this process (or a library in it:
+    # NCCL's version banner, warnings) writes to file descriptor 1 goes to stderr instead
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
-        # rank 0 prints exactly one line on stdout: keep NCCL's version banner out of it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
     lib = _lib.load_library()
 
@@ -324,8 +326,11 @@ def run_cuda(args):
         model.update_parameters(parameters)
         return model.compute_model()
 
-    # two different bursts per rank, alternated between steps (each 134 MB > L2).
-    bursts = [make_burst(args, 1000 * rank + k, model_fn) for k in range(2)]
+    # two different bursts, alternated between steps (each 134 MB > L2). Every rank generates,
+    # uploads and fits its own copies of the SAME two bursts: the number of trust-region
+    # evaluations depends on the noise realisation (7 for these two, 13 for seed 1001), and weak
+    # scaling is about equal work per GPU, not about which rank drew the harder burst.
+    bursts = [make_burst(args, k, model_fn) for k in range(2)]
     pinned = [torch.from_numpy(b[3]).pin_memory() for b in bursts]
     host_data = [p.numpy() for p in pinned]
 
@@ -544,7 +549,8 @@ def run_cuda(args):
             line["cpu_baseline"], _ = cpu_baseline(args)
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        sys.stdout.flush()
+        os.write(stdout_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
