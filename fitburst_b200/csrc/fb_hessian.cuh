@@ -772,7 +772,7 @@ constexpr int kHess3Chunk = 15;
 __host__ __device__ inline size_t hess3_smem_bytes(int nc, int num_pairs) {
   size_t n = sizeof(CompTab) * nc + 2 * sizeof(ChanTab) * nc;
   n += sizeof(double) * (size_t)kHess3Chunk * (kFastBlock + 1);         // flush stage
-  n += sizeof(double) * ((size_t)nc * kFastWarps * 16 + (size_t)nc * 32);  // column partials, totals
+  n += sizeof(double) * ((size_t)nc * kFastWarps * 32 + (size_t)nc * 32);  // warp totals, block totals
   n += sizeof(double) * (size_t)num_pairs;
   n += sizeof(double) * ((size_t)kFastWarps * 3 * nc);                  // per-warp moments
   n += sizeof(double) * 2 * nc;                                         // x mapping per component
@@ -794,8 +794,8 @@ __global__ void __launch_bounds__(kFastBlock, FB_H3_MINB) k_hess3(const HessAccA
   char* tabs = sp;
   sp += 2 * sizeof(ChanTab) * NC;
   double* stage = reinterpret_cast<double*>(sp);             // [kHess3Chunk][kFastBlock + 1]
-  double* part = stage + (size_t)kHess3Chunk * (kFastBlock + 1);  // [NC][warps][16]
-  double* total = part + NC * kFastWarps * 16;               // [NC][32]
+  double* part = stage + (size_t)kHess3Chunk * (kFastBlock + 1);  // [NC][warps][32]
+  double* total = part + NC * kFastWarps * 32;               // [NC][32]
   double* pacc = total + NC * 32;
   double* musum = pacc + npairs;                             // [warps][3 NC]
   double* xmap = musum + kFastWarps * 3 * NC;                // [NC][2]: x = tj * xmap[0] + xmap[1]
@@ -899,14 +899,20 @@ __global__ void __launch_bounds__(kFastBlock, FB_H3_MINB) k_hess3(const HessAccA
     __syncthreads();
 
     // phase B: one item per thread -- the near samples of every component with the full term
-    // evaluation, plus 3 node items per component that contract the far-sample moments
+    // evaluation, plus 3 node items per component that contract the far-sample moments. The 30
+    // term values of the 32 items of a warp are summed per component by a halving exchange (31
+    // double shuffles: afterwards lane k holds the warp's sum of term k) into registers that live
+    // for the whole channel; the block meets once per channel, not once per pass and chunk.
     const int n_near = offs[NC];
     const int n_items = n_near + (shortcut ? 3 * NC : 0);
+    double tot[NC];  // lane k: this warp's sum of term k for component c over the channel
+#pragma unroll
+    for (int c = 0; c < NC; ++c) tot[c] = 0.0;
     for (int base = 0; base < n_items; base += kFastBlock) {
       const int e = base + tid;
-      double acc[kNumTerms];
+      double acc[32];
 #pragma unroll
-      for (int k = 0; k < kNumTerms; ++k) acc[k] = 0.0;
+      for (int k = 0; k < 32; ++k) acc[k] = 0.0;
       int my_c = -1;
       if (e < n_near) {
         int c = 0;
@@ -932,7 +938,7 @@ __global__ void __launch_bounds__(kFastBlock, FB_H3_MINB) k_hess3(const HessAccA
         const double td = fma(comp[c].t_step, tj, comp[c].t_start) - chan[c].mean_delay;
         D2Ctx ctx;
         make_d2ctx(A, chan[c], comp[c], chan[c].amp, mc, td, sdm, chan[0].amp_pbf, ctx);
-        accumulate_terms(ctx, rho, H.need[c], acc);
+        accumulate_terms(ctx, rho, H.need[c], reinterpret_cast<double (&)[kNumTerms]>(acc));
         my_c = c;
       } else if (e < n_items) {
         const int c = (e - n_near) / 3, q = (e - n_near) % 3;
@@ -952,51 +958,52 @@ __global__ void __launch_bounds__(kFastBlock, FB_H3_MINB) k_hess3(const HessAccA
           const double t_node = q == 0 ? t_lo : (q == 2 ? t_hi : 0.5 * (t_lo + t_hi));
           D2Ctx ctx;
           make_d2ctx(A, ch, ct, ch.amp, 1.0, t_node, 0.0, chan[0].amp_pbf, ctx, true);
-          accumulate_terms(ctx, lam, H.need[c], acc);
+          accumulate_terms(ctx, lam, H.need[c], reinterpret_cast<double (&)[kNumTerms]>(acc));
           my_c = c;
         }
       }
-      compid[tid] = my_c;
-      // flush: per-component column sums in fixed order
-      for (int k0 = 0; k0 < kNumTerms; k0 += kHess3Chunk) {
 #pragma unroll
-        for (int k = 0; k < kHess3Chunk; ++k) stage[k * (kFastBlock + 1) + tid] = acc[k0 + k];
-        __syncthreads();
-        if (lane < kHess3Chunk) {
-          const double* col = stage + lane * (kFastBlock + 1) + warp * 32;
-          const int* cid = compid + warp * 32;
-          double sum[NC];
-#pragma unroll
-          for (int c = 0; c < NC; ++c) sum[c] = 0.0;
-          for (int r = 0; r < 32; ++r) {
-            const double v = col[r];
-            const int id = cid[r];
-#pragma unroll
-            for (int c = 0; c < NC; ++c) sum[c] += (id == c) ? v : 0.0;
-          }
-#pragma unroll
-          for (int c = 0; c < NC; ++c) part[(c * kFastWarps + warp) * 16 + lane] = sum[c];
-        }
-        __syncthreads();
-        if (tid < kHess3Chunk * NC) {
-          const int c = tid / kHess3Chunk, k = tid % kHess3Chunk;
-          double sum = 0.0;
-          for (int wv = 0; wv < kFastWarps; ++wv) sum += part[(c * kFastWarps + wv) * 16 + k];
-          total[c * 32 + k0 + k] = sum;
-        }
-        __syncthreads();
-      }
       for (int c = 0; c < NC; ++c) {
-        const double lf = chan[c].logf;
-        const int lo = H.comp_off[c], cnt = H.comp_off[c + 1] - lo;
-        for (int p = tid; p < cnt; p += kFastBlock) {
-          const int pair = H.comp_list[lo + p];
-          const HessDesc d = H.desc[pair];
-          const double factor = d.code == 0 ? 1.0 : (d.code == 1 ? kLn10 : (d.code == 2 ? lf : lf * lf));
-          pacc[pair] += factor * total[c * 32 + d.idx];
+        if (__ballot_sync(kFullMask, my_c == c) == 0u) continue;  // warp-uniform
+        const bool mine = my_c == c;
+        double r16[16], r8[8], r4[4], r2[2];
+        const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0, h4 = (lane & 4) != 0, h2 = (lane & 2) != 0,
+                   h1 = (lane & 1) != 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          const double lo = mine ? acc[k] : 0.0, hi = mine ? acc[k + 16] : 0.0;
+          r16[k] = (h16 ? hi : lo) + __shfl_xor_sync(kFullMask, h16 ? lo : hi, 16);
         }
-        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 8; ++k) r8[k] = (h8 ? r16[k + 8] : r16[k]) + __shfl_xor_sync(kFullMask, h8 ? r16[k] : r16[k + 8], 8);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r4[k] = (h4 ? r8[k + 4] : r8[k]) + __shfl_xor_sync(kFullMask, h4 ? r8[k] : r8[k + 4], 4);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) r2[k] = (h2 ? r4[k + 2] : r4[k]) + __shfl_xor_sync(kFullMask, h2 ? r4[k] : r4[k + 2], 2);
+        tot[c] += (h1 ? r2[1] : r2[0]) + __shfl_xor_sync(kFullMask, h1 ? r2[0] : r2[1], 1);
       }
+    }
+    // channel flush: warp totals -> block totals (warp order) -> pair accumulators
+#pragma unroll
+    for (int c = 0; c < NC; ++c) part[(c * kFastWarps + warp) * 32 + lane] = tot[c];
+    __syncthreads();
+    if (tid < 32 * NC) {
+      const int c = tid >> 5, k = tid & 31;
+      double sum = 0.0;
+      for (int wv = 0; wv < kFastWarps; ++wv) sum += part[(c * kFastWarps + wv) * 32 + k];
+      total[c * 32 + k] = sum;
+    }
+    __syncthreads();
+    for (int c = 0; c < NC; ++c) {
+      const double lf = chan[c].logf;
+      const int lo = H.comp_off[c], cnt = H.comp_off[c + 1] - lo;
+      for (int p = tid; p < cnt; p += kFastBlock) {
+        const int pair = H.comp_list[lo + p];
+        const HessDesc d = H.desc[pair];
+        const double factor = d.code == 0 ? 1.0 : (d.code == 1 ? kLn10 : (d.code == 2 ? lf : lf * lf));
+        pacc[pair] += factor * total[c * 32 + d.idx];
+      }
+      __syncthreads();
     }
   }
   cp_async_wait<0>();
