@@ -864,24 +864,36 @@ __global__ void __launch_bounds__(kFastBlock, FB_H3_MINB) k_hess3(const HessAccA
       double mu[NC][3];
 #pragma unroll
       for (int c = 0; c < NC; ++c) mu[c][0] = mu[c][1] = mu[c][2] = 0.0;
-      for (int wt = warp; wt < wtiles; wt += kFastWarps) {
-        const int j = wt * 32 + lane;
-        if (j < nt) {
-          double m[NC], msum = 0.0;
+      // four tiles of the warp per round: all their loads are issued before the first use (with
+      // one tile at a time every tile paid a full DRAM latency)
+      constexpr int kRound = 4;
+      for (int wt = warp; wt < wtiles; wt += kRound * kFastWarps) {
+        double m[kRound][NC], dv[kRound];
 #pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            m[c] = __ldg(srow + (size_t)c * nt + j);
-            msum += m[c];
-          }
-          const double rho = (__ldg(drow + j) - msum) * w2;
-          const double tj = (double)(j * kt) + kt_mid;
+        for (int r = 0; r < kRound; ++r) {
+          const int j = (wt + r * kFastWarps) * 32 + lane;
+          const bool ok = j < nt;
 #pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            if (j < range[2 * c] || j >= range[2 * c + 1]) {
-              const double x = fma(tj, xmap[2 * c], xmap[2 * c + 1]), rm = rho * m[c];
-              mu[c][0] += rm;
-              mu[c][1] = fma(rm, x, mu[c][1]);
-              mu[c][2] = fma(rm * x, x, mu[c][2]);
+          for (int c = 0; c < NC; ++c) m[r][c] = ok ? __ldg(srow + (size_t)c * nt + j) : 0.0;
+          dv[r] = ok ? __ldg(drow + j) : 0.0;
+        }
+#pragma unroll
+        for (int r = 0; r < kRound; ++r) {
+          const int j = (wt + r * kFastWarps) * 32 + lane;
+          if (j < nt) {
+            double msum = 0.0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) msum += m[r][c];
+            const double rho = (dv[r] - msum) * w2;
+            const double tj = (double)(j * kt) + kt_mid;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+              if (j < range[2 * c] || j >= range[2 * c + 1]) {
+                const double x = fma(tj, xmap[2 * c], xmap[2 * c + 1]), rm = rho * m[r][c];
+                mu[c][0] += rm;
+                mu[c][1] = fma(rm, x, mu[c][1]);
+                mu[c][2] = fma(rm * x, x, mu[c][2]);
+              }
             }
           }
         }
