@@ -94,6 +94,30 @@ def _strip_lazy(results):
     return results
 
 
+def _host_tensor(data):
+    """Host spectrum as a torch tensor WITHOUT a host-side dtype conversion for float32 input
+    (telescope data usually are float32: half the upload, widened exactly on the device)."""
+    if isinstance(data, torch.Tensor):
+        return data if data.dtype in (torch.float32, torch.float64) else data.to(torch.float64)
+    array = np.asarray(data)
+    if array.dtype not in (np.float32, np.float64):
+        array = array.astype(np.float64)
+    return torch.from_numpy(np.ascontiguousarray(array))
+
+
+def _upload(buffer, source, staging):
+    """buffer (float64, device) <- source (host, float32 or float64) on the current stream.
+    Returns the float32 staging buffer (created on first use) so that the caller can keep it."""
+    if source.dtype == torch.float64:
+        buffer.copy_(source, non_blocking=True)
+        return staging
+    if staging is None:
+        staging = torch.empty(buffer.shape, dtype=torch.float32, device=buffer.device)
+    staging.copy_(source, non_blocking=True)
+    buffer.copy_(staging)
+    return staging
+
+
 def _clone_model(model):
     """A second SpectrumModeler with the configuration of `model` (own plan, own device tables)."""
     from .analysis.model import SpectrumModeler
@@ -139,17 +163,17 @@ def fit_stream(model, bursts, fixed_parameters, weighted_fit=True, weight_range=
     buffers = [torch.empty(shape, dtype=torch.float64, device=device) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     free = [torch.cuda.Event() for _ in range(2)]
+    staging = [None]  # float32 staging buffer, only for float32 input (uploads are serial on `copier`)
     iterator = iter(bursts)
 
     def upload(slot, item):
         data = item[0]
         if isinstance(data, torch.Tensor) and data.is_cuda:
             return data.to(dtype=torch.float64).contiguous(), None
-        source = data if isinstance(data, torch.Tensor) else torch.from_numpy(
-            np.ascontiguousarray(data, dtype=np.float64))
+        source = _host_tensor(data)
         with torch.cuda.stream(copier):
             copier.wait_event(free[slot])  # the fit that used this buffer two bursts ago is done
-            buffers[slot].copy_(source, non_blocking=True)
+            staging[0] = _upload(buffers[slot], source, staging[0])
             ready[slot].record(copier)
         return buffers[slot], ready[slot]
 
@@ -224,11 +248,11 @@ def _fit_stream_concurrent(model, bursts, fixed_parameters, weighted_fit, weight
                         stream.wait_stream(caller_stream)  # whatever produced the tensor
                         data_dev = data.to(dtype=torch.float64).contiguous()
                     else:
-                        source = data if isinstance(data, torch.Tensor) else torch.from_numpy(
-                            np.ascontiguousarray(data, dtype=np.float64))
+                        source = _host_tensor(data)
                         if buffer is None:
                             buffer = slot["buffer"] = torch.empty(shape, dtype=torch.float64, device=device)
-                        buffer.copy_(source, non_blocking=True)  # ordered after this worker's previous fit
+                        # ordered after this worker's previous fit (same stream)
+                        slot["staging"] = _upload(buffer, source, slot.get("staging"))
                         data_dev = buffer
                     clone.update_parameters(start)
                     fitter = fitter_module.LSFitter(data_dev, clone, good_freq, weighted_fit=weighted_fit,
@@ -289,35 +313,57 @@ def _fit_stream_concurrent(model, bursts, fixed_parameters, weighted_fit, weight
             thread.join()
 
 
-def fit_bursts(freqs, times, bursts, fixed_parameters, model_kwargs=None, weighted_fit=True, weight_range=None,
-               device=None, workers=1):
+class BurstFitter:
     """
     Fits independent bursts that share the axes but not the number of components (BASELINE.json
     config 3: "1-3 components, random DM/scattering"). The reference would build one
     SpectrumModeler(num_components=k) per burst (pipelines/fitburst_pipeline.py:413-424); here the
     bursts are grouped by component count, every group shares one modeler (one plan, one set of
-    device tables) and runs through fit_stream, so uploads overlap fits inside a group.
-
-    bursts: sequence of (data, good_freq, start_parameters); the component count of a burst is
-    len(start_parameters["amplitude"]). Returns one fit_stream() dict per burst, in input order,
-    with the extra key "num_components".
+    device tables, its fit_stream worker contexts) that lives as long as this object, and runs
+    through fit_stream, so uploads and fits of different bursts overlap inside a group.
     """
-    from .analysis.model import SpectrumModeler
 
-    model_kwargs = dict(model_kwargs or {})
-    model_kwargs.pop("num_components", None)
-    if device is not None:
-        model_kwargs["device"] = device
-    groups = {}
-    for index, item in enumerate(bursts):
-        groups.setdefault(len(item[2]["amplitude"]), []).append(index)
-    out = [None] * len(bursts)
-    for num_components in sorted(groups):
-        members = groups[num_components]
-        model = SpectrumModeler(freqs, times, num_components=num_components, **model_kwargs)
-        stream = fit_stream(model, (bursts[i] for i in members), fixed_parameters, weighted_fit=weighted_fit,
-                            weight_range=weight_range, workers=workers)
-        for index, result in zip(members, stream):
-            result["num_components"] = num_components
-            out[index] = result
-    return out
+    def __init__(self, freqs, times, fixed_parameters, model_kwargs=None, weighted_fit=True, weight_range=None,
+                 device=None, workers=1):
+        self.freqs, self.times = freqs, times
+        self.fixed_parameters = list(fixed_parameters)
+        self.model_kwargs = dict(model_kwargs or {})
+        self.model_kwargs.pop("num_components", None)
+        if device is not None:
+            self.model_kwargs["device"] = device
+        self.weighted_fit, self.weight_range, self.workers = weighted_fit, weight_range, int(workers)
+        self.models = {}
+
+    def model_for(self, num_components: int):
+        from .analysis.model import SpectrumModeler
+        if num_components not in self.models:
+            self.models[num_components] = SpectrumModeler(self.freqs, self.times, num_components=num_components,
+                                                          **self.model_kwargs)
+        return self.models[num_components]
+
+    def fit(self, bursts) -> list:
+        """
+        bursts: sequence of (data, good_freq, start_parameters); the component count of a burst is
+        len(start_parameters["amplitude"]). Returns one fit_stream() dict per burst, in input
+        order, with the extra key "num_components".
+        """
+        groups = {}
+        for index, item in enumerate(bursts):
+            groups.setdefault(len(item[2]["amplitude"]), []).append(index)
+        out = [None] * len(bursts)
+        for num_components in sorted(groups):
+            members = groups[num_components]
+            stream = fit_stream(self.model_for(num_components), (bursts[i] for i in members), self.fixed_parameters,
+                                weighted_fit=self.weighted_fit, weight_range=self.weight_range, workers=self.workers)
+            for index, result in zip(members, stream):
+                result["num_components"] = num_components
+                out[index] = result
+        return out
+
+
+def fit_bursts(freqs, times, bursts, fixed_parameters, model_kwargs=None, weighted_fit=True, weight_range=None,
+               device=None, workers=1):
+    """One-shot form of BurstFitter(...).fit(bursts) (plans and device tables are built and
+    dropped inside the call: keep a BurstFitter when there is more than one batch)."""
+    return BurstFitter(freqs, times, fixed_parameters, model_kwargs, weighted_fit, weight_range, device,
+                       workers).fit(bursts)

@@ -1010,8 +1010,17 @@ __global__ void __launch_bounds__(256) k_gram3_finish(const double* __restrict__
     const double* src = is_far ? partials + near_sets * near_entries + (e - near_entries) : partials + e;
     const int stride = is_far ? far_entries : near_entries;
     const int count = is_far ? nblocks : (int)near_sets;
-    double s = 0.0;
-    for (int b = lane; b < count; b += 32) s += src[(size_t)b * stride];
+    // four independent partial sums per lane: the loads of a lane no longer wait for each other
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int b = lane;
+    for (; b + 96 < count; b += 128) {
+      s0 += src[(size_t)b * stride];
+      s1 += src[(size_t)(b + 32) * stride];
+      s2 += src[(size_t)(b + 64) * stride];
+      s3 += src[(size_t)(b + 96) * stride];
+    }
+    for (; b < count; b += 32) s0 += src[(size_t)b * stride];
+    double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(kFullMask, s, off);
     if (lane == 0) {

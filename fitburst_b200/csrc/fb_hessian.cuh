@@ -864,9 +864,9 @@ __global__ void __launch_bounds__(kFastBlock, FB_H3_MINB) k_hess3(const HessAccA
       double mu[NC][3];
 #pragma unroll
       for (int c = 0; c < NC; ++c) mu[c][0] = mu[c][1] = mu[c][2] = 0.0;
-      // four tiles of the warp per round: all their loads are issued before the first use (with
+      // eight tiles of the warp per round (a whole channel at 1024 samples): all their loads are issued before the first use (with
       // one tile at a time every tile paid a full DRAM latency)
-      constexpr int kRound = 4;
+      constexpr int kRound = 8;
       for (int wt = warp; wt < wtiles; wt += kRound * kFastWarps) {
         double m[kRound][NC], dv[kRound];
 #pragma unroll

@@ -195,6 +195,15 @@ def test_fit_stream_concurrent_workers_identical(native_lib):
         assert a["results"].status == b["results"].status and a["results"].nfev == b["results"].nfev
         np.testing.assert_array_equal(a["results"].x, b["results"].x)
         assert a["fit_statistics"]["bestfit_uncertainties"] == b["fit_statistics"]["bestfit_uncertainties"]
+    # float32 host spectra are uploaded as float32 and widened on the device: same results as
+    # fitting the widened array
+    as_f32 = [(d.astype(np.float32), g, st) for d, g, st in bursts[:4]]
+    widened = [(d.astype(np.float64), g, st) for d, g, st in as_f32]
+    for workers in (1, 2):
+        got = list(fit_stream(cuda, as_f32, fixed, workers=workers))
+        want = list(fit_stream(cuda, widened, fixed, workers=workers))
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a["results"].x, b["results"].x)
     # device-resident inputs and an early stop of the consumer
     import torch
     resident = [(torch.from_numpy(d).cuda(), g, s) for d, g, s in bursts]
