@@ -74,7 +74,7 @@ __host__ __device__ inline size_t vals3_smem_bytes(int nc, int kf) {
   size_t n = 0;
   n += sizeof(CompTab) * nc;
   n += 2 * (sizeof(ChanTab) * nc + sizeof(SubTab) * nc * kf);  // double-buffered channel tables
-  n += sizeof(double) * (size_t)nc * kf * 33;                 // R, D
+  n += sizeof(double) * (size_t)nc * kf * 65;                 // R (64 sample offsets), D
   n += sizeof(double) * (size_t)kFastWarps * vals3_bw_stride(nc * kf);  // B per warp
   n += sizeof(int) * (kFastWarps * kValsQueue + 4 + 2 * FB_MAX_COMPONENTS);  // per-warp queues, regime boundaries
   n += sizeof(TayTab) * nc + 16;
@@ -212,77 +212,90 @@ __device__ inline void vals3_boundaries(const PlanConst& pc, const CompTab& ct, 
   while (jt < nt && !tail(jt)) ++jt;
 }
 
-// Spectrum value of component c for the 32 samples of one warp tile (one per lane). Samples in
-// the rise region are pushed on the block's queue (*deferred = true for that lane) unless the
-// queue is full or the sub-grid is too small to share, in which case they are done here.
+// Spectrum values of component c for the 64 samples of one warp tile, two CONSECUTIVE samples per
+// lane (j0 + 2 lane, j0 + 2 lane + 1: 16-byte table reads and stores, two independent FMA chains
+// per lane in the tail dot product). Samples in the rise region are pushed on the warp's queue
+// (deferred[s] = true for that lane) unless the queue is full or the sub-grid is too small to
+// share, in which case they are done here.
 template <int KF>
-__device__ __forceinline__ double vals3_component(const PlanConst& pc, const CompTab& ct, const ChanTab& ch,
-                                                  const SubTab* __restrict__ sb, const double* __restrict__ r_lane,
-                                                  const double* __restrict__ bw, int c, int jp, int jt, int j0,
-                                                  int lane, bool valid, int* __restrict__ queue,
-                                                  int& qcount, bool* deferred) {
+__device__ __forceinline__ double2 vals3_component64(const PlanConst& pc, const CompTab& ct, const ChanTab& ch,
+                                                     const SubTab* __restrict__ sb, const double* __restrict__ r_lane,
+                                                     const double* __restrict__ bw, int c, int jp, int jt, int j0,
+                                                     int lane, int nt, int* __restrict__ queue, int& qcount,
+                                                     bool (&deferred)[2]) {
   const int kf = KF > 0 ? KF : pc.kf, kt = pc.kt;
-  *deferred = false;
+  deferred[0] = deferred[1] = false;
   if (j0 >= jt && j0 >= jp) {  // whole tile in the exponential tail
-    // four interleaved partial sums: the kf-long dependent FMA chain was the critical path of a tile
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
     int a = 0;
 #pragma unroll
-    for (; a + 3 < kf; a += 4) {
-      s0 = fma(bw[a], r_lane[a * 32], s0);
-      s1 = fma(bw[a + 1], r_lane[(a + 1) * 32], s1);
-      s2 = fma(bw[a + 2], r_lane[(a + 2) * 32], s2);
-      s3 = fma(bw[a + 3], r_lane[(a + 3) * 32], s3);
+    for (; a + 1 < kf; a += 2) {
+      const double b0 = bw[a], b1 = bw[a + 1];
+      const double2 r0 = *reinterpret_cast<const double2*>(r_lane + a * 64);
+      const double2 r1 = *reinterpret_cast<const double2*>(r_lane + (a + 1) * 64);
+      s0.x = fma(b0, r0.x, s0.x);
+      s0.y = fma(b0, r0.y, s0.y);
+      s1.x = fma(b1, r1.x, s1.x);
+      s1.y = fma(b1, r1.y, s1.y);
     }
-    for (; a < kf; ++a) s0 = fma(bw[a], r_lane[a * 32], s0);
-    return (s0 + s1) + (s2 + s3);
+    for (; a < kf; ++a) {
+      const double b0 = bw[a];
+      const double2 r0 = *reinterpret_cast<const double2*>(r_lane + a * 64);
+      s0.x = fma(b0, r0.x, s0.x);
+      s0.y = fma(b0, r0.y, s0.y);
+    }
+    return make_double2(s0.x + s1.x, s0.y + s1.y);
   }
-  if (j0 + 32 <= jp) return ch.plateau_ps;  // whole tile on the clamp plateau
-  const int j = j0 + lane;
-  const bool plateau = j < jp;
-  const bool tail = !plateau && j >= jt;
-  const bool general = valid && !plateau && !tail;
-  const unsigned gm = __ballot_sync(kFullMask, general);
-  double val = 0.0;
-  if (plateau) {
-    val = ch.plateau_ps;
-  } else if (tail) {
-    const double u0 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, j * kt, pc.ntk);
-    double s_ps = 0.0;
+  if (j0 + 64 <= jp) return make_double2(ch.plateau_ps, ch.plateau_ps);  // whole tile on the clamp plateau
+  double out[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    const int j = j0 + 2 * lane + s;
+    const bool plateau = j < jp;
+    const bool tail = !plateau && j >= jt;
+    const bool general = j < nt && !plateau && !tail;
+    const unsigned gm = __ballot_sync(kFullMask, general);
+    double val = 0.0;
+    if (plateau) {
+      val = ch.plateau_ps;
+    } else if (tail) {
+      const double u0 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, j * kt, pc.ntk);
+      double s_ps = 0.0;
 #pragma unroll 4
-    for (int a = 0; a < kf; ++a) {
-      const SubTab& st = sb[a];
-      const double earg = fma(-u0, st.inv_tau, st.tail_e);
-      const double p = (earg < -746.0) ? 0.0 : st.tail_c * fb_exp(earg);
-      s_ps = fma(p, st.sed, s_ps);
+      for (int a = 0; a < kf; ++a) {
+        const SubTab& st = sb[a];
+        const double earg = fma(-u0, st.inv_tau, st.tail_e);
+        const double p = (earg < -746.0) ? 0.0 : st.tail_c * fb_exp(earg);
+        s_ps = fma(p, st.sed, s_ps);
+      }
+      val = ct.amp10 * s_ps;
     }
-    val = ct.amp10 * s_ps;
-  }
-  if (gm == 0u) return val;
-  if (kf * kt < 16) {
-    if (general) val = eval_sample_general(pc, ct, ch, sb, j).spectrum;
-    return val;
-  }
-  if (ch.fast_ok) {
-    // the queue is private to the warp (its own tiles feed it, it alone drains it after its
-    // tiles): the counter is a warp-uniform register, a request that does not fit is refused
-    // whole and its samples are evaluated in place
-    const int cnt = __popc(gm);
-    if (qcount + cnt <= kValsQueue) {
-      if (general) queue[qcount + __popc(gm & ((1u << lane) - 1u))] = (c << 27) | j;
-      qcount += cnt;
-      *deferred = general;
-      return val;
+    if (gm != 0u) {
+      if (kf * kt < 16) {
+        if (general) val = eval_sample_general(pc, ct, ch, sb, j).spectrum;
+      } else {
+        // the queue is private to the warp (its own tiles feed it, it alone drains it after
+        // its tiles): the counter is a warp-uniform register, a request that does not fit is
+        // refused whole and its samples are evaluated in place
+        const int cnt = __popc(gm);
+        if (ch.fast_ok && qcount + cnt <= kValsQueue) {
+          if (general) queue[qcount + __popc(gm & ((1u << lane) - 1u))] = (c << 27) | j;
+          qcount += cnt;
+          deferred[s] = general;
+        } else {
+          unsigned rem = gm;
+          while (rem) {
+            const int src = __ffs(rem) - 1;
+            rem &= rem - 1;
+            const double v = vals3_general_warp<KF>(pc, ct, ch, sb, j0 + 2 * src + s, lane);
+            if (lane == src) val = v;
+          }
+        }
+      }
     }
+    out[s] = val;
   }
-  unsigned rem = gm;
-  while (rem) {
-    const int s = __ffs(rem) - 1;
-    rem &= rem - 1;
-    const double v = vals3_general_warp<KF>(pc, ct, ch, sb, j0 + s, lane);
-    if (lane == s) val = v;
-  }
-  return val;
+  return make_double2(out[0], out[1]);
 }
 
 // Stores the spectrum value of every (good channel, component, sample):
@@ -300,9 +313,9 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
   const size_t tab_bytes = sizeof(ChanTab) * nc + sizeof(SubTab) * nck;
   char* tabs = sp;  // [2][ChanTab nc | SubTab nc*kf]
   sp += 2 * tab_bytes;
-  double* R = reinterpret_cast<double*>(sp);
-  sp += sizeof(double) * (size_t)nck * 32;
-  double* D = reinterpret_cast<double*>(sp);  // tile-to-tile decay exp(-32 kt step / tau)
+  double* R = reinterpret_cast<double*>(sp);  // [nck][64]: tail factors at the 64 sample offsets of a tile
+  sp += sizeof(double) * (size_t)nck * 64;
+  double* D = reinterpret_cast<double*>(sp);  // decay between two tiles of a warp
   sp += sizeof(double) * (size_t)nck;
   const int bws = vals3_bw_stride(nck);
   double* bw = reinterpret_cast<double*>(sp) + (size_t)warp * bws;
@@ -316,8 +329,9 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
     double* dst = reinterpret_cast<double*>(comp);
     for (int e = tid; e < nc * (int)(sizeof(CompTab) / sizeof(double)); e += kFastBlock) dst[e] = src[e];
   }
-  const int wtiles = (nt + 31) / 32;
-  // tiles of a warp: wt = warp + k * kFastWarps (interleaved: the few expensive tiles around the
+  const int wtiles = (nt + 63) / 64;
+  const bool pair_store = (nt & 1) == 0;  // rows start on 16-byte boundaries
+  // 64-sample tiles of a warp: wt = warp + k * kFastWarps (interleaved: the few expensive tiles around the
   // burst spread over the warps; with contiguous ranges one or two warps held the block)
   const int chan_chunks = (int)(sizeof(ChanTab) * nc / 16), sub_chunks = (int)(sizeof(SubTab) * nck / 16);
   // channel numbers are read two iterations ahead: chan_list[] -> table address is a dependent
@@ -353,20 +367,23 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
       bounds[2 * (tid - 32) + 1] = jt;
     }
     if (tid >= 64 && tid < 64 + nc) make_tay_tab(pc, comp[tid - 64], chan[tid - 64], sub + (tid - 64) * kf, kf, tay[tid - 64]);
-    for (int e = tid; e < nck * 32; e += kFastBlock) {
+    for (int e = tid; e < nck * 32; e += kFastBlock) {  // a warp covers one (component, sub-frequency) row
       const int l = e & 31, ca = e >> 5, c = ca / kf;
       const SubTab& st = sub[ca];
       const double decay = fb_exp(-((double)(l * kt) * comp[c].t_step) * st.inv_tau);
-      R[e] = ((comp[c].amp10 * st.tail_c) * st.sed) * decay;
+      // offsets 32..63: decay(l + 32) = decay(l) decay(31) decay(1), no second exp
+      const double d32 = __shfl_sync(kFullMask, decay, 31) * __shfl_sync(kFullMask, decay, 1);
+      const double base = (comp[c].amp10 * st.tail_c) * st.sed;
+      R[ca * 64 + l] = base * decay;
+      R[ca * 64 + 32 + l] = base * (decay * d32);
     }
     for (int e = tid; e < nck; e += kFastBlock)
-      D[e] = fb_exp(-((double)(32 * kFastWarps * kt) * comp[e / kf].t_step) * sub[e].inv_tau);
+      D[e] = fb_exp(-((double)(64 * kFastWarps * kt) * comp[e / kf].t_step) * sub[e].inv_tau);
     __syncthreads();
     double* out = gvals + (size_t)chi * nc * nt;
     // phase A: closed-form regimes tile by tile (uniform cost), rise-region samples queued
     for (int wt = warp, k = 0; wt < wtiles; wt += kFastWarps, ++k) {
-      const int j0 = wt * 32, j = j0 + lane;
-      const bool valid = j < nt;
+      const int j0 = wt * 64, j = j0 + 2 * lane;
       // tail base factors B of every (component, sub-frequency) at the first sample of the tile:
       // one exp per lane every 8th tile of the warp, the decay recurrence (over kFastWarps tiles)
       // in between (a factor that overflowed ahead of the burst is recomputed: inf * decay would
@@ -385,11 +402,17 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
       }
       __syncwarp();
       for (int c = 0; c < nc; ++c) {
-        bool deferred;
-        const double v = vals3_component<KF>(pc, comp[c], chan[c], sub + c * kf, R + (size_t)c * kf * 32 + lane,
-                                             bw + c * kf, c, bounds[2 * c], bounds[2 * c + 1], j0, lane, valid,
-                                             queue, qcount, &deferred);
-        if (valid && !deferred) out[(size_t)c * nt + j] = v;
+        bool deferred[2];
+        const double2 v = vals3_component64<KF>(pc, comp[c], chan[c], sub + c * kf,
+                                                R + (size_t)c * kf * 64 + 2 * lane, bw + c * kf, c, bounds[2 * c],
+                                                bounds[2 * c + 1], j0, lane, nt, queue, qcount, deferred);
+        double* dst = out + (size_t)c * nt + j;
+        if (pair_store && j + 1 < nt && !deferred[0] && !deferred[1]) {
+          *reinterpret_cast<double2*>(dst) = v;
+        } else {
+          if (j < nt && !deferred[0]) dst[0] = v.x;
+          if (j + 1 < nt && !deferred[1]) dst[1] = v.y;
+        }
       }
       __syncwarp();
     }
