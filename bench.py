@@ -104,6 +104,7 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--repeats", type=int, default=3, help="timed repetitions of the K-step batch (median reported)")
     ap.add_argument("--workers", type=int, default=0,
                     help="fits in flight per GPU in fit_stream (0 = min(4, host cores / ranks))")
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
@@ -418,20 +419,25 @@ def run_cuda(args):
 
     def timed_batch(source, steps, warmup):
         """Warm-up fits, then EXACTLY `steps` fits inside barrier + synchronize brackets (the
-        pipeline fills and drains inside the timed region). Returns ms (max over ranks)."""
+        pipeline fills and drains inside the timed region), max over ranks. The K-step batch is
+        timed `args.repeats` times and the MEDIAN is reported (one run in ten showed a one-off
+        stall of several hundred ms in one batch; every repeat is listed in the output line)."""
         import gc
         run_batch(source, max(warmup, 2 * workers))
         gc.collect()
-        barrier()
-        t0 = time.perf_counter()
-        run_batch(source, steps)
-        torch.cuda.synchronize()  # every stream of the device
-        wall_ms = (time.perf_counter() - t0) * 1e3
-        barrier()
-        t = torch.tensor([wall_ms], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0])
+        times_ms = []
+        for _ in range(max(1, args.repeats)):
+            barrier()
+            t0 = time.perf_counter()
+            run_batch(source, steps)
+            torch.cuda.synchronize()  # every stream of the device
+            wall_ms = (time.perf_counter() - t0) * 1e3
+            barrier()
+            t = torch.tensor([wall_ms], dtype=torch.float64, device=device)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            times_ms.append(float(t[0]))
+        return float(np.median(times_ms)), times_ms
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -439,15 +445,15 @@ def run_cuda(args):
     # (1) value: spectra resident in HBM
     run_batch(dev_bursts, 2 * workers)  # creates the worker clones before launches are counted
     launch_total(True)
-    ms_value = timed_batch(dev_bursts, args.steps, args.warmup)
+    ms_value, ms_value_repeats = timed_batch(dev_bursts, args.steps, args.warmup)
     counted = launch_total(True)
-    gpu_launches = int(round(counted * args.steps / (args.steps + max(args.warmup, 2 * workers))))
+    gpu_launches = int(round(counted * args.steps / (max(1, args.repeats) * args.steps + max(args.warmup, 2 * workers))))
     ms_step = ms_value / args.steps
     value = world * 1e3 / ms_step
 
     # (2) e2e: the same call with HOST spectra (page-locked): every step uploads its own 134 MB
     # spectrum and reads its results back inside the timed region
-    ms_e2e = timed_batch(host_bursts, args.steps, args.warmup)
+    ms_e2e, ms_e2e_repeats = timed_batch(host_bursts, args.steps, args.warmup)
     ms_step_e = ms_e2e / args.steps
     e2e_value = world * 1e3 / ms_step_e
 
@@ -530,13 +536,15 @@ def run_cuda(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args),
             "e2e": {"value": e2e_value, "unit": "fits/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_step_e,
+                    "ms_per_step": ms_step_e, "ms_per_step_repeats": [t / args.steps for t in ms_e2e_repeats],
                     "api": f"fitburst_b200.batch.fit_stream(workers={workers}) on page-locked host spectra: "
                            "uploads and fits of different bursts overlap",
                     "single_call": {"value": world * 1e3 / ms_step_1, "ms_per_step": ms_step_1,
                                     "api": "LSFitter(host_array, ...).fit(), upload then fit, one at a time"}},
             "api": f"fitburst_b200.batch.fit_stream(workers={workers}) on device-resident spectra",
             "fits_in_flight": workers,
+            "ms_per_step_repeats": [t / args.steps for t in ms_value_repeats],
+            "repeats_note": f"the {args.steps}-step batch is timed {max(1, args.repeats)} times, median reported",
             "single_fit_latency_ms": ms_single,
             "gpu_launches": gpu_launches, "clocks": sampler.summary(), "roofline": roofline,
             "fit": {"status": int(res.status), "nfev": nfev, "njev": int(res.njev),

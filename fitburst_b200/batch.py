@@ -8,6 +8,7 @@ Batched workloads of the hot path on one GPU (through the C ABI):
 Multi-GPU sharding of both lives in fitburst_b200.distributed.
 """
 import ctypes
+import time
 
 import numpy as np
 import torch
@@ -86,6 +87,9 @@ def pinned_like(array) -> np.ndarray:
     host->device copy of a pageable array is staged by the driver and cannot overlap a fit)."""
     tensor = torch.from_numpy(np.ascontiguousarray(array, dtype=np.float64)).pin_memory()
     return tensor.numpy()
+
+
+TRACE = None  # set to a list to collect (burst index, worker, t_taken, t_fit_start, t_fit_end) per concurrent fit
 
 
 def _strip_lazy(results):
@@ -244,6 +248,7 @@ def _fit_stream_concurrent(model, bursts, fixed_parameters, weighted_fit, weight
                     if taken is None:
                         break
                     index, (data, good_freq, start) = taken
+                    t_taken = time.perf_counter()
                     if isinstance(data, torch.Tensor) and data.is_cuda:
                         stream.wait_stream(caller_stream)  # whatever produced the tensor
                         data_dev = data.to(dtype=torch.float64).contiguous()
@@ -255,6 +260,7 @@ def _fit_stream_concurrent(model, bursts, fixed_parameters, weighted_fit, weight
                         slot["staging"] = _upload(buffer, source, slot.get("staging"))
                         data_dev = buffer
                     clone.update_parameters(start)
+                    t_start = time.perf_counter()
                     fitter = fitter_module.LSFitter(data_dev, clone, good_freq, weighted_fit=weighted_fit,
                                                     weight_range=weight_range)
                     fitter.fix_parameter(list(fixed_parameters))
@@ -262,6 +268,8 @@ def _fit_stream_concurrent(model, bursts, fixed_parameters, weighted_fit, weight
                     out = {"results": _strip_lazy(getattr(fitter, "results", None)),
                            "fit_statistics": fitter.fit_statistics, "success": fitter.success}
                     del fitter
+                    if TRACE is not None:
+                        TRACE.append((index, worker_index, t_taken, t_start, time.perf_counter()))
                     with cond:
                         done[index] = out
                         cond.notify_all()

@@ -221,8 +221,8 @@ template <int KF>
 __device__ __forceinline__ double2 vals3_component64(const PlanConst& pc, const CompTab& ct, const ChanTab& ch,
                                                      const SubTab* __restrict__ sb, const double* __restrict__ r_lane,
                                                      const double* __restrict__ bw, int c, int jp, int jt, int j0,
-                                                     int lane, int nt, int* __restrict__ queue, int& qcount,
-                                                     bool (&deferred)[2]) {
+                                                     int lane, int nt, bool tail_dot_ok,
+                                                     int* __restrict__ queue, int& qcount, bool (&deferred)[2]) {
   const int kf = KF > 0 ? KF : pc.kf, kt = pc.kt;
   deferred[0] = deferred[1] = false;
   if (j0 >= jt && j0 >= jp) {  // whole tile in the exponential tail
@@ -258,6 +258,18 @@ __device__ __forceinline__ double2 vals3_component64(const PlanConst& pc, const 
     double val = 0.0;
     if (plateau) {
       val = ch.plateau_ps;
+    } else if (tail && tail_dot_ok) {
+      // tail samples of a mixed tile: the same dot product as in whole-tail tiles (every base
+      // factor of the component at the tile start is finite: the tail begins inside this tile)
+      double s0 = 0.0, s1 = 0.0;
+      int a = 0;
+#pragma unroll
+      for (; a + 1 < kf; a += 2) {
+        s0 = fma(bw[a], r_lane[a * 64 + s], s0);
+        s1 = fma(bw[a + 1], r_lane[(a + 1) * 64 + s], s1);
+      }
+      for (; a < kf; ++a) s0 = fma(bw[a], r_lane[a * 64 + s], s0);
+      val = s0 + s1;
     } else if (tail) {
       const double u0 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, j * kt, pc.ntk);
       double s_ps = 0.0;
@@ -331,6 +343,7 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
   }
   const int wtiles = (nt + 63) / 64;
   const bool pair_store = (nt & 1) == 0;  // rows start on 16-byte boundaries
+  const unsigned kf_mask = kf >= 32 ? kFullMask : ((1u << kf) - 1u);
   // 64-sample tiles of a warp: wt = warp + k * kFastWarps (interleaved: the few expensive tiles around the
   // burst spread over the warps; with contiguous ranges one or two warps held the block)
   const int chan_chunks = (int)(sizeof(ChanTab) * nc / 16), sub_chunks = (int)(sizeof(SubTab) * nck / 16);
@@ -389,23 +402,32 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
       // in between (a factor that overflowed ahead of the burst is recomputed: inf * decay would
       // stay inf)
       const bool refresh = (k & 7) == 0;
+      bool b_finite = true;
       for (int e = lane; e < nck; e += 32) {
         const double prev = bw[e];
+        double next;
         if (refresh || !(prev < 1e290)) {
           const CompTab& ct = comp[e / kf];
           const double u0b = linspace_at(ct.t_start, ct.t_step, ct.t_stop, j0 * kt, pc.ntk);
           const double earg = fma(-u0b, sub[e].inv_tau, sub[e].tail_e);
-          bw[e] = (earg < -746.0) ? 0.0 : fb_exp(earg);
+          next = (earg < -746.0) ? 0.0 : fb_exp(earg);
         } else {
-          bw[e] = prev * D[e];
+          next = prev * D[e];
         }
+        bw[e] = next;
+        b_finite = b_finite && next < 1e290;
       }
+      // bit e set: base factor e is finite (usable for tail samples of a mixed tile); only
+      // meaningful when the nc * kf factors fit one pass of the warp
+      const unsigned bmask = nck <= 32 ? __ballot_sync(kFullMask, b_finite) : 0u;
       __syncwarp();
       for (int c = 0; c < nc; ++c) {
         bool deferred[2];
         const double2 v = vals3_component64<KF>(pc, comp[c], chan[c], sub + c * kf,
                                                 R + (size_t)c * kf * 64 + 2 * lane, bw + c * kf, c, bounds[2 * c],
-                                                bounds[2 * c + 1], j0, lane, nt, queue, qcount, deferred);
+                                                bounds[2 * c + 1], j0, lane, nt,
+                                                nck <= 32 && ((bmask >> (c * kf)) & kf_mask) == kf_mask,
+                                                queue, qcount, deferred);
         double* dst = out + (size_t)c * nt + j;
         if (pair_store && j + 1 < nt && !deferred[0] && !deferred[1]) {
           *reinterpret_cast<double2*>(dst) = v;
@@ -665,7 +687,9 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
   double* accw = A.partials + ((size_t)blockIdx.x * kFastWarps + warp) * kAcc * 64 + (lane >> 2) * 8 + (lane & 3) * 2;
 #pragma unroll
   for (int k = 0; k < kAcc; ++k) *reinterpret_cast<double2*>(accw + k * 64) = make_double2(0.0, 0.0);
-  double cf0 = 0.0, cf1 = 0.0;  // far-tile block B of the current channel
+  // far-tile block B of the current channel, even and odd k-steps in separate accumulators (a
+  // tile is 8 DMMA on the same C fragment: one chain of 8 dependent tensor instructions)
+  double cf0 = 0.0, cf1 = 0.0, cg0 = 0.0, cg1 = 0.0;
   // full-matrix accumulators of the far tiles: thread e owns upper-triangle entries e and e + 256
   const int nent = ncols * (ncols + 1) / 2;
   double gacc[2] = {0.0, 0.0};
@@ -867,9 +891,11 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
         for (int a = 2 * NC + 1; a < 8; ++a) row[a * kMmaRowStride] = 0.0;
         __syncwarp();
 #pragma unroll
-        for (int step = 0; step < 8; ++step) {
+        for (int step = 0; step < 8; step += 2) {
           const double f = xt[fc * kMmaRowStride + 4 * step + fr];
+          const double g = xt[fc * kMmaRowStride + 4 * step + 4 + fr];
           dmma8x8x4(cf0, cf1, f, f);
+          dmma8x8x4(cg0, cg1, g, g);
         }
         __syncwarp();
         continue;
@@ -970,9 +996,9 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
       // far tiles of the channel: every warp parks its block B; the contraction G += T (sum B) T^T
       // happens at the top of the block's next channel (or after the loop), inside barriers that
       // are there anyway -- three block barriers per channel less than flushing here
-      Bw[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2] = cf0;
-      Bw[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2 + 1] = cf1;
-      cf0 = cf1 = 0.0;
+      Bw[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2] = cf0 + cg0;
+      Bw[warp * 64 + (lane >> 2) * 8 + (lane & 3) * 2 + 1] = cf1 + cg1;
+      cf0 = cf1 = cg0 = cg1 = 0.0;
       have_prev = true;
     }
   }
