@@ -520,6 +520,7 @@ static bool fast_path_ok(const fb_plan_s* p, bool for_gram) {
     if (!(p->h_params[FB_REF_FREQ * nc + c] > 0.0)) return false;
   }
   if (for_gram && gram3_layout(p).nr > 24) return false;
+  if (vals3_smem_bytes(nc, p->pc.kf) > 200 * 1024) return false;  // tail tables of nc * kf rows do not fit
   return true;
 }
 
@@ -1514,7 +1515,8 @@ extern "C" int fb_chisq_grid(fb_plan_t p, const double* data_dev, const double* 
     return FB_OK;
   }
   // fast kernels (fb_fast.cuh) whenever the grid point is on the scattered branch
-  bool fast_grid = !env_off("FITBURST_B200_FAST") && !p->pc.scintillation && !p->pc.is_folded && nc <= 4;
+  bool fast_grid = !env_off("FITBURST_B200_FAST") && !p->pc.scintillation && !p->pc.is_folded && nc <= 4 &&
+                   vals3_smem_bytes(nc, p->pc.kf) <= 200 * 1024;
   for (int c = 0; c < nc; ++c)
     fast_grid = fast_grid && p->h_params[FB_BURST_WIDTH * nc + c] > 0.0 && p->h_params[FB_REF_FREQ * nc + c] > 0.0;
   for (int a = 0; a < num_dm; ++a)

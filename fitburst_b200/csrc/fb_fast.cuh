@@ -59,6 +59,12 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
 
 // ---- model side ---------------------------------------------------------------------------
 constexpr int kValsQueue = 256;  // rise-region (sample, component) items queued per warp and channel
+#ifndef FB_V3_SPL
+#define FB_V3_SPL 2  // measured: 2 (64-sample tiles) 0.454 ms per evaluation, 4 (128-sample tiles, two per warp) 0.510
+#endif
+constexpr int kSpl = FB_V3_SPL;    // consecutive samples per lane in k_vals3 (even)
+constexpr int kVTile = 32 * kSpl;  // samples per warp tile
+static_assert(kSpl % 2 == 0 && kSpl >= 2 && kSpl <= 8, "k_vals3 handles samples in 16-byte pairs");
 
 // Per (channel, component) constants of the sub-frequency expansion (see make_tay_tab).
 struct TayTab {
@@ -74,7 +80,7 @@ __host__ __device__ inline size_t vals3_smem_bytes(int nc, int kf) {
   size_t n = 0;
   n += sizeof(CompTab) * nc;
   n += 2 * (sizeof(ChanTab) * nc + sizeof(SubTab) * nc * kf);  // double-buffered channel tables
-  n += sizeof(double) * (size_t)nc * kf * 65;                 // R (64 sample offsets), D
+  n += sizeof(double) * (size_t)nc * kf * (kVTile + 1);       // R (sample offsets of a tile), D
   n += sizeof(double) * (size_t)kFastWarps * vals3_bw_stride(nc * kf);  // B per warp
   n += sizeof(int) * (kFastWarps * kValsQueue + 4 + 2 * FB_MAX_COMPONENTS);  // per-warp queues, regime boundaries
   n += sizeof(TayTab) * nc + 16;
@@ -212,45 +218,43 @@ __device__ inline void vals3_boundaries(const PlanConst& pc, const CompTab& ct, 
   while (jt < nt && !tail(jt)) ++jt;
 }
 
-// Spectrum values of component c for the 64 samples of one warp tile, two CONSECUTIVE samples per
-// lane (j0 + 2 lane, j0 + 2 lane + 1: 16-byte table reads and stores, two independent FMA chains
-// per lane in the tail dot product). Samples in the rise region are pushed on the warp's queue
+// Spectrum values of component c for the kVTile samples of one warp tile, kSpl CONSECUTIVE samples
+// per lane (j0 + kSpl lane + s: 16-byte table reads and stores, kSpl independent FMA chains per
+// lane in the tail dot product). Samples in the rise region are pushed on the warp's queue
 // (deferred[s] = true for that lane) unless the queue is full or the sub-grid is too small to
 // share, in which case they are done here.
 template <int KF>
-__device__ __forceinline__ double2 vals3_component64(const PlanConst& pc, const CompTab& ct, const ChanTab& ch,
+__device__ __forceinline__ void vals3_component_tile(const PlanConst& pc, const CompTab& ct, const ChanTab& ch,
                                                      const SubTab* __restrict__ sb, const double* __restrict__ r_lane,
                                                      const double* __restrict__ bw, int c, int jp, int jt, int j0,
-                                                     int lane, int nt, bool tail_dot_ok,
-                                                     int* __restrict__ queue, int& qcount, bool (&deferred)[2]) {
+                                                     int lane, int nt, bool tail_dot_ok, int* __restrict__ queue,
+                                                     int& qcount, double (&out)[kSpl], bool (&deferred)[kSpl]) {
   const int kf = KF > 0 ? KF : pc.kf, kt = pc.kt;
-  deferred[0] = deferred[1] = false;
+#pragma unroll
+  for (int s = 0; s < kSpl; ++s) deferred[s] = false;
   if (j0 >= jt && j0 >= jp) {  // whole tile in the exponential tail
-    double2 s0 = make_double2(0.0, 0.0), s1 = make_double2(0.0, 0.0);
-    int a = 0;
 #pragma unroll
-    for (; a + 1 < kf; a += 2) {
-      const double b0 = bw[a], b1 = bw[a + 1];
-      const double2 r0 = *reinterpret_cast<const double2*>(r_lane + a * 64);
-      const double2 r1 = *reinterpret_cast<const double2*>(r_lane + (a + 1) * 64);
-      s0.x = fma(b0, r0.x, s0.x);
-      s0.y = fma(b0, r0.y, s0.y);
-      s1.x = fma(b1, r1.x, s1.x);
-      s1.y = fma(b1, r1.y, s1.y);
+    for (int s = 0; s < kSpl; ++s) out[s] = 0.0;
+#pragma unroll
+    for (int a = 0; a < kf; ++a) {
+      const double b = bw[a];
+#pragma unroll
+      for (int h = 0; h < kSpl / 2; ++h) {
+        const double2 r = *reinterpret_cast<const double2*>(r_lane + a * kVTile + 2 * h);
+        out[2 * h] = fma(b, r.x, out[2 * h]);
+        out[2 * h + 1] = fma(b, r.y, out[2 * h + 1]);
+      }
     }
-    for (; a < kf; ++a) {
-      const double b0 = bw[a];
-      const double2 r0 = *reinterpret_cast<const double2*>(r_lane + a * 64);
-      s0.x = fma(b0, r0.x, s0.x);
-      s0.y = fma(b0, r0.y, s0.y);
-    }
-    return make_double2(s0.x + s1.x, s0.y + s1.y);
+    return;
   }
-  if (j0 + 64 <= jp) return make_double2(ch.plateau_ps, ch.plateau_ps);  // whole tile on the clamp plateau
-  double out[2];
+  if (j0 + kVTile <= jp) {  // whole tile on the clamp plateau
 #pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    const int j = j0 + 2 * lane + s;
+    for (int s = 0; s < kSpl; ++s) out[s] = ch.plateau_ps;
+    return;
+  }
+#pragma unroll
+  for (int s = 0; s < kSpl; ++s) {
+    const int j = j0 + kSpl * lane + s;
     const bool plateau = j < jp;
     const bool tail = !plateau && j >= jt;
     const bool general = j < nt && !plateau && !tail;
@@ -265,10 +269,10 @@ __device__ __forceinline__ double2 vals3_component64(const PlanConst& pc, const 
       int a = 0;
 #pragma unroll
       for (; a + 1 < kf; a += 2) {
-        s0 = fma(bw[a], r_lane[a * 64 + s], s0);
-        s1 = fma(bw[a + 1], r_lane[(a + 1) * 64 + s], s1);
+        s0 = fma(bw[a], r_lane[a * kVTile + s], s0);
+        s1 = fma(bw[a + 1], r_lane[(a + 1) * kVTile + s], s1);
       }
-      for (; a < kf; ++a) s0 = fma(bw[a], r_lane[a * 64 + s], s0);
+      for (; a < kf; ++a) s0 = fma(bw[a], r_lane[a * kVTile + s], s0);
       val = s0 + s1;
     } else if (tail) {
       const double u0 = linspace_at(ct.t_start, ct.t_step, ct.t_stop, j * kt, pc.ntk);
@@ -299,7 +303,7 @@ __device__ __forceinline__ double2 vals3_component64(const PlanConst& pc, const 
           while (rem) {
             const int src = __ffs(rem) - 1;
             rem &= rem - 1;
-            const double v = vals3_general_warp<KF>(pc, ct, ch, sb, j0 + 2 * src + s, lane);
+            const double v = vals3_general_warp<KF>(pc, ct, ch, sb, j0 + kSpl * src + s, lane);
             if (lane == src) val = v;
           }
         }
@@ -307,7 +311,6 @@ __device__ __forceinline__ double2 vals3_component64(const PlanConst& pc, const 
     }
     out[s] = val;
   }
-  return make_double2(out[0], out[1]);
 }
 
 // Stores the spectrum value of every (good channel, component, sample):
@@ -325,8 +328,8 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
   const size_t tab_bytes = sizeof(ChanTab) * nc + sizeof(SubTab) * nck;
   char* tabs = sp;  // [2][ChanTab nc | SubTab nc*kf]
   sp += 2 * tab_bytes;
-  double* R = reinterpret_cast<double*>(sp);  // [nck][64]: tail factors at the 64 sample offsets of a tile
-  sp += sizeof(double) * (size_t)nck * 64;
+  double* R = reinterpret_cast<double*>(sp);  // [nck][kVTile]: tail factors at the sample offsets of a tile
+  sp += sizeof(double) * (size_t)nck * kVTile;
   double* D = reinterpret_cast<double*>(sp);  // decay between two tiles of a warp
   sp += sizeof(double) * (size_t)nck;
   const int bws = vals3_bw_stride(nck);
@@ -341,10 +344,10 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
     double* dst = reinterpret_cast<double*>(comp);
     for (int e = tid; e < nc * (int)(sizeof(CompTab) / sizeof(double)); e += kFastBlock) dst[e] = src[e];
   }
-  const int wtiles = (nt + 63) / 64;
+  const int wtiles = (nt + kVTile - 1) / kVTile;
   const bool pair_store = (nt & 1) == 0;  // rows start on 16-byte boundaries
   const unsigned kf_mask = kf >= 32 ? kFullMask : ((1u << kf) - 1u);
-  // 64-sample tiles of a warp: wt = warp + k * kFastWarps (interleaved: the few expensive tiles around the
+  // tiles (kVTile samples) of a warp: wt = warp + k * kFastWarps (interleaved: the few expensive tiles around the
   // burst spread over the warps; with contiguous ranges one or two warps held the block)
   const int chan_chunks = (int)(sizeof(ChanTab) * nc / 16), sub_chunks = (int)(sizeof(SubTab) * nck / 16);
   // channel numbers are read two iterations ahead: chan_list[] -> table address is a dependent
@@ -384,19 +387,23 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
       const int l = e & 31, ca = e >> 5, c = ca / kf;
       const SubTab& st = sub[ca];
       const double decay = fb_exp(-((double)(l * kt) * comp[c].t_step) * st.inv_tau);
-      // offsets 32..63: decay(l + 32) = decay(l) decay(31) decay(1), no second exp
+      // offsets 32 m + l: decay(l + 32) = decay(l) decay(31) decay(1), no further exp
       const double d32 = __shfl_sync(kFullMask, decay, 31) * __shfl_sync(kFullMask, decay, 1);
       const double base = (comp[c].amp10 * st.tail_c) * st.sed;
-      R[ca * 64 + l] = base * decay;
-      R[ca * 64 + 32 + l] = base * (decay * d32);
+      double dl = decay;
+#pragma unroll
+      for (int m = 0; m < kSpl; ++m) {
+        R[ca * kVTile + 32 * m + l] = base * dl;
+        dl *= d32;
+      }
     }
     for (int e = tid; e < nck; e += kFastBlock)
-      D[e] = fb_exp(-((double)(64 * kFastWarps * kt) * comp[e / kf].t_step) * sub[e].inv_tau);
+      D[e] = fb_exp(-((double)(kVTile * kFastWarps * kt) * comp[e / kf].t_step) * sub[e].inv_tau);
     __syncthreads();
     double* out = gvals + (size_t)chi * nc * nt;
     // phase A: closed-form regimes tile by tile (uniform cost), rise-region samples queued
     for (int wt = warp, k = 0; wt < wtiles; wt += kFastWarps, ++k) {
-      const int j0 = wt * 64, j = j0 + 2 * lane;
+      const int j0 = wt * kVTile, j = j0 + kSpl * lane;
       // tail base factors B of every (component, sub-frequency) at the first sample of the tile:
       // one exp per lane every 8th tile of the warp, the decay recurrence (over kFastWarps tiles)
       // in between (a factor that overflowed ahead of the burst is recomputed: inf * decay would
@@ -422,18 +429,20 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
       const unsigned bmask = nck <= 32 ? __ballot_sync(kFullMask, b_finite) : 0u;
       __syncwarp();
       for (int c = 0; c < nc; ++c) {
-        bool deferred[2];
-        const double2 v = vals3_component64<KF>(pc, comp[c], chan[c], sub + c * kf,
-                                                R + (size_t)c * kf * 64 + 2 * lane, bw + c * kf, c, bounds[2 * c],
-                                                bounds[2 * c + 1], j0, lane, nt,
-                                                nck <= 32 && ((bmask >> (c * kf)) & kf_mask) == kf_mask,
-                                                queue, qcount, deferred);
+        bool deferred[kSpl];
+        double v[kSpl];
+        vals3_component_tile<KF>(pc, comp[c], chan[c], sub + c * kf, R + (size_t)c * kf * kVTile + kSpl * lane,
+                                 bw + c * kf, c, bounds[2 * c], bounds[2 * c + 1], j0, lane, nt,
+                                 nck <= 32 && ((bmask >> (c * kf)) & kf_mask) == kf_mask, queue, qcount, v, deferred);
         double* dst = out + (size_t)c * nt + j;
-        if (pair_store && j + 1 < nt && !deferred[0] && !deferred[1]) {
-          *reinterpret_cast<double2*>(dst) = v;
-        } else {
-          if (j < nt && !deferred[0]) dst[0] = v.x;
-          if (j + 1 < nt && !deferred[1]) dst[1] = v.y;
+#pragma unroll
+        for (int h = 0; h < kSpl / 2; ++h) {
+          if (pair_store && j + 2 * h + 1 < nt && !deferred[2 * h] && !deferred[2 * h + 1]) {
+            *reinterpret_cast<double2*>(dst + 2 * h) = make_double2(v[2 * h], v[2 * h + 1]);
+          } else {
+            if (j + 2 * h < nt && !deferred[2 * h]) dst[2 * h] = v[2 * h];
+            if (j + 2 * h + 1 < nt && !deferred[2 * h + 1]) dst[2 * h + 1] = v[2 * h + 1];
+          }
         }
       }
       __syncwarp();
