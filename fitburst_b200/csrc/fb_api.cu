@@ -62,6 +62,7 @@ struct fb_plan_s {
   bool last_eval_split = false;
   int vals_layout = 2;       // 2: k_vals planes (spectrum, timediff) per tile; 3: k_vals3 rows (spectrum only)
   double* d_racc = nullptr;  // k_gram3 accumulators summed over blocks
+  double* d_slices = nullptr;  // k_gram3_finish: per-slice sums of every accumulator entry
   double* d_far = nullptr;   // k_gram3 far-tile matrix (upper triangle) summed over blocks
   unsigned* d_counter = nullptr;  // k_gram3_finish: blocks done (self-resetting)
   int occ_cache[64];         // occupancy of the fast kernels by instantiation (0 = not queried yet)
@@ -177,6 +178,7 @@ extern "C" int fb_plan_create(const fb_plan_desc* desc, const double* freqs_host
   chk(cudaMalloc(&p->d_err, sizeof(int)));
   chk(cudaMalloc(&p->d_gram, gsz));
   chk(cudaMalloc(&p->d_racc, sizeof(double) * 64 * 16));
+  chk(cudaMalloc(&p->d_slices, sizeof(double) * kFinishSlices * (64 * 16 + (FB_MAX_FREE + 1) * (FB_MAX_FREE + 2) / 2)));
   chk(cudaMalloc(&p->d_far, sizeof(double) * (FB_MAX_FREE + 1) * (FB_MAX_FREE + 2) / 2));
   chk(cudaMalloc(&p->d_comp, sizeof(CompTab) * FB_MAX_COMPONENTS));
   chk(cudaMalloc(&p->d_sub, sizeof(SubTab) * (size_t)nf * desc->num_components * kf));
@@ -218,6 +220,7 @@ extern "C" int fb_plan_destroy(fb_plan_t p) {
   cudaFree(p->d_comp_list);
   cudaFree(p->d_vals);
   cudaFree(p->d_racc);
+  cudaFree(p->d_slices);
   cudaFree(p->d_far);
   cudaFree(p->d_counter);
   cudaFree(p->d_desc);
@@ -660,8 +663,8 @@ static int launch_fast_gram(fb_plan_s* p, EvalArgs& A, int ncols, double* gram_d
   X.factor[ncols - 1] = 1.0;
   X.shift[ncols - 1] = 0.0;
   const int far_entries = F.enabled ? nent : 0;
-  k_gram3_finish<<<(entries + far_entries + 7) / 8, 256, 0, st>>>(p->d_partials, grid, kFastWarps, entries, far_entries,
-                                                                 p->d_racc, p->d_far, X, p->d_counter, gram_dev);
+  k_gram3_finish<<<dim3(gram3_finish_groups(entries, far_entries), kFinishSlices), 256, 0, st>>>(
+      p->d_partials, grid, kFastWarps, entries, far_entries, p->d_slices, p->d_racc, p->d_far, X, p->d_counter, gram_dev);
   CUDA_TRY(cudaGetLastError());
   p->launches += 1;
   return FB_OK;
