@@ -74,15 +74,15 @@ def regime_census(freqs, times, params, good, kf, kt, dm_const=4149.377593360996
 
 def ncu_profile_summary():
     """Per-kernel figures of the committed `ncu --set full` capture of this same command
-    (profiles/r1_fast_ncu_full_summary.csv): DRAM bytes per launch and pipe utilisation."""
+    (profiles/r1_end_ncu_full_summary.csv): DRAM bytes per launch and pipe utilisation."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r1_fast_ncu_full_summary.csv")
+    path = os.path.join(ROOT, "profiles", "r1_end_ncu_full_summary.csv")
     if not os.path.exists(path):
         return {}
     rows = list(csv.reader(open(path)))
     head = rows[0]
     col = {name: head.index(name) for name in head}
-    kernels, total = {}, 0.0
+    kernels = {}
     for row in rows[2:]:
         name = row[col["Kernel Name"]].split("(")[0].replace("void ", "")
         dram = (float(row[col["dram__bytes_read.sum"]]) + float(row[col["dram__bytes_write.sum"]])) * 1e6
@@ -94,9 +94,10 @@ def ncu_profile_summary():
             "dmma_pipe_pct": float(row[col["sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active"]]),
             "registers": int(row[col["launch__registers_per_thread"]]),
         }
-        total += dram
+    total = sum(k["dram_bytes_per_launch"] for k in kernels.values())  # one launch of each kernel of an evaluation
     return {"kernels": kernels, "dram_bytes_per_evaluation": total,
-            "source": "profiles/r1_fast_ncu_full_summary.csv (ncu --set full --clock-control none, one launch each)"}
+            "source": "profiles/r1_end_ncu_full_summary.csv (ncu --set full --clock-control none; the last captured "
+                      "launch of each kernel)"}
 
 
 def parse_args():
