@@ -425,7 +425,11 @@ def run_cuda(args):
         stall of several hundred ms in one batch; every repeat is listed in the output line)."""
         import gc
         run_batch(source, max(warmup, 2 * workers))
+        # a full cyclic-GC pass over the ~1e6 objects torch / scipy / numpy leave on the heap takes
+        # 0.1-0.6 s with the GIL held and stalls every fit in flight: collect now, then move the
+        # survivors out of the collector's sight (what long-running services do after start-up)
         gc.collect()
+        gc.freeze()
         times_ms = []
         for _ in range(max(1, args.repeats)):
             barrier()
