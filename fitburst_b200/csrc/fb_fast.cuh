@@ -565,9 +565,15 @@ __host__ __device__ constexpr int g3_acc_offset(int nb, int bi, int bj) {
 }
 __host__ __device__ constexpr int g3_nacc(int nb) { return g3_acc_offset(nb, nb, nb); }
 
-// Near range of one (channel, component): samples whose arg_exp (first_derivatives) is >= -746.
+// Near range of one (channel, component): samples whose arg_exp (first_derivatives) is >= -kNearCut,
+// i.e. where the Gaussian factor G = g0 exp(arg_exp) of the derivatives is kept. The reference's
+// own cut is the exp underflow (arg_exp < -746, |T| > 38.6 w: G exactly zero); outside
+// |T| <= 10 w the factor is below e^-50 = 2e-22 of its peak, twelve orders of magnitude under
+// the 1e-10 contract, and treating it as zero there makes three quarters of the former near
+// samples far ones (a basis-block tile in k_gram3, three moments in k_hess3).
 // arg_exp is a concave quadratic of the time difference, so the set is an interval; the guess
 // from its roots is fixed up with the exact predicate.
+constexpr double kNearCut = 50.0;
 __device__ inline void near_range(const PlanConst& pc, const CompTab& ct, const ChanTab& ch, int& j_lo,
                                         int& j_hi) {
   const int nt = pc.num_time;
@@ -582,10 +588,10 @@ __device__ inline void near_range(const PlanConst& pc, const CompTab& ct, const 
     const double arg_erf = (td - ct.w * ct.w * ch.inv_tau) * ct.inv_w * kSqrtHalf;
     const double ws = ct.w * ch.inv_tau;
     const double arg_exp = 0.5 * ws * ws - td * ch.inv_tau - arg_erf * arg_erf;
-    return arg_exp < -746.0;
+    return arg_exp < -kNearCut;
   };
-  // arg_exp = -td^2 / (2 w^2): near where |td| <= w sqrt(2 * 746)
-  const double half = ct.w * sqrt(2.0 * 746.0);
+  // arg_exp = -td^2 / (2 w^2): near where |td| <= w sqrt(2 kNearCut)
+  const double half = ct.w * sqrt(2.0 * kNearCut);
   const double span = ct.t_step * (double)pc.kt;
   const double t0 = fma(ct.t_step, kt_mid, ct.t_start) - ch.mean_delay;  // td of sample 0
   double g = floor((-half - t0) / span);
