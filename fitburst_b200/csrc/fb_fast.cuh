@@ -749,19 +749,30 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
   // tiles of this warp within a channel: wt = warp + k * kFastWarps, k < nk
   const int nk = wtiles > warp ? (wtiles - warp + kFastWarps - 1) / kFastWarps : 0;
   unsigned q_issue = 0, q_use = 0;  // ring positions (one cp.async group per issued tile, even if empty)
-  auto issue_tile = [&](int chi_t, int i_t, int k) {
-    const int j = (warp + k * kFastWarps) * 32 + lane;
-    if (i_t >= 0 && k < nk && j < nt) {
-      double* dst = pref + (size_t)(q_issue % kG3Ring) * (NC + 1) * 32;
-      const double* srow_t = gvals + (size_t)chi_t * NC * nt;
+  // The prefetch runs kG3Depth tiles ahead of the consumer along the warp's own sequence of
+  // (channel, tile) pairs -- across as many channel boundaries as that takes (a window of 256
+  // samples has two tiles per warp and channel: three tiles ahead is the channel after the next).
+  int is_chi = blockIdx.x, is_i = i_cur, is_k = 0;  // issue cursor
+  auto issue_next = [&]() {
+    if (is_i >= 0 && nk > 0) {
+      const int j = (warp + is_k * kFastWarps) * 32 + lane;
+      if (j < nt) {
+        double* dst = pref + (size_t)(q_issue % kG3Ring) * (NC + 1) * 32;
+        const double* srow_t = gvals + (size_t)is_chi * NC * nt;
 #pragma unroll
-      for (int c = 0; c < NC; ++c) cp_async8(dst + c * 32, srow_t + (size_t)c * nt + j);
-      cp_async8(dst + NC * 32, A.data + (size_t)i_t * nt + j);
+        for (int c = 0; c < NC; ++c) cp_async8(dst + c * 32, srow_t + (size_t)c * nt + j);
+        cp_async8(dst + NC * 32, A.data + (size_t)is_i * nt + j);
+      }
+      if (++is_k >= nk) {
+        is_k = 0;
+        is_chi += gridDim.x;
+        is_i = channel_of(is_chi);
+      }
     }
     cp_async_commit();
     ++q_issue;
   };
-  for (int k = 0; k < kG3Depth; ++k) issue_tile(blockIdx.x, i_cur, k);
+  for (int k = 0; k < kG3Depth; ++k) issue_next();
   bool have_prev = false;  // a previous channel of this block left far-tile blocks to contract
   auto far_accumulate = [&](const double* Tm) {
 #pragma unroll
@@ -785,7 +796,6 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
     else cp_async_wait<0>();
     __syncthreads();
     prefetch_tables(i_next, buf ^ 1);
-    const int i_ahead = i_next, chi_ahead = chi + gridDim.x;  // where the look-ahead continues
     i_cur = i_next;
     i_next = i_after;
     w_cur = w_next;
@@ -875,9 +885,7 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
       const int wt = warp + k * kFastWarps;
       const int j0 = wt * 32, j = j0 + lane;
       const bool valid = j < nt;
-      // look-ahead: tile k + depth of this channel, or the first tiles of the block's next channel
-      if (k + kG3Depth < nk) issue_tile(chi, i, k + kG3Depth);
-      else issue_tile(chi_ahead, i_ahead, k + kG3Depth - nk);
+      issue_next();  // the tile kG3Depth positions ahead of this one
       cp_async_wait<kG3Depth>();
       double m[NC], dval = 0.0;
       {

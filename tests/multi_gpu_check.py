@@ -60,10 +60,12 @@ def main():
     sharded = fbd.ChannelShardedFitter(local_fitter, num_freq_total=num_freq)
     res = sharded.fit()
     full_model.update_parameters(start)
-    with quiet:
+    log = io.StringIO()
+    with contextlib.redirect_stdout(log):
         single = LSFitter(data, full_model, good)
         single.fix_parameter(fixed)
         single.fit()
+    assert getattr(single, "results", None) is not None, "single-GPU fit failed:\n" + log.getvalue()
     assert res["status"] == single.results.status, (res["status"], single.results.status)
     assert res["nfev"] == single.results.nfev
     np.testing.assert_allclose(res["x"], single.results.x, rtol=1e-9)

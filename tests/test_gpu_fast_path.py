@@ -85,6 +85,10 @@ GRAM_CASES = {
     "incoherent_dm": (dict(dm_inc=30.0, dm=0.05, kf=4, kt=2), ["dm_index", "scattering_index"]),
     "only_shapes_free": (dict(), ["amplitude", "spectral_index", "spectral_running", "dm_index", "scattering_index"]),
     "wide_bursts_no_far_tiles": (dict(num_time=512, widths=[6e-3, 8e-3, 5e-3]), ["dm_index", "scattering_index"]),
+    # short windows with more channels than blocks: the prefetch ring of k_gram3 runs ahead across
+    # several channel boundaries (two / one tiles per warp and channel)
+    "short_window_many_channels": (dict(num_freq=2048, num_time=256, kf=2, kt=2), ["dm_index", "scattering_index"]),
+    "tutorial_window_many_channels": (dict(num_freq=1500, num_time=162, kf=1, kt=1), ["dm_index", "scattering_index"]),
 }
 
 
