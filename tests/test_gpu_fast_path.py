@@ -109,6 +109,27 @@ def test_normal_equations_fast_vs_oracle_and_general(name, native_lib):
     assert np.array_equal(fast, fast.T)
 
 
+@pytest.mark.parametrize("num_time,kf,kt", [(33, 2, 2), (64, 1, 1), (97, 2, 2), (130, 4, 2), (200, 1, 2), (320, 2, 1),
+                                            (450, 2, 2)])
+def test_window_lengths_with_several_channels_per_block(num_time, kf, kt, native_lib):
+    """More good channels than blocks at window lengths around every tile-count boundary of the
+    fast kernels (64-sample tiles in k_vals3, 32-sample tiles and a three-tile prefetch ring in
+    k_gram3, eight-tile rounds in k_hess3): normal equations and Hessian equal the general
+    kernels'."""
+    fc, _ = _fitters(dict(num_freq=1300, num_time=num_time, kf=kf, kt=kt), ["dm_index", "scattering_index"])
+    fast = _gram(fc, native_lib)
+    with contextlib.redirect_stdout(io.StringIO()):
+        h_fast, _ = fc.compute_hessian(fc.data, fc.fit_parameters)
+        with general_kernels():
+            general = _gram(fc, native_lib)
+            h_general, _ = fc.compute_hessian(fc.data, fc.fit_parameters)
+    assert np.all(np.isfinite(fast)) and np.all(np.isfinite(h_fast))
+    scale = np.sqrt(np.outer(np.diag(general), np.diag(general)))
+    assert np.max(np.abs(fast - general) / scale) < 1e-11
+    hs = np.sqrt(np.outer(np.abs(np.diag(h_general)), np.abs(np.diag(h_general))))
+    assert np.all(np.abs(h_fast - h_general) <= 1e-9 * hs + 1e-12 * np.abs(h_general))
+
+
 @pytest.mark.parametrize("case,fixed", [
     (dict(num_freq=8), ["dm_index", "scattering_index"]),
     (dict(num_freq=6, num_comp=2, kf=2, kt=2), ["dm_index"]),
