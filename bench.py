@@ -483,6 +483,11 @@ def run_cuda(args):
     nfev = int(res.nfev)
     n_free = len(res.x)
     h2d = int(host_data[0].nbytes + args.nfreq)  # spectrum + flag mask
+    if os.environ.get("FITBURST_B200_ROW_UPLOAD", "0") == "1":
+        # opt-in fb_upload_rows: only the usable channels cross the host link (rows of the good
+        # channels + their int32 index list + the flag mask for the weights)
+        num_good_0 = int(np.sum(bursts[0][2]))
+        h2d = int(num_good_0 * args.ntime * 8 + 4 * num_good_0 + args.nfreq)
     d2h = int(8 * ((n_free + 1) ** 2 * nfev + n_free * n_free + args.nfreq + 10 * args.ncomp))
 
     # ---- dominant kernel alone: fused model + Jacobian + normal equations --------------------

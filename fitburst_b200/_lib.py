@@ -116,6 +116,7 @@ SIGNATURES = {
     "fb_pre_downsample_2d": (ctypes.c_int, [_P, _I32, _I32, _I32, _I32, _P, _P]),
     "fb_pre_window": (ctypes.c_int, [_P, _I32, _I32, _P, _I32, _P, _P]),
     "fb_pre_time_series": (ctypes.c_int, [_P, _I32, _I32, _P, _P, _P]),
+    "fb_upload_rows": (ctypes.c_int, [_P, _I32, _P, _I32, _I32, _I32, _P, _P]),
     "fb_measure_fp64_peak": (ctypes.c_int, [_D, _P]),
     "fb_launch_count": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int64), _I32]),
 }

@@ -8,6 +8,7 @@ Batched workloads of the hot path on one GPU (through the C ABI):
 Multi-GPU sharding of both lives in fitburst_b200.distributed.
 """
 import ctypes
+import os
 import time
 
 import numpy as np
@@ -109,9 +110,24 @@ def _host_tensor(data):
     return torch.from_numpy(np.ascontiguousarray(array))
 
 
-def _upload(buffer, source, staging):
+def _upload(buffer, source, staging, good_freq=None):
     """buffer (float64, device) <- source (host, float32 or float64) on the current stream.
-    Returns the float32 staging buffer (created on first use) so that the caller can keep it."""
+    Returns the float32 staging buffer (created on first use) so that the caller can keep it.
+
+    FITBURST_B200_ROW_UPLOAD=1 (opt-in): page-locked sources go through fb_upload_rows -- only the
+    rows of the usable channels cross the host link (flagged channels have weight 0 and are never
+    read by the fit; their rows of `buffer` keep whatever an earlier burst left there, the buffers
+    start zeroed), read by a kernel straight from the pinned array, float32 widened on the way.
+    Meant for hosts whose link is the bound (eight GPUs uploading at once); on one GPU the copy
+    engine is faster than the kernel (297 vs 220 fits/s end to end), hence off by default."""
+    if good_freq is not None and os.environ.get("FITBURST_B200_ROW_UPLOAD", "0") == "1" and source.is_pinned():
+        rows = np.flatnonzero(np.asarray(good_freq, dtype=bool)).astype(np.int32)
+        rows_dev = torch.from_numpy(rows).to(buffer.device, non_blocking=True)
+        with torch.cuda.device(buffer.device):
+            _lib.check(_lib.load_library().fb_upload_rows(
+                source.data_ptr(), source.element_size(), rows_dev.data_ptr(), len(rows), buffer.shape[0],
+                buffer.shape[1], buffer.data_ptr(), torch.cuda.current_stream(buffer.device).cuda_stream))
+        return staging
     if source.dtype == torch.float64:
         buffer.copy_(source, non_blocking=True)
         return staging
@@ -164,7 +180,7 @@ def fit_stream(model, bursts, fixed_parameters, weighted_fit=True, weight_range=
     shape = (model.num_freq, model.num_time)
     main = torch.cuda.current_stream(device)
     copier = torch.cuda.Stream(device=device)
-    buffers = [torch.empty(shape, dtype=torch.float64, device=device) for _ in range(2)]
+    buffers = [torch.zeros(shape, dtype=torch.float64, device=device) for _ in range(2)]
     ready = [torch.cuda.Event() for _ in range(2)]
     free = [torch.cuda.Event() for _ in range(2)]
     staging = [None]  # float32 staging buffer, only for float32 input (uploads are serial on `copier`)
@@ -177,7 +193,7 @@ def fit_stream(model, bursts, fixed_parameters, weighted_fit=True, weight_range=
         source = _host_tensor(data)
         with torch.cuda.stream(copier):
             copier.wait_event(free[slot])  # the fit that used this buffer two bursts ago is done
-            staging[0] = _upload(buffers[slot], source, staging[0])
+            staging[0] = _upload(buffers[slot], source, staging[0], item[1])
             ready[slot].record(copier)
         return buffers[slot], ready[slot]
 
@@ -255,9 +271,9 @@ def _fit_stream_concurrent(model, bursts, fixed_parameters, weighted_fit, weight
                     else:
                         source = _host_tensor(data)
                         if buffer is None:
-                            buffer = slot["buffer"] = torch.empty(shape, dtype=torch.float64, device=device)
+                            buffer = slot["buffer"] = torch.zeros(shape, dtype=torch.float64, device=device)
                         # ordered after this worker's previous fit (same stream)
-                        slot["staging"] = _upload(buffer, source, slot.get("staging"))
+                        slot["staging"] = _upload(buffer, source, slot.get("staging"), good_freq)
                         data_dev = buffer
                     clone.update_parameters(start)
                     t_start = time.perf_counter()

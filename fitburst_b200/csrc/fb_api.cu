@@ -1119,6 +1119,35 @@ extern "C" int fb_pre_time_series(const double* in_dev, int32_t nf, int32_t nt, 
   return FB_OK;
 }
 
+extern "C" int fb_upload_rows(const void* host_pinned, int32_t elem_size, const int32_t* rows_dev, int32_t num_rows,
+                              int32_t nf, int32_t nt, double* dst_dev, void* stream) {
+  if (!host_pinned || !dst_dev || (num_rows > 0 && !rows_dev)) return fail(FB_ERR_INVALID, "null argument");
+  if (elem_size != 4 && elem_size != 8) return fail(FB_ERR_INVALID, "element size must be 4 (float32) or 8 (float64)");
+  if (nf < 1 || nt < 1 || num_rows < 0 || num_rows > nf) return fail(FB_ERR_INVALID, "bad shape");
+  if (num_rows == 0) return FB_OK;
+  cudaPointerAttributes attr;
+  CUDA_TRY(cudaPointerGetAttributes(&attr, host_pinned));
+  if (attr.type != cudaMemoryTypeHost || !attr.devicePointer)
+    return fail(FB_ERR_INVALID, "fb_upload_rows needs page-locked host memory");
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // a modest grid: the copy is bound by the host link, and the SMs are shared with the fits of
+  // the other streams
+  const int grid = std::min(num_rows, 2 * sm_count);
+  if (elem_size == 8)
+    k_upload_rows<double><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const double*>(attr.devicePointer),
+                                                                  rows_dev, num_rows, nt, dst_dev);
+  else
+    k_upload_rows<float><<<grid, 256, 0, (cudaStream_t)stream>>>(static_cast<const float*>(attr.devicePointer),
+                                                                 rows_dev, num_rows, nt, dst_dev);
+  CUDA_TRY(cudaGetLastError());
+  return FB_OK;
+}
+
 extern "C" int fb_launch_count(fb_plan_t p, int64_t* count_out, int32_t reset) {
   if (!p || !count_out) return fail(FB_ERR_INVALID, "null argument");
   *count_out = p->launches;

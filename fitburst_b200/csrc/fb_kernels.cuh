@@ -1037,6 +1037,13 @@ __global__ void __launch_bounds__(kBlock) k_weights(const double* __restrict__ d
                                                    double* __restrict__ chan_sumsq) {
   __shared__ double red[2][kBlock];
   const int i = blockIdx.x, tid = threadIdx.x;
+  if (!good[i]) {  // weight 0 whatever the row holds (it may not even have been uploaded: fb_upload_rows)
+    if (tid == 0) {
+      weights[i] = 0.0;
+      chan_sumsq[i] = 0.0;
+    }
+    return;
+  }
   const double* rowp = data + (size_t)i * num_time;
   double s_range = 0.0, s_all = 0.0;
   for (int j = tid; j < num_time; j += kBlock) {

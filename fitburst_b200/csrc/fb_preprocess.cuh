@@ -164,4 +164,43 @@ __global__ void __launch_bounds__(kPreBlock) k_pre_colmean_final(const double* _
   out[j] = s / (double)nf;
 }
 
+
+// ---- upload of the usable channels of a host spectrum -----------------------------------------
+// Copies the rows listed in rows_dev from a PAGE-LOCKED host array (read directly over PCIe:
+// pinned memory is device-accessible under unified addressing) into the device spectrum and
+// widens float32 input on the way. Flagged channels (analysis/fitter.py:506-542: weight 0) are
+// never read by the fit, so their rows are not transferred: at 35 % flagged channels a third of
+// the host-to-device traffic, which is what bounds the end-to-end rate of eight GPUs on one host.
+template <typename T>
+__global__ void __launch_bounds__(256) k_upload_rows(const T* __restrict__ host, const int* __restrict__ rows_dev,
+                                                     int num_rows, int nt, double* __restrict__ dst) {
+  for (int r = blockIdx.x; r < num_rows; r += gridDim.x) {
+    const int i = rows_dev[r];
+    const T* src = host + (size_t)i * nt;
+    double* out = dst + (size_t)i * nt;
+    if (sizeof(T) == 8) {
+      const bool vec = (nt % 2 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+      if (vec) {
+        const double2* s2 = reinterpret_cast<const double2*>(src);
+        double2* o2 = reinterpret_cast<double2*>(out);
+        for (int j = threadIdx.x; j < nt / 2; j += blockDim.x) o2[j] = s2[j];
+      } else {
+        for (int j = threadIdx.x; j < nt; j += blockDim.x) out[j] = (double)src[j];
+      }
+    } else {
+      const bool vec = (nt % 4 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+      if (vec) {
+        const float4* s4 = reinterpret_cast<const float4*>(src);
+        for (int j = threadIdx.x; j < nt / 4; j += blockDim.x) {
+          const float4 v = s4[j];
+          reinterpret_cast<double2*>(out)[2 * j] = make_double2((double)v.x, (double)v.y);
+          reinterpret_cast<double2*>(out)[2 * j + 1] = make_double2((double)v.z, (double)v.w);
+        }
+      } else {
+        for (int j = threadIdx.x; j < nt; j += blockDim.x) out[j] = (double)src[j];
+      }
+    }
+  }
+}
+
 }  // namespace fb

@@ -249,6 +249,14 @@ int fb_pre_window(const double* in_dev, int32_t num_freq, int32_t num_time, cons
 int fb_pre_time_series(const double* in_dev, int32_t num_freq, int32_t num_time, double* scratch_dev,
                        double* out_dev, void* stream);
 
+/* Host-to-device transfer of the usable channels only: copies rows rows_dev[0..num_rows) of a
+ * PAGE-LOCKED host spectrum (num_freq x num_time, float32 or float64: elem_size 4 / 8) into the
+ * float64 device spectrum dst_dev, reading the host memory directly over PCIe. Channels with
+ * good_freq == False get weight 0 (LSFitter._set_weights, analysis/fitter.py:506-542) and are
+ * never read by the fit, so their rows are left as they are on the device. */
+int fb_upload_rows(const void* host_pinned, int32_t elem_size, const int32_t* rows_dev, int32_t num_rows,
+                   int32_t num_freq, int32_t num_time, double* dst_dev, void* stream);
+
 /* Measured FP64 FMA peak of the device (dependent-free DFMA chains on every SM), TFLOP/s.
  * MEASURED_PEAKS.json carries no FP64 figure; bench.py reports this one as the roofline peak. */
 int fb_measure_fp64_peak(double* tflops_out, void* stream);

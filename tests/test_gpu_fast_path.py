@@ -229,6 +229,20 @@ def test_fit_stream_concurrent_workers_identical(native_lib):
         want = list(fit_stream(cuda, widened, fixed, workers=workers))
         for a, b in zip(got, want):
             np.testing.assert_array_equal(a["results"].x, b["results"].x)
+    # page-locked spectra: plain copy, and the opt-in fb_upload_rows path (only the usable
+    # channels cross the host link)
+    from fitburst_b200.batch import pinned_like
+    pinned = [(pinned_like(d), g, st) for d, g, st in bursts]
+    for row_upload in ("0", "1"):
+        os.environ["FITBURST_B200_ROW_UPLOAD"] = row_upload
+        try:
+            for workers in (1, 3):
+                for a, b in zip(serial, fit_stream(cuda, pinned, fixed, workers=workers)):
+                    assert a["results"].nfev == b["results"].nfev
+                    np.testing.assert_array_equal(a["results"].x, b["results"].x)
+                    assert a["fit_statistics"] == b["fit_statistics"]
+        finally:
+            del os.environ["FITBURST_B200_ROW_UPLOAD"]
     # device-resident inputs and an early stop of the consumer
     import torch
     resident = [(torch.from_numpy(d).cuda(), g, s) for d, g, s in bursts]
@@ -315,3 +329,25 @@ def test_normal_equations_queue_overflow(native_lib):
     tame = ~wild[:, None] & ~wild[None, :]
     assert np.max(err[tame]) < 1e-10
     assert np.max(err) < 1e-2
+
+
+@pytest.mark.parametrize("dtype,num_time", [(np.float64, 256), (np.float64, 131), (np.float32, 256), (np.float32, 130)])
+def test_upload_rows_copies_exactly_the_listed_channels(dtype, num_time, native_lib):
+    import torch
+    from fitburst_b200 import _lib
+    rng = np.random.default_rng(11)
+    num_freq = 300
+    host = torch.from_numpy(rng.normal(size=(num_freq, num_time)).astype(dtype)).pin_memory()
+    good = rng.uniform(size=num_freq) > 0.4
+    rows = torch.from_numpy(np.flatnonzero(good).astype(np.int32)).cuda()
+    dst = torch.full((num_freq, num_time), -7.0, dtype=torch.float64, device="cuda")
+    _lib.check(native_lib.fb_upload_rows(host.data_ptr(), host.element_size(), rows.data_ptr(), int(good.sum()),
+                                         num_freq, num_time, dst.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    got = dst.cpu().numpy()
+    np.testing.assert_array_equal(got[good], host.numpy()[good].astype(np.float64))
+    assert np.all(got[~good] == -7.0)
+    # pageable memory is refused, not copied through a fallback
+    pageable = np.zeros((num_freq, num_time), dtype=dtype)
+    rc = native_lib.fb_upload_rows(pageable.ctypes.data, pageable.itemsize, rows.data_ptr(), int(good.sum()), num_freq,
+                                   num_time, dst.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc != 0
