@@ -103,7 +103,8 @@ def _host_tensor(data):
     """Host spectrum as a torch tensor WITHOUT a host-side dtype conversion for float32 input
     (telescope data usually are float32: half the upload, widened exactly on the device)."""
     if isinstance(data, torch.Tensor):
-        return data if data.dtype in (torch.float32, torch.float64) else data.to(torch.float64)
+        data = data if data.dtype in (torch.float32, torch.float64) else data.to(torch.float64)
+        return data.contiguous()
     array = np.asarray(data)
     if array.dtype not in (np.float32, np.float64):
         array = array.astype(np.float64)
