@@ -117,6 +117,11 @@ SIGNATURES = {
     "fb_pre_window": (ctypes.c_int, [_P, _I32, _I32, _P, _I32, _P, _P]),
     "fb_pre_time_series": (ctypes.c_int, [_P, _I32, _I32, _P, _P, _P]),
     "fb_upload_rows": (ctypes.c_int, [_P, _I32, _P, _I32, _I32, _I32, _P, _P]),
+    "fb_spectrum_rpl": (ctypes.c_int, [_P, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double, _P, _P]),
+    "fb_ism_times": (ctypes.c_int, [_I32, _P, ctypes.c_int64, ctypes.c_double, ctypes.c_double, ctypes.c_double,
+                                    ctypes.c_double, _P, _P]),
+    "fb_amplitude_per_channel": (ctypes.c_int, [_P, _P, _I32, _I32, _P, _P]),
+    "fb_widen_f32": (ctypes.c_int, [_P, ctypes.c_int64, _P, _P]),
     "fb_measure_fp64_peak": (ctypes.c_int, [_D, _P]),
     "fb_launch_count": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int64), _I32]),
 }

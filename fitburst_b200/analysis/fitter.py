@@ -8,9 +8,7 @@ J^T r and J^T J without ever materialising the Jacobian; the exact Hessian and t
 uncertainties come from a second fused pass. Same attributes, methods, print-outs, error
 convention ("fit() never raises") and fit_statistics keys as the reference.
 """
-import contextlib
 import ctypes
-import threading
 import traceback
 import weakref
 
@@ -20,25 +18,7 @@ from scipy.optimize import OptimizeResult, least_squares
 
 from .. import _lib
 
-_thread_state = threading.local()
-
-
-@contextlib.contextmanager
-def quiet():
-    """Silences the reference's progress print-outs of LSFitter for the calling THREAD only
-    (contextlib.redirect_stdout swaps sys.stdout for the whole process, which concurrent fits on
-    several threads must not do)."""
-    previous = getattr(_thread_state, "quiet", False)
-    _thread_state.quiet = True
-    try:
-        yield
-    finally:
-        _thread_state.quiet = previous
-
-
-def _say(*args, **kwargs):
-    if not getattr(_thread_state, "quiet", False):
-        print(*args, **kwargs)
+from .._say import quiet, say as _say  # thread-local silencing, see fitburst_b200/_say.py
 
 
 _TERMINATION_MESSAGES = {  # scipy/optimize/_lsq/least_squares.py TERMINATION_MESSAGES
@@ -106,6 +86,7 @@ class LSFitter:
 
         self._data_dev = None
         self._weights_loaded = None
+        self._weights_token = object()  # identifies this fitter's weights on the model's plan
         self._chisq_initial = None
         self._set_weights()
 
@@ -122,15 +103,24 @@ class LSFitter:
         return self._data_dev
 
     def _sync_weights(self):
-        """Pushes self.weights to the plan when user code replaced the array."""
+        """Pushes self.weights to the plan when they are not the ones it holds: user code replaced
+        the array, the plan was rebuilt, or ANOTHER fitter on the same model loaded its own since
+        (the weights and the good-channel list live on the model's plan; in the reference every
+        fitter owns its weights, analysis/fitter.py:506-542, so two live fitters on one model
+        must not see each other's)."""
         plan = self.model._ensure_plan()
         weights = np.ascontiguousarray(self.weights, dtype=np.float64)
-        if self._weights_loaded is None or self._weights_plan is not plan or \
-                not np.array_equal(weights, self._weights_loaded, equal_nan=True):
+        changed = self._weights_loaded is None or \
+            not np.array_equal(weights, self._weights_loaded, equal_nan=True)
+        if changed and self._weights_loaded is not None:
+            self._chisq_initial = None  # stale: recomputed from the current weights when needed
+        if changed or self._weights_plan is not plan or \
+                self.model.__dict__.get("_weights_owner") is not self._weights_token:
             with torch.cuda.device(self.model._device):
                 _lib.check(self._lib().fb_load_weights(plan, _lib.dptr(weights), self._stream()))
             self._weights_loaded = weights.copy()
             self._weights_plan = plan
+            self.model.__dict__["_weights_owner"] = self._weights_token
         return plan
 
     def _sync_free_parameters(self, plan):
@@ -252,7 +242,8 @@ class LSFitter:
         # the reference leaves the model at the LAST EVALUATED point (analysis/fitter.py:258);
         # mirror that on the python side from the plan's parameter block.
         packed = np.zeros((_lib.FB_NUM_PARAMETERS, int(self.model.num_components)), dtype=np.float64)
-        _lib.check(self._lib().fb_get_parameters(plan, _lib.dptr(packed), self._stream()))
+        with torch.cuda.device(self.model._device):
+            _lib.check(self._lib().fb_get_parameters(plan, _lib.dptr(packed), self._stream()))
         last_x = []
         for name in self.model.parameters:
             if name in self.fit_parameters:
@@ -423,4 +414,5 @@ class LSFitter:
         self.weights = weights
         self._weights_loaded = weights.copy()
         self._weights_plan = plan
+        self.model.__dict__["_weights_owner"] = self._weights_token
         self._chisq_initial = chisq_initial.value

@@ -147,6 +147,10 @@ class SpectrumModeler:
             return None
         if isinstance(array, torch.Tensor):
             return array.to(device=self._device, dtype=torch.float64).contiguous()
+        if isinstance(array, np.ndarray) and array.dtype == np.float32 and array.ndim == 2:
+            # float32 spectra cross the host link as float32 and are widened exactly on the device
+            from ..utilities.bases import upload_spectrum
+            return upload_spectrum(array, self._device)
         return torch.from_numpy(np.ascontiguousarray(array, dtype=np.float64)).to(self._device)
 
     def compute_model_device(self, data_dev=None, packed=None) -> torch.Tensor:

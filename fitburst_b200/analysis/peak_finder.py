@@ -11,6 +11,7 @@ import torch
 from scipy.signal import find_peaks
 
 from .. import _lib
+from .._say import say
 
 
 class FindPeak:
@@ -48,7 +49,7 @@ class FindPeak:
         self.peak_mean_intensities = self.mean_intensity_freq[peaks_location[0]]
 
         self.rms_intensity = np.sqrt(np.mean((self.mean_intensity_freq) ** 2))
-        print(f"The rms intensity is {self.rms_intensity} \n")
+        say(f"The rms intensity is {self.rms_intensity} \n")
 
         if self.rms is not None:
             shifted_rms_intensity = self.rms * np.max(self.mean_intensity_freq)
@@ -71,9 +72,9 @@ class FindPeak:
             self.burst_widths = above_peak_time - below_peak_time
             self.time_of_arrivals = self.times_peaks_greater_rms * 1000
 
-        print("   Times of Arrivals  Burst_Widths")
+        say("   Times of Arrivals  Burst_Widths")
         for idx, toa in enumerate(np.atleast_1d(self.time_of_arrivals)):
-            print(f"{idx}  {toa}  {self.burst_widths}")
+            say(f"{idx}  {toa}  {self.burst_widths}")
 
     def get_parameters_dict(self, original_dict: dict, update_width=False):
         """

@@ -1,21 +1,88 @@
 """
-DataReader: drop-in mirror of fitburst.backend.generic.DataReader (reference
-backend/generic.py:10-99) on top of the device ReaderBaseClass of this package: the ".npz generic
-format" (docs/usage/formatting_data_generic.md: `data_full`, `metadata`, `burst_parameters`) is
-parsed on the host exactly like the reference does, the spectrum then lives on the GPU for
-preprocess_data / downsample / window_data and is handed to LSFitter without coming back.
+DataReader for the ".npz generic format" (docs/usage/formatting_data_generic.md:32-64; reference
+reader backend/generic.py:10-99) as a page-locked, dtype-preserving loader for the device path.
+
+What a fit needs from a file is the spectrum in HBM. The reference's reader materialises
+`data_full` as a pageable float64 array and a second (num_freq, num_time) float64 array of
+weights; uploading those costs a driver-staged copy of twice the spectrum. Here
+
+ * the `data_full.npy` member of the zip archive is streamed straight into PAGE-LOCKED host
+   memory in its stored dtype (float32 telescope data stay float32: half the bytes over the host
+   link; widened exactly on the device by fb_widen_f32), so the upload is one asynchronous DMA
+   that overlaps the fit of the previous file (pipelines.run_many, batch.fit_stream);
+ * the weights are kept as the per-channel mask they are (the format only records `bad_chans`)
+   and expanded on the device on first use;
+ * `metadata` / `burst_parameters` are validated against one schema table.
+
+The attributes the rest of fitburst reads (data_full, data_weights, freqs, times, num_freq,
+num_time, res_freq, res_time, times_bin0, is_dedispersed, burst_parameters) have the same meaning
+and values as after the reference's load_data().
 """
 import os
+import zipfile
 
 import numpy as np
+import torch
 
 from ..utilities import bases
+
+# key -> (required python types, what it is) of the `metadata` dictionary (format spec :40-58)
+_METADATA_SCHEMA = {
+    "bad_chans": ((list, tuple, np.ndarray), "indices of masked channels"),
+    "freqs_bin0": ((int, float, np.integer, np.floating), "leading-edge frequency of channel 0 [MHz]"),
+    "is_dedispersed": ((bool, np.bool_, int), "whether data_full is already de-dispersed"),
+    "num_freq": ((int, np.integer), "number of channels"),
+    "num_time": ((int, np.integer), "number of time samples"),
+    "times_bin0": ((int, float, np.integer, np.floating), "MJD of sample 0"),
+    "res_freq": ((int, float, np.integer, np.floating), "channel width [MHz]"),
+    "res_time": ((int, float, np.integer, np.floating), "sampling time [s]"),
+}
+_MEMBERS = ("data_full", "metadata", "burst_parameters")
+
+
+def _pinned_empty(shape, dtype):
+    """Host tensor of the given numpy dtype, page-locked when a GPU is there to DMA from it."""
+    tensor = torch.empty(shape, dtype=torch.float32 if dtype == np.float32 else torch.float64)
+    if torch.cuda.is_available():
+        tensor = tensor.pin_memory()
+    return tensor
+
+
+def read_spectrum_pinned(path: str, member: str = "data_full") -> torch.Tensor:
+    """
+    The 2-D array `member` of an .npz archive as a (page-locked) host tensor, float32 or float64.
+    C-ordered float32 / float64 members are read from the (possibly deflated) zip stream directly
+    into the destination buffer -- no intermediate pageable array; anything else (other dtypes,
+    Fortran order) goes through numpy and is converted to float64.
+    """
+    with zipfile.ZipFile(path) as archive:
+        with archive.open(member + ".npy") as stream:
+            version = np.lib.format.read_magic(stream)
+            read_header = np.lib.format.read_array_header_1_0 if version == (1, 0) else np.lib.format.read_array_header_2_0
+            shape, fortran_order, dtype = read_header(stream)
+            direct = len(shape) == 2 and not fortran_order and dtype in (np.dtype("<f4"), np.dtype("<f8"))
+            if direct:
+                tensor = _pinned_empty(shape, dtype.type)
+                view = memoryview(tensor.numpy()).cast("B")
+                filled = 0
+                while filled < len(view):
+                    got = stream.readinto(view[filled:])
+                    if not got:
+                        raise IOError(f"{path}: member {member} is truncated")
+                    filled += got
+                return tensor
+    array = np.load(path, allow_pickle=True)[member]
+    if array.ndim != 2:
+        raise AssertionError(f"{member} must be a two-dimensional (num_freq, num_time) array, got shape {array.shape}")
+    tensor = _pinned_empty(array.shape, np.float64)
+    tensor.numpy()[...] = array
+    return tensor
 
 
 class DataReader(bases.ReaderBaseClass):
     """
-    A child class of I/O and processing for generic data stored in a .npz file, inheriting the
-    basic structure defined in ReaderBaseClass().
+    Reader of generic .npz files on top of the device ReaderBaseClass; same constructor and
+    load_data() contract as fitburst.backend.generic.DataReader.
     """
 
     def __init__(self, fname, device=None):
@@ -23,56 +90,51 @@ class DataReader(bases.ReaderBaseClass):
         self.file_path = fname
         if not os.path.isfile(self.file_path):
             raise IOError(f"Data file not found: {self.file_path}")
+        self.data_pinned = None  # the spectrum as loaded: page-locked, stored dtype (see read_spectrum_pinned)
+
+    def _read_dictionaries(self):
+        with np.load(self.file_path, allow_pickle=True) as archive:
+            missing = [name for name in _MEMBERS if name not in archive.files]
+            if missing:
+                raise AssertionError(
+                    f"Data file does not contain one of more of the following keys: {list(_MEMBERS)}")
+            return archive["metadata"].item(), archive["burst_parameters"].item()
 
     def load_data(self):
         """
-        Loads `data_full`, `metadata` and `burst_parameters` from the .npz file and derives the
-        axis labels and the weights array (backend/generic.py:28-99, same checks and messages).
+        Reads the three members of the file, checks them, and derives the axis labels and the
+        channel mask; afterwards the object is in the state the reference's load_data() leaves
+        (backend/generic.py:28-99), with the spectrum page-locked for the upload.
         """
-        unpacked_data_set = np.load(self.file_path, allow_pickle=True)
+        metadata, burst_parameters = self._read_dictionaries()
+        for key, (types, meaning) in _METADATA_SCHEMA.items():
+            if key not in metadata:
+                raise KeyError(f"metadata entry '{key}' ({meaning}) is missing")
+            if not isinstance(metadata[key], types):
+                raise AssertionError(f"metadata entry '{key}' ({meaning}) has type {type(metadata[key]).__name__}")
+        # one list per parameter, one element per burst component
+        self.burst_parameters = {key: (value if isinstance(value, list) else [value])
+                                 for key, value in burst_parameters.items()}
 
-        expected_subfile_names = ["data_full", "metadata", "burst_parameters"]
-        retrieved_subfile_names = unpacked_data_set.files
-        if not all(f in retrieved_subfile_names for f in expected_subfile_names):
-            raise AssertionError(
-                f"Data file does not contain one of more of the following keys: "
-                f"{expected_subfile_names}"
-            )
+        self.data_pinned = read_spectrum_pinned(self.file_path)
+        shape = tuple(self.data_pinned.shape)
+        for axis, key, what in ((0, "num_freq", "channels"), (1, "num_time", "time samples")):
+            if shape[axis] != metadata[key]:
+                raise AssertionError(
+                    f"Data shape does not match recorded number of {what}({shape[axis]} != {metadata[key]})")
+        self.num_freq, self.num_time = shape
+        self._data_full.set_host(self.data_pinned.numpy())
 
-        metadata = unpacked_data_set["metadata"].item()
-        burst_parameters = unpacked_data_set["burst_parameters"].item()
-        # each parameter has its values in a list (one entry per component), generic.py:53-57
-        for key, value in burst_parameters.items():
-            self.burst_parameters[key] = value if isinstance(value, list) else [value]
+        # the format records masked channels only: usable = 1, masked = 0 for every sample of a row
+        keep = np.ones(self.num_freq, dtype=bool)
+        keep[np.asarray(metadata["bad_chans"], dtype=int)] = False
+        self._data_weights.set_rows(keep, self.num_time)
 
-        self.data_full = unpacked_data_set["data_full"]
-        self.num_freq, self.num_time = self.data_full.shape
-        if self.num_freq != metadata["num_freq"]:
-            raise AssertionError(
-                "Data shape does not match recorded number of channels"
-                f"({self.num_freq} != {metadata['num_freq']})"
-            )
-        if self.num_time != metadata["num_time"]:
-            raise AssertionError(
-                "Data shape does not match recorded number of time samples"
-                f"({self.num_time} != {metadata['num_time']})"
-            )
-
-        # weights: 1 = usable, 0 = masked channel (generic.py:75-78)
-        data_weights = np.ones((self.num_freq, self.num_time), dtype=float)
-        data_weights[metadata["bad_chans"], :] = 0.
-        self.data_weights = data_weights
-
-        # time labels in seconds since the start of the spectrum (generic.py:80-86)
-        self.res_time = metadata["res_time"]
-        self.times = np.arange(self.num_time, dtype=np.float64) * self.res_time
+        self.res_time, self.res_freq = metadata["res_time"], metadata["res_freq"]
         self.times_bin0 = metadata["times_bin0"]
-
-        # channel-centre labels: leading edge + half a channel (generic.py:88-96)
-        self.res_freq = metadata["res_freq"]
-        freqs = np.arange(self.num_freq, dtype=np.float64) * self.res_freq
-        freqs += metadata["freqs_bin0"]
-        freqs += self.res_freq / 2.0
-        self.freqs = freqs
-
+        self.times = np.arange(self.num_time, dtype=np.float64) * self.res_time
+        # channel centres: leading edge of channel 0 + k channel widths + half a channel, summed
+        # in the reference's order (arange * res, then + freqs_bin0, then + res / 2)
+        self.freqs = (np.arange(self.num_freq, dtype=np.float64) * self.res_freq + metadata["freqs_bin0"]) \
+            + self.res_freq / 2.0
         self.is_dedispersed = metadata["is_dedispersed"]

@@ -135,7 +135,9 @@ def _upload(buffer, source, staging, good_freq=None):
     if staging is None:
         staging = torch.empty(buffer.shape, dtype=torch.float32, device=buffer.device)
     staging.copy_(source, non_blocking=True)
-    buffer.copy_(staging)
+    with torch.cuda.device(buffer.device):  # exact widening by the library's own kernel
+        _lib.check(_lib.load_library().fb_widen_f32(staging.data_ptr(), staging.numel(), buffer.data_ptr(),
+                                                    torch.cuda.current_stream(buffer.device).cuda_stream))
     return staging
 
 

@@ -310,11 +310,9 @@ static int launch_eval(fb_plan_s* p, const EvalArgs& A, int ncols_main, cudaStre
   }
   const size_t smem = smem_bytes(p->pc.num_comp, p->pc.kf, ncols_main, p->pc.scintillation != 0);
   if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request %zu B exceeds 227 KB", smem);
-  static thread_local size_t configured[4] = {0, 0, 0, 0};
-  if (smem > 48 * 1024 && smem > configured[MODE]) {
+  // the opt-in is per device: set it on every launch that needs it (a thread may switch devices)
+  if (smem > 48 * 1024)
     CUDA_TRY(cudaFuncSetAttribute(k_eval<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured[MODE] = smem;
-  }
   int occ = 1;
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_eval<MODE>, kBlock, smem));
   if (occ < 1) occ = 1;
@@ -1148,6 +1146,62 @@ extern "C" int fb_upload_rows(const void* host_pinned, int32_t elem_size, const 
   return FB_OK;
 }
 
+// ---- small public routines (routines/spectrum.py, routines/ism.py) ----------------------------------
+static unsigned elementwise_grid(long long count) {
+  return (unsigned)std::max<long long>(1, std::min<long long>((count + 255) / 256, 148LL * 16));
+}
+
+extern "C" int fb_spectrum_rpl(const double* freqs_dev, int64_t count, double freq_ref, double sp_idx, double sp_run,
+                               double* out_dev, void* stream) {
+  if (!freqs_dev || !out_dev) return fail(FB_ERR_INVALID, "null argument");
+  if (count < 1) return fail(FB_ERR_INVALID, "empty array");
+  k_spectrum_rpl<<<elementwise_grid(count), 256, 0, (cudaStream_t)stream>>>(freqs_dev, count, freq_ref, sp_idx, sp_run, out_dev);
+  CUDA_TRY(cudaGetLastError());
+  return FB_OK;
+}
+
+extern "C" int fb_ism_times(int32_t kind, const double* freqs_dev, int64_t count, double a, double b, double c, double d,
+                            double* out_dev, void* stream) {
+  if (!freqs_dev || !out_dev) return fail(FB_ERR_INVALID, "null argument");
+  if (kind < 0 || kind > 2) return fail(FB_ERR_INVALID, "kind must be 0 (dm delay), 1 (dm smear) or 2 (scattering time)");
+  if (count < 1) return fail(FB_ERR_INVALID, "empty array");
+  k_ism_times<<<elementwise_grid(count), 256, 0, (cudaStream_t)stream>>>(kind, freqs_dev, count, a, b, c, d, out_dev);
+  CUDA_TRY(cudaGetLastError());
+  return FB_OK;
+}
+
+extern "C" int fb_amplitude_per_channel(const double* data_dev, const double* model_dev, int32_t num_time, int32_t num_comp,
+                                        double* amplitudes_dev, void* stream) {
+  if (!data_dev || !model_dev || !amplitudes_dev) return fail(FB_ERR_INVALID, "null argument");
+  if (num_time < 1 || num_comp < 1 || num_comp > FB_MAX_COMPONENTS)
+    return fail(FB_ERR_INVALID, "need num_time >= 1 and 1 <= num_components <= %d", FB_MAX_COMPONENTS);
+  cudaStream_t st = (cudaStream_t)stream;
+  int* d_flag = nullptr;
+  CUDA_TRY(cudaMalloc(&d_flag, sizeof(int)));
+  cudaMemsetAsync(d_flag, 0, sizeof(int), st);
+  const size_t smem = sizeof(double) * (256 + (size_t)num_comp * (num_comp + 1));
+  k_amplitude_per_channel<<<1, 256, smem, st>>>(data_dev, model_dev, num_time, num_comp, amplitudes_dev, d_flag);
+  int flag = 0;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_flag);
+  if (e != cudaSuccess) return fail(FB_ERR_CUDA, "fb_amplitude_per_channel: %s", cudaGetErrorString(e));
+  if (flag) return fail(FB_ERR_SINGULAR, "Singular matrix");  // numpy.linalg.LinAlgError text, routines/ism.py:46
+  return FB_OK;
+}
+
+extern "C" int fb_widen_f32(const float* src_dev, int64_t count, double* dst_dev, void* stream) {
+  if (!src_dev || !dst_dev) return fail(FB_ERR_INVALID, "null argument");
+  if (count < 0) return fail(FB_ERR_INVALID, "negative count");
+  if (count == 0) return FB_OK;
+  if ((reinterpret_cast<uintptr_t>(src_dev) & 15) || (reinterpret_cast<uintptr_t>(dst_dev) & 15))
+    return fail(FB_ERR_INVALID, "fb_widen_f32 needs 16-byte aligned buffers");
+  k_widen_f32<<<elementwise_grid((count + 3) / 4), 256, 0, (cudaStream_t)stream>>>(src_dev, count, dst_dev);
+  CUDA_TRY(cudaGetLastError());
+  return FB_OK;
+}
+
 extern "C" int fb_launch_count(fb_plan_t p, int64_t* count_out, int32_t reset) {
   if (!p || !count_out) return fail(FB_ERR_INVALID, "null argument");
   *count_out = p->launches;
@@ -1799,7 +1853,10 @@ extern "C" int fb_fit_batched(fb_plan_t p, int32_t count, const double* data_dev
       int rc = fb_load_weights(p, w.data(), stream);
       if (rc == FB_OK) rc = fb_set_parameters(p, pr.data(), stream);
       if (rc == FB_OK) rc = fb_hessian_impl(p, data_dev + (size_t)b * spec, H.data(), st);
-      if (rc != FB_OK) continue;
+      if (rc != FB_OK) {
+        for (int k = 0; k < n; ++k) results_host[b].uncertainty[k] = NAN;  // never a silent 0.0
+        continue;
+      }
       invert_half_hessian(H, n, results_host[b].uncertainty);
       continue;
     }
@@ -1825,6 +1882,8 @@ extern "C" int fb_fit_batched(fb_plan_t p, int32_t count, const double* data_dev
       if (rc == FB_OK) rc = fb_hessian_impl(p, data_dev + (size_t)b * spec, H.data(), st);
       if (rc == FB_OK) {
         invert_half_hessian(H, n, results_host[b].uncertainty);
+      } else {
+        for (int k = 0; k < n; ++k) results_host[b].uncertainty[k] = NAN;
       }
     }
     CUDA_TRY(cudaStreamSynchronize(st));

@@ -151,6 +151,9 @@ __global__ void __launch_bounds__(32) k_trf_batched(const BatchedTrfArgs T) {
       if (!isfinite(gram[n * ncols + n])) {  // "Residuals are not finite in the initial point."
         S.status = -1;
         S.finished = 1;
+        S.cost = NAN;  // nothing was accepted: no garbage from the cudaMalloc'ed state in the result
+        S.g_norm = 0.0;
+        for (int i = 0; i < n; ++i) S.g[i] = 0.0;
       } else {
         trf_load_accepted(S, gram);
         S.nfev = 1;

@@ -8,6 +8,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "fb_kernels.cuh"  // solve_small
+
 namespace fb {
 
 constexpr int kPreBlock = 256;
@@ -200,6 +202,86 @@ __global__ void __launch_bounds__(256) k_upload_rows(const T* __restrict__ host,
         for (int j = threadIdx.x; j < nt; j += blockDim.x) out[j] = (double)src[j];
       }
     }
+  }
+}
+
+// ---- small public routines of the reference (routines/spectrum.py, routines/ism.py) ---------------
+// Elementwise over an array of frequencies, same expression order as the reference.
+// routines/spectrum.py:39-41: exp(sp_idx * log(f / ref) + sp_run * log(f / ref) ** 2)
+__global__ void __launch_bounds__(256) k_spectrum_rpl(const double* __restrict__ freqs, long long count, double ref,
+                                                      double sp_idx, double sp_run, double* __restrict__ out) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x) {
+    const double lf = log(freqs[e] / ref);
+    out[e] = exp(sp_idx * lf + sp_run * (lf * lf));
+  }
+}
+
+// kind 0: compute_time_dm_delay   a * b * (f ** c - d ** c)          (routines/ism.py:78)
+// kind 1: compute_time_dm_smear   2 * a * b * d * f ** (c - 1)       (routines/ism.py:110)
+// kind 2: compute_time_scattering b * (f / a) ** c                   (routines/ism.py:139)
+__global__ void __launch_bounds__(256) k_ism_times(int kind, const double* __restrict__ freqs, long long count, double a,
+                                                   double b, double c, double d, double* __restrict__ out) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x) {
+    const double f = freqs[e];
+    double v;
+    if (kind == 0) v = a * b * (pow(f, c) - pow(d, c));
+    else if (kind == 1) v = 2.0 * a * b * d * pow(f, c - 1.0);
+    else v = b * pow(f / a, c);
+    out[e] = v;
+  }
+}
+
+// float32 -> float64 widening of an uploaded spectrum (exact), 16-byte loads / 32-byte stores
+__global__ void __launch_bounds__(256) k_widen_f32(const float* __restrict__ src, long long count, double* __restrict__ dst) {
+  const long long quads = count >> 2;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += stride) {
+    const float4 v = __ldcs(reinterpret_cast<const float4*>(src) + q);
+    double2* o = reinterpret_cast<double2*>(dst) + 2 * q;
+    o[0] = make_double2((double)v.x, (double)v.y);
+    o[1] = make_double2((double)v.z, (double)v.w);
+  }
+  for (long long e = 4 * quads + (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += stride) dst[e] = (double)src[e];
+}
+
+// compute_amplitude_per_channel (routines/ism.py:11-48) for ONE channel: G = P^T P, b = P^T d over
+// the num_time samples (P is (num_time, num_comp) C order), then solve G a = b with partial
+// pivoting like LAPACK gesv. One block; fixed-order tree sums. err_flag is set on a zero pivot.
+__global__ void __launch_bounds__(256) k_amplitude_per_channel(const double* __restrict__ data, const double* __restrict__ model,
+                                                               int num_time, int nc, double* __restrict__ amplitudes,
+                                                               int* __restrict__ err_flag) {
+  extern __shared__ double amp_sm[];  // [256] reduction scratch, then G (nc*nc) and b (nc)
+  double* G = amp_sm + 256;
+  double* b = G + nc * nc;
+  const int tid = threadIdx.x;
+  for (int e = 0; e < nc * (nc + 1); ++e) {
+    const int r = e / (nc + 1), q = e % (nc + 1);
+    if (q < nc && q < r) continue;  // symmetric: lower triangle copied below
+    double acc = 0.0;
+    for (int j = tid; j < num_time; j += 256) {
+      const double pr = model[(size_t)j * nc + r];
+      acc = fma(pr, q < nc ? model[(size_t)j * nc + q] : data[j], acc);
+    }
+    amp_sm[tid] = acc;
+    __syncthreads();
+    for (int off = 128; off > 0; off >>= 1) {
+      if (tid < off) amp_sm[tid] += amp_sm[tid + off];
+      __syncthreads();
+    }
+    if (tid == 0) {
+      if (q < nc) {
+        G[r * nc + q] = amp_sm[0];
+        G[q * nc + r] = amp_sm[0];
+      } else {
+        b[r] = amp_sm[0];
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const bool ok = solve_small(G, b, nc, nc);
+    for (int c = 0; c < nc; ++c) amplitudes[c] = ok ? b[c] : nan("");
+    if (!ok && err_flag) atomicExch(err_flag, 1);
   }
 }
 

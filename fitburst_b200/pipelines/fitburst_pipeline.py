@@ -25,6 +25,7 @@ from ..analysis.fitter import LSFitter
 from ..analysis.model import SpectrumModeler
 from ..analysis.peak_finder import FindPeak
 from ..backend.generic import DataReader
+from .._say import quiet as _quiet, say
 
 DEFAULTS = dict(
     amplitude=None, arrival_time=None, dm=None, dm_index=None, factor_freq_downsample=1,
@@ -106,9 +107,9 @@ def prepare(input_file: str, device=None, **overrides) -> dict:
             with open(opt["solution_file"], "r") as handle:
                 existing_results = json.load(handle)
         except Exception:  # noqa: BLE001 - like the reference's bare except
-            print("WARNING: input solution cannot be read; using basic initial parameters...")
+            say("WARNING: input solution cannot be read; using basic initial parameters...")
     else:
-        print("INFO: no solution file found or provided; proceeding with fit...")
+        say("INFO: no solution file found or provided; proceeding with fit...")
 
     outfile_substring = ""
     if opt["use_outfile_substring"]:
@@ -119,7 +120,7 @@ def prepare(input_file: str, device=None, **overrides) -> dict:
 
     data = DataReader(input_file, device=device)
     data.load_data()
-    print(f"INFO: there are {data.num_freq} frequencies and {data.num_time} time samples.")
+    say(f"INFO: there are {data.num_freq} frequencies and {data.num_time} time samples.")
 
     # fitburst_pipeline.py:364-372 (the second assignment wins, like in the reference)
     data.good_freq = np.sum(data.data_weights, axis=1) != 0.
@@ -127,12 +128,12 @@ def prepare(input_file: str, device=None, **overrides) -> dict:
     data.good_freq = np.sum(data_full, axis=1) != 0.
     row_min, row_max = data_full.min(axis=1), data_full.max(axis=1)
     for idx_freq in np.flatnonzero(data.good_freq & (row_min == row_max)):
-        print(f"ERROR: bad data value of {row_min[idx_freq]} in channel {idx_freq}!")
+        say(f"ERROR: bad data value of {row_min[idx_freq]} in channel {idx_freq}!")
         data.good_freq[idx_freq] = False
 
     if opt["preprocess_data"]:
         data.preprocess_data(normalize_variance=True, variance_range=opt["variance_range"])
-    print(f"INFO: there are {data.good_freq.sum()} good frequencies...")
+    say(f"INFO: there are {data.good_freq.sum()} good frequencies...")
     data.downsample(opt["factor_freq_downsample"], opt["factor_time_downsample"])
 
     # initial guesses, fitburst_pipeline.py:382-455
@@ -145,7 +146,7 @@ def prepare(input_file: str, device=None, **overrides) -> dict:
     }
     for current_parameter in initial_parameters.keys():
         if len(initial_parameters[current_parameter]) == 0:
-            print(f"WARNING: parameter '{current_parameter}' has no value in data file, overloading a basic guess...")
+            say(f"WARNING: parameter '{current_parameter}' has no value in data file, overloading a basic guess...")
             initial_parameters[current_parameter] = basic_parameters[current_parameter] * num_components
     for current_parameter in basic_parameters.keys():
         if current_parameter not in initial_parameters:
@@ -154,8 +155,8 @@ def prepare(input_file: str, device=None, **overrides) -> dict:
 
     dm_incoherent = initial_parameters["dm"][0]
     if data.is_dedispersed:
-        print("INFO: input data cube is already dedispersed!")
-        print("INFO: setting 'dm' entry to 0, now considered a dm-offset parameter...")
+        say("INFO: input data cube is already dedispersed!")
+        say("INFO: setting 'dm' entry to 0, now considered a dm-offset parameter...")
         current_parameters["dm"] = [0.0] * len(initial_parameters["dm"])
     if not opt["remove_dispersion_smearing"]:
         dm_incoherent = 0.
@@ -175,11 +176,11 @@ def prepare(input_file: str, device=None, **overrides) -> dict:
         current_parameters["ref_freq"] = [opt["ref_freq"]] * num_components
 
     if opt["verbose"]:
-        print(f"INFO: initial guess for {len(current_parameters['dm'])}-component model:")
+        say(f"INFO: initial guess for {len(current_parameters['dm'])}-component model:")
         for label, values in current_parameters.items():
-            print(f"    * {label}: {values}")
+            say(f"    * {label}: {values}")
 
-    print("INFO: computing dedispersion-index matrix")
+    say("INFO: computing dedispersion-index matrix")
     data.dedisperse(initial_parameters["dm"][0], current_parameters["arrival_time"][0],
                     ref_freq=initial_parameters["ref_freq"][0], dm_offset=0.0)
 
@@ -191,7 +192,7 @@ def prepare(input_file: str, device=None, **overrides) -> dict:
         data_windowed = data._data_full.get_dev(data._device)  # the spectrum stays on the device
 
     if opt["peakfind_rms"] is not None:
-        print("INFO: running FindPeak to isolate burst components...")
+        say("INFO: running FindPeak to isolate burst components...")
         peaks = FindPeak(data_windowed, times_windowed, data.freqs, rms=opt["peakfind_rms"])
         peaks.find_peak(distance=opt["peakfind_dist"])
         current_parameters = peaks.get_parameters_dict(current_parameters)
@@ -208,7 +209,7 @@ def fit_prepared(state: dict, output_dir: str = ".", write_json: bool = True) ->
     opt, data = state["options"], state["data"]
     num_components = state["num_components"]
     parameters_to_fix = _fixed_parameters(opt)
-    print("INFO: initializing model")
+    say("INFO: initializing model")
     model = SpectrumModeler(
         data.freqs, state["times_windowed"], dm_incoherent=state["dm_incoherent"],
         factor_freq_upsample=opt["factor_freq_upsample"], factor_time_upsample=opt["factor_time_upsample"],
@@ -235,9 +236,9 @@ def fit_prepared(state: dict, output_dir: str = ".", write_json: bool = True) ->
         if current_iteration == opt["num_iterations"] - 1:
             if opt["verbose"]:
                 uncertainties = fitter.fit_statistics["bestfit_uncertainties"]
-                print(f"INFO: best-fit estimate for {num_components}-component model:")
+                say(f"INFO: best-fit estimate for {num_components}-component model:")
                 for label, values in bestfit_params.items():
-                    print(f"    * {label}: {values} +/- {uncertainties[label]}")
+                    say(f"    * {label}: {values} +/- {uncertainties[label]}")
             output = {
                 "initial_dm": state["initial_parameters"]["dm"][0],
                 "initial_time": data.times_bin0,
@@ -274,8 +275,7 @@ def run_many(input_files, output_dir: str = ".", write_json: bool = True, device
     def prepare_on_side_stream(path):
         dev = torch.device(device if device is not None else "cuda")
         stream = torch.cuda.Stream(device=dev)
-        sink = io.StringIO()
-        with torch.cuda.stream(stream), (contextlib.redirect_stdout(sink) if quiet else contextlib.nullcontext()):
+        with torch.cuda.stream(stream), _quiet(quiet):  # thread-local: sys.stdout is never swapped
             state = prepare(path, device=dev, **overrides)
         stream.synchronize()
         return state
@@ -291,8 +291,9 @@ def run_many(input_files, output_dir: str = ".", write_json: bool = True, device
             if isinstance(state, Exception):
                 yield {"input_file": path, "results": None, "error": repr(state)}
                 continue
-            with (contextlib.redirect_stdout(io.StringIO()) if quiet else contextlib.nullcontext()):
-                yield fit_prepared(state, output_dir, write_json)
+            with _quiet(quiet):
+                result = fit_prepared(state, output_dir, write_json)
+            yield result  # outside the quiet block: the consumer's own prints are not swallowed
 
 
 def main(argv=None):

@@ -21,25 +21,42 @@ import torch
 
 from .. import _lib
 from ..backend import general
+from .._say import say
 
 
 class _MirroredArray:
-    """A (num_freq, num_time) array with a host and a device copy and validity flags."""
+    """A (num_freq, num_time) array with a host and a device copy and validity flags. The host
+    side may also be a per-channel row pattern (set_rows) that is expanded only where a full array
+    is asked for -- the generic format's weights are a channel mask, not num_freq x num_time values."""
 
     def __init__(self):
         self.host = None
         self.dev = None
         self.host_valid = False
         self.dev_valid = False
+        self.rows = None  # (per-channel values, num_time) of a row-constant array not yet expanded
 
     def set_host(self, array):
         self.host = array
         self.host_valid = array is not None
         self.dev = None
         self.dev_valid = False
+        self.rows = None
+
+    def set_rows(self, values, num_time):
+        self.set_host(None)
+        self.rows = (np.asarray(values, dtype=np.float64), int(num_time))
+        self.host_valid = True
+
+    def _expand_rows(self):
+        if self.rows is not None:
+            values, num_time = self.rows
+            self.host = np.repeat(values[:, None], num_time, axis=1)
+            self.rows = None
 
     def get_host(self):
         if self.host_valid:
+            self._expand_rows()
             # the caller may modify the array in place: the device copy can no longer be trusted
             self.dev_valid = False
             return self.host
@@ -54,7 +71,11 @@ class _MirroredArray:
         if not self.dev_valid:
             if not self.host_valid:
                 return None
-            self.dev = torch.from_numpy(np.ascontiguousarray(self.host, dtype=np.float64)).to(device)
+            if self.rows is not None:
+                values, num_time = self.rows
+                self.dev = torch.from_numpy(values).to(device)[:, None].expand(len(values), num_time).contiguous()
+            else:
+                self.dev = upload_spectrum(self.host, device)
             self.dev_valid = True
         return self.dev
 
@@ -63,6 +84,33 @@ class _MirroredArray:
         self.dev_valid = True
         self.host = None
         self.host_valid = False
+        self.rows = None
+
+
+def upload_spectrum(array, device, out=None):
+    """
+    Host spectrum -> float64 device tensor on the current stream. float32 sources cross the host
+    link as float32 (half the bytes) and are widened exactly by fb_widen_f32; page-locked sources
+    (backend.generic.read_spectrum_pinned, batch.pinned_like) are copied asynchronously.
+    """
+    source = array if isinstance(array, torch.Tensor) else None
+    if source is None:
+        array = np.asarray(array)
+        if array.dtype not in (np.float32, np.float64):
+            array = array.astype(np.float64)
+        source = torch.from_numpy(np.ascontiguousarray(array))
+    source = source.contiguous()
+    if out is None:
+        out = torch.empty(source.shape, dtype=torch.float64, device=device)
+    if source.dtype == torch.float64:
+        out.copy_(source, non_blocking=True)
+        return out
+    staging = torch.empty(source.shape, dtype=torch.float32, device=device)
+    staging.copy_(source, non_blocking=True)
+    with torch.cuda.device(device):
+        _lib.check(_lib.load_library().fb_widen_f32(staging.data_ptr(), staging.numel(), out.data_ptr(),
+                                                    torch.cuda.current_stream(device).cuda_stream))
+    return out
 
 
 class ReaderBaseClass:
@@ -197,7 +245,7 @@ class ReaderBaseClass:
             mask_freq = mom[:, 0].copy()
             good_freq = mask_freq != 0
             for idx_freq in np.flatnonzero(good_freq & (mom[:, 2] == mom[:, 3])):  # bases.py:255-260
-                print(f"ERROR: bad data value of {mom[idx_freq, 2]} in channel {idx_freq}!")
+                say(f"ERROR: bad data value of {mom[idx_freq, 2]} in channel {idx_freq}!")
                 good_freq[idx_freq] = False
             mean_spectrum = mom[:, 1].copy()
             mean_spectrum[good_freq] /= mask_freq[good_freq]
@@ -228,7 +276,7 @@ class ReaderBaseClass:
         self._data_full.set_dev(data)
         self.good_freq = good_freq
         num_freq_bad = self.num_freq - np.sum(self.good_freq)
-        print(f"INFO: flagged and removed {num_freq_bad} out of {self.num_freq} channels!")
+        say(f"INFO: flagged and removed {num_freq_bad} out of {self.num_freq} channels!")
 
     def window_data(self, arrival_time: float, window: float = 0.08, as_tensor: bool = False) -> tuple:
         """

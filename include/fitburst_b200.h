@@ -257,6 +257,24 @@ int fb_pre_time_series(const double* in_dev, int32_t num_freq, int32_t num_time,
 int fb_upload_rows(const void* host_pinned, int32_t elem_size, const int32_t* rows_dev, int32_t num_rows,
                    int32_t num_freq, int32_t num_time, double* dst_dev, void* stream);
 
+/* ---- small public routines of the reference, elementwise over device arrays ------------------ */
+/* compute_spectrum_rpl, routines/spectrum.py:11-43: exp(sp_idx L + sp_run L^2), L = ln(f / freq_ref) */
+int fb_spectrum_rpl(const double* freqs_dev, int64_t count, double freq_ref, double sp_idx, double sp_run,
+                    double* out_dev, void* stream);
+/* routines/ism.py:50-140 over an array of frequencies f:
+ *   kind 0 compute_time_dm_delay   a = dm_value, b = dm_const, c = dm_idx, d = freq2
+ *   kind 1 compute_time_dm_smear   a = dm_value, b = dm_const, c = dm_idx, d = width_chan
+ *   kind 2 compute_time_scattering a = ref_freq, b = sc_time_ref, c = sc_idx (d unused) */
+int fb_ism_times(int32_t kind, const double* freqs_dev, int64_t count, double a, double b, double c, double d,
+                 double* out_dev, void* stream);
+/* compute_amplitude_per_channel, routines/ism.py:11-48: data_dev (num_time), model_dev (num_time,
+ * num_components) C order -> amplitudes_dev (num_components); FB_ERR_SINGULAR like np.linalg.solve */
+int fb_amplitude_per_channel(const double* data_dev, const double* model_dev, int32_t num_time, int32_t num_comp,
+                             double* amplitudes_dev, void* stream);
+/* exact float32 -> float64 widening of an uploaded spectrum (telescope data are float32; the
+ * upload then moves half the bytes); both buffers 16-byte aligned */
+int fb_widen_f32(const float* src_dev, int64_t count, double* dst_dev, void* stream);
+
 /* Measured FP64 FMA peak of the device (dependent-free DFMA chains on every SM), TFLOP/s.
  * MEASURED_PEAKS.json carries no FP64 figure; bench.py reports this one as the roofline peak. */
 int fb_measure_fp64_peak(double* tflops_out, void* stream);

@@ -137,8 +137,8 @@ def test_scintillation_model(native_lib):
     data = plain.compute_model() * np.exp(rng.normal(0, 0.5, size=(len(freqs), 1))) + rng.normal(0, 0.05, size=(len(freqs), len(times)))
     got = cuda.compute_model(data=data)
     want = oracle.compute_model(data=data)
-    assert_close(got, want, 1e-9, "scintillation model")
-    assert_close(cuda.amplitude_per_component, oracle.amplitude_per_component, 1e-9, "scintillation amplitudes")
+    assert_close(got, want, 1e-10, "scintillation model")
+    assert_close(cuda.amplitude_per_component, oracle.amplitude_per_component, 1e-10, "scintillation amplitudes")
 
 
 @pytest.mark.parametrize("case", [dict(kf=2, kt=2), dict(kf=2, kt=2, tau=0.0, num_comp=2), dict(kf=1, kt=1, dm=0.2, num_comp=2)])
