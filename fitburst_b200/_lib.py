@@ -107,6 +107,11 @@ SIGNATURES = {
     "fb_trf_propose": (ctypes.c_int, [_P, _D]),
     "fb_trf_update": (ctypes.c_int, [_P, _D]),
     "fb_trf_result": (ctypes.c_int, [_P, ctypes.POINTER(FitResult), _D]),
+    "fb_fit_device_begin": (ctypes.c_int, [_P, ctypes.POINTER(FitOptions), ctypes.c_int64, _P]),
+    "fb_fit_device_evaluate": (ctypes.c_int, [_P, _P, _P, _P]),
+    "fb_fit_device_step": (ctypes.c_int, [_P, _P, _P]),
+    "fb_fit_device_poll": (ctypes.c_int, [_P, ctypes.POINTER(_I32), ctypes.POINTER(_I32), _P]),
+    "fb_fit_device_end": (ctypes.c_int, [_P, ctypes.POINTER(FitResult), _D, ctypes.POINTER(_I32), _P]),
     "fb_fit_batched": (ctypes.c_int, [_P, _I32, _P, _P, _P, ctypes.POINTER(FitOptions), ctypes.POINTER(FitResult), _P]),
     "fb_chisq_grid": (ctypes.c_int, [_P, _P, _D, _I32, _D, _I32, _P, _P]),
     "fb_pre_channel_moments": (ctypes.c_int, [_P, _P, _I32, _I32, _P, _P]),

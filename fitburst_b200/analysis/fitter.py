@@ -143,6 +143,11 @@ class LSFitter:
         (analysis/fitter.py:81-178). Returns (hessian, labels).
         """
         _say("INFO: computing hessian matrix with best-fit parameters.")
+        cached = getattr(self, "_hessian_native", None)
+        if cached is not None and data is self.data and cached[1] == tuple(self.fit_parameters) and \
+                cached[0] == self.model._packed_parameters().tobytes() and \
+                np.array_equal(np.ascontiguousarray(self.weights, dtype=np.float64), self._weights_loaded, equal_nan=True):
+            return cached[2].copy(), self._parameter_labels()  # computed by fb_fit at this very state
         plan, num_free = self._prepare()
         self.model._push_parameters()
         data_dev = self._data_on_device() if data is self.data else self.model._to_device(data)
@@ -231,19 +236,21 @@ class LSFitter:
         if num_free != len(parameter_list):
             raise ValueError("free-parameter layout mismatch between model and fitter")
         self.model._push_parameters()
-        options = _lib.FitOptions(1e-8, 1e-8, 1e-8, 0, 0)
+        options = _lib.FitOptions(1e-8, 1e-8, 1e-8, 0, 1)
         result = _lib.FitResult()
         gram = np.zeros((num_free + 1, num_free + 1), dtype=np.float64)
+        hessian = np.zeros((num_free, num_free), dtype=np.float64)
+        packed = np.zeros((_lib.FB_NUM_PARAMETERS, int(self.model.num_components)), dtype=np.float64)
+        self._hessian_native = None
         with torch.cuda.device(self.model._device):
+            # one call: device-driven trust-region loop + exact Hessian at the last evaluated point
             _lib.check(self._lib().fb_fit(
                 plan, self._data_on_device().data_ptr(), ctypes.byref(options), ctypes.byref(result),
-                _lib.dptr(gram), None, self._stream()))
-        x = np.array(result.x[:num_free], dtype=np.float64)
-        # the reference leaves the model at the LAST EVALUATED point (analysis/fitter.py:258);
-        # mirror that on the python side from the plan's parameter block.
-        packed = np.zeros((_lib.FB_NUM_PARAMETERS, int(self.model.num_components)), dtype=np.float64)
-        with torch.cuda.device(self.model._device):
+                _lib.dptr(gram), _lib.dptr(hessian), self._stream()))
+            # the reference leaves the model at the LAST EVALUATED point (analysis/fitter.py:258);
+            # mirror that on the python side from the plan's parameter block.
             _lib.check(self._lib().fb_get_parameters(plan, _lib.dptr(packed), self._stream()))
+        x = np.array(result.x[:num_free], dtype=np.float64)
         last_x = []
         for name in self.model.parameters:
             if name in self.fit_parameters:
@@ -254,6 +261,8 @@ class LSFitter:
                                    self._data_on_device() if self.model.scintillation else None)
         self.model._cache_host = {}
         self._gram_final = gram
+        # compute_hessian() right after the fit (what _compute_fit_statistics does) is this matrix
+        self._hessian_native = (self.model._packed_parameters().tobytes(), tuple(self.fit_parameters), hessian)
 
         # the lazy members must not keep the fitter alive through a reference cycle
         # (fitter -> results -> closure -> fitter): dead fitters would hold their 134 MB device

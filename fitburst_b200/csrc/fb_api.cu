@@ -92,6 +92,24 @@ struct fb_plan_s {
   std::vector<double> gram_cache, gram_cache_params;
   const double* gram_cache_data = nullptr;
   bool vals_match_cache = false;  // d_vals holds k_vals output of the cached evaluation
+  // device-driven fit loop (k_trf_single): solver state, flags and results stay on the GPU
+  TrfState* d_trf = nullptr;
+  int* d_fit_flags = nullptr;        // FitFlag
+  double* d_gram_accepted = nullptr; // (FB_MAX_FREE+1)^2
+  fb_fit_result* d_fit_result = nullptr;
+  int* h_fit_flags = nullptr;        // pinned, two slots of kFitFlagCount
+  fb_fit_result* h_fit_result = nullptr;  // pinned
+  double* h_fit_grams = nullptr;     // pinned: last evaluated + accepted matrix
+  double* h_fit_params = nullptr;    // pinned parameter block
+  cudaEvent_t fit_events[2] = {nullptr, nullptr};
+  SingleTrfArgs* fit_session = nullptr;  // fb_fit_device_* between _begin and _end
+  // pair descriptors of the exact Hessian for the current free-parameter layout (fb_hessian_impl)
+  bool hess_layout_valid = false;
+  std::vector<int> hess_pair_a, hess_pair_b;
+  std::vector<int> hess_comp_off;
+  int hess_npairs = 0;
+  unsigned hess_need[FB_MAX_COMPONENTS];
+  int hess_need_sum_dmidx = 0;
 };
 
 extern "C" const char* fb_last_error(void) { return g_err; }
@@ -195,6 +213,7 @@ extern "C" int fb_plan_create(const fb_plan_desc* desc, const double* freqs_host
   }
   pc.freqs = p->d_freqs;
   pc.subfreqs = p->d_subfreqs;
+  pc.stop = nullptr;
   memset(p->h_params, 0, sizeof(p->h_params));
   memset(p->occ_cache, 0, sizeof(p->occ_cache));
   for (int k = 0; k < 9; ++k) p->free_mask[k] = 1;
@@ -228,6 +247,17 @@ extern "C" int fb_plan_destroy(fb_plan_t p) {
   cudaFree(p->d_sub);
   cudaFree(p->d_chan);
   if (p->h_gram) cudaFreeHost(p->h_gram);
+  cudaFree(p->d_trf);
+  delete p->fit_session;
+  cudaFree(p->d_fit_flags);
+  cudaFree(p->d_gram_accepted);
+  cudaFree(p->d_fit_result);
+  if (p->h_fit_flags) cudaFreeHost(p->h_fit_flags);
+  if (p->h_fit_result) cudaFreeHost(p->h_fit_result);
+  if (p->h_fit_grams) cudaFreeHost(p->h_fit_grams);
+  if (p->h_fit_params) cudaFreeHost(p->h_fit_params);
+  for (int k = 0; k < 2; ++k)
+    if (p->fit_events[k]) cudaEventDestroy(p->fit_events[k]);
   delete p;
   return FB_OK;
 }
@@ -662,7 +692,8 @@ static int launch_fast_gram(fb_plan_s* p, EvalArgs& A, int ncols, double* gram_d
   X.shift[ncols - 1] = 0.0;
   const int far_entries = F.enabled ? nent : 0;
   k_gram3_finish<<<dim3(gram3_finish_groups(entries, far_entries), kFinishSlices), 256, 0, st>>>(
-      p->d_partials, grid, kFastWarps, entries, far_entries, p->d_slices, p->d_racc, p->d_far, X, p->d_counter, gram_dev);
+      p->d_partials, grid, kFastWarps, entries, far_entries, p->d_slices, p->d_racc, p->d_far, X, p->d_counter, gram_dev,
+      p->pc.stop);
   CUDA_TRY(cudaGetLastError());
   p->launches += 1;
   return FB_OK;
@@ -786,10 +817,10 @@ static int normal_equations_async(fb_plan_s* p, const double* data_dev, double* 
   if (rc != FB_OK) return rc;
   if (mma_warps > 0) {
     const int nb = (ncols + 7) / 8, entries = nb * (nb + 1) / 2 * 64;
-    k_gram_finalize_mma<<<(entries + 7) / 8, 256, 0, st>>>(p->d_partials, mma_warps, ncols, nb, gram_dev);
+    k_gram_finalize_mma<<<(entries + 7) / 8, 256, 0, st>>>(p->d_partials, mma_warps, ncols, nb, gram_dev, p->pc.stop);
   } else {
     const int entries = gram_ntiles(ncols) * kTile * kTile;
-    k_gram_finalize<<<(entries + 7) / 8, 256, 0, st>>>(p->d_partials, grid, ncols, gram_dev);
+    k_gram_finalize<<<(entries + 7) / 8, 256, 0, st>>>(p->d_partials, grid, ncols, gram_dev, p->pc.stop);
   }
   CUDA_TRY(cudaGetLastError());
   p->launches += 1;
@@ -892,46 +923,14 @@ static void unpack_free(fb_plan_s* p, const double* x) {
 
 int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, cudaStream_t st);
 
-extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options* options,
-                      fb_fit_result* result, double* gram_final_host, double* hessian_host,
-                      void* stream) {
-  if (!p || !data_dev || !result) return fail(FB_ERR_INVALID, "null argument");
-  if (!p->have_weights) return fail(FB_ERR_INVALID, "fb_set_weights / fb_load_weights must be called first");
-  const int n = p->n_free;
-  if (n < 1) return fail(FB_ERR_INVALID, "no free parameters");
-  cudaStream_t st = (cudaStream_t)stream;
-  fb_fit_options opt;
-  opt.ftol = opt.xtol = opt.gtol = 1e-8;
-  opt.max_nfev = 0;
-  opt.compute_hessian = 0;
-  if (options) opt = *options;
-  const int ncols = n + 1;
-  std::vector<double> gram((size_t)ncols * ncols), accepted((size_t)ncols * ncols);
-  TrfState* stt = new (std::nothrow) TrfState();
-  if (!stt) return fail(FB_ERR_NOMEM, "out of host memory");
-  TrfState& S = *stt;
-  double x0[FB_MAX_FREE];
-  pack_free(p, x0);
-  int rc = fb_set_parameters(p, p->h_params, stream);
-  if (rc == FB_OK) rc = fb_normal_equations(p, data_dev, gram.data(), stream);
-  if (rc != FB_OK) {
-    delete stt;
-    return rc;
-  }
-  memset(result, 0, sizeof(*result));
-  result->num_free = n;
-  const long long m = (long long)p->desc.num_freq * p->desc.num_time;
-  trf_init(S, n, m, x0, opt.ftol, opt.xtol, opt.gtol, opt.max_nfev);
-  if (!std::isfinite(gram[(size_t)n * ncols + n])) {
-    // scipy raises "Residuals are not finite in the initial point." (least_squares.py:945-946)
-    delete stt;
-    result->status = -1;
-    return fail(FB_ERR_INVALID, "Residuals are not finite in the initial point.");
-  }
-  trf_load_accepted(S, gram.data());
-  accepted = gram;
-  S.nfev = 1;
-  S.njev = 1;
+static fb_fit_options default_options(const fb_fit_options* options);
+
+// Host-driven trust-region loop (one stream synchronisation per trial point): the scintillation
+// mode, whose singular-system flag must be read after every evaluation, and the continuation of a
+// device-driven fit whose trial point left the domain of the fast kernels (pending_trial: S.x_new
+// is proposed but not evaluated yet). `gram` holds the last evaluated matrix on return.
+static int fit_host_loop(fb_plan_s* p, const double* data_dev, TrfState& S, std::vector<double>& gram,
+                         std::vector<double>& accepted, bool pending_trial, void* stream) {
   // FITBURST_B200_TIMING=1: host-side breakdown of the loop on stderr
   const bool timing = getenv("FITBURST_B200_TIMING") != nullptr;
   using clk = std::chrono::steady_clock;
@@ -943,11 +942,14 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
     t_prev = now;
   };
   for (;;) {
-    const bool more = trf_propose(S);
-    if (timing) lap(t_host);
-    if (!more) break;
+    if (!pending_trial) {
+      const bool more = trf_propose(S);
+      if (timing) lap(t_host);
+      if (!more) break;
+    }
+    pending_trial = false;
     unpack_free(p, S.x_new);
-    rc = fb_set_parameters(p, p->h_params, stream);
+    int rc = fb_set_parameters(p, p->h_params, stream);
     if (rc == FB_OK) rc = fb_normal_equations(p, data_dev, gram.data(), stream);
     if (rc != FB_OK) {
       if (getenv("FITBURST_B200_DEBUG")) {  // the trial point an evaluation failed at
@@ -955,7 +957,6 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
         for (int k = 0; k < FB_NUM_PARAMETERS * p->desc.num_components; ++k) fprintf(stderr, " %.17g", p->h_params[k]);
         fprintf(stderr, "\n");
       }
-      delete stt;
       return rc;
     }
     if (timing) lap(t_eval);
@@ -966,17 +967,208 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
   }
   if (timing)
     fprintf(stderr, "fb_fit: nfev %d, host TRF %.1f us, evaluations (launch + wait) %.1f us\n", S.nfev, t_host, t_eval);
-  result->status = S.status;
-  result->nfev = S.nfev;
-  result->njev = S.njev;
-  result->cost = S.cost;
-  result->optimality = S.g_norm;
-  for (int i = 0; i < n; ++i) {
-    result->x[i] = S.x[i];
-    result->grad[i] = S.g[i];
+  return FB_OK;
+}
+
+static int ensure_device_fit(fb_plan_s* p) {
+  if (p->d_trf) return FB_OK;
+  const size_t gsz = sizeof(double) * (FB_MAX_FREE + 1) * (FB_MAX_FREE + 1);
+  CUDA_TRY(cudaMalloc(&p->d_trf, sizeof(TrfState)));
+  CUDA_TRY(cudaMalloc(&p->d_fit_flags, sizeof(int) * kFitFlagCount));
+  CUDA_TRY(cudaMalloc(&p->d_gram_accepted, gsz));
+  CUDA_TRY(cudaMalloc(&p->d_fit_result, sizeof(fb_fit_result)));
+  CUDA_TRY(cudaMallocHost(&p->h_fit_flags, sizeof(int) * 2 * kFitFlagCount));
+  CUDA_TRY(cudaMallocHost(&p->h_fit_result, sizeof(fb_fit_result)));
+  CUDA_TRY(cudaMallocHost(&p->h_fit_grams, 2 * gsz));
+  CUDA_TRY(cudaMallocHost(&p->h_fit_params, sizeof(double) * FB_NUM_PARAMETERS * FB_MAX_COMPONENTS));
+  for (int k = 0; k < 2; ++k) CUDA_TRY(cudaEventCreateWithFlags(&p->fit_events[k], cudaEventDisableTiming));
+  return FB_OK;
+}
+
+// Arguments of k_trf_single for the plan's current free-parameter layout; resets the flags and
+// arms the early-out of the evaluation kernels.
+static int device_fit_setup(fb_plan_s* p, const fb_fit_options& opt, long long num_residuals, SingleTrfArgs& T,
+                            cudaStream_t st) {
+  int rc = ensure_device_fit(p);
+  if (rc != FB_OK) return rc;
+  const int n = p->n_free;
+  CUDA_TRY(cudaMemsetAsync(p->d_fit_flags, 0, sizeof(int) * kFitFlagCount, st));
+  memset(&T, 0, sizeof(T));
+  T.nc = p->desc.num_components;
+  T.n_free = n;
+  for (int k = 0; k < 9; ++k) T.col_of[k] = p->col_of[k];
+  T.num_residuals = num_residuals;
+  T.ftol = opt.ftol;
+  T.xtol = opt.xtol;
+  T.gtol = opt.gtol;
+  T.max_nfev = opt.max_nfev;
+  const bool split = !p->pc.scintillation && !env_off("FITBURST_B200_SPLIT");
+  T.guard_fast = (split && fast_path_ok(p, true)) ? 1 : 0;
+  T.gram = p->d_gram;
+  T.gram_accepted = p->d_gram_accepted;
+  T.params = p->d_params;
+  T.state = p->d_trf;
+  T.flags = p->d_fit_flags;
+  T.result = p->d_fit_result;
+  const size_t trf_smem = trf_single_smem_bytes(n);
+  if (trf_smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(k_trf_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trf_smem));
+  p->pc.stop = p->d_fit_flags;
+  p->gram_cache_valid = false;
+  return FB_OK;
+}
+
+// One evaluation at the plan's DEVICE parameter block followed by the trust-region step on the
+// device (k_trf_single). Nothing here waits for the GPU.
+static int enqueue_eval_and_step(fb_plan_s* p, const double* data_dev, const SingleTrfArgs& T, cudaStream_t st) {
+  p->tables_dirty = true;  // the parameter block changes on the device between evaluations
+  int rc = normal_equations_async(p, data_dev, p->d_gram, st);
+  if (rc != FB_OK) return rc;
+  k_trf_single<<<1, 32, trf_single_smem_bytes(T.n_free), st>>>(T);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 1;
+  return FB_OK;
+}
+
+extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options* options,
+                      fb_fit_result* result, double* gram_final_host, double* hessian_host,
+                      void* stream) {
+  if (!p || !data_dev || !result) return fail(FB_ERR_INVALID, "null argument");
+  if (!p->have_weights) return fail(FB_ERR_INVALID, "fb_set_weights / fb_load_weights must be called first");
+  const int n = p->n_free;
+  if (n < 1) return fail(FB_ERR_INVALID, "no free parameters");
+  cudaStream_t st = (cudaStream_t)stream;
+  const fb_fit_options opt = default_options(options);
+  const int ncols = n + 1;
+  const size_t gcount = (size_t)ncols * ncols;
+  const size_t nparam = (size_t)FB_NUM_PARAMETERS * p->desc.num_components;
+  const long long m = (long long)p->desc.num_freq * p->desc.num_time;
+  std::vector<double> gram(gcount), accepted(gcount);
+  TrfState* stt = new (std::nothrow) TrfState();
+  if (!stt) return fail(FB_ERR_NOMEM, "out of host memory");
+  struct Guard {
+    TrfState* s;
+    fb_plan_s* p;
+    ~Guard() {
+      delete s;
+      p->pc.stop = nullptr;
+    }
+  } guard{stt, p};
+  TrfState& S = *stt;
+  memset(result, 0, sizeof(*result));
+  result->num_free = n;
+  int rc = fb_set_parameters(p, p->h_params, stream);
+  if (rc != FB_OK) return rc;
+
+  // The loop stays on the device unless the mode needs a host check after every evaluation
+  // (scintillation: singular per-channel systems) or FITBURST_B200_DEVICE_LOOP=0 asks for the
+  // host-driven loop (kept as the cross-check of the device driver in the tests).
+  const bool device_loop = !p->pc.scintillation && p->num_good > 0 && !env_off("FITBURST_B200_DEVICE_LOOP");
+  bool pending_trial = false, need_host_loop = !device_loop;
+  if (device_loop) {
+    SingleTrfArgs T;
+    rc = device_fit_setup(p, opt, m, T, st);
+    if (rc != FB_OK) return rc;
+    // Evaluations are enqueued in chunks, one chunk ahead of what is known to be needed; the
+    // flags are read back after each chunk. Launches past the end of the fit return at once.
+    const int max_evals = (opt.max_nfev > 0 ? opt.max_nfev : 100 * n) + 2;
+    int enqueued = 0;
+    auto enqueue_chunk = [&](int count, int slot) -> int {
+      for (int k = 0; k < count; ++k) {
+        const int rc2 = enqueue_eval_and_step(p, data_dev, T, st);
+        if (rc2 != FB_OK) return rc2;
+      }
+      enqueued += count;
+      CUDA_TRY(cudaMemcpyAsync(p->h_fit_flags + slot * kFitFlagCount, p->d_fit_flags, sizeof(int) * kFitFlagCount,
+                               cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(cudaEventRecord(p->fit_events[slot], st));
+      return FB_OK;
+    };
+    rc = enqueue_chunk(6, 0);
+    if (rc != FB_OK) return rc;
+    for (int k = 0;; ++k) {
+      const int cur = k & 1;
+      const bool room = enqueued < max_evals;
+      if (room) {
+        rc = enqueue_chunk(4, cur ^ 1);
+        if (rc != FB_OK) return rc;
+      }
+      CUDA_TRY(cudaEventSynchronize(p->fit_events[cur]));
+      if (p->h_fit_flags[cur * kFitFlagCount + kFitStop]) break;
+      if (!room) return fail(FB_ERR_CUDA, "device-driven fit did not terminate within %d evaluations", max_evals);
+    }
+    // everything the host needs, in one go: results, the last evaluated and the accepted matrix,
+    // the parameter block (last evaluated point), the flags
+    CUDA_TRY(cudaMemcpyAsync(p->h_fit_result, p->d_fit_result, sizeof(fb_fit_result), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(p->h_fit_grams, p->d_gram, sizeof(double) * gcount, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(p->h_fit_grams + gcount, p->d_gram_accepted, sizeof(double) * gcount, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(p->h_fit_params, p->d_params, sizeof(double) * nparam, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(p->h_fit_flags, p->d_fit_flags, sizeof(int) * kFitFlagCount, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    p->pc.stop = nullptr;
+    gram.assign(p->h_fit_grams, p->h_fit_grams + gcount);
+    accepted.assign(p->h_fit_grams + gcount, p->h_fit_grams + 2 * gcount);
+    memcpy(p->h_params, p->h_fit_params, sizeof(double) * nparam);
+    if (p->h_fit_flags[kFitBail]) {
+      // a trial point left the fast kernels' domain: continue on the host from the device state
+      CUDA_TRY(cudaMemcpy(stt, p->d_trf, sizeof(TrfState), cudaMemcpyDeviceToHost));
+      pending_trial = true;
+      need_host_loop = true;
+    } else {
+      const fb_fit_result& R = *p->h_fit_result;
+      if (R.status == -1) {
+        result->status = -1;
+        return fail(FB_ERR_INVALID, "Residuals are not finite in the initial point.");
+      }
+      result->status = R.status;
+      result->nfev = R.nfev;
+      result->njev = R.njev;
+      result->cost = R.cost;
+      result->optimality = R.optimality;
+      for (int i = 0; i < n; ++i) {
+        result->x[i] = R.x[i];
+        result->grad[i] = R.grad[i];
+      }
+      // the last evaluation is what the exact Hessian starts from (analysis/fitter.py:105-108)
+      p->gram_cache.assign(gram.begin(), gram.end());
+      p->gram_cache_params.assign(p->h_params, p->h_params + nparam);
+      p->gram_cache_data = data_dev;
+      p->gram_cache_valid = true;
+      p->vals_match_cache = p->last_eval_split;
+      p->tables_dirty = false;  // tables, spectrum rows and parameters all belong to the last evaluation
+    }
+  } else {
+    rc = fb_normal_equations(p, data_dev, gram.data(), stream);
+    if (rc != FB_OK) return rc;
   }
-  if (gram_final_host) memcpy(gram_final_host, accepted.data(), sizeof(double) * ncols * ncols);
-  delete stt;
+  if (need_host_loop) {
+    if (!pending_trial) {
+      double x0[FB_MAX_FREE];
+      pack_free(p, x0);
+      trf_init(S, n, m, x0, opt.ftol, opt.xtol, opt.gtol, opt.max_nfev);
+      if (!std::isfinite(gram[(size_t)n * ncols + n])) {
+        // scipy raises "Residuals are not finite in the initial point." (least_squares.py:945-946)
+        result->status = -1;
+        return fail(FB_ERR_INVALID, "Residuals are not finite in the initial point.");
+      }
+      trf_load_accepted(S, gram.data());
+      accepted = gram;
+      S.nfev = 1;
+      S.njev = 1;
+    }
+    rc = fit_host_loop(p, data_dev, S, gram, accepted, pending_trial, stream);
+    if (rc != FB_OK) return rc;
+    result->status = S.status;
+    result->nfev = S.nfev;
+    result->njev = S.njev;
+    result->cost = S.cost;
+    result->optimality = S.g_norm;
+    for (int i = 0; i < n; ++i) {
+      result->x[i] = S.x[i];
+      result->grad[i] = S.g[i];
+    }
+  }
+  if (gram_final_host) memcpy(gram_final_host, accepted.data(), sizeof(double) * gcount);
   // the model is left at the LAST EVALUATED point, like analysis/fitter.py:258 leaves it.
   if (opt.compute_hessian || hessian_host) {
     std::vector<double> H((size_t)n * n);
@@ -984,6 +1176,87 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
     if (rc != FB_OK) return rc;
     if (hessian_host) memcpy(hessian_host, H.data(), sizeof(double) * n * n);
   }
+  return FB_OK;
+}
+
+// ---- the device-driven fit in steps (channel-sharded multi-GPU fits) ------------------------------
+// Same kernels as fb_fit's loop, but the caller owns the matrix buffer and may reduce it over
+// the ranks of a process group (NCCL all-reduce on the same stream) between fb_fit_device_evaluate
+// and fb_fit_device_step. Nothing waits for the GPU except _poll and _end.
+extern "C" int fb_fit_device_begin(fb_plan_t p, const fb_fit_options* options, int64_t num_residuals_total,
+                                   void* stream) {
+  if (!p) return fail(FB_ERR_INVALID, "null argument");
+  if (!p->have_weights) return fail(FB_ERR_INVALID, "fb_set_weights / fb_load_weights must be called first");
+  if (p->n_free < 1) return fail(FB_ERR_INVALID, "no free parameters");
+  if (p->pc.scintillation)
+    return fail(FB_ERR_INVALID, "the device-driven loop does not cover scintillation mode (singular-system check)");
+  const fb_fit_options opt = default_options(options);
+  int rc = fb_set_parameters(p, p->h_params, stream);
+  if (rc != FB_OK) return rc;
+  if (!p->fit_session) p->fit_session = new (std::nothrow) SingleTrfArgs();
+  if (!p->fit_session) return fail(FB_ERR_NOMEM, "out of host memory");
+  const long long m = num_residuals_total > 0 ? (long long)num_residuals_total
+                                              : (long long)p->desc.num_freq * p->desc.num_time;
+  return device_fit_setup(p, opt, m, *p->fit_session, (cudaStream_t)stream);
+}
+
+extern "C" int fb_fit_device_evaluate(fb_plan_t p, const double* data_dev, double* gram_dev, void* stream) {
+  if (!p || !data_dev || !gram_dev) return fail(FB_ERR_INVALID, "null argument");
+  if (!p->fit_session || p->pc.stop == nullptr) return fail(FB_ERR_INVALID, "fb_fit_device_begin must be called first");
+  p->tables_dirty = true;
+  return normal_equations_async(p, data_dev, gram_dev, (cudaStream_t)stream);
+}
+
+extern "C" int fb_fit_device_step(fb_plan_t p, const double* gram_dev, void* stream) {
+  if (!p || !gram_dev) return fail(FB_ERR_INVALID, "null argument");
+  if (!p->fit_session || p->pc.stop == nullptr) return fail(FB_ERR_INVALID, "fb_fit_device_begin must be called first");
+  SingleTrfArgs T = *p->fit_session;
+  T.gram = gram_dev;
+  k_trf_single<<<1, 32, trf_single_smem_bytes(T.n_free), (cudaStream_t)stream>>>(T);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 1;
+  return FB_OK;
+}
+
+extern "C" int fb_fit_device_poll(fb_plan_t p, int32_t* stopped_out, int32_t* evaluations_out, void* stream) {
+  if (!p || !stopped_out) return fail(FB_ERR_INVALID, "null argument");
+  if (!p->fit_session || p->pc.stop == nullptr) return fail(FB_ERR_INVALID, "fb_fit_device_begin must be called first");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemcpyAsync(p->h_fit_flags, p->d_fit_flags, sizeof(int) * kFitFlagCount, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *stopped_out = p->h_fit_flags[kFitStop];
+  if (evaluations_out) *evaluations_out = p->h_fit_flags[kFitEvals];
+  return FB_OK;
+}
+
+extern "C" int fb_fit_device_end(fb_plan_t p, fb_fit_result* result, double* gram_accepted_host, int32_t* bailed_out,
+                                 void* stream) {
+  if (!p || !result) return fail(FB_ERR_INVALID, "null argument");
+  if (!p->fit_session || p->pc.stop == nullptr) return fail(FB_ERR_INVALID, "fb_fit_device_begin must be called first");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = p->n_free, ncols = n + 1;
+  const size_t gcount = (size_t)ncols * ncols, nparam = (size_t)FB_NUM_PARAMETERS * p->desc.num_components;
+  p->pc.stop = nullptr;
+  CUDA_TRY(cudaMemcpyAsync(p->h_fit_result, p->d_fit_result, sizeof(fb_fit_result), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(p->h_fit_grams, p->d_gram_accepted, sizeof(double) * gcount, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(p->h_fit_params, p->d_params, sizeof(double) * nparam, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(p->h_fit_flags, p->d_fit_flags, sizeof(int) * kFitFlagCount, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  memcpy(p->h_params, p->h_fit_params, sizeof(double) * nparam);  // the last evaluated point
+  p->tables_dirty = true;
+  p->gram_cache_valid = false;  // the caller's matrix may be a sum over ranks: never reused for the local Hessian
+  if (bailed_out) *bailed_out = p->h_fit_flags[kFitBail];
+  memset(result, 0, sizeof(*result));
+  result->num_free = n;
+  if (p->h_fit_flags[kFitBail]) {
+    result->status = -100;
+    return FB_OK;
+  }
+  if (!p->h_fit_flags[kFitFinished]) return fail(FB_ERR_INVALID, "fb_fit_device_end before the fit has finished");
+  *result = *p->h_fit_result;
+  result->num_free = n;
+  if (gram_accepted_host) memcpy(gram_accepted_host, p->h_fit_grams, sizeof(double) * gcount);
+  if (result->status == -1) return fail(FB_ERR_INVALID, "Residuals are not finite in the initial point.");
   return FB_OK;
 }
 

@@ -30,7 +30,14 @@ struct PlanConst {
   double time_first, time_last;  // times[0], times[num_time - 1]
   const double* freqs;           // (num_freq) channel centres
   const double* subfreqs;        // (num_freq, kf) routines/manipulate.py:99-105 labels
+  // device-driven fit loop (fb_batched.cuh, k_trf_single): when non-null and *stop != 0 every
+  // kernel of an evaluation returns at once -- launches enqueued past the end of a fit are no-ops
+  const int* stop;
 };
+
+__device__ __forceinline__ bool fit_stopped(const PlanConst& pc) {
+  return pc.stop != nullptr && *reinterpret_cast<const volatile int*>(pc.stop) != 0;
+}
 
 // Per-component constants (depend on parameters only).
 struct CompTab {

@@ -319,6 +319,7 @@ template <int KF>
 __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs A, double* __restrict__ gvals) {
   extern __shared__ __align__(16) unsigned char fast_smem[];
   const PlanConst& pc = A.pc;
+  if (fit_stopped(pc)) return;
   const int nc = pc.num_comp, kf = KF > 0 ? KF : pc.kf, kt = pc.kt, nt = pc.num_time;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nck = nc * kf;
@@ -655,6 +656,7 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
                                                          double* __restrict__ far_partials) {
   extern __shared__ __align__(16) unsigned char fast_smem[];
   const PlanConst& pc = A.pc;
+  if (fit_stopped(pc)) return;
   const int kt = pc.kt, nt = pc.num_time;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   char* sp = reinterpret_cast<char*>(fast_smem);
@@ -1081,7 +1083,9 @@ __global__ void __launch_bounds__(256) k_gram3_finish(const double* __restrict__
                                                       int warps_per_block, int near_entries, int far_entries,
                                                       double* __restrict__ slices, double* __restrict__ racc,
                                                       double* __restrict__ far, const ExpandArgs X,
-                                                      unsigned* __restrict__ counter, double* __restrict__ gram) {
+                                                      unsigned* __restrict__ counter, double* __restrict__ gram,
+                                                      const int* __restrict__ stop) {
+  if (stop != nullptr && *stop != 0) return;
   __shared__ bool last;
   __shared__ double red[8][33];
   const int total_entries = near_entries + far_entries;

@@ -242,6 +242,7 @@ __device__ __forceinline__ void gram_accumulate_parked(const SmemLayout& L, int 
 __global__ void __launch_bounds__(128) k_tables(const PlanConst pc, const double* __restrict__ params,
                                                 CompTab* __restrict__ g_comp, SubTab* __restrict__ g_sub,
                                                 ChanTab* __restrict__ g_chan) {
+  if (fit_stopped(pc)) return;
   const int nc = pc.num_comp;
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= pc.num_freq * nc) return;
@@ -262,6 +263,7 @@ __global__ void __launch_bounds__(128) k_tables_group(const PlanConst pc, const 
                                                       CompTab* __restrict__ g_comp, SubTab* __restrict__ g_sub,
                                                       ChanTab* __restrict__ g_chan, const int* __restrict__ chan_list,
                                                       int num_chan) {
+  if (fit_stopped(pc)) return;
   const int nc = pc.num_comp;
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int a = (int)(gid % KF), lane = threadIdx.x & 31;
@@ -674,6 +676,7 @@ __device__ __forceinline__ void eval_body(const EvalArgs& A, const int block_id,
 
 template <int MODE>
 __global__ void __launch_bounds__(kBlock, 4) k_eval(const EvalArgs A) {
+  if (fit_stopped(A.pc)) return;
   eval_body<MODE>(A, blockIdx.x, gridDim.x);
 }
 
@@ -731,6 +734,7 @@ __global__ void __launch_bounds__(128) k_tables_batched(const PlanConst pc, cons
 __global__ void __launch_bounds__(kBlock, 6) k_vals(const EvalArgs A, double* __restrict__ gvals) {
   extern __shared__ double smem_raw[];
   const PlanConst& pc = A.pc;
+  if (fit_stopped(pc)) return;
   const int nc = pc.num_comp, kf = pc.kf;
   SmemLayout L = carve(smem_raw, nc, kf, false, SM_QUEUE);
   load_comp_tables(A, L);
@@ -753,6 +757,7 @@ __global__ void __launch_bounds__(kBlock, 6) k_vals(const EvalArgs A, double* __
 __global__ void __launch_bounds__(kBlock, 6) k_gram2(const EvalArgs A, const double* __restrict__ gvals) {
   extern __shared__ double smem_raw[];
   const PlanConst& pc = A.pc;
+  if (fit_stopped(pc)) return;
   const int nc = pc.num_comp, kf = pc.kf, tid = threadIdx.x;
   SmemLayout L = carve(smem_raw, nc, kf, false, SM_PARK | SM_X);
   load_comp_tables(A, L);
@@ -827,6 +832,7 @@ template <int NB>
 __global__ void __launch_bounds__(kBlock, 6) k_gram2_mma(const EvalArgs A, const double* __restrict__ gvals) {
   extern __shared__ double smem_raw[];
   const PlanConst& pc = A.pc;
+  if (fit_stopped(pc)) return;
   const int nc = pc.num_comp, kf = pc.kf, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   SmemLayout L = carve(smem_raw, nc, kf, false, 0);
   double* xt = smem_raw + smem_bytes(nc, kf, 1, false, false, 0) / sizeof(double) +
@@ -913,7 +919,9 @@ __global__ void __launch_bounds__(kBlock, 6) k_gram2_mma(const EvalArgs A, const
 // Sums the per-warp C fragments and writes the symmetric (ncols x ncols) matrix: one warp per
 // matrix entry, lanes stride over the contributing warps, fixed-shape shuffle tree (deterministic).
 __global__ void __launch_bounds__(256) k_gram_finalize_mma(const double* __restrict__ partials, int nwarps,
-                                                          int ncols, int nb, double* __restrict__ gram) {
+                                                          int ncols, int nb, double* __restrict__ gram,
+                                                          const int* __restrict__ stop) {
+  if (stop != nullptr && *stop != 0) return;
   const int pairs = nb * (nb + 1) / 2;
   const int e = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (e >= pairs * 64) return;
@@ -939,7 +947,9 @@ __global__ void __launch_bounds__(256) k_gram_finalize_mma(const double* __restr
 // Second stage: sums the per-block partial tiles (one warp per entry, lanes stride over the
 // blocks, fixed-shape shuffle tree) and writes the symmetric (ncols x ncols) matrix.
 __global__ void __launch_bounds__(256) k_gram_finalize(const double* __restrict__ partials, int nblocks,
-                                                      int ncols, double* __restrict__ gram) {
+                                                      int ncols, double* __restrict__ gram,
+                                                      const int* __restrict__ stop) {
+  if (stop != nullptr && *stop != 0) return;
   const int side = gram_side(ncols), ntiles = gram_ntiles(ncols);
   constexpr int kk = kTile * kTile;
   const int e = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;

@@ -141,11 +141,63 @@ class ChannelShardedFitter:
                 plan, f._data_on_device().data_ptr(), gram.data_ptr(), f._stream()))
         return gram
 
-    def fit(self):
+    def _fit_device_loop(self, x0, m_total):
+        """
+        The trust-region loop on the device (fb_fit_device_*): per evaluation the local kernels, ONE
+        all-reduce of the (n+1)^2 matrix on the same stream, then the one-warp solver step -- all
+        enqueued ahead in chunks, no host synchronisation per trial point. Every rank sees the same
+        reduced matrix, takes the same decisions and therefore stops in the same chunk.
+        Returns (FitResult, accepted matrix, evaluations) or None when a trial point left the
+        domain of the fast kernels (the caller then runs the host-driven loop).
+        """
+        f = self.fitter
+        lib = _lib.load_library()
+        world = _world(self.group)[1]
+        plan, n = f._prepare()
+        f.model._push_parameters()
+        device = f.model._device
+        gram = torch.zeros((n + 1, n + 1), dtype=torch.float64, device=device)
+        data_ptr = f._data_on_device().data_ptr()
+        options = _lib.FitOptions(1e-8, 1e-8, 1e-8, 0, 0)
+        stopped, evaluations = ctypes.c_int32(0), ctypes.c_int32(0)
+        with torch.cuda.device(device):
+            stream = f._stream()
+            _lib.check(lib.fb_fit_device_begin(plan, ctypes.byref(options), int(m_total), stream))
+            chunk, enqueued, limit = 6, 0, 100 * n + 8
+            while True:
+                for _ in range(chunk):
+                    _lib.check(lib.fb_fit_device_evaluate(plan, data_ptr, gram.data_ptr(), stream))
+                    if world > 1:
+                        dist.all_reduce(gram, op=dist.ReduceOp.SUM, group=self.group)
+                    _lib.check(lib.fb_fit_device_step(plan, gram.data_ptr(), stream))
+                enqueued += chunk
+                _lib.check(lib.fb_fit_device_poll(plan, ctypes.byref(stopped), ctypes.byref(evaluations), stream))
+                if stopped.value or enqueued > limit:
+                    break
+                chunk = 4
+            res = _lib.FitResult()
+            accepted = np.zeros((n + 1, n + 1), dtype=np.float64)
+            bailed = ctypes.c_int32(0)
+            _lib.check(lib.fb_fit_device_end(plan, ctypes.byref(res), _lib.dptr(accepted), ctypes.byref(bailed), stream))
+        if bailed.value or not stopped.value:
+            return None
+        return res, accepted, int(res.nfev)
+
+    def fit(self, device_loop=True):
+        """device_loop=False keeps the trust-region state machine on the host (one all-reduce AND
+        one device->host read of the matrix per trial point): the cross-check of the device loop."""
         f = self.fitter
         x0 = f.get_fit_parameters_list()
         m_total = self.num_freq_total * f.model.num_time
-        res, gram, _ = sharded_trust_region_fit(x0, m_total, self._local_gram, group=self.group)
+        out = None
+        if device_loop and not f.model.scintillation and f._data_on_device().is_cuda:
+            start = {key: list(value) for key, value in f.load_fit_parameters_list(list(x0)).items()}
+            out = self._fit_device_loop(x0, m_total)
+            if out is None:  # rare: restart from x0 with the host-driven loop on the general kernels
+                f.model.update_parameters(start)
+        if out is None:
+            out = sharded_trust_region_fit(x0, m_total, self._local_gram, group=self.group)
+        res, gram, _ = out
         n = len(x0)
         x = np.array(res.x[:n])
         f.model.update_parameters(f.load_fit_parameters_list(x.tolist()))

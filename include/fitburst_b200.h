@@ -205,6 +205,26 @@ int fb_trf_propose(fb_trf_t trf, double* x_trial_host);
 int fb_trf_update(fb_trf_t trf, const double* gram_host);
 int fb_trf_result(fb_trf_t trf, fb_fit_result* result, double* gram_accepted_host);
 
+/* fb_fit keeps the whole trust-region loop on the device: after every evaluation one warp runs
+ * the state machine above on the finished matrix and writes the next trial point into the plan's
+ * device parameter block, evaluations are enqueued ahead in chunks and return at once after the
+ * fit has stopped (one flag read-back per chunk instead of one synchronisation per trial point).
+ * The same loop in steps, for callers that reduce the matrix over several GPUs in between (the
+ * channel-sharded fit: NCCL all-reduce of gram_dev on the same stream between _evaluate and
+ * _step; every rank then takes identical decisions):
+ *   _begin(x0 = the plan's parameters) -> repeat { _evaluate(gram_dev); [all-reduce]; _step(gram_dev) }
+ *   in chunks, _poll after each chunk until *stopped_out != 0 -> _end().
+ * num_residuals_total: number of residuals of the WHOLE problem (scipy's full-rank threshold,
+ * scipy/optimize/_lsq/common.py:94-101); <= 0 means the plan's own num_freq * num_time.
+ * *bailed_out != 0: a trial point left the domain of the fast kernels (scattering_timescale or a
+ * burst_width <= 0); result->status is -100 and the caller continues with the fb_trf_* protocol. */
+int fb_fit_device_begin(fb_plan_t plan, const fb_fit_options* options, int64_t num_residuals_total, void* stream);
+int fb_fit_device_evaluate(fb_plan_t plan, const double* data_dev, double* gram_dev, void* stream);
+int fb_fit_device_step(fb_plan_t plan, const double* gram_dev, void* stream);
+int fb_fit_device_poll(fb_plan_t plan, int32_t* stopped_out, int32_t* evaluations_out, void* stream);
+int fb_fit_device_end(fb_plan_t plan, fb_fit_result* result, double* gram_accepted_host, int32_t* bailed_out,
+                      void* stream);
+
 /* Batched independent fits (BASELINE.json config 3): `count` bursts of identical shape, burst b
  * occupying data_dev + b*num_freq*num_time, weights_dev + b*num_freq, params_dev + b *
  * FB_NUM_PARAMETERS*num_components (start point in, best fit out; all on the device). Bursts

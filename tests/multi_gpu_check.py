@@ -58,7 +58,12 @@ def main():
         local_fitter = LSFitter(data[lo:hi], local_model, good[lo:hi])
         local_fitter.fix_parameter(fixed)
     sharded = fbd.ChannelShardedFitter(local_fitter, num_freq_total=num_freq)
-    res = sharded.fit()
+    res = sharded.fit()  # trust-region loop on the device, all-reduce enqueued between evaluation and step
+    local_model.update_parameters(start)
+    res_host = sharded.fit(device_loop=False)  # host-driven loop: one matrix read-back per trial point
+    assert (res["status"], res["nfev"], res["njev"]) == (res_host["status"], res_host["nfev"], res_host["njev"]), \
+        (res["status"], res["nfev"], res_host["status"], res_host["nfev"])
+    np.testing.assert_allclose(res["x"], res_host["x"], rtol=1e-10)
     full_model.update_parameters(start)
     log = io.StringIO()
     with contextlib.redirect_stdout(log):
