@@ -174,8 +174,19 @@ def fit_stream(model, bursts, fixed_parameters, weighted_fit=True, weight_range=
     computation). `model` itself is left untouched in that mode.
     """
     if workers > 1:
-        yield from _fit_stream_concurrent(model, bursts, fixed_parameters, weighted_fit, weight_range,
-                                          exact_jacobian, int(workers))
+        # A full pass of Python's cyclic garbage collector over the ~1e6 objects torch / scipy /
+        # numpy leave on the heap holds the GIL for 0.1-0.6 s and stalls every fit in flight; the
+        # collector is suspended while the worker threads run (the fits create no reference
+        # cycles: LSFitter's lazy results hold a weak reference) and restored afterwards.
+        import gc
+        was_enabled = gc.isenabled()
+        gc.disable()
+        try:
+            yield from _fit_stream_concurrent(model, bursts, fixed_parameters, weighted_fit, weight_range,
+                                              exact_jacobian, int(workers))
+        finally:
+            if was_enabled:
+                gc.enable()
         return
     from .analysis import fitter as fitter_module
 

@@ -97,11 +97,11 @@ struct fb_plan_s {
   int* d_fit_flags = nullptr;        // FitFlag
   double* d_gram_accepted = nullptr; // (FB_MAX_FREE+1)^2
   fb_fit_result* d_fit_result = nullptr;
-  int* h_fit_flags = nullptr;        // pinned, two slots of kFitFlagCount
+  int* h_fit_flags = nullptr;        // pinned, kFitRing slots of kFitFlagCount (slot 0 doubles as the final copy)
   fb_fit_result* h_fit_result = nullptr;  // pinned
   double* h_fit_grams = nullptr;     // pinned: last evaluated + accepted matrix
   double* h_fit_params = nullptr;    // pinned parameter block
-  cudaEvent_t fit_events[2] = {nullptr, nullptr};
+  cudaEvent_t fit_events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   SingleTrfArgs* fit_session = nullptr;  // fb_fit_device_* between _begin and _end
   // pair descriptors of the exact Hessian for the current free-parameter layout (fb_hessian_impl)
   bool hess_layout_valid = false;
@@ -256,7 +256,7 @@ extern "C" int fb_plan_destroy(fb_plan_t p) {
   if (p->h_fit_result) cudaFreeHost(p->h_fit_result);
   if (p->h_fit_grams) cudaFreeHost(p->h_fit_grams);
   if (p->h_fit_params) cudaFreeHost(p->h_fit_params);
-  for (int k = 0; k < 2; ++k)
+  for (int k = 0; k < 8; ++k)
     if (p->fit_events[k]) cudaEventDestroy(p->fit_events[k]);
   delete p;
   return FB_OK;
@@ -977,11 +977,11 @@ static int ensure_device_fit(fb_plan_s* p) {
   CUDA_TRY(cudaMalloc(&p->d_fit_flags, sizeof(int) * kFitFlagCount));
   CUDA_TRY(cudaMalloc(&p->d_gram_accepted, gsz));
   CUDA_TRY(cudaMalloc(&p->d_fit_result, sizeof(fb_fit_result)));
-  CUDA_TRY(cudaMallocHost(&p->h_fit_flags, sizeof(int) * 2 * kFitFlagCount));
+  CUDA_TRY(cudaMallocHost(&p->h_fit_flags, sizeof(int) * 8 * kFitFlagCount));
   CUDA_TRY(cudaMallocHost(&p->h_fit_result, sizeof(fb_fit_result)));
   CUDA_TRY(cudaMallocHost(&p->h_fit_grams, 2 * gsz));
   CUDA_TRY(cudaMallocHost(&p->h_fit_params, sizeof(double) * FB_NUM_PARAMETERS * FB_MAX_COMPONENTS));
-  for (int k = 0; k < 2; ++k) CUDA_TRY(cudaEventCreateWithFlags(&p->fit_events[k], cudaEventDisableTiming));
+  for (int k = 0; k < 8; ++k) CUDA_TRY(cudaEventCreateWithFlags(&p->fit_events[k], cudaEventDisableTiming));
   return FB_OK;
 }
 
@@ -1013,21 +1013,37 @@ static int device_fit_setup(fb_plan_s* p, const fb_fit_options& opt, long long n
   const size_t trf_smem = trf_single_smem_bytes(n);
   if (trf_smem > 48 * 1024)
     CUDA_TRY(cudaFuncSetAttribute(k_trf_single, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trf_smem));
+  CUDA_TRY(cudaFuncSetAttribute(k_trf_block, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trf_block_smem_bytes(n)));
+  CUDA_TRY(cudaFuncSetAttribute(k_trf_chol, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)trf_chol_smem_bytes(n)));
   p->pc.stop = p->d_fit_flags;
   p->gram_cache_valid = false;
   return FB_OK;
 }
 
+// The trust-region step on the device. Default: k_trf_chol (More's iteration on Cholesky
+// factorisations, ~10-30 us). FITBURST_B200_TRF=block / warp select the eigen-decomposition forms
+// (block-parallel with warm-started Jacobi unless FITBURST_B200_TRF_WARM=0: 130-190 us; one warp:
+// 340 us) that restate scipy's SVD route literally -- kept as cross-checks.
+static int launch_trf_step(fb_plan_s* p, const SingleTrfArgs& T, cudaStream_t st) {
+  const char* mode = getenv("FITBURST_B200_TRF");
+  if (mode && !strcmp(mode, "warp"))
+    k_trf_single<<<1, 32, trf_single_smem_bytes(T.n_free), st>>>(T);
+  else if (mode && !strcmp(mode, "block"))
+    k_trf_block<<<1, kTrfThreads, trf_block_smem_bytes(T.n_free), st>>>(T, env_off("FITBURST_B200_TRF_WARM") ? 0 : 1);
+  else
+    k_trf_chol<<<1, 32, trf_chol_smem_bytes(T.n_free), st>>>(T);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 1;
+  return FB_OK;
+}
+
 // One evaluation at the plan's DEVICE parameter block followed by the trust-region step on the
-// device (k_trf_single). Nothing here waits for the GPU.
+// device. Nothing here waits for the GPU.
 static int enqueue_eval_and_step(fb_plan_s* p, const double* data_dev, const SingleTrfArgs& T, cudaStream_t st) {
   p->tables_dirty = true;  // the parameter block changes on the device between evaluations
   int rc = normal_equations_async(p, data_dev, p->d_gram, st);
   if (rc != FB_OK) return rc;
-  k_trf_single<<<1, 32, trf_single_smem_bytes(T.n_free), st>>>(T);
-  CUDA_TRY(cudaGetLastError());
-  p->launches += 1;
-  return FB_OK;
+  return launch_trf_step(p, T, st);
 }
 
 extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options* options,
@@ -1069,33 +1085,36 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
     SingleTrfArgs T;
     rc = device_fit_setup(p, opt, m, T, st);
     if (rc != FB_OK) return rc;
-    // Evaluations are enqueued in chunks, one chunk ahead of what is known to be needed; the
-    // flags are read back after each chunk. Launches past the end of the fit return at once.
+    // Evaluations are enqueued AHEAD of what is known to be needed: the first kFirst at once
+    // (fits rarely end earlier), then one more whenever the flags of evaluation e - kAhead have
+    // come back without the stop bit, so the GPU always has the next evaluation queued and at
+    // most kAhead evaluations (no-op launches of a few microseconds) are enqueued past the end.
+    constexpr int kFirst = 5, kAhead = 2, kRing = 8;
     const int max_evals = (opt.max_nfev > 0 ? opt.max_nfev : 100 * n) + 2;
     int enqueued = 0;
-    auto enqueue_chunk = [&](int count, int slot) -> int {
-      for (int k = 0; k < count; ++k) {
-        const int rc2 = enqueue_eval_and_step(p, data_dev, T, st);
-        if (rc2 != FB_OK) return rc2;
-      }
-      enqueued += count;
+    auto enqueue_one = [&]() -> int {
+      const int rc2 = enqueue_eval_and_step(p, data_dev, T, st);
+      if (rc2 != FB_OK) return rc2;
+      const int slot = enqueued % kRing;
       CUDA_TRY(cudaMemcpyAsync(p->h_fit_flags + slot * kFitFlagCount, p->d_fit_flags, sizeof(int) * kFitFlagCount,
                                cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaEventRecord(p->fit_events[slot], st));
+      ++enqueued;
       return FB_OK;
     };
-    rc = enqueue_chunk(6, 0);
-    if (rc != FB_OK) return rc;
-    for (int k = 0;; ++k) {
-      const int cur = k & 1;
-      const bool room = enqueued < max_evals;
-      if (room) {
-        rc = enqueue_chunk(4, cur ^ 1);
+    for (int k = 0; k < kFirst; ++k) {
+      rc = enqueue_one();
+      if (rc != FB_OK) return rc;
+    }
+    for (int checked = 0;; ++checked) {  // `checked`: the evaluation whose flags are inspected next
+      if (checked >= enqueued) return fail(FB_ERR_CUDA, "device-driven fit did not terminate within %d evaluations", max_evals);
+      const int slot = checked % kRing;
+      CUDA_TRY(cudaEventSynchronize(p->fit_events[slot]));
+      if (p->h_fit_flags[slot * kFitFlagCount + kFitStop]) break;
+      while (enqueued < max_evals && enqueued - (checked + 1) < kAhead) {
+        rc = enqueue_one();
         if (rc != FB_OK) return rc;
       }
-      CUDA_TRY(cudaEventSynchronize(p->fit_events[cur]));
-      if (p->h_fit_flags[cur * kFitFlagCount + kFitStop]) break;
-      if (!room) return fail(FB_ERR_CUDA, "device-driven fit did not terminate within %d evaluations", max_evals);
     }
     // everything the host needs, in one go: results, the last evaluated and the accepted matrix,
     // the parameter block (last evaluated point), the flags
@@ -1112,7 +1131,15 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
     if (p->h_fit_flags[kFitBail]) {
       // a trial point left the fast kernels' domain: continue on the host from the device state
       CUDA_TRY(cudaMemcpy(stt, p->d_trf, sizeof(TrfState), cudaMemcpyDeviceToHost));
-      pending_trial = true;
+      // bail code 1: S.x_new is proposed but not evaluated; 2: the device solver broke down before
+      // proposing (re-propose here). Either way the host needs its own decomposition of J^T J if
+      // the hand-over happened inside an outer iteration (the Cholesky step keeps none).
+      pending_trial = p->h_fit_flags[kFitBail] == 1;
+      if (S.decomposed) {
+        for (int i = 0; i < n * n; ++i) S.work[i] = S.A[i];
+        jacobi_eigh(S.work, S.V, S.lam, n, n);
+        trf_after_decomposition(S);
+      }
       need_host_loop = true;
     } else {
       const fb_fit_result& R = *p->h_fit_result;
@@ -1212,10 +1239,7 @@ extern "C" int fb_fit_device_step(fb_plan_t p, const double* gram_dev, void* str
   if (!p->fit_session || p->pc.stop == nullptr) return fail(FB_ERR_INVALID, "fb_fit_device_begin must be called first");
   SingleTrfArgs T = *p->fit_session;
   T.gram = gram_dev;
-  k_trf_single<<<1, 32, trf_single_smem_bytes(T.n_free), (cudaStream_t)stream>>>(T);
-  CUDA_TRY(cudaGetLastError());
-  p->launches += 1;
-  return FB_OK;
+  return launch_trf_step(p, T, (cudaStream_t)stream);
 }
 
 extern "C" int fb_fit_device_poll(fb_plan_t p, int32_t* stopped_out, int32_t* evaluations_out, void* stream) {

@@ -228,10 +228,11 @@ FB_HD inline void trf_load_accepted(TrfState& st, const double* gram) {
   st.decomposed = 0;
 }
 
-// Top of trf.py's outer loop (trf.py:465-482). Returns 0 when the fit has finished, 1 when
-// J^T J must be decomposed for a new outer iteration, 2 when the current decomposition is still
-// valid (the inner loop is retrying with a smaller radius).
-FB_HD inline int trf_head(TrfState& st) {
+// Top of trf.py's outer loop (trf.py:465-482), scalar part: gtol / status / max_nfev checks.
+// Returns 0 when the fit has finished, 1 when a new outer iteration starts (the caller must
+// decompose J^T J), 2 when the current decomposition is still valid (the inner loop is retrying
+// with a smaller radius).
+FB_HD inline int trf_head_decide(TrfState& st) {
   const int n = st.n;
   if (st.decomposed) return 2;
   double gn = 0.0;
@@ -243,8 +244,15 @@ FB_HD inline int trf_head(TrfState& st) {
     st.finished = 1;
     return 0;
   }
-  for (int i = 0; i < n * n; ++i) st.work[i] = st.A[i];
   return 1;
+}
+
+// trf_head_decide + the scratch copy of J^T J the eigen-solver destroys.
+FB_HD inline int trf_head(TrfState& st) {
+  const int h = trf_head_decide(st);
+  if (h == 1)
+    for (int i = 0; i < st.n * st.n; ++i) st.work[i] = st.A[i];
+  return h;
 }
 
 // After s^2, V = eigh(work): s * U^T f = V^T g.
@@ -287,12 +295,13 @@ FB_HD inline int trf_propose(TrfState& st) {
   return 1;
 }
 
-// Remainder of the inner loop after evaluating the trial point (trf.py:514-567): `gram` is
-// [J r]^T [J r] at st.x_new. Returns 1 when another proposal is needed, 0 when finished.
-FB_HD inline int trf_update(TrfState& st, const double* gram) {
-  const int n = st.n, ld = n + 1;
+// Remainder of the inner loop after evaluating the trial point (trf.py:514-567), scalar part:
+// cost_new = 0.5 chi^2 at st.x_new. Returns 0 when the inner loop goes on (same point, new
+// radius), 1 when it was left with the trial point ACCEPTED (the caller copies x_new -> x, loads
+// the new J^T J / J^T r and counts a Jacobian evaluation), 2 when it was left without acceptance.
+FB_HD inline int trf_update_decide(TrfState& st, double cost_new) {
+  const int n = st.n;
   st.nfev += 1;
-  const double cost_new = 0.5 * gram[n * ld + n];
   bool inner_break = false;
   if (!isfinite(cost_new)) {
     st.Delta = 0.25 * st.step_norm;  // trf.py:519-521
@@ -321,14 +330,20 @@ FB_HD inline int trf_update(TrfState& st, const double* gram) {
     }
   }
   const bool loop_again = !inner_break && st.actual <= 0.0 && st.nfev < st.max_nfev;
-  if (loop_again) return 1;  // same outer iteration: re-solve with the new radius
-  // leaving the inner loop, trf.py:543-567
-  if (st.actual > 0.0) {
+  if (loop_again) return 0;  // same outer iteration: re-solve with the new radius
+  st.decomposed = 0;  // next call runs the outer-loop head (gtol / status / max_nfev checks)
+  return st.actual > 0.0 ? 1 : 2;
+}
+
+// trf_update_decide + the array part of an accepted step (trf.py:543-567): `gram` is
+// [J r]^T [J r] at st.x_new. Returns 1 (another proposal / the final head check is needed).
+FB_HD inline int trf_update(TrfState& st, const double* gram) {
+  const int n = st.n, ld = n + 1;
+  if (trf_update_decide(st, 0.5 * gram[n * ld + n]) == 1) {
     for (int i = 0; i < n; ++i) st.x[i] = st.x_new[i];
     trf_load_accepted(st, gram);  // f = f_new, J = jac(x), g = J^T f
     st.njev += 1;
   }
-  st.decomposed = 0;  // next call runs the outer-loop head (gtol / status / max_nfev checks)
   return 1;
 }
 

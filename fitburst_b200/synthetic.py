@@ -109,3 +109,62 @@ def add_noise(model: np.ndarray, good_freq: np.ndarray, sigma: float, seed: int)
     data = model + rng.normal(0.0, sigma, size=model.shape)
     data[~good_freq, :] = 0.0
     return data
+
+
+# ---- config 1: the tutorial workload (BASELINE.json configs[0]) ------------------------------------
+# The .npz of the tutorial is not shipped with the reference (.MISSING_LARGE_BLOBS:1); SURVEY.md
+# section 8d defines this stand-in from what the notebooks print: 16384 channels x 162 samples,
+# one Gaussian (unscattered) component with the best-fit values of tutorial_3_model.ipynb cell 13,
+# 5672 flagged channels (tutorial_2 cell 12), S/N ~ 40, seed 20220502, no up-sampling, and the
+# pipeline's default fit (dm_index, scattering_index, scattering_timescale fixed: n = 6,
+# pipelines/fitburst_pipeline.py:331).
+CONFIG1_NUM_FREQ, CONFIG1_NUM_TIME, CONFIG1_SEED, CONFIG1_NUM_BAD = 16384, 162, 20220502, 5672
+CONFIG1_FIXED = ["dm_index", "scattering_index", "scattering_timescale"]
+
+
+def config1_truth(num_time: int = CONFIG1_NUM_TIME, res_time: float = CHIME_RES_TIME_S) -> dict:
+    times = np.arange(num_time, dtype=float) * res_time
+    return {
+        "amplitude": [-0.4812764314320905],
+        "arrival_time": [float(np.mean(times))],  # tutorial_3 cell 17
+        "burst_width": [2.7258462551453457e-4],
+        "dm": [0.0],
+        "dm_index": [-2.0],
+        "ref_freq": [400.1953125],
+        "scattering_timescale": [0.0],
+        "scattering_index": [-4.0],
+        "spectral_index": [2.8705490561459213],
+        "spectral_running": [-15.86167822219646],
+    }
+
+
+def config1_start(truth: dict) -> dict:
+    """dm + 0.02, width x 1.5, amplitude - 0.1, arrival time + 2e-4."""
+    start = copy.deepcopy(truth)
+    start["dm"] = [truth["dm"][0] + 0.02]
+    start["burst_width"] = [truth["burst_width"][0] * 1.5]
+    start["amplitude"] = [truth["amplitude"][0] - 0.1]
+    start["arrival_time"] = [truth["arrival_time"][0] + 2e-4]
+    return start
+
+
+def config1_good_freq(num_freq: int = CONFIG1_NUM_FREQ, seed: int = CONFIG1_SEED) -> np.ndarray:
+    """Exactly round(5672 / 16384 * num_freq) randomly chosen flagged channels."""
+    rng = np.random.default_rng(seed)
+    good = np.ones(num_freq, dtype=bool)
+    good[rng.choice(num_freq, size=int(round(CONFIG1_NUM_BAD * num_freq / CONFIG1_NUM_FREQ)), replace=False)] = False
+    return good
+
+
+def config1_data(clean: np.ndarray, good_freq: np.ndarray, snr: float = 40.0, seed: int = CONFIG1_SEED):
+    """Noise level such that the matched-filter S/N over the usable channels is `snr`."""
+    sigma = float(np.sqrt(np.sum(clean[good_freq] ** 2)) / snr)
+    return add_noise(clean, good_freq, sigma, seed), sigma
+
+
+def channel_subset(num_freq: int, stride: int, offset: int = 0) -> np.ndarray:
+    """Indices of every `stride`-th channel, keeping the first pair adjacent: the models take the
+    channel width from freqs[1] - freqs[0] (analysis/model.py:87), so a decimated axis must start
+    with two neighbouring channels to keep the ORIGINAL width."""
+    idx = np.arange(offset % stride, num_freq - 1, stride)
+    return np.unique(np.concatenate([idx[:1], idx[:1] + 1, idx[1:]]))

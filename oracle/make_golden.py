@@ -35,10 +35,20 @@ CASES = {
     "incoherent_dm": (dict(num_freq=12, num_time=48, num_comp=1, kf=4, kt=2, dm_inc=50.0, dm=0.05), None, {}),
     "normalized_pbf": (dict(num_freq=12, num_time=48, num_comp=2, kf=2, kt=2), None, dict(normalize=True)),
     "scintillation": (dict(num_freq=12, num_time=96, num_comp=2, kf=1, kt=1, scint=True), None, {}),
+    # BASELINE.json configs[0] stand-in: every 341st of the 16384 channels x 162 samples, Gaussian
+    # component, pipeline-default fit (n = 6)
+    "config1_tutorial": (dict(config1=True, stride=341), list(syn.CONFIG1_FIXED), {}),
 }
 
 
 def case_inputs(case, tau=2e-3, dm=0.0):
+    if case.get("config1"):
+        # the tutorial stand-in on a decimated channel axis
+        freqs_full, times = syn.chime_axes(syn.CONFIG1_NUM_FREQ, syn.CONFIG1_NUM_TIME)
+        freqs = freqs_full[syn.channel_subset(syn.CONFIG1_NUM_FREQ, case["stride"])]
+        kwargs = dict(dm_incoherent=0.0, factor_freq_upsample=1, factor_time_upsample=1, num_components=1,
+                      is_folded=False, scintillation=False)
+        return freqs, times, syn.config1_truth(), kwargs
     freqs, times = syn.chime_axes(case["num_freq"], case["num_time"])
     truth = syn.truncate_components(syn.config2_truth(case["num_time"]), case["num_comp"])
     truth["scattering_timescale"] = [case.get("tau", tau)] * case["num_comp"]
@@ -78,9 +88,14 @@ def make_one(name):
     for cache in ("amplitude", "spectrum", "timediff", "timeprof"):
         out[f"cache_{cache}"] = getattr(model, f"{cache}_per_component").copy()
     if fixed is not None:
-        good = syn.make_good_freq(len(freqs), 0.3, 2)
-        data = syn.add_noise(out["model"], good, 0.1, 2)
-        start = syn.config2_start(truth)
+        if case.get("config1"):
+            good = syn.config1_good_freq(syn.CONFIG1_NUM_FREQ)[syn.channel_subset(syn.CONFIG1_NUM_FREQ, case["stride"])]
+            data, _ = syn.config1_data(out["model"], good)
+            start = syn.config1_start(truth)
+        else:
+            good = syn.make_good_freq(len(freqs), 0.3, 2)
+            data = syn.add_noise(out["model"], good, 0.1, 2)
+            start = syn.config2_start(truth)
         model.update_parameters(start)
         with ref_shim.quiet():
             fitter = LSFitter(data, model, good, weighted_fit=True)
@@ -106,7 +121,8 @@ def make_one(name):
 
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
-    for name in CASES:
+    names = sys.argv[1:] or list(CASES)  # `python oracle/make_golden.py config1_tutorial` adds one case
+    for name in names:
         out = make_one(name)
         size = os.path.getsize(os.path.join(GOLDEN_DIR, f"{name}.npz"))
         print(f"{name}: {size / 1024:.0f} KiB, keys={len(out)}")

@@ -167,3 +167,26 @@ def test_stepwise_device_fit_single_rank(native_lib):
     plan, _ = local._prepare()
     stopped = ctypes.c_int32(0)
     assert native_lib.fb_fit_device_poll(plan, ctypes.byref(stopped), None, local._stream()) != 0
+
+
+@pytest.mark.parametrize("name", ["fast_config2_shape", "fast_two_components_all_global", "general_eight_components"])
+def test_trf_step_kernels_agree(name, native_lib):
+    """The Cholesky step (default), the block-parallel eigen step (warm-started and cold Jacobi) and
+    the one-warp eigen step take the same decisions and end at the same point."""
+    case, fixed, seed = CASES[name]
+    freqs, times, kwargs, truth, start, good, data = _problem(case, seed)
+    runs = {}
+    for label, env in (("chol", {}), ("block_warm", {"FITBURST_B200_TRF": "block"}),
+                       ("block_cold", {"FITBURST_B200_TRF": "block", "FITBURST_B200_TRF_WARM": "0"}),
+                       ("warp", {"FITBURST_B200_TRF": "warp"})):
+        os.environ.update(env)
+        try:
+            runs[label] = _fit(freqs, times, kwargs, start, good, data, fixed).results
+        finally:
+            for key in env:
+                del os.environ[key]
+    ref = runs["warp"]
+    for label in ("chol", "block_warm", "block_cold"):
+        r = runs[label]
+        assert (r.status, r.nfev, r.njev) == (ref.status, ref.nfev, ref.njev), label
+        np.testing.assert_allclose(r.x, ref.x, rtol=1e-9, err_msg=label)
