@@ -90,6 +90,28 @@ def pinned_like(array) -> np.ndarray:
     return tensor.numpy()
 
 
+_HEAP_FROZEN = False
+
+
+def _freeze_heap_once():
+    """
+    A full pass of Python's cyclic garbage collector over the ~1e6 objects that torch / scipy /
+    numpy leave on the heap after import holds the GIL for 0.1-0.8 s and stalls every fit in
+    flight (measured: one 24-fit batch in four took 0.2-0.5 s longer). Those objects are module
+    level and immortal in practice: the first concurrent fit_stream call of a process collects
+    once and moves them to the permanent generation (gc.freeze), after which full collections only
+    look at what was allocated since and take microseconds. The collector stays enabled.
+    FITBURST_B200_GC_FREEZE=0 opts out.
+    """
+    global _HEAP_FROZEN
+    if _HEAP_FROZEN or os.environ.get("FITBURST_B200_GC_FREEZE", "1") == "0":
+        return
+    import gc
+    gc.collect()
+    gc.freeze()
+    _HEAP_FROZEN = True
+
+
 TRACE = None  # set to a list to collect (burst index, worker, t_taken, t_fit_start, t_fit_end) per concurrent fit
 
 
@@ -174,19 +196,9 @@ def fit_stream(model, bursts, fixed_parameters, weighted_fit=True, weight_range=
     computation). `model` itself is left untouched in that mode.
     """
     if workers > 1:
-        # A full pass of Python's cyclic garbage collector over the ~1e6 objects torch / scipy /
-        # numpy leave on the heap holds the GIL for 0.1-0.6 s and stalls every fit in flight; the
-        # collector is suspended while the worker threads run (the fits create no reference
-        # cycles: LSFitter's lazy results hold a weak reference) and restored afterwards.
-        import gc
-        was_enabled = gc.isenabled()
-        gc.disable()
-        try:
-            yield from _fit_stream_concurrent(model, bursts, fixed_parameters, weighted_fit, weight_range,
-                                              exact_jacobian, int(workers))
-        finally:
-            if was_enabled:
-                gc.enable()
+        _freeze_heap_once()
+        yield from _fit_stream_concurrent(model, bursts, fixed_parameters, weighted_fit, weight_range,
+                                          exact_jacobian, int(workers))
         return
     from .analysis import fitter as fitter_module
 

@@ -14,6 +14,7 @@
 
 #include "fb_kernels.cuh"
 #include "fb_fast.cuh"
+#include "fb_fast4.cuh"
 #include "fb_hessian.cuh"
 #include "fb_batched.cuh"
 #include "fb_preprocess.cuh"
@@ -54,6 +55,8 @@ struct fb_plan_s {
   double* h_gram = nullptr;  // pinned
   double* d_vals = nullptr;  // split evaluation: (spectrum, timediff, timeprof) per (sample, component)
   size_t vals_cap = 0;
+  int* d_bounds = nullptr;   // k_rise3: regime boundaries (jp, jt) per (good channel, component)
+  size_t bounds_cap = 0;
   CompTab* d_comp = nullptr;
   SubTab* d_sub = nullptr;
   ChanTab* d_chan = nullptr;
@@ -97,7 +100,8 @@ struct fb_plan_s {
   int* d_fit_flags = nullptr;        // FitFlag
   double* d_gram_accepted = nullptr; // (FB_MAX_FREE+1)^2
   fb_fit_result* d_fit_result = nullptr;
-  int* h_fit_flags = nullptr;        // pinned, kFitRing slots of kFitFlagCount (slot 0 doubles as the final copy)
+  int* h_fit_flags = nullptr;        // pinned + device-mapped, 8 slots of kFitFlagCount (slot 0 doubles as the final copy)
+  int* h_fit_flags_dev = nullptr;    // device address of h_fit_flags
   fb_fit_result* h_fit_result = nullptr;  // pinned
   double* h_fit_grams = nullptr;     // pinned: last evaluated + accepted matrix
   double* h_fit_params = nullptr;    // pinned parameter block
@@ -238,6 +242,7 @@ extern "C" int fb_plan_destroy(fb_plan_t p) {
   cudaFree(p->d_pairs);
   cudaFree(p->d_comp_list);
   cudaFree(p->d_vals);
+  cudaFree(p->d_bounds);
   cudaFree(p->d_racc);
   cudaFree(p->d_slices);
   cudaFree(p->d_far);
@@ -621,6 +626,82 @@ static int launch_gram3_nc(fb_plan_s* p, const EvalArgs& A, const GramLayout& G,
   }
 }
 
+template <int KF>
+static int launch_rise3_t(fb_plan_s* p, const EvalArgs& A, double* out, int* bounds, cudaStream_t st) {
+  const int nc = p->pc.num_comp, kf = p->pc.kf;
+  const size_t smem = rise3_smem_bytes(nc, kf);
+  if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request exceeds 227 KB");
+  int& occ = p->occ_cache[48 + (KF == 0 ? 0 : KF == 1 ? 1 : KF == 2 ? 2 : KF == 4 ? 3 : 4)];
+  if (occ == 0 || KF == 0) {
+    if (smem > 48 * 1024)
+      CUDA_TRY(cudaFuncSetAttribute(k_rise3<KF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_rise3<KF>, kFastBlock, smem));
+    if (occ < 1) occ = 1;
+  }
+  const int grid = std::min(A.num_chan, p->sm_count * occ);
+  k_rise3<KF><<<grid, kFastBlock, smem, st>>>(A, out, bounds);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 1;
+  return FB_OK;
+}
+
+static int launch_rise3(fb_plan_s* p, const EvalArgs& A, double* out, int* bounds, cudaStream_t st) {
+  switch (p->pc.kf) {
+    case 1: return launch_rise3_t<1>(p, A, out, bounds, st);
+    case 2: return launch_rise3_t<2>(p, A, out, bounds, st);
+    case 4: return launch_rise3_t<4>(p, A, out, bounds, st);
+    case 8: return launch_rise3_t<8>(p, A, out, bounds, st);
+    default: return launch_rise3_t<0>(p, A, out, bounds, st);
+  }
+}
+
+template <int NC, int NB>
+static int launch_gram4_t(fb_plan_s* p, const EvalArgs& A, const GramLayout& G, const FarLayout& F, cudaStream_t st,
+                          int* grid_out) {
+  const size_t smem = gram4_smem_bytes(NC, NB, p->pc.kf, F.ncols);
+  if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request exceeds 227 KB");
+  int& occ = p->occ_cache[28 + (NC - 1) * 3 + (NB - 1)];
+  if (occ == 0 || smem > 48 * 1024) {
+    if (smem > 48 * 1024)
+      CUDA_TRY(cudaFuncSetAttribute(k_gram4<NC, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gram4<NC, NB>, kFastBlock, smem));
+    if (occ < 1) occ = 1;
+  }
+  const int grid = std::min(A.num_chan, p->sm_count * occ);
+  const int nent = F.ncols * (F.ncols + 1) / 2;
+  const size_t near_sz = (size_t)grid * kFastWarps * g3_nacc(NB) * 64;
+  int rc = ensure_capacity(&p->d_partials, &p->partials_cap, near_sz + (size_t)grid * nent);
+  if (rc != FB_OK) return rc;
+  EvalArgs B = A;
+  B.partials = p->d_partials;
+  k_gram4<NC, NB><<<grid, kFastBlock, smem, st>>>(B, G, F, p->d_vals, p->d_bounds, p->d_partials + near_sz);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 1;
+  *grid_out = grid;
+  return FB_OK;
+}
+
+template <int NC>
+static int launch_gram4_nc(fb_plan_s* p, const EvalArgs& A, const GramLayout& G, const FarLayout& F, int nb,
+                           cudaStream_t st, int* grid_out) {
+  switch (nb) {
+    case 1: return launch_gram4_t<NC, 1>(p, A, G, F, st, grid_out);
+    case 2: return launch_gram4_t<NC, 2>(p, A, G, F, st, grid_out);
+    default: return launch_gram4_t<NC, 3>(p, A, G, F, st, grid_out);
+  }
+}
+
+// FITBURST_B200_EVAL=4 selects k_rise3 + k_gram4 (no spectrum-row round trip through HBM) instead
+// of k_vals3 + k_gram3. Measured on B200 at config 2 it cuts the DRAM traffic of an evaluation
+// but is SLOWER (0.54 ms against 0.42 ms: k_gram4 438 us + k_rise3 92 us against 206 + 206 us --
+// the dot products cost more issue slots at 32-sample tiles than the round trip costs time at
+// 1.4 of 6.5 TB/s), so it is opt-in; see profiles/README.md.
+static bool eval_gen4(const fb_plan_s* p) {
+  const char* v = getenv("FITBURST_B200_EVAL");
+  if (!(v && !strcmp(v, "4"))) return false;
+  return gram4_smem_bytes(p->pc.num_comp, 3, p->pc.kf, p->n_free + 1) <= 200 * 1024;
+}
+
 // k_vals3 + k_gram3 + reduction + expansion into the full (n+1)^2 matrix at gram_dev.
 static int launch_fast_gram(fb_plan_s* p, EvalArgs& A, int ncols, double* gram_dev, cudaStream_t st) {
   int rc = ensure_tables(p, st, true);
@@ -628,7 +709,21 @@ static int launch_fast_gram(fb_plan_s* p, EvalArgs& A, int ncols, double* gram_d
   const int nc = p->pc.num_comp, nt = p->pc.num_time;
   rc = ensure_capacity(&p->d_vals, &p->vals_cap, (size_t)A.num_chan * nc * nt);
   if (rc != FB_OK) return rc;
-  rc = launch_vals3(p, A, p->d_vals, st, nullptr);
+  const bool gen4 = eval_gen4(p);
+  if (gen4) {
+    const size_t need_b = (size_t)A.num_chan * nc * 2;
+    if (need_b > p->bounds_cap) {
+      cudaFree(p->d_bounds);
+      p->d_bounds = nullptr;
+      p->bounds_cap = 0;
+      CUDA_TRY(cudaMalloc(&p->d_bounds, sizeof(int) * need_b));
+      p->bounds_cap = need_b;
+    }
+    rc = launch_rise3(p, A, p->d_vals, p->d_bounds, st);
+    p->last_eval_split = false;  // d_vals holds rise-region values only: nothing for k_hess3 to reuse
+  } else {
+    rc = launch_vals3(p, A, p->d_vals, st, nullptr);
+  }
   if (rc != FB_OK) return rc;
   const GramLayout G = gram3_layout(p);
   const int nb = (G.nr + 7) / 8;
@@ -654,11 +749,20 @@ static int launch_fast_gram(fb_plan_s* p, EvalArgs& A, int ncols, double* gram_d
   F.param[ncols - 1] = 9;
   F.comp[ncols - 1] = -1;
   int grid = 0;
-  switch (nc) {
-    case 1: rc = launch_gram3_nc<1>(p, A, G, F, nb, st, &grid); break;
-    case 2: rc = launch_gram3_nc<2>(p, A, G, F, nb, st, &grid); break;
-    case 3: rc = launch_gram3_nc<3>(p, A, G, F, nb, st, &grid); break;
-    default: rc = launch_gram3_nc<4>(p, A, G, F, nb, st, &grid); break;
+  if (gen4) {
+    switch (nc) {
+      case 1: rc = launch_gram4_nc<1>(p, A, G, F, nb, st, &grid); break;
+      case 2: rc = launch_gram4_nc<2>(p, A, G, F, nb, st, &grid); break;
+      case 3: rc = launch_gram4_nc<3>(p, A, G, F, nb, st, &grid); break;
+      default: rc = launch_gram4_nc<4>(p, A, G, F, nb, st, &grid); break;
+    }
+  } else {
+    switch (nc) {
+      case 1: rc = launch_gram3_nc<1>(p, A, G, F, nb, st, &grid); break;
+      case 2: rc = launch_gram3_nc<2>(p, A, G, F, nb, st, &grid); break;
+      case 3: rc = launch_gram3_nc<3>(p, A, G, F, nb, st, &grid); break;
+      default: rc = launch_gram3_nc<4>(p, A, G, F, nb, st, &grid); break;
+    }
   }
   if (rc != FB_OK) return rc;
   const int entries = g3_nacc(nb) * 64;
@@ -977,7 +1081,8 @@ static int ensure_device_fit(fb_plan_s* p) {
   CUDA_TRY(cudaMalloc(&p->d_fit_flags, sizeof(int) * kFitFlagCount));
   CUDA_TRY(cudaMalloc(&p->d_gram_accepted, gsz));
   CUDA_TRY(cudaMalloc(&p->d_fit_result, sizeof(fb_fit_result)));
-  CUDA_TRY(cudaMallocHost(&p->h_fit_flags, sizeof(int) * 8 * kFitFlagCount));
+  CUDA_TRY(cudaHostAlloc(&p->h_fit_flags, sizeof(int) * 8 * kFitFlagCount, cudaHostAllocMapped));
+  CUDA_TRY(cudaHostGetDevicePointer(&p->h_fit_flags_dev, p->h_fit_flags, 0));
   CUDA_TRY(cudaMallocHost(&p->h_fit_result, sizeof(fb_fit_result)));
   CUDA_TRY(cudaMallocHost(&p->h_fit_grams, 2 * gsz));
   CUDA_TRY(cudaMallocHost(&p->h_fit_params, sizeof(double) * FB_NUM_PARAMETERS * FB_MAX_COMPONENTS));
@@ -1038,12 +1143,16 @@ static int launch_trf_step(fb_plan_s* p, const SingleTrfArgs& T, cudaStream_t st
 }
 
 // One evaluation at the plan's DEVICE parameter block followed by the trust-region step on the
-// device. Nothing here waits for the GPU.
-static int enqueue_eval_and_step(fb_plan_s* p, const double* data_dev, const SingleTrfArgs& T, cudaStream_t st) {
+// device, which also writes the flags to host slot `slot`. Nothing here waits for the GPU.
+static int enqueue_eval_and_step(fb_plan_s* p, const double* data_dev, const SingleTrfArgs& T, int slot, int seq,
+                                 cudaStream_t st) {
   p->tables_dirty = true;  // the parameter block changes on the device between evaluations
   int rc = normal_equations_async(p, data_dev, p->d_gram, st);
   if (rc != FB_OK) return rc;
-  return launch_trf_step(p, T, st);
+  SingleTrfArgs T2 = T;
+  T2.host_flags = p->h_fit_flags_dev + slot * kFitFlagCount;
+  T2.seq = seq;
+  return launch_trf_step(p, T2, st);
 }
 
 extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options* options,
@@ -1089,16 +1198,19 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
     // (fits rarely end earlier), then one more whenever the flags of evaluation e - kAhead have
     // come back without the stop bit, so the GPU always has the next evaluation queued and at
     // most kAhead evaluations (no-op launches of a few microseconds) are enqueued past the end.
-    constexpr int kFirst = 5, kAhead = 2, kRing = 8;
+    constexpr int kRing = 8;
+    static const int kFirst = std::max(1, std::min(6, getenv("FITBURST_B200_FIRST") ? atoi(getenv("FITBURST_B200_FIRST")) : 5));
+    static const int kAhead = std::max(1, std::min(6, getenv("FITBURST_B200_AHEAD") ? atoi(getenv("FITBURST_B200_AHEAD")) : 2));
+    static const bool kPoll = getenv("FITBURST_B200_POLL") && atoi(getenv("FITBURST_B200_POLL")) != 0;
     const int max_evals = (opt.max_nfev > 0 ? opt.max_nfev : 100 * n) + 2;
     int enqueued = 0;
+    volatile int* hflags = reinterpret_cast<volatile int*>(p->h_fit_flags);
+    for (int k = 0; k < kRing; ++k) hflags[k * kFitFlagCount + kFitSeq] = -1;
     auto enqueue_one = [&]() -> int {
-      const int rc2 = enqueue_eval_and_step(p, data_dev, T, st);
-      if (rc2 != FB_OK) return rc2;
       const int slot = enqueued % kRing;
-      CUDA_TRY(cudaMemcpyAsync(p->h_fit_flags + slot * kFitFlagCount, p->d_fit_flags, sizeof(int) * kFitFlagCount,
-                               cudaMemcpyDeviceToHost, st));
-      CUDA_TRY(cudaEventRecord(p->fit_events[slot], st));
+      const int rc2 = enqueue_eval_and_step(p, data_dev, T, slot, enqueued, st);
+      if (rc2 != FB_OK) return rc2;
+      if (!kPoll) CUDA_TRY(cudaEventRecord(p->fit_events[slot], st));
       ++enqueued;
       return FB_OK;
     };
@@ -1109,8 +1221,22 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
     for (int checked = 0;; ++checked) {  // `checked`: the evaluation whose flags are inspected next
       if (checked >= enqueued) return fail(FB_ERR_CUDA, "device-driven fit did not terminate within %d evaluations", max_evals);
       const int slot = checked % kRing;
-      CUDA_TRY(cudaEventSynchronize(p->fit_events[slot]));
-      if (p->h_fit_flags[slot * kFitFlagCount + kFitStop]) break;
+      if (kPoll) {
+        // the step kernel writes the flags and then its sequence number into page-locked host memory
+        long spins = 0;
+        while (hflags[slot * kFitFlagCount + kFitSeq] != checked) {
+          if ((++spins & 0xfff) == 0) {
+            const cudaError_t q = cudaStreamQuery(st);
+            if (q != cudaSuccess && q != cudaErrorNotReady)
+              return fail(FB_ERR_CUDA, "device-driven fit: %s", cudaGetErrorString(q));
+            if (q == cudaSuccess && hflags[slot * kFitFlagCount + kFitSeq] != checked)
+              return fail(FB_ERR_CUDA, "device-driven fit: the stream drained without step %d reporting", checked);
+          }
+        }
+      } else {
+        CUDA_TRY(cudaEventSynchronize(p->fit_events[slot]));
+      }
+      if (hflags[slot * kFitFlagCount + kFitStop]) break;
       while (enqueued < max_evals && enqueued - (checked + 1) < kAhead) {
         rc = enqueue_one();
         if (rc != FB_OK) return rc;

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(32) k_trf_batched(const BatchedTrfArgs T) {
 // ever waiting for one (fb_fit: chunks of launches, one flag read-back per chunk). Every kernel
 // of an evaluation returns at once when flags[kFitStop] is set, so launches enqueued past the end
 // of the fit cost a few microseconds.
-enum FitFlag { kFitStop = 0, kFitFinished = 1, kFitBail = 2, kFitStarted = 3, kFitEvals = 4, kFitFlagCount = 8 };
+enum FitFlag { kFitStop = 0, kFitFinished = 1, kFitBail = 2, kFitStarted = 3, kFitEvals = 4, kFitSeq = 7, kFitFlagCount = 8 };
 
 struct SingleTrfArgs {
   int nc, n_free;
@@ -224,7 +224,20 @@ struct SingleTrfArgs {
   TrfState* state;
   int* flags;              // FitFlag
   fb_fit_result* result;
+  // when non-null: the flags are also written to this (page-locked, device-mapped) host slot at the
+  // end of the step, so that the host can follow the fit without a device-to-host copy in the
+  // stream (copies of several streams share one copy-engine queue and serialise the fits)
+  int* host_flags;
+  int seq;                 // written last into host_flags[kFitSeq]: the slot belongs to this step
 };
+
+__device__ __forceinline__ void publish_fit_flags(const SingleTrfArgs& T) {
+  if (T.host_flags == nullptr) return;
+  for (int k = 0; k < kFitSeq; ++k) T.host_flags[k] = T.flags[k];
+  __threadfence_system();
+  *reinterpret_cast<volatile int*>(T.host_flags + kFitSeq) = T.seq;
+  __threadfence_system();
+}
 
 // Two-sided Jacobi with the rotations of one round-robin step applied together: the n/2 pivot
 // pairs of a step are disjoint, their 2x2 diagonal blocks are untouched by each other's rotations,
@@ -370,7 +383,10 @@ __global__ void __launch_bounds__(32) k_trf_single(const SingleTrfArgs T) {
   extern __shared__ double sm[];
   const int lane = threadIdx.x;
   int* flags = T.flags;
-  if (flags[kFitStop]) return;
+  if (flags[kFitStop]) {
+    if (lane == 0) publish_fit_flags(T);
+    return;
+  }
   const int n = T.n_free, ncols = n + 1;
   TrfState& S = *T.state;
   const double* gram = T.gram;
@@ -457,6 +473,7 @@ __global__ void __launch_bounds__(32) k_trf_single(const SingleTrfArgs T) {
       __threadfence();
       flags[kFitStop] = 1;
     }
+    publish_fit_flags(T);
   }
 }
 
@@ -646,7 +663,10 @@ __global__ void __launch_bounds__(kTrfThreads) k_trf_block(const SingleTrfArgs T
   extern __shared__ __align__(16) unsigned char trf_smem[];
   const int tid = threadIdx.x;
   int* flags = T.flags;
-  if (*reinterpret_cast<volatile int*>(flags + kFitStop)) return;
+  if (*reinterpret_cast<volatile int*>(flags + kFitStop)) {
+    if (tid == 0) publish_fit_flags(T);
+    return;
+  }
   const int n = T.n_free, ncols = n + 1;
   TrfState& S = *reinterpret_cast<TrfState*>(trf_smem);
   double* a1 = reinterpret_cast<double*>(trf_smem + sizeof(TrfState));
@@ -734,6 +754,7 @@ __global__ void __launch_bounds__(kTrfThreads) k_trf_block(const SingleTrfArgs T
   }
   __syncthreads();
   trf_state_copy(*T.state, S, n, tid);  // persistent copy for the next step / a host hand-over
+  if (tid == 0) publish_fit_flags(T);
 }
 
 // ---- Cholesky form of the single-fit step ---------------------------------------------------------
@@ -883,7 +904,10 @@ __global__ void __launch_bounds__(32) k_trf_chol(const SingleTrfArgs T) {
   extern __shared__ __align__(16) unsigned char trf_smem[];
   const int lane = threadIdx.x;
   int* flags = T.flags;
-  if (*reinterpret_cast<volatile int*>(flags + kFitStop)) return;
+  if (*reinterpret_cast<volatile int*>(flags + kFitStop)) {
+    if (lane == 0) publish_fit_flags(T);
+    return;
+  }
   const int n = T.n_free, ncols = n + 1;
   TrfState& S = *reinterpret_cast<TrfState*>(trf_smem);
   double* M = reinterpret_cast<double*>(trf_smem + sizeof(TrfState));
@@ -1059,6 +1083,7 @@ __global__ void __launch_bounds__(32) k_trf_chol(const SingleTrfArgs T) {
     O.status = S.status;
     O.finished = S.finished;
     O.g_norm = S.g_norm;
+    publish_fit_flags(T);
   }
 }
 

@@ -97,15 +97,21 @@ def test_normal_equations_fast_vs_oracle_and_general(name, native_lib):
     case, fixed = GRAM_CASES[name]
     fc, fo = _fitters(case, fixed)
     x0 = fo.get_fit_parameters_list()
-    fast = _gram(fc, native_lib)
+    fast = _gram(fc, native_lib)  # k_vals3 + k_gram3
     with general_kernels():
         general = _gram(fc, native_lib)
+    os.environ["FITBURST_B200_EVAL"] = "4"  # opt-in second generation: k_rise3 + k_gram4 (no HBM round trip)
+    try:
+        gen4 = _gram(fc, native_lib)
+    finally:
+        del os.environ["FITBURST_B200_EVAL"]
     resid = fo.compute_residuals(x0)  # also refreshes the caches the oracle Jacobian reads
     full = np.concatenate([fo.compute_jacobian(x0), resid[:, None]], axis=1)
     want = full.T @ full
     scale = np.sqrt(np.outer(np.diag(want), np.diag(want)))
     assert np.max(np.abs(fast - want) / scale) < 1e-9, "fast kernels vs oracle"
     assert np.max(np.abs(fast - general) / scale) < 1e-11, "fast vs general kernels"
+    assert np.max(np.abs(gen4 - general) / scale) < 1e-11, "second-generation fast vs general kernels"
     assert np.array_equal(fast, fast.T)
 
 
