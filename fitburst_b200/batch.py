@@ -24,6 +24,8 @@ def chisq_grid(fitter, dm_values, sc_values) -> np.ndarray:
     """
     dm_values = np.ascontiguousarray(dm_values, dtype=np.float64)
     sc_values = np.ascontiguousarray(sc_values, dtype=np.float64)
+    if len(dm_values) == 0 or len(sc_values) == 0:  # a rank that was dealt no rows of a sharded sweep
+        return np.zeros((len(dm_values), len(sc_values)), dtype=np.float64)
     plan, _ = fitter._prepare()
     fitter.model._push_parameters()
     device = fitter.model._device

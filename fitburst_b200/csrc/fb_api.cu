@@ -1086,7 +1086,11 @@ static int ensure_device_fit(fb_plan_s* p) {
   CUDA_TRY(cudaMallocHost(&p->h_fit_result, sizeof(fb_fit_result)));
   CUDA_TRY(cudaMallocHost(&p->h_fit_grams, 2 * gsz));
   CUDA_TRY(cudaMallocHost(&p->h_fit_params, sizeof(double) * FB_NUM_PARAMETERS * FB_MAX_COMPONENTS));
-  for (int k = 0; k < 8; ++k) CUDA_TRY(cudaEventCreateWithFlags(&p->fit_events[k], cudaEventDisableTiming));
+  // blocking-sync events: a host thread that follows a fit sleeps instead of spinning (several
+  // fits in flight per GPU, one process per GPU: 32+ threads on an 8-GPU box); the look-ahead of
+  // two evaluations hides the wake-up latency
+  for (int k = 0; k < 8; ++k)
+    CUDA_TRY(cudaEventCreateWithFlags(&p->fit_events[k], cudaEventDisableTiming | cudaEventBlockingSync));
   return FB_OK;
 }
 
