@@ -1,6 +1,7 @@
 // C ABI of fitburst_b200 (see include/fitburst_b200.h). Host-side plan management and the
 // launch logic for the kernels in fb_kernels.cuh / fb_hessian.cuh / fb_batched.cuh.
 #include <cuda_runtime.h>
+#include <sched.h>
 #include <stdarg.h>
 #include <stdlib.h>
 #include <stdio.h>
@@ -108,10 +109,12 @@ struct fb_plan_s {
   cudaEvent_t fit_events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   SingleTrfArgs* fit_session = nullptr;  // fb_fit_device_* between _begin and _end
   // pair descriptors of the exact Hessian for the current free-parameter layout (fb_hessian_impl)
-  bool hess_layout_valid = false;
-  std::vector<int> hess_pair_a, hess_pair_b;
-  std::vector<int> hess_comp_off;
-  int hess_npairs = 0;
+  bool hess_layout_valid = false;  // the device copies below belong to the current free-parameter layout
+  std::vector<HessPair> hess_pairs;
+  std::vector<int> hess_pair_a, hess_pair_b, hess_comp_list;
+  int hess_comp_off[FB_MAX_COMPONENTS + 1];
+  bool hess_desc_valid = false;
+  std::vector<HessDesc> hess_desc;
   unsigned hess_need[FB_MAX_COMPONENTS];
   int hess_need_sum_dmidx = 0;
 };
@@ -496,7 +499,11 @@ extern "C" int fb_set_free_parameters(fb_plan_t p, const int32_t* free_mask, int
   }
   layout_free(p);
   for (int k = 0; k < 9; ++k)
-    if (saved[k] != p->free_mask[k]) p->gram_cache_valid = false;
+    if (saved[k] != p->free_mask[k]) {
+      p->gram_cache_valid = false;
+      p->hess_layout_valid = false;
+      p->hess_desc_valid = false;
+    }
   if (p->n_free > FB_MAX_FREE) {
     const int n = p->n_free;
     for (int k = 0; k < 9; ++k) p->free_mask[k] = saved[k];
@@ -595,11 +602,17 @@ static int launch_gram3_t(fb_plan_s* p, const EvalArgs& A, const GramLayout& G, 
                           int* grid_out) {
   const size_t smem = gram3_smem_bytes(NC, NB, F.ncols);
   if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request exceeds 227 KB");
+  // row tiles through the bulk-copy (TMA) unit: opt-in (slower, see k_gram3), and only when every
+  // row segment is 16-byte aligned and sized
+  static const bool bulk_env = getenv("FITBURST_B200_BULK") && atoi(getenv("FITBURST_B200_BULK")) != 0;
+  const bool bulk = bulk_env && p->pc.num_time % 2 == 0 && (reinterpret_cast<uintptr_t>(A.data) & 15) == 0;
   int& occ = p->occ_cache[16 + (NC - 1) * 3 + (NB - 1)];
   if (occ == 0 || smem > 48 * 1024) {
-    if (smem > 48 * 1024)
-      CUDA_TRY(cudaFuncSetAttribute(k_gram3<NC, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gram3<NC, NB>, kFastBlock, smem));
+    if (smem > 48 * 1024) {
+      CUDA_TRY(cudaFuncSetAttribute(k_gram3<NC, NB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CUDA_TRY(cudaFuncSetAttribute(k_gram3<NC, NB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_gram3<NC, NB, false>, kFastBlock, smem));
     if (occ < 1) occ = 1;
   }
   const int grid = std::min(A.num_chan, p->sm_count * occ);
@@ -609,7 +622,9 @@ static int launch_gram3_t(fb_plan_s* p, const EvalArgs& A, const GramLayout& G, 
   if (rc != FB_OK) return rc;
   EvalArgs B = A;
   B.partials = p->d_partials;
-  k_gram3<NC, NB><<<grid, kFastBlock, smem, st>>>(B, G, F, p->d_vals, p->d_partials + near_sz);
+  B.bulk_rows = bulk ? 1 : 0;
+  if (bulk) k_gram3<NC, NB, true><<<grid, kFastBlock, smem, st>>>(B, G, F, p->d_vals, p->d_partials + near_sz);
+  else k_gram3<NC, NB, false><<<grid, kFastBlock, smem, st>>>(B, G, F, p->d_vals, p->d_partials + near_sz);
   CUDA_TRY(cudaGetLastError());
   p->launches += 1;
   *grid_out = grid;
@@ -1086,9 +1101,8 @@ static int ensure_device_fit(fb_plan_s* p) {
   CUDA_TRY(cudaMallocHost(&p->h_fit_result, sizeof(fb_fit_result)));
   CUDA_TRY(cudaMallocHost(&p->h_fit_grams, 2 * gsz));
   CUDA_TRY(cudaMallocHost(&p->h_fit_params, sizeof(double) * FB_NUM_PARAMETERS * FB_MAX_COMPONENTS));
-  // blocking-sync events: a host thread that follows a fit sleeps instead of spinning (several
-  // fits in flight per GPU, one process per GPU: 32+ threads on an 8-GPU box); the look-ahead of
-  // two evaluations hides the wake-up latency
+  // (FITBURST_B200_POLL=0 only) blocking-sync events: a host thread that follows a fit sleeps instead
+  // of spinning inside the driver
   for (int k = 0; k < 8; ++k)
     CUDA_TRY(cudaEventCreateWithFlags(&p->fit_events[k], cudaEventDisableTiming | cudaEventBlockingSync));
   return FB_OK;
@@ -1188,6 +1202,13 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
   result->num_free = n;
   int rc = fb_set_parameters(p, p->h_params, stream);
   if (rc != FB_OK) return rc;
+  // FITBURST_B200_TIMING=1: wall-clock breakdown of the call on stderr
+  const bool fit_timing = getenv("FITBURST_B200_TIMING") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto since = [&](const std::chrono::steady_clock::time_point& t0) {
+    return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count();
+  };
+  double us_loop = 0.0, us_readback = 0.0;
 
   // The loop stays on the device unless the mode needs a host check after every evaluation
   // (scintillation: singular per-channel systems) or FITBURST_B200_DEVICE_LOOP=0 asks for the
@@ -1205,7 +1226,9 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
     constexpr int kRing = 8;
     static const int kFirst = std::max(1, std::min(6, getenv("FITBURST_B200_FIRST") ? atoi(getenv("FITBURST_B200_FIRST")) : 5));
     static const int kAhead = std::max(1, std::min(6, getenv("FITBURST_B200_AHEAD") ? atoi(getenv("FITBURST_B200_AHEAD")) : 2));
-    static const bool kPoll = getenv("FITBURST_B200_POLL") && atoi(getenv("FITBURST_B200_POLL")) != 0;
+    // the host follows the fit by polling the page-locked flag slots the step kernel writes (no CUDA
+    // call, microsecond reaction); FITBURST_B200_POLL=0 waits on CUDA events instead
+    static const bool kPoll = !(getenv("FITBURST_B200_POLL") && atoi(getenv("FITBURST_B200_POLL")) == 0);
     const int max_evals = (opt.max_nfev > 0 ? opt.max_nfev : 100 * n) + 2;
     int enqueued = 0;
     volatile int* hflags = reinterpret_cast<volatile int*>(p->h_fit_flags);
@@ -1229,7 +1252,8 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
         // the step kernel writes the flags and then its sequence number into page-locked host memory
         long spins = 0;
         while (hflags[slot * kFitFlagCount + kFitSeq] != checked) {
-          if ((++spins & 0xfff) == 0) {
+          if ((++spins & 0x3f) == 0) sched_yield();  // other fits' host threads may share the core
+          if ((spins & 0xffff) == 0) {
             const cudaError_t q = cudaStreamQuery(st);
             if (q != cudaSuccess && q != cudaErrorNotReady)
               return fail(FB_ERR_CUDA, "device-driven fit: %s", cudaGetErrorString(q));
@@ -1246,6 +1270,7 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
         if (rc != FB_OK) return rc;
       }
     }
+    us_loop = since(t_begin);
     // everything the host needs, in one go: results, the last evaluated and the accepted matrix,
     // the parameter block (last evaluated point), the flags
     CUDA_TRY(cudaMemcpyAsync(p->h_fit_result, p->d_fit_result, sizeof(fb_fit_result), cudaMemcpyDeviceToHost, st));
@@ -1254,6 +1279,7 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
     CUDA_TRY(cudaMemcpyAsync(p->h_fit_params, p->d_params, sizeof(double) * nparam, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaMemcpyAsync(p->h_fit_flags, p->d_fit_flags, sizeof(int) * kFitFlagCount, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    us_readback = since(t_begin) - us_loop;
     p->pc.stop = nullptr;
     gram.assign(p->h_fit_grams, p->h_fit_grams + gcount);
     accepted.assign(p->h_fit_grams + gcount, p->h_fit_grams + 2 * gcount);
@@ -1327,12 +1353,17 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
   }
   if (gram_final_host) memcpy(gram_final_host, accepted.data(), sizeof(double) * gcount);
   // the model is left at the LAST EVALUATED point, like analysis/fitter.py:258 leaves it.
+  const double us_before_hessian = since(t_begin);
   if (opt.compute_hessian || hessian_host) {
     std::vector<double> H((size_t)n * n);
     rc = fb_hessian_impl(p, data_dev, H.data(), st);
     if (rc != FB_OK) return rc;
     if (hessian_host) memcpy(hessian_host, H.data(), sizeof(double) * n * n);
   }
+  if (fit_timing)
+    fprintf(stderr, "fb_fit: nfev %d  loop %.0f us  readback %.0f us  host tail %.0f us  hessian %.0f us  total %.0f us\n",
+            result->nfev, us_loop, us_readback, us_before_hessian - us_loop - us_readback,
+            since(t_begin) - us_before_hessian, since(t_begin));
   return FB_OK;
 }
 
@@ -1693,50 +1724,59 @@ int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, 
       }
     }
   }
-  std::vector<HessPair> pairs;
-  std::vector<int> pair_a, pair_b;
-  for (int a = 0; a < n; ++a)
-    for (int b = a; b < n; ++b) {
-      const bool la = cc[a] >= 0, lb = cc[b] >= 0;
-      if (la && lb && cc[a] != cc[b]) continue;  // mixed partial skipped, analysis/fitter.py:158-160
-      HessPair hp;
-      hp.pa = (int8_t)cp[a];
-      hp.pb = (int8_t)cp[b];
-      hp.component = (int8_t)(lb ? cc[b] : (la ? cc[a] : 0));  // analysis/fitter.py:163-168
-      hp.is_sum = d2_is_sum(cp[a], cp[b]) ? 1 : 0;
-      pairs.push_back(hp);
-      pair_a.push_back(a);
-      pair_b.push_back(b);
+  // pair list of the current free-parameter layout: built and uploaded once per layout
+  std::vector<HessPair>& pairs = p->hess_pairs;
+  std::vector<int>&pair_a = p->hess_pair_a, &pair_b = p->hess_pair_b, &comp_list = p->hess_comp_list;
+  int* comp_off = p->hess_comp_off;
+  if (!p->hess_layout_valid) {
+    pairs.clear();
+    pair_a.clear();
+    pair_b.clear();
+    comp_list.clear();
+    for (int a = 0; a < n; ++a)
+      for (int b = a; b < n; ++b) {
+        const bool la = cc[a] >= 0, lb = cc[b] >= 0;
+        if (la && lb && cc[a] != cc[b]) continue;  // mixed partial skipped, analysis/fitter.py:158-160
+        HessPair hp;
+        hp.pa = (int8_t)cp[a];
+        hp.pb = (int8_t)cp[b];
+        hp.component = (int8_t)(lb ? cc[b] : (la ? cc[a] : 0));  // analysis/fitter.py:163-168
+        hp.is_sum = d2_is_sum(cp[a], cp[b]) ? 1 : 0;
+        pairs.push_back(hp);
+        pair_a.push_back(a);
+        pair_b.push_back(b);
+      }
+    const int np0 = (int)pairs.size();
+    if ((size_t)np0 > p->pairs_cap) {
+      cudaFree(p->d_pairs);
+      p->d_pairs = nullptr;
+      p->pairs_cap = 0;
+      CUDA_TRY(cudaMalloc(&p->d_pairs, sizeof(HessPair) * np0));
+      p->pairs_cap = np0;
     }
+    CUDA_TRY(cudaMemcpyAsync(p->d_pairs, pairs.data(), sizeof(HessPair) * np0, cudaMemcpyHostToDevice, st));
+    // per component: the pairs it contributes to (summing functions: all components; others: the
+    // one `component` the reference passes)
+    for (int c = 0; c < nc; ++c) {
+      comp_off[c] = (int)comp_list.size();
+      for (int k = 0; k < np0; ++k)
+        if (pairs[k].is_sum || pairs[k].component == c) comp_list.push_back(k);
+    }
+    comp_off[nc] = (int)comp_list.size();
+    if (comp_list.size() > p->comp_list_cap) {
+      cudaFree(p->d_comp_list);
+      p->d_comp_list = nullptr;
+      p->comp_list_cap = 0;
+      CUDA_TRY(cudaMalloc(&p->d_comp_list, sizeof(int) * comp_list.size()));
+      p->comp_list_cap = comp_list.size();
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->d_comp_list, comp_list.data(), sizeof(int) * comp_list.size(),
+                             cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    p->hess_layout_valid = true;
+    p->hess_desc_valid = false;
+  }
   const int npairs = (int)pairs.size();
-  if ((size_t)npairs > p->pairs_cap) {
-    cudaFree(p->d_pairs);
-    p->d_pairs = nullptr;
-    p->pairs_cap = 0;
-    CUDA_TRY(cudaMalloc(&p->d_pairs, sizeof(HessPair) * npairs));
-    p->pairs_cap = npairs;
-  }
-  CUDA_TRY(cudaMemcpyAsync(p->d_pairs, pairs.data(), sizeof(HessPair) * npairs, cudaMemcpyHostToDevice, st));
-  // per component: the pairs it contributes to (summing functions: all components; others: the
-  // one `component` the reference passes)
-  std::vector<int> comp_list;
-  int comp_off[FB_MAX_COMPONENTS + 1];
-  for (int c = 0; c < nc; ++c) {
-    comp_off[c] = (int)comp_list.size();
-    for (int k = 0; k < npairs; ++k)
-      if (pairs[k].is_sum || pairs[k].component == c) comp_list.push_back(k);
-  }
-  comp_off[nc] = (int)comp_list.size();
-  if (comp_list.size() > p->comp_list_cap) {
-    cudaFree(p->d_comp_list);
-    p->d_comp_list = nullptr;
-    p->comp_list_cap = 0;
-    CUDA_TRY(cudaMalloc(&p->d_comp_list, sizeof(int) * comp_list.size()));
-    p->comp_list_cap = comp_list.size();
-  }
-  CUDA_TRY(cudaMemcpyAsync(p->d_comp_list, comp_list.data(), sizeof(int) * comp_list.size(),
-                           cudaMemcpyHostToDevice, st));
-  CUDA_TRY(cudaStreamSynchronize(st));  // host vectors go out of scope
   const int ncols = n + 1;
   std::vector<double> gram((size_t)ncols * ncols), S(npairs, 0.0);
   // first-derivative products = J^T J of the weighted Jacobian at the model's current state;
@@ -1758,28 +1798,35 @@ int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, 
   }
   if (p->num_good > 0 && !p->pc.scintillation) {
     // fast path: register accumulation of the 30 term values per (sample, component)
-    std::vector<HessDesc> desc(npairs);
+    std::vector<HessDesc>& desc = p->hess_desc;
     HessAccArgs H;
     memset(&H, 0, sizeof(H));
-    for (int c = 0; c < nc; ++c) H.need[c] = 0u;
-    for (int k = 0; k < npairs; ++k) {
-      int code, idx;
-      pair_descriptor(pairs[k].pa, pairs[k].pb, code, idx);
-      desc[k].code = (int8_t)code;
-      desc[k].idx = (int8_t)idx;
-      for (int c = 0; c < nc; ++c)
-        if (pairs[k].is_sum || pairs[k].component == c) H.need[c] |= (1u << idx);
-      if (idx == 12 || idx == 21) H.need_sum_dmidx = 1;
+    if (!p->hess_desc_valid) {
+      desc.assign(npairs, HessDesc());
+      for (int c = 0; c < nc; ++c) p->hess_need[c] = 0u;
+      p->hess_need_sum_dmidx = 0;
+      for (int k = 0; k < npairs; ++k) {
+        int code, idx;
+        pair_descriptor(pairs[k].pa, pairs[k].pb, code, idx);
+        desc[k].code = (int8_t)code;
+        desc[k].idx = (int8_t)idx;
+        for (int c = 0; c < nc; ++c)
+          if (pairs[k].is_sum || pairs[k].component == c) p->hess_need[c] |= (1u << idx);
+        if (idx == 12 || idx == 21) p->hess_need_sum_dmidx = 1;
+      }
+      if ((size_t)npairs > p->desc_cap) {
+        cudaFree(p->d_desc);
+        p->d_desc = nullptr;
+        p->desc_cap = 0;
+        CUDA_TRY(cudaMalloc(&p->d_desc, sizeof(HessDesc) * npairs));
+        p->desc_cap = npairs;
+      }
+      CUDA_TRY(cudaMemcpyAsync(p->d_desc, desc.data(), sizeof(HessDesc) * npairs, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaStreamSynchronize(st));
+      p->hess_desc_valid = true;
     }
-    if ((size_t)npairs > p->desc_cap) {
-      cudaFree(p->d_desc);
-      p->d_desc = nullptr;
-      p->desc_cap = 0;
-      CUDA_TRY(cudaMalloc(&p->d_desc, sizeof(HessDesc) * npairs));
-      p->desc_cap = npairs;
-    }
-    CUDA_TRY(cudaMemcpyAsync(p->d_desc, desc.data(), sizeof(HessDesc) * npairs, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int c = 0; c < nc; ++c) H.need[c] = p->hess_need[c];
+    H.need_sum_dmidx = p->hess_need_sum_dmidx;
     H.E = base_args(p);
     H.E.data = data_dev;
     H.E.weights = p->d_weights;

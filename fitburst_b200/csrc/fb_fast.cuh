@@ -57,6 +57,40 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(gmem_src) : "memory");
 }
 
+// ---- bulk asynchronous copies (TMA unit, 1-D) completing on an mbarrier ----------------------------
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+// orders this thread's earlier generic-proxy accesses to shared memory before later async-proxy ones
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+
+// bytes: multiple of 16; dst / src 16-byte aligned
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+               "l"(src), "r"(bytes), "r"(smem_addr(bar))
+               : "memory");
+}
+
+// Waits for the phase with the given parity; traps instead of hanging if it never completes.
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned addr = smem_addr(bar);
+  unsigned done = 0;
+  for (int spins = 0; !done; ++spins) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && spins > (1 << 24)) __trap();
+  }
+}
+
 // ---- model side ---------------------------------------------------------------------------
 constexpr int kValsQueue = 256;  // rise-region (sample, component) items queued per warp and channel
 #ifndef FB_V3_SPL
@@ -647,10 +681,16 @@ __host__ __device__ inline size_t gram3_smem_bytes(int nc, int nb, int ncols) {
   if (red > stage) stage = red;  // the stage doubles as the block-reduction buffer
   const size_t pref = sizeof(double) * kG3Ring * (size_t)(nc + 1) * kFastBlock;  // ring of prefetched tiles
   return sizeof(CompTab) * nc + 2 * sizeof(ChanTab) * nc + sizeof(GTab) * nc + stage + pref +
-         gram3_far_smem_bytes(ncols);
+         gram3_far_smem_bytes(ncols) + sizeof(unsigned long long) * kFastWarps * kG3Ring + 32;
 }
 
-template <int NC, int NB>
+// BULK: the spectrum-row / data tiles are fetched with cp.async.bulk (one elected lane per warp,
+// completion on an mbarrier per ring slot: SASS UBLKCP + SYNCS) instead of one 8-byte cp.async
+// per lane (LDGSTS). Measured on B200 at config 2 (ncu, profiles/README.md): 262 us against 233 us
+// under ncu, 0.476 against 0.445 ms per evaluation -- the consumers' try_wait loops add 2.4e7 warp
+// instructions to a kernel that is issue-bound -- so the per-lane ring stays the default
+// (FITBURST_B200_BULK=1 selects this variant; it needs an even num_time).
+template <int NC, int NB, bool BULK = false>
 __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs A, const GramLayout G, const FarLayout F,
                                                          const double* __restrict__ gvals,
                                                          double* __restrict__ far_partials) {
@@ -675,7 +715,9 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
     sp += stage;
   }
   // [kG3Ring][NC + 1][32] per warp: every lane copies and later reads only its own elements, so
-  // cp.async.wait_group is the only synchronisation the prefetch needs
+  // cp.async.wait_group is the only synchronisation the prefetch needs (16-byte aligned: the
+  // bulk-copy mode writes whole row segments)
+  if constexpr (BULK) sp = reinterpret_cast<char*>((reinterpret_cast<uintptr_t>(sp) + 15) & ~(uintptr_t)15);
   double* pref = reinterpret_cast<double*>(sp) + (size_t)warp * kG3Ring * (NC + 1) * 32 + lane;
   sp += sizeof(double) * kG3Ring * (size_t)(NC + 1) * kFastBlock;
   const int ncols = F.ncols;
@@ -684,8 +726,13 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
   double* Bw = Um + (size_t)8 * ncols;              // [warps][64]
   double* Bs = Bw + kFastWarps * 64;                // [64]
   int* range = reinterpret_cast<int*>(Bs + 64);     // [NC][2] near range of every component
+  // one mbarrier per ring slot of every warp (bulk-copy mode), after the ranges, 8-byte aligned
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(
+                                 (reinterpret_cast<uintptr_t>(range + 2 * FB_MAX_COMPONENTS) + 7) & ~(uintptr_t)7) +
+                             warp * kG3Ring;
   constexpr bool kFarFits = 2 * NC + 1 <= 8;
   const bool far_on = kFarFits && F.enabled && nt > 2;
+  constexpr bool bulk = BULK;
 
   {
     const double* src = reinterpret_cast<const double*>(A.g_comp);
@@ -693,6 +740,13 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
     for (int e = tid; e < NC * (int)(sizeof(CompTab) / sizeof(double)); e += kFastBlock) dst[e] = src[e];
   }
   for (int e = lane; e < NB * 8 * kMmaRowStride; e += 32) xt[e] = 0.0;  // padding columns stay zero
+  if (bulk) {
+    if (lane == 0) {
+      for (int s = 0; s < kG3Ring; ++s) mbar_init(bars + s, 1);
+      fence_proxy_async();  // the barriers are visible to the copy unit before the first copy arrives
+    }
+    __syncwarp();
+  }
 
   constexpr int kPairs = g3_pairs(NB), kAcc = g3_nacc(NB);
   double c0[kPairs], c1[kPairs];
@@ -757,10 +811,24 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
   int is_chi = blockIdx.x, is_i = i_cur, is_k = 0;  // issue cursor
   auto issue_next = [&]() {
     if (is_i >= 0 && nk > 0) {
-      const int j = (warp + is_k * kFastWarps) * 32 + lane;
-      if (j < nt) {
+      const int j0i = (warp + is_k * kFastWarps) * 32, j = j0i + lane;
+      const double* srow_t = gvals + (size_t)is_chi * NC * nt;
+      if (bulk) {
+        // one lane hands the NC + 1 row segments of the tile to the copy unit; the slot's mbarrier
+        // completes when all their bytes have landed. The slot was last read by this warp one
+        // iteration ago (a __syncwarp lies in between): the proxy fence orders those reads first.
+        if (lane == 0) {
+          const unsigned slot = q_issue % kG3Ring;
+          const unsigned bytes = (unsigned)(min(32, nt - j0i) * (int)sizeof(double));
+          double* dst = pref - lane + (size_t)slot * (NC + 1) * 32;
+          fence_proxy_async();
+          mbar_expect_tx(bars + slot, (NC + 1) * bytes);
+#pragma unroll
+          for (int c = 0; c < NC; ++c) bulk_copy_g2s(dst + c * 32, srow_t + (size_t)c * nt + j0i, bytes, bars + slot);
+          bulk_copy_g2s(dst + NC * 32, A.data + (size_t)is_i * nt + j0i, bytes, bars + slot);
+        }
+      } else if (j < nt) {
         double* dst = pref + (size_t)(q_issue % kG3Ring) * (NC + 1) * 32;
-        const double* srow_t = gvals + (size_t)is_chi * NC * nt;
 #pragma unroll
         for (int c = 0; c < NC; ++c) cp_async8(dst + c * 32, srow_t + (size_t)c * nt + j);
         cp_async8(dst + NC * 32, A.data + (size_t)is_i * nt + j);
@@ -771,7 +839,7 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
         is_i = channel_of(is_chi);
       }
     }
-    cp_async_commit();
+    if (!bulk) cp_async_commit();
     ++q_issue;
   };
   for (int k = 0; k < kG3Depth; ++k) issue_next();
@@ -793,8 +861,9 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
     const double wi = w_cur;
     const int i_after = channel_of(chi + 2 * gridDim.x);
     const double w_next = i_next >= 0 ? __ldg(A.weights + i_next) : 0.0;
-    // the table group of this channel is older than the nk tile groups committed since
-    if (nk >= kG3Depth) cp_async_wait<kG3Depth>();
+    // the table group of this channel is older than the nk tile groups committed since (in
+    // bulk-copy mode the tables are the only cp.async groups)
+    if (nk >= kG3Depth && !bulk) cp_async_wait<kG3Depth>();
     else cp_async_wait<0>();
     __syncthreads();
     prefetch_tables(i_next, buf ^ 1);
@@ -888,7 +957,8 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
       const int j0 = wt * 32, j = j0 + lane;
       const bool valid = j < nt;
       issue_next();  // the tile kG3Depth positions ahead of this one
-      cp_async_wait<kG3Depth>();
+      if (bulk) mbar_wait(bars + q_use % kG3Ring, (q_use / kG3Ring) & 1u);
+      else cp_async_wait<kG3Depth>();
       double m[NC], dval = 0.0;
       {
         const double* src = pref + (size_t)(q_use % kG3Ring) * (NC + 1) * 32;

@@ -45,6 +45,9 @@ struct EvalArgs {
   // values stored per (sample, component): 3 = spectrum, timediff, timeprof; 2 = without timeprof
   // (only the caches and the scintillation solve need the mean profile). 0 means 3.
   int vals_spc;
+  // k_gram3: the spectrum-row / data tiles are fetched with cp.async.bulk (one elected lane, completion
+  // on an mbarrier per ring slot) instead of one 8-byte cp.async per lane; needs an even num_time
+  int bulk_rows;
 };
 
 __host__ __device__ inline bool is_fit_global(int p) {

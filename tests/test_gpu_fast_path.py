@@ -105,6 +105,11 @@ def test_normal_equations_fast_vs_oracle_and_general(name, native_lib):
         gen4 = _gram(fc, native_lib)
     finally:
         del os.environ["FITBURST_B200_EVAL"]
+    # opt-in row fetch through the bulk-copy (TMA) unit: same arithmetic, bit-identical result
+    # (read at the first fast launch of the process: set for the whole test run by
+    # FITBURST_B200_BULK=1 python -m pytest ...; here only when the variable is already set)
+    if os.environ.get("FITBURST_B200_BULK") == "1":
+        assert np.array_equal(fast, _gram(fc, native_lib))
     resid = fo.compute_residuals(x0)  # also refreshes the caches the oracle Jacobian reads
     full = np.concatenate([fo.compute_jacobian(x0), resid[:, None]], axis=1)
     want = full.T @ full
