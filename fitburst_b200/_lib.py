@@ -139,6 +139,15 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
+    path = os.environ.get("FITBURST_B200_LIB", LIB_PATH)  # developer switch: A/B of kernel build variants
+    if path != LIB_PATH and os.path.exists(path):
+        lib = ctypes.CDLL(path)
+        for name, (restype, argtypes) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = restype
+            fn.argtypes = argtypes
+        _lib = lib
+        return lib
     if not os.path.exists(LIB_PATH):
         raise FitburstB200Error(
             f"{LIB_PATH} is missing: build it with `python -m fitburst_b200.build` "

@@ -673,7 +673,10 @@ __host__ __device__ inline size_t gram3_far_smem_bytes(int ncols) {
 // Tiles of spectrum rows + data in flight per warp: with one tile ahead the kernel was bound by
 // memory latency (16 KB in flight per SM, 2.2 TB/s: an ablation with all arithmetic removed still
 // took 165 of 230 us); three tiles ahead, across channel boundaries, lift that bound.
-constexpr int kG3Depth = 3, kG3Ring = kG3Depth + 1;
+#ifndef FB_G3_DEPTH
+#define FB_G3_DEPTH 3  // measured 2 / 3 / 5 tiles ahead: 0.424 / 0.427 / 0.420 ms per evaluation (insensitive)
+#endif
+constexpr int kG3Depth = FB_G3_DEPTH, kG3Ring = kG3Depth + 1;
 
 __host__ __device__ inline size_t gram3_smem_bytes(int nc, int nb, int ncols) {
   size_t stage = sizeof(double) * (size_t)kFastWarps * nb * 8 * kMmaRowStride;
