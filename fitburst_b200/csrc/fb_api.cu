@@ -1706,10 +1706,10 @@ static int launch_hessian(fb_plan_s* p, HessArgs& H, cudaStream_t st, int* grid_
   return FB_OK;
 }
 
-int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, cudaStream_t st) {
-  if (!p->have_weights) return fail(FB_ERR_INVALID, "fb_set_weights / fb_load_weights must be called first");
+// Pair list (analysis/fitter.py:132-176) and term descriptors of the exact Hessian for the plan's
+// current free-parameter layout: built and uploaded once per layout.
+static int ensure_hessian_layout(fb_plan_s* p, cudaStream_t st) {
   const int n = p->n_free, nc = p->desc.num_components;
-  if (n < 1) return fail(FB_ERR_INVALID, "no free parameters");
   // packed columns -> (parameter, component), analysis/fitter.py:116-127
   std::vector<int> cp(n), cc(n);
   for (int k = 0; k < 9; ++k) {
@@ -1777,6 +1777,44 @@ int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, 
     p->hess_desc_valid = false;
   }
   const int npairs = (int)pairs.size();
+  if (!p->hess_desc_valid) {
+    std::vector<HessDesc>& desc = p->hess_desc;
+    desc.assign(npairs, HessDesc());
+    for (int c = 0; c < nc; ++c) p->hess_need[c] = 0u;
+    p->hess_need_sum_dmidx = 0;
+    for (int k = 0; k < npairs; ++k) {
+      int code, idx;
+      pair_descriptor(pairs[k].pa, pairs[k].pb, code, idx);
+      desc[k].code = (int8_t)code;
+      desc[k].idx = (int8_t)idx;
+      for (int c = 0; c < nc; ++c)
+        if (pairs[k].is_sum || pairs[k].component == c) p->hess_need[c] |= (1u << idx);
+      if (idx == 12 || idx == 21) p->hess_need_sum_dmidx = 1;
+    }
+    if ((size_t)npairs > p->desc_cap) {
+      cudaFree(p->d_desc);
+      p->d_desc = nullptr;
+      p->desc_cap = 0;
+      CUDA_TRY(cudaMalloc(&p->d_desc, sizeof(HessDesc) * (npairs > 0 ? npairs : 1)));
+      p->desc_cap = npairs;
+    }
+    CUDA_TRY(cudaMemcpyAsync(p->d_desc, desc.data(), sizeof(HessDesc) * npairs, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    p->hess_desc_valid = true;
+  }
+  return FB_OK;
+}
+
+int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, cudaStream_t st) {
+  if (!p->have_weights) return fail(FB_ERR_INVALID, "fb_set_weights / fb_load_weights must be called first");
+  const int n = p->n_free, nc = p->desc.num_components;
+  if (n < 1) return fail(FB_ERR_INVALID, "no free parameters");
+  int rc_layout = ensure_hessian_layout(p, st);
+  if (rc_layout != FB_OK) return rc_layout;
+  const std::vector<HessPair>& pairs = p->hess_pairs;
+  const std::vector<int>&pair_a = p->hess_pair_a, &pair_b = p->hess_pair_b;
+  const int* comp_off = p->hess_comp_off;
+  const int npairs = (int)pairs.size();
   const int ncols = n + 1;
   std::vector<double> gram((size_t)ncols * ncols), S(npairs, 0.0);
   // first-derivative products = J^T J of the weighted Jacobian at the model's current state;
@@ -1798,33 +1836,8 @@ int fb_hessian_impl(fb_plan_s* p, const double* data_dev, double* hessian_host, 
   }
   if (p->num_good > 0 && !p->pc.scintillation) {
     // fast path: register accumulation of the 30 term values per (sample, component)
-    std::vector<HessDesc>& desc = p->hess_desc;
     HessAccArgs H;
     memset(&H, 0, sizeof(H));
-    if (!p->hess_desc_valid) {
-      desc.assign(npairs, HessDesc());
-      for (int c = 0; c < nc; ++c) p->hess_need[c] = 0u;
-      p->hess_need_sum_dmidx = 0;
-      for (int k = 0; k < npairs; ++k) {
-        int code, idx;
-        pair_descriptor(pairs[k].pa, pairs[k].pb, code, idx);
-        desc[k].code = (int8_t)code;
-        desc[k].idx = (int8_t)idx;
-        for (int c = 0; c < nc; ++c)
-          if (pairs[k].is_sum || pairs[k].component == c) p->hess_need[c] |= (1u << idx);
-        if (idx == 12 || idx == 21) p->hess_need_sum_dmidx = 1;
-      }
-      if ((size_t)npairs > p->desc_cap) {
-        cudaFree(p->d_desc);
-        p->d_desc = nullptr;
-        p->desc_cap = 0;
-        CUDA_TRY(cudaMalloc(&p->d_desc, sizeof(HessDesc) * npairs));
-        p->desc_cap = npairs;
-      }
-      CUDA_TRY(cudaMemcpyAsync(p->d_desc, desc.data(), sizeof(HessDesc) * npairs, cudaMemcpyHostToDevice, st));
-      CUDA_TRY(cudaStreamSynchronize(st));
-      p->hess_desc_valid = true;
-    }
     for (int c = 0; c < nc; ++c) H.need[c] = p->hess_need[c];
     H.need_sum_dmidx = p->hess_need_sum_dmidx;
     H.E = base_args(p);
@@ -2290,7 +2303,74 @@ static int fit_batched_device(fb_plan_s* p, int count, const double* data_dev, c
   CUDA_TRY(cudaMemcpyAsync(results_host, d_results.ptr, sizeof(fb_fit_result) * (size_t)count, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   p->tables_dirty = true;
-  return check_err_flag(p, st);
+  int rc_err = check_err_flag(p, st);
+  if (rc_err != FB_OK || !opt.compute_hessian || p->pc.scintillation) return rc_err;
+
+  // ---- exact Hessians of all bursts at once, at their best-fit points (the parameter blocks hold
+  // them): tables, second-derivative sums S_ab (k_hessian_acc, blockIdx.y = burst), J^T J from the
+  // solver states; H = 2 J^T J - 2 S and the 1-sigma uncertainties on the host (n x n per burst).
+  int rc = ensure_hessian_layout(p, st);
+  if (rc != FB_OK) return rc;
+  const int npairs = (int)p->hess_pairs.size();
+  std::vector<int> skip(count);
+  for (int b = 0; b < count; ++b) skip[b] = results_host[b].status < 0 ? 1 : 0;
+  CUDA_TRY(cudaMemcpyAsync(d_done.ptr, skip.data(), sizeof(int) * count, cudaMemcpyHostToDevice, st));
+  k_tables_batched<<<tgrid, 128, 0, st>>>(p->pc, params_dev, d_comp.as<CompTab>(), d_sub.as<SubTab>(),
+                                          d_chan.as<ChanTab>(), d_done.as<int>());
+  CUDA_TRY(cudaGetLastError());
+  const int supers = (tiles + kHessSuper - 1) / kHessSuper;
+  const int hblocks = (int)std::max(1LL, std::min(64LL, ((long long)max_good * supers + 3) / 4));
+  DevBuf d_hpart, d_hsum;
+  if (d_hpart.alloc(sizeof(double) * (size_t)count * hblocks * npairs) != cudaSuccess ||
+      d_hsum.alloc(sizeof(double) * (size_t)count * npairs) != cudaSuccess)
+    return fail(FB_ERR_NOMEM, "batched Hessian allocation failed");
+  HessAccArgs H;
+  memset(&H, 0, sizeof(H));
+  H.E = A;
+  H.desc = p->d_desc;
+  H.num_pairs = npairs;
+  H.comp_list = p->d_comp_list;
+  for (int c = 0; c <= nc; ++c) H.comp_off[c] = p->hess_comp_off[c];
+  for (int c = 0; c < nc; ++c) H.need[c] = p->hess_need[c];
+  H.need_sum_dmidx = p->hess_need_sum_dmidx;
+  H.partials = d_hpart.as<double>();
+  H.gvals = nullptr;
+  H.gvals_layout = 2;
+  BatchArgs BH = B;
+  BH.partials_stride = (size_t)hblocks * npairs;
+  const size_t hsmem = hess_acc_smem_bytes(nc, kf, npairs);
+  if (hsmem > 227 * 1024) return fail(FB_ERR_INVALID, "Hessian shared-memory request %zu B exceeds 227 KB", hsmem);
+  if (hsmem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(k_hessian_acc_batched, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+  k_hessian_acc_batched<<<dim3(hblocks, count), kBlock, hsmem, st>>>(H, BH, d_done.as<int>());
+  CUDA_TRY(cudaGetLastError());
+  k_hess_finalize_batched<<<dim3((npairs + 3) / 4, count), 128, 0, st>>>(d_hpart.as<double>(), hblocks, npairs,
+                                                                         (size_t)hblocks * npairs, d_hsum.as<double>());
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 3;
+  std::vector<double> S((size_t)count * npairs), JtJ((size_t)count * n * n), Hm((size_t)n * n);
+  CUDA_TRY(cudaMemcpyAsync(S.data(), d_hsum.ptr, sizeof(double) * S.size(), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpy2DAsync(JtJ.data(), sizeof(double) * n * n,
+                             reinterpret_cast<const char*>(d_states.ptr) + offsetof(TrfState, A), sizeof(TrfState),
+                             sizeof(double) * n * n, count, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (int b = 0; b < count; ++b) {
+    if (skip[b]) {
+      for (int k = 0; k < n; ++k) results_host[b].uncertainty[k] = NAN;
+      continue;
+    }
+    const double* Ab = JtJ.data() + (size_t)b * n * n;  // J^T J at the accepted point (row-major, ld = n)
+    for (int a = 0; a < n * n; ++a) Hm[a] = 2.0 * Ab[a];
+    for (int k = 0; k < npairs; ++k) {
+      const int a = p->hess_pair_a[k], c = p->hess_pair_b[k];
+      const double v = 2.0 * S[(size_t)b * npairs + k];
+      Hm[(size_t)a * n + c] -= v;
+      if (a != c) Hm[(size_t)c * n + a] -= v;
+    }
+    invert_half_hessian(Hm, n, results_host[b].uncertainty);
+  }
+  p->tables_dirty = true;
+  return FB_OK;
 }
 
 // ---- batched independent fits (BASELINE.json config 3) ---------------------------------------------
@@ -2319,8 +2399,8 @@ extern "C" int fb_fit_batched(fb_plan_t p, int32_t count, const double* data_dev
   }
   for (int b = 0; b < count; ++b) {
     if (fitted_on_device) {
-      if (!opt.compute_hessian || results_host[b].status < 0) continue;
-      // uncertainties: exact Hessian at the best fit, burst by burst
+      if (!opt.compute_hessian || results_host[b].status < 0 || !p->pc.scintillation) continue;  // done on the device
+      // scintillation mode: exact Hessian at the best fit, burst by burst (general kernel)
       CUDA_TRY(cudaMemcpyAsync(w.data(), weights_dev + (size_t)b * nf, sizeof(double) * nf, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaMemcpyAsync(pr.data(), params_dev + (size_t)b * nparam, sizeof(double) * nparam, cudaMemcpyDeviceToHost, st));
       CUDA_TRY(cudaStreamSynchronize(st));

@@ -100,6 +100,9 @@ constexpr int kSpl = FB_V3_SPL;    // consecutive samples per lane in k_vals3 (e
 constexpr int kVTile = 32 * kSpl;  // samples per warp tile
 static_assert(kSpl % 2 == 0 && kSpl >= 2 && kSpl <= 8, "k_vals3 handles samples in 16-byte pairs");
 
+#ifndef FB_TAY_BOUND
+#define FB_TAY_BOUND 5e-13  // largest truncation-error bound at which the sub-frequency expansion is used
+#endif
 // Per (channel, component) constants of the sub-frequency expansion (see make_tay_tab).
 struct TayTab {
   double d_bar, rho_bar, dz_max;
@@ -192,7 +195,7 @@ __device__ inline void make_tay_tab(const PlanConst& pc, const CompTab& ct, cons
   t.c3rrr = c3rrr * (1.0 / 6.0);
   const double s = fabs(rho_bar) + 8.5, d = dz_max + dr_max;
   const double bound = (s * s) * (s * s) * (1.0 / 24.0) * (d * d) * (d * d);
-  t.ok = ch.fast_ok && !pc.is_folded && bound < 5e-13 && rho_bar > 0.0;
+  t.ok = ch.fast_ok && !pc.is_folded && bound < FB_TAY_BOUND && rho_bar > 0.0;
   t.pad_ = 0;
 }
 

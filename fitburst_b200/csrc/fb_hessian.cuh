@@ -539,7 +539,7 @@ __host__ __device__ inline size_t hess_acc_smem_bytes(int nc, int kf, int num_pa
 // are accumulated, and at the end of the channel the term polynomials are evaluated at the three
 // nodes x = -1, 0, 1 with the SAME device functions (M = 1, G = 0) and contracted with the
 // Lagrange weights of the moments: exact for quadratics, no per-term algebra to keep in sync.
-__global__ void __launch_bounds__(kBlock, 4) k_hessian_acc(const HessAccArgs H) {
+__device__ __forceinline__ void hessian_acc_body(const HessAccArgs& H, const int block_id, const int num_blocks) {
   extern __shared__ double smem_raw[];
   const EvalArgs& A = H.E;
   const PlanConst& pc = A.pc;
@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_hessian_acc(const HessAccArgs H) 
   const double tj_last = (double)((pc.num_time - 1) * pc.kt) + kt_mid;
   const bool shortcut = !H.need_sum_dmidx && pc.num_time > 2;
   const long long total_items = (long long)A.num_chan * supers;
-  const long long begin = total_items * blockIdx.x / gridDim.x, end = total_items * (blockIdx.x + 1) / gridDim.x;
+  const long long begin = total_items * block_id / num_blocks, end = total_items * (block_id + 1) / num_blocks;
 
   // contracts the moments of the channel whose tables are in shared memory; block-uniform
   auto flush_moments = [&]() {
@@ -755,7 +755,44 @@ __global__ void __launch_bounds__(kBlock, 4) k_hessian_acc(const HessAccArgs H) 
   }
   if (cur >= 0 && shortcut) flush_moments();
   __syncthreads();
-  for (int e = tid; e < npairs; e += kBlock) H.partials[(size_t)blockIdx.x * npairs + e] = pacc[e];
+  for (int e = tid; e < npairs; e += kBlock) H.partials[(size_t)block_id * npairs + e] = pacc[e];
+}
+
+__global__ void __launch_bounds__(kBlock, 4) k_hessian_acc(const HessAccArgs H) {
+  hessian_acc_body(H, blockIdx.x, gridDim.x);
+}
+
+// Batched variant (the on-device batched solver, fb_batched.cuh): blockIdx.y = burst, every
+// per-burst buffer offset like k_eval_batched does; bursts whose fit failed are skipped.
+__global__ void __launch_bounds__(kBlock, 4) k_hessian_acc_batched(const HessAccArgs H, const BatchArgs B,
+                                                                   const int* __restrict__ skip) {
+  const int y = blockIdx.y;
+  if (skip[y]) return;
+  HessAccArgs Hb = H;
+  Hb.E.data = H.E.data + y * B.data_stride;
+  Hb.E.weights = H.E.weights + y * B.weights_stride;
+  Hb.E.params = H.E.params + y * B.params_stride;
+  Hb.E.g_comp = H.E.g_comp + y * B.comp_stride;
+  Hb.E.g_sub = H.E.g_sub + y * B.sub_stride;
+  Hb.E.g_chan = H.E.g_chan + y * B.chan_stride;
+  Hb.E.chan_list = H.E.chan_list + y * B.list_stride;
+  Hb.E.num_chan = B.num_good[y];
+  Hb.partials = H.partials + y * B.partials_stride;
+  hessian_acc_body(Hb, blockIdx.x, gridDim.x);
+}
+
+// Sums the per-block partials of every (burst, pair): out[y * npairs + pair].
+__global__ void __launch_bounds__(128) k_hess_finalize_batched(const double* __restrict__ partials, int nblocks,
+                                                              int npairs, size_t burst_stride, double* __restrict__ out) {
+  const int y = blockIdx.y;
+  const int pi = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (pi >= npairs) return;
+  const double* part = partials + (size_t)y * burst_stride;
+  double s = 0.0;
+  for (int b = lane; b < nblocks; b += 32) s += part[(size_t)b * npairs + pi];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) out[(size_t)y * npairs + pi] = s;
 }
 
 // ---- warp-granular Hessian contraction for the fast path (fb_fast.cuh conventions) ------------

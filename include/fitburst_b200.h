@@ -230,6 +230,10 @@ int fb_fit_device_end(fb_plan_t plan, fb_fit_result* result, double* gram_accept
  * FB_NUM_PARAMETERS*num_components (start point in, best fit out; all on the device). Bursts
  * are fitted back to back, each using the whole GPU; results_host[b] receives the scalar fields
  * and, when options->compute_hessian is set, the 1-sigma uncertainties. */
+/* With options->compute_hessian the exact Hessian is evaluated at the BEST FIT of every burst
+ * (fb_fit / LSFitter evaluate it at the last evaluated point like the reference, analysis/fitter.py:
+ * 105-108; the two coincide whenever the last trial step was accepted) -- for small bursts all
+ * Hessians in one launch on the device. A burst whose Hessian cannot be computed gets NaN. */
 int fb_fit_batched(fb_plan_t plan, int32_t count, const double* data_dev, const double* weights_dev,
                    double* params_dev, const fb_fit_options* options, fb_fit_result* results_host,
                    void* stream);

@@ -71,6 +71,22 @@ def test_fit_batched_matches_individual_fits(native_lib):
         assert out[b]["nfev"] == oracles[b].results.nfev
         np.testing.assert_allclose(out[b]["x"], oracles[b].results.x, rtol=1e-6)
         assert np.all(np.isfinite(out[b]["uncertainties"])) and np.all(out[b]["uncertainties"] > 0)
+        # uncertainties of the batched device Hessian (all bursts in one launch) = those of an
+        # individual LSFitter fit of the same burst
+        import contextlib, io
+        from fitburst_b200.analysis.fitter import LSFitter
+        single_model = SpectrumModeler(freqs, times, **kwargs)
+        single_model.update_parameters(starts[b])
+        with contextlib.redirect_stdout(io.StringIO()):
+            single = LSFitter(datas[b], single_model, goods[b])
+            single.fix_parameter(["dm_index", "scattering_index"])
+            single.fit()
+            # fb_fit_batched evaluates the Hessian at the accepted best fit (include/fitburst_b200.h),
+            # LSFitter at the last evaluated point like the reference: move the model to the best fit
+            single.model.update_parameters(single.load_fit_parameters_list(single.results.x.tolist()))
+            hessian, _ = single.compute_hessian(single.data, single.fit_parameters)
+        want = np.sqrt(np.diag(np.linalg.inv(0.5 * hessian)))
+        np.testing.assert_allclose(out[b]["uncertainties"], want, rtol=1e-6)
 
 
 def test_channel_sharded_driver_single_rank(native_lib):
