@@ -1226,9 +1226,13 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
     constexpr int kRing = 8;
     static const int kFirst = std::max(1, std::min(6, getenv("FITBURST_B200_FIRST") ? atoi(getenv("FITBURST_B200_FIRST")) : 5));
     static const int kAhead = std::max(1, std::min(6, getenv("FITBURST_B200_AHEAD") ? atoi(getenv("FITBURST_B200_AHEAD")) : 2));
-    // the host follows the fit by polling the page-locked flag slots the step kernel writes (no CUDA
-    // call, microsecond reaction); FITBURST_B200_POLL=0 waits on CUDA events instead
-    static const bool kPoll = !(getenv("FITBURST_B200_POLL") && atoi(getenv("FITBURST_B200_POLL")) == 0);
+    // The host follows the fit through the page-locked flag slots the step kernel writes: a short
+    // spin on that memory (no CUDA call, microsecond reaction when the step has already run, which
+    // is the rule with two evaluations of look-ahead), then a blocking wait on the evaluation's
+    // event so that the threads of several fits in flight sleep instead of burning host cores.
+    // FITBURST_B200_POLL=1: spin only; =0: events only.
+    static const int kPollMode = getenv("FITBURST_B200_POLL") ? atoi(getenv("FITBURST_B200_POLL")) : 2;
+    static const bool kPoll = kPollMode != 0;
     const int max_evals = (opt.max_nfev > 0 ? opt.max_nfev : 100 * n) + 2;
     int enqueued = 0;
     volatile int* hflags = reinterpret_cast<volatile int*>(p->h_fit_flags);
@@ -1237,7 +1241,7 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
       const int slot = enqueued % kRing;
       const int rc2 = enqueue_eval_and_step(p, data_dev, T, slot, enqueued, st);
       if (rc2 != FB_OK) return rc2;
-      if (!kPoll) CUDA_TRY(cudaEventRecord(p->fit_events[slot], st));
+      if (kPollMode != 1) CUDA_TRY(cudaEventRecord(p->fit_events[slot], st));
       ++enqueued;
       return FB_OK;
     };
@@ -1252,6 +1256,12 @@ extern "C" int fb_fit(fb_plan_t p, const double* data_dev, const fb_fit_options*
         // the step kernel writes the flags and then its sequence number into page-locked host memory
         long spins = 0;
         while (hflags[slot * kFitFlagCount + kFitSeq] != checked) {
+          if (kPollMode == 2 && ++spins > 2000) {  // ~10-20 us of spinning: now sleep until the step is done
+            CUDA_TRY(cudaEventSynchronize(p->fit_events[slot]));
+            if (hflags[slot * kFitFlagCount + kFitSeq] != checked)
+              return fail(FB_ERR_CUDA, "device-driven fit: step %d finished without reporting", checked);
+            break;
+          }
           if ((++spins & 0x3f) == 0) sched_yield();  // other fits' host threads may share the core
           if ((spins & 0xffff) == 0) {
             const cudaError_t q = cudaStreamQuery(st);

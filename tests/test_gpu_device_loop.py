@@ -190,3 +190,24 @@ def test_trf_step_kernels_agree(name, native_lib):
         r = runs[label]
         assert (r.status, r.nfev, r.njev) == (ref.status, ref.nfev, ref.njev), label
         np.testing.assert_allclose(r.x, ref.x, rtol=1e-9, err_msg=label)
+
+
+def test_fit_stream_float32_host_spectra(native_lib):
+    """fit_stream on page-locked float32 spectra (uploaded as float32, widened by fb_widen_f32) gives
+    the fits of the same values held as float64, with one and with several fits in flight."""
+    from fitburst_b200.analysis.model import SpectrumModeler
+    from fitburst_b200.batch import fit_stream, pinned_like
+    import torch
+    case, fixed, _ = CASES["fast_config2_shape"]
+    bursts32, bursts64 = [], []
+    for seed in (31, 32, 33):
+        freqs, times, kwargs, truth, start, good, data = _problem(case, seed)
+        d32 = data.astype(np.float32)
+        bursts32.append((torch.from_numpy(d32).pin_memory().numpy(), good, start))
+        bursts64.append((pinned_like(d32.astype(np.float64)), good, start))
+    model = SpectrumModeler(freqs, times, **kwargs)
+    want = [o["results"].x for o in fit_stream(model, bursts64, fixed, workers=1)]
+    for workers in (1, 3):
+        got = [o["results"].x for o in fit_stream(model, bursts32, fixed, workers=workers)]
+        for a, b in zip(got, want):
+            np.testing.assert_array_equal(a, b)

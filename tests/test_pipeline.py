@@ -164,3 +164,42 @@ def test_find_peak_on_device_tensor(native_lib):
         dev.find_peak()
     np.testing.assert_allclose(dev.mean_intensity_freq, host.mean_intensity_freq, rtol=1e-12, atol=1e-15)
     np.testing.assert_array_equal(dev.time_of_arrivals, host.time_of_arrivals)
+
+
+@pytest.mark.gpu
+def test_float32_file_through_pinned_loader_and_quiet_run_many(native_lib, tmp_path, capsys):
+    """A float32 .npz (what telescopes write) goes through the page-locked loader as float32, is
+    widened on the device and gives the fit of the same values stored as float64; run_many(quiet=True)
+    silences the workers without touching sys.stdout (the consumer's own prints survive)."""
+    import sys
+    from fitburst_b200.pipelines.fitburst_pipeline import build_parser, run, run_many
+    name = CASES[0]
+    golden = json.load(open(os.path.join(GOLDEN_DIR, f"{name}.json")))
+    src = np.load(os.path.join(GOLDEN_DIR, f"{name}.npz"), allow_pickle=True)
+    data32 = src["data_full"].astype(np.float32)
+    paths = {}
+    for label, data in (("f32", data32), ("f64", data32.astype(np.float64))):
+        paths[label] = str(tmp_path / f"burst_{label}.npz")
+        np.savez(paths[label], data_full=data, metadata=src["metadata"], burst_parameters=src["burst_parameters"])
+    args = vars(build_parser().parse_args([paths["f32"]] + golden["cli_options"]))
+    args.pop("file")
+    results = {}
+    for label in ("f32", "f64"):
+        out_dir = tmp_path / label
+        out_dir.mkdir()
+        with contextlib.redirect_stdout(io.StringIO()):
+            results[label] = run(paths[label], output_dir=str(out_dir), **args)["results"]
+    assert results["f32"] is not None
+    for key, values in results["f64"]["model_parameters"].items():
+        np.testing.assert_array_equal(np.asarray(results["f32"]["model_parameters"][key], dtype=float),
+                                      np.asarray(values, dtype=float))
+    assert results["f32"]["fit_statistics"]["chisq_final"] == results["f64"]["fit_statistics"]["chisq_final"]
+    stdout_before = sys.stdout
+    seen = []
+    for item in run_many([paths["f32"], paths["f64"]], output_dir=str(tmp_path), quiet=True, **args):
+        print("consumer line")
+        seen.append(item["results"]["fit_statistics"]["chisq_final"])
+    assert sys.stdout is stdout_before
+    captured = capsys.readouterr().out
+    assert captured.count("consumer line") == 2 and "INFO" not in captured
+    assert seen[0] == seen[1] == results["f64"]["fit_statistics"]["chisq_final"]
