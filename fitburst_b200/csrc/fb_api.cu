@@ -567,24 +567,36 @@ static bool fast_path_ok(const fb_plan_s* p, bool for_gram) {
   return true;
 }
 
-template <int KF>
-static int launch_vals3_t(fb_plan_s* p, const EvalArgs& A, double* out, cudaStream_t st, int* grid_out) {
+template <int KF, int NC>
+static int launch_vals3_tn(fb_plan_s* p, const EvalArgs& A, double* out, cudaStream_t st, int* grid_out) {
   const int nc = p->pc.num_comp, kf = p->pc.kf;
   const size_t smem = vals3_smem_bytes(nc, kf);
   if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request exceeds 227 KB");
-  int& occ = p->occ_cache[KF == 0 ? 0 : KF == 1 ? 1 : KF == 2 ? 2 : KF == 4 ? 3 : 4];
-  if (occ == 0 || KF == 0) {
+  static int occ_table[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // per instantiation (function-local static of the template)
+  int& occ = occ_table[0];
+  if (occ == 0 || KF == 0 || NC == 0 || smem > 48 * 1024) {
     if (smem > 48 * 1024)
-      CUDA_TRY(cudaFuncSetAttribute(k_vals3<KF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_vals3<KF>, kFastBlock, smem));
+      CUDA_TRY(cudaFuncSetAttribute(k_vals3<KF, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_vals3<KF, NC>, kFastBlock, smem));
     if (occ < 1) occ = 1;
   }
   const int grid = std::min(A.num_chan, p->sm_count * occ);
-  k_vals3<KF><<<grid, kFastBlock, smem, st>>>(A, out);
+  k_vals3<KF, NC><<<grid, kFastBlock, smem, st>>>(A, out);
   CUDA_TRY(cudaGetLastError());
   p->launches += 1;
   if (grid_out) *grid_out = grid;
   return FB_OK;
+}
+
+template <int KF>
+static int launch_vals3_t(fb_plan_s* p, const EvalArgs& A, double* out, cudaStream_t st, int* grid_out) {
+  if (KF == 0) return launch_vals3_tn<0, 0>(p, A, out, st, grid_out);
+  switch (p->pc.num_comp) {
+    case 1: return launch_vals3_tn<KF, 1>(p, A, out, st, grid_out);
+    case 2: return launch_vals3_tn<KF, 2>(p, A, out, st, grid_out);
+    case 3: return launch_vals3_tn<KF, 3>(p, A, out, st, grid_out);
+    default: return launch_vals3_tn<KF, 0>(p, A, out, st, grid_out);
+  }
 }
 
 static int launch_vals3(fb_plan_s* p, const EvalArgs& A, double* out, cudaStream_t st, int* grid_out) {

@@ -81,6 +81,12 @@ struct ChanTab {
   double ref_freq;
   int scattered;      // any(sc_time(f_ia) > 0) over the sub-frequencies, analysis/model.py:339
   int fast_ok;        // regime fast paths usable (scattered, not folded, finite tables)
+  // integer sample boundaries the fast kernels need once per (channel, component); computed here,
+  // by the table kernel (one thread per pair, all channels in parallel), because inside the fast
+  // kernels they were a serial section behind a block barrier (ncu source view, round 2: a fifth
+  // of k_gram3's stall samples sat on the two barriers around it)
+  int near_lo, near_hi;  // near range of the derivatives' Gaussian factor (near_range)
+  int jp, jt;            // first sample off the clamp plateau / first pure-tail sample (vals3_boundaries)
   int pad_[2];        // sizeof % 16 == 0: the fast kernels stage the tables with 16-byte cp.async
 };
 static_assert(sizeof(ChanTab) % 16 == 0 && sizeof(SubTab) % 16 == 0 && sizeof(CompTab) % 16 == 0,
@@ -153,6 +159,84 @@ __device__ __forceinline__ double emg_shape(double z, double ratio) {
   if (arg >= 0.0) return e;
   return 2.0 * fb_exp(ratio * (0.5 * ratio - z)) - e;
 }
+
+// First sample that is NOT on the clamp plateau (jp) and first sample in the pure exponential
+// tail (jt) of one (channel, component): closed-form guess, then fixed up with the very
+// predicates of eval_sample_fast so that the classification is identical to the per-sample one.
+__device__ inline void vals3_boundaries(const PlanConst& pc, const CompTab& ct, const ChanTab& ch, int& jp, int& jt) {
+  const int nt = pc.num_time, kt = pc.kt, n = pc.ntk;
+  if (!ch.fast_ok) {
+    jp = 0;
+    jt = nt;
+    return;
+  }
+  auto plateau = [&](int j) {
+    return (linspace_at(ct.t_start, ct.t_step, ct.t_stop, j * kt + kt - 1, n) - ch.min_delay) < ct.neg5w;
+  };
+  auto tail = [&](int j) { return linspace_at(ct.t_start, ct.t_step, ct.t_stop, j * kt, n) >= ch.tail_lo; };
+  const double span = ct.t_step * (double)kt;
+  double g = ceil((ct.neg5w + ch.min_delay - ct.t_start) / span);
+  jp = (int)fmin(fmax(g, 0.0), (double)nt);
+  while (jp > 0 && !plateau(jp - 1)) --jp;
+  while (jp < nt && plateau(jp)) ++jp;
+  g = ceil((ch.tail_lo - ct.t_start) / span);
+  jt = (int)fmin(fmax(g, 0.0), (double)nt);
+  while (jt > 0 && tail(jt - 1)) --jt;
+  while (jt < nt && !tail(jt)) ++jt;
+}
+
+
+// Near range of one (channel, component): samples whose arg_exp (first_derivatives) is >= -kNearCut,
+// i.e. where the Gaussian factor G = g0 exp(arg_exp) of the derivatives is kept. The reference's
+// own cut is the exp underflow (arg_exp < -746, |T| > 38.6 w: G exactly zero); outside
+// |T| <= 10 w the factor is below e^-50 = 2e-22 of its peak, twelve orders of magnitude under
+// the 1e-10 contract, and treating it as zero there makes three quarters of the former near
+// samples far ones (a basis-block tile in k_gram3, three moments in k_hess3).
+// arg_exp is a concave quadratic of the time difference, so the set is an interval; the guess
+// from its roots is fixed up with the exact predicate.
+constexpr double kNearCut = 50.0;
+__device__ inline void near_range(const PlanConst& pc, const CompTab& ct, const ChanTab& ch, int& j_lo,
+                                        int& j_hi) {
+  const int nt = pc.num_time;
+  if (ch.sc_time == 0.0) {  // Gaussian branch: no shortcut
+    j_lo = 0;
+    j_hi = nt;
+    return;
+  }
+  const double kt_mid = 0.5 * (double)(pc.kt - 1);
+  auto far = [&](int j) {
+    const double td = fma(ct.t_step, (double)(j * pc.kt) + kt_mid, ct.t_start) - ch.mean_delay;
+    const double arg_erf = (td - ct.w * ct.w * ch.inv_tau) * ct.inv_w * kSqrtHalf;
+    const double ws = ct.w * ch.inv_tau;
+    const double arg_exp = 0.5 * ws * ws - td * ch.inv_tau - arg_erf * arg_erf;
+    return arg_exp < -kNearCut;
+  };
+  // arg_exp = -td^2 / (2 w^2): near where |td| <= w sqrt(2 kNearCut)
+  const double half = ct.w * sqrt(2.0 * kNearCut);
+  const double span = ct.t_step * (double)pc.kt;
+  const double t0 = fma(ct.t_step, kt_mid, ct.t_start) - ch.mean_delay;  // td of sample 0
+  double g = floor((-half - t0) / span);
+  j_lo = (int)fmin(fmax(g, 0.0), (double)nt);
+  g = ceil((half - t0) / span) + 1.0;
+  j_hi = (int)fmin(fmax(g, 0.0), (double)nt);
+  if (!(j_lo <= j_hi)) {  // NaN tables: no shortcut
+    j_lo = 0;
+    j_hi = nt;
+    return;
+  }
+  if (j_lo == j_hi) {  // guess says "no near sample": make sure by probing the closest one
+    const int jc = min(max((int)((0.0 - t0) / span), 0), nt - 1);
+    if (far(jc)) return;
+    j_lo = jc;
+    j_hi = jc + 1;
+  }
+  while (j_lo > 0 && !far(j_lo - 1)) --j_lo;
+  while (j_lo < j_hi && far(j_lo)) ++j_lo;
+  while (j_hi < nt && !far(j_hi)) ++j_hi;
+  while (j_hi > j_lo && far(j_hi - 1)) --j_hi;
+}
+
+
 
 __device__ inline void make_comp_tab(const PlanConst& pc, const double* params, int c, CompTab& ct) {
   const int nc = pc.num_comp;
@@ -309,6 +393,8 @@ __device__ inline void finish_chan_tab(const PlanConst& pc, const double* params
   ch.fast_ok = sm.scattered && !pc.is_folded && isfinite(ch.tail_lo) && isfinite(ch.plateau_ps) &&
                isfinite(sm.min_delay) && w > 0.0 && tau0 > 0.0;
   ch.pad_[0] = ch.pad_[1] = 0;
+  vals3_boundaries(pc, ct, ch, ch.jp, ch.jt);
+  near_range(pc, ct, ch, ch.near_lo, ch.near_hi);
 }
 
 // All tables of one (channel, component): kf SubTab entries + the ChanTab. One thread.

@@ -230,31 +230,6 @@ __device__ __forceinline__ double tay_eval(const TayTab& t, double z) {
   return g * s;
 }
 
-// First sample that is NOT on the clamp plateau (jp) and first sample in the pure exponential
-// tail (jt) of one (channel, component): closed-form guess, then fixed up with the very
-// predicates of eval_sample_fast so that the classification is identical to the per-sample one.
-__device__ inline void vals3_boundaries(const PlanConst& pc, const CompTab& ct, const ChanTab& ch, int& jp, int& jt) {
-  const int nt = pc.num_time, kt = pc.kt, n = pc.ntk;
-  if (!ch.fast_ok) {
-    jp = 0;
-    jt = nt;
-    return;
-  }
-  auto plateau = [&](int j) {
-    return (linspace_at(ct.t_start, ct.t_step, ct.t_stop, j * kt + kt - 1, n) - ch.min_delay) < ct.neg5w;
-  };
-  auto tail = [&](int j) { return linspace_at(ct.t_start, ct.t_step, ct.t_stop, j * kt, n) >= ch.tail_lo; };
-  const double span = ct.t_step * (double)kt;
-  double g = ceil((ct.neg5w + ch.min_delay - ct.t_start) / span);
-  jp = (int)fmin(fmax(g, 0.0), (double)nt);
-  while (jp > 0 && !plateau(jp - 1)) --jp;
-  while (jp < nt && plateau(jp)) ++jp;
-  g = ceil((ch.tail_lo - ct.t_start) / span);
-  jt = (int)fmin(fmax(g, 0.0), (double)nt);
-  while (jt > 0 && tail(jt - 1)) --jt;
-  while (jt < nt && !tail(jt)) ++jt;
-}
-
 // Spectrum values of component c for the kVTile samples of one warp tile, kSpl CONSECUTIVE samples
 // per lane (j0 + kSpl lane + s: 16-byte table reads and stores, kSpl independent FMA chains per
 // lane in the tail dot product). Samples in the rise region are pushed on the warp's queue
@@ -352,12 +327,15 @@ __device__ __forceinline__ void vals3_component_tile(const PlanConst& pc, const 
 
 // Stores the spectrum value of every (good channel, component, sample):
 // gvals[(chi * nc + c) * num_time + j].
-template <int KF>
+// NC > 0: the number of components is a compile-time constant (the component loops unroll and
+// their address arithmetic is hoisted: the source-line profile put a fifth of the stall samples on
+// per-(tile, component) pointer and index arithmetic); NC = 0: run-time value.
+template <int KF, int NC = 0>
 __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs A, double* __restrict__ gvals) {
   extern __shared__ __align__(16) unsigned char fast_smem[];
   const PlanConst& pc = A.pc;
   if (fit_stopped(pc)) return;
-  const int nc = pc.num_comp, kf = KF > 0 ? KF : pc.kf, kt = pc.kt, nt = pc.num_time;
+  const int nc = NC > 0 ? NC : pc.num_comp, kf = KF > 0 ? KF : pc.kf, kt = pc.kt, nt = pc.num_time;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nck = nc * kf;
   char* sp = reinterpret_cast<char*>(fast_smem);
@@ -415,10 +393,8 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
     const SubTab* sub = reinterpret_cast<const SubTab*>(tabs + (size_t)buf * tab_bytes + sizeof(ChanTab) * nc);
     int qcount = 0;
     if (tid >= 32 && tid < 32 + nc) {
-      int jp, jt;
-      vals3_boundaries(pc, comp[tid - 32], chan[tid - 32], jp, jt);
-      bounds[2 * (tid - 32)] = jp;
-      bounds[2 * (tid - 32) + 1] = jt;
+      bounds[2 * (tid - 32)] = chan[tid - 32].jp;  // precomputed by the table kernel (finish_chan_tab)
+      bounds[2 * (tid - 32) + 1] = chan[tid - 32].jt;
     }
     if (tid >= 64 && tid < 64 + nc) make_tay_tab(pc, comp[tid - 64], chan[tid - 64], sub + (tid - 64) * kf, kf, tay[tid - 64]);
     for (int e = tid; e < nck * 32; e += kFastBlock) {  // a warp covers one (component, sub-frequency) row
@@ -466,6 +442,7 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
       // meaningful when the nc * kf factors fit one pass of the warp
       const unsigned bmask = nck <= 32 ? __ballot_sync(kFullMask, b_finite) : 0u;
       __syncwarp();
+#pragma unroll
       for (int c = 0; c < nc; ++c) {
         bool deferred[kSpl];
         double v[kSpl];
@@ -602,57 +579,6 @@ __host__ __device__ constexpr int g3_acc_offset(int nb, int bi, int bj) {
   return off;
 }
 __host__ __device__ constexpr int g3_nacc(int nb) { return g3_acc_offset(nb, nb, nb); }
-
-// Near range of one (channel, component): samples whose arg_exp (first_derivatives) is >= -kNearCut,
-// i.e. where the Gaussian factor G = g0 exp(arg_exp) of the derivatives is kept. The reference's
-// own cut is the exp underflow (arg_exp < -746, |T| > 38.6 w: G exactly zero); outside
-// |T| <= 10 w the factor is below e^-50 = 2e-22 of its peak, twelve orders of magnitude under
-// the 1e-10 contract, and treating it as zero there makes three quarters of the former near
-// samples far ones (a basis-block tile in k_gram3, three moments in k_hess3).
-// arg_exp is a concave quadratic of the time difference, so the set is an interval; the guess
-// from its roots is fixed up with the exact predicate.
-constexpr double kNearCut = 50.0;
-__device__ inline void near_range(const PlanConst& pc, const CompTab& ct, const ChanTab& ch, int& j_lo,
-                                        int& j_hi) {
-  const int nt = pc.num_time;
-  if (ch.sc_time == 0.0) {  // Gaussian branch: no shortcut
-    j_lo = 0;
-    j_hi = nt;
-    return;
-  }
-  const double kt_mid = 0.5 * (double)(pc.kt - 1);
-  auto far = [&](int j) {
-    const double td = fma(ct.t_step, (double)(j * pc.kt) + kt_mid, ct.t_start) - ch.mean_delay;
-    const double arg_erf = (td - ct.w * ct.w * ch.inv_tau) * ct.inv_w * kSqrtHalf;
-    const double ws = ct.w * ch.inv_tau;
-    const double arg_exp = 0.5 * ws * ws - td * ch.inv_tau - arg_erf * arg_erf;
-    return arg_exp < -kNearCut;
-  };
-  // arg_exp = -td^2 / (2 w^2): near where |td| <= w sqrt(2 kNearCut)
-  const double half = ct.w * sqrt(2.0 * kNearCut);
-  const double span = ct.t_step * (double)pc.kt;
-  const double t0 = fma(ct.t_step, kt_mid, ct.t_start) - ch.mean_delay;  // td of sample 0
-  double g = floor((-half - t0) / span);
-  j_lo = (int)fmin(fmax(g, 0.0), (double)nt);
-  g = ceil((half - t0) / span) + 1.0;
-  j_hi = (int)fmin(fmax(g, 0.0), (double)nt);
-  if (!(j_lo <= j_hi)) {  // NaN tables: no shortcut
-    j_lo = 0;
-    j_hi = nt;
-    return;
-  }
-  if (j_lo == j_hi) {  // guess says "no near sample": make sure by probing the closest one
-    const int jc = min(max((int)((0.0 - t0) / span), 0), nt - 1);
-    if (far(jc)) return;
-    j_lo = jc;
-    j_hi = jc + 1;
-  }
-  while (j_lo > 0 && !far(j_lo - 1)) --j_lo;
-  while (j_lo < j_hi && far(j_lo)) ++j_lo;
-  while (j_hi < nt && !far(j_hi)) ++j_hi;
-  while (j_hi > j_lo && far(j_hi - 1)) --j_hi;
-}
-
 
 // Far tiles (every sample outside the near range of every component: the shared factor G of
 // the first derivatives is exactly zero there): each column of [J r] is a per-channel linear
@@ -904,7 +830,10 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
       t.mean_delay = ch.mean_delay;
       gt[tid] = t;
       int j_lo = 0, j_hi = nt;
-      if (far_on && std_ok) near_range(pc, ct, ch, j_lo, j_hi);
+      if (far_on && std_ok) {  // precomputed by the table kernel (finish_chan_tab)
+        j_lo = ch.near_lo;
+        j_hi = ch.near_hi;
+      }
       range[2 * tid] = j_lo;
       range[2 * tid + 1] = j_hi;
     } else if (far_on && have_prev) {

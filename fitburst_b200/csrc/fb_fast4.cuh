@@ -96,8 +96,7 @@ __global__ void __launch_bounds__(kFastBlock, FB_R3_MINB) k_rise3(const EvalArgs
     const ChanTab* chan = reinterpret_cast<const ChanTab*>(tabs + (size_t)buf * tab_bytes);
     const SubTab* sub = reinterpret_cast<const SubTab*>(tabs + (size_t)buf * tab_bytes + sizeof(ChanTab) * nc);
     if (tid < nc) {
-      int jp, jt;
-      vals3_boundaries(pc, comp[tid], chan[tid], jp, jt);
+      int jp = chan[tid].jp, jt = chan[tid].jt;  // precomputed by the table kernel
       if (jt < jp) jt = jp;  // a component that is clamped past its own tail start has no rise region
       bounds[2 * tid] = jp;
       bounds[2 * tid + 1] = jt;
@@ -353,7 +352,10 @@ __global__ void __launch_bounds__(kFastBlock, FB_G4_MINB) k_gram4(const EvalArgs
       t.mean_delay = ch.mean_delay;
       gt[tid] = t;
       int j_lo = 0, j_hi = nt;
-      if (far_on && std_ok) near_range(pc, ct, ch, j_lo, j_hi);
+      if (far_on && std_ok) {
+        j_lo = ch.near_lo;
+        j_hi = ch.near_hi;
+      }
       range[2 * tid] = j_lo;
       range[2 * tid + 1] = j_hi;
       bnd[2 * tid] = __ldcg(gbounds + ((size_t)chi * NC + tid) * 2);

@@ -873,7 +873,10 @@ __global__ void __launch_bounds__(kFastBlock, FB_H3_MINB) k_hess3(const HessAccA
       const CompTab& ct = comp[tid];
       const ChanTab& ch = chan[tid];
       int j_lo = 0, j_hi = nt;
-      if (shortcut) near_range(pc, ct, ch, j_lo, j_hi);
+      if (shortcut) {  // precomputed by the table kernel (finish_chan_tab)
+        j_lo = ch.near_lo;
+        j_hi = ch.near_hi;
+      }
       range[2 * tid] = j_lo;
       range[2 * tid + 1] = j_hi;
       const double tc_lo = fma(ct.t_step, kt_mid, ct.t_start) - ch.mean_delay;
