@@ -823,7 +823,8 @@ static int launch_fast_gram(fb_plan_s* p, EvalArgs& A, int ncols, double* gram_d
   X.shift[ncols - 1] = 0.0;
   const int far_entries = F.enabled ? nent : 0;
   k_gram3_finish<<<dim3(gram3_finish_groups(entries, far_entries), kFinishSlices), 256, 0, st>>>(
-      p->d_partials, grid, kFastWarps, entries, far_entries, p->d_slices, p->d_racc, p->d_far, X, p->d_counter, gram_dev,
+      p->d_partials, grid, kFastWarps, gen4 ? 1 : kFastWarps, entries, far_entries, p->d_slices, p->d_racc, p->d_far, X,
+      p->d_counter, gram_dev,
       p->pc.stop);
   CUDA_TRY(cudaGetLastError());
   p->launches += 1;

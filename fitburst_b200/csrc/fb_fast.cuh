@@ -1066,6 +1066,18 @@ __global__ void __launch_bounds__(kFastBlock, FB_G3_MINB) k_gram3(const EvalArgs
     for (int s2 = 0; s2 < 2; ++s2)
       if (tid + s2 * kFastBlock < nent) far_partials[(size_t)blockIdx.x * nent + tid + s2 * kFastBlock] = gacc[s2];
   }
+  // the four per-warp accumulator sets of this block are summed into the first one (warp order):
+  // k_gram3_finish then reads one set per block instead of one per warp
+  __syncthreads();
+  {
+    double* base = A.partials + (size_t)blockIdx.x * kFastWarps * kAcc * 64;
+    for (int e = tid; e < kAcc * 64; e += kFastBlock) {
+      double t = base[e];
+#pragma unroll
+      for (int w = 1; w < kFastWarps; ++w) t += base[(size_t)w * kAcc * 64 + e];
+      base[e] = t;
+    }
+  }
 }
 
 // Full column k of [J r] = factor * (L + shift)^power * reduced column `red` (per channel).
@@ -1095,7 +1107,7 @@ __host__ __device__ inline int gram3_finish_groups(int near_entries, int far_ent
 }
 
 __global__ void __launch_bounds__(256) k_gram3_finish(const double* __restrict__ partials, int nblocks,
-                                                      int warps_per_block, int near_entries, int far_entries,
+                                                      int warps_per_block, int near_stride, int near_entries, int far_entries,
                                                       double* __restrict__ slices, double* __restrict__ racc,
                                                       double* __restrict__ far, const ExpandArgs X,
                                                       unsigned* __restrict__ counter, double* __restrict__ gram,
@@ -1110,9 +1122,12 @@ __global__ void __launch_bounds__(256) k_gram3_finish(const double* __restrict__
     const bool is_far = (int)blockIdx.x >= near_groups;
     const int e = (is_far ? (int)blockIdx.x - near_groups : (int)blockIdx.x) * 32 + lane;
     const int entries = is_far ? far_entries : near_entries;
+    // near accumulators: `nblocks * warps_per_block` sets were allocated; every near_stride-th one is
+    // read (k_gram3 pre-sums the sets of a block into its first: near_stride = warps_per_block)
     const size_t near_sets = (size_t)nblocks * warps_per_block;
     const double* src = is_far ? partials + near_sets * near_entries : partials;
-    const int count = is_far ? nblocks : (int)near_sets;
+    const int count = is_far ? nblocks : (int)(near_sets / near_stride);
+    const size_t set_pitch = is_far ? (size_t)far_entries : (size_t)near_stride * near_entries;
     const int stride = 8 * (int)gridDim.y;
     double a[8];
 #pragma unroll
@@ -1121,9 +1136,9 @@ __global__ void __launch_bounds__(256) k_gram3_finish(const double* __restrict__
       int b = (int)blockIdx.y * 8 + warp;
       for (; b + 7 * stride < count; b += 8 * stride) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) a[u] += __ldcg(src + (size_t)(b + u * stride) * entries + e);
+        for (int u = 0; u < 8; ++u) a[u] += __ldcg(src + (size_t)(b + u * stride) * set_pitch + e);
       }
-      for (; b < count; b += stride) a[0] += __ldcg(src + (size_t)b * entries + e);
+      for (; b < count; b += stride) a[0] += __ldcg(src + (size_t)b * set_pitch + e);
     }
     red[warp][lane] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     __syncthreads();
