@@ -7,10 +7,9 @@ O=gpurun_out
 $CMD > $O/r2_prof_plain.log 2>&1 || { echo "plain run failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum --clock-control none -c 500 --csv --log-file $O/r2_end_launches.csv $CMD > $O/r2_prof_ncu1.log 2>&1
 echo "launch list EXIT $?"
-ncu --set full --clock-control none --import-source on -k regex:'k_vals3|k_gram3<' -s 12 -c 4 -f -o /tmp/r2_hot $CMD > $O/r2_prof_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_vals3|k_gram3' -s 12 -c 6 -f -o /tmp/r2_hot $CMD > $O/r2_prof_ncu2.log 2>&1
 echo "hot EXIT $?"
 ncu -i /tmp/r2_hot.ncu-rep --page raw --csv > $O/r2_end_hot_raw.csv
-ncu -i /tmp/r2_hot.ncu-rep --page source --csv > $O/r2_end_hot_source.csv 2>/dev/null
 ncu --set full --clock-control none -k regex:'k_tables_group|k_trf_chol|k_hess3|k_gram3_finish' -s 12 -c 8 -f -o /tmp/r2_small $CMD > $O/r2_prof_ncu3.log 2>&1
 echo "small EXIT $?"
 ncu -i /tmp/r2_small.ncu-rep --page raw --csv > $O/r2_end_small_raw.csv
@@ -18,6 +17,5 @@ FITBURST_B200_EVAL=4 $CMD > $O/r2_prof_plain4.log 2>&1 || { echo "plain gen4 run
 FITBURST_B200_EVAL=4 ncu --set full --clock-control none --import-source on -k regex:'k_rise3|k_gram4' -s 6 -c 4 -f -o /tmp/r2_gen4 $CMD > $O/r2_prof_ncu4.log 2>&1
 echo "gen4 EXIT $?"
 ncu -i /tmp/r2_gen4.ncu-rep --page raw --csv > $O/r2_gen4_raw.csv
-ncu -i /tmp/r2_gen4.ncu-rep --page source --csv > $O/r2_gen4_source.csv 2>/dev/null
 ls -la /tmp/*.ncu-rep $O/r2_*csv
 du -sh $O
