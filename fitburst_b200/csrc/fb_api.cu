@@ -567,21 +567,21 @@ static bool fast_path_ok(const fb_plan_s* p, bool for_gram) {
   return true;
 }
 
-template <int KF, int NC>
+template <int KF, int NC, bool CHI2 = false>
 static int launch_vals3_tn(fb_plan_s* p, const EvalArgs& A, double* out, cudaStream_t st, int* grid_out) {
   const int nc = p->pc.num_comp, kf = p->pc.kf;
-  const size_t smem = vals3_smem_bytes(nc, kf);
+  const size_t smem = vals3_smem_bytes(nc, kf, CHI2);
   if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request exceeds 227 KB");
   static int occ_table[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // per instantiation (function-local static of the template)
   int& occ = occ_table[0];
   if (occ == 0 || KF == 0 || NC == 0 || smem > 48 * 1024) {
     if (smem > 48 * 1024)
-      CUDA_TRY(cudaFuncSetAttribute(k_vals3<KF, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_vals3<KF, NC>, kFastBlock, smem));
+      CUDA_TRY(cudaFuncSetAttribute(k_vals3<KF, NC, CHI2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_vals3<KF, NC, CHI2>, kFastBlock, smem));
     if (occ < 1) occ = 1;
   }
   const int grid = std::min(A.num_chan, p->sm_count * occ);
-  k_vals3<KF, NC><<<grid, kFastBlock, smem, st>>>(A, out);
+  k_vals3<KF, NC, CHI2><<<grid, kFastBlock, smem, st>>>(A, out);
   CUDA_TRY(cudaGetLastError());
   p->launches += 1;
   if (grid_out) *grid_out = grid;
@@ -606,6 +606,23 @@ static int launch_vals3(fb_plan_s* p, const EvalArgs& A, double* out, cudaStream
     case 4: return launch_vals3_t<4>(p, A, out, st, grid_out);
     case 8: return launch_vals3_t<8>(p, A, out, st, grid_out);
     default: return launch_vals3_t<0>(p, A, out, st, grid_out);
+  }
+}
+
+// chi^2 variant of k_vals3 (grid sweeps): A.chi2_partials receives kFastWarps partials per block
+// (at most 16 resident blocks of 128 threads per SM)
+static int launch_chisq3(fb_plan_s* p, const EvalArgs& A, cudaStream_t st, int* grid) {
+  const int nc = p->pc.num_comp;
+  switch (p->pc.kf) {
+    case 1: return launch_vals3_tn<1, 0, true>(p, A, nullptr, st, grid);
+    case 2: return launch_vals3_tn<2, 0, true>(p, A, nullptr, st, grid);
+    case 4: return launch_vals3_tn<4, 0, true>(p, A, nullptr, st, grid);
+    case 8:
+      if (nc == 1) return launch_vals3_tn<8, 1, true>(p, A, nullptr, st, grid);
+      if (nc == 2) return launch_vals3_tn<8, 2, true>(p, A, nullptr, st, grid);
+      if (nc == 3) return launch_vals3_tn<8, 3, true>(p, A, nullptr, st, grid);
+      return launch_vals3_tn<8, 0, true>(p, A, nullptr, st, grid);
+    default: return launch_vals3_tn<0, 0, true>(p, A, nullptr, st, grid);
   }
 }
 
@@ -2115,6 +2132,10 @@ extern "C" int fb_chisq_grid(fb_plan_t p, const double* data_dev, const double* 
                    vals3_smem_bytes(nc, p->pc.kf) <= 200 * 1024;
   for (int c = 0; c < nc; ++c)
     fast_grid = fast_grid && p->h_params[FB_BURST_WIDTH * nc + c] > 0.0 && p->h_params[FB_REF_FREQ * nc + c] > 0.0;
+  // FITBURST_B200_GRID_FUSED=0: spectrum values stored and reduced by a second kernel (the
+  // round-1 sweep; kept for comparison)
+  const bool fused_grid = fast_grid && !env_off("FITBURST_B200_GRID_FUSED") &&
+                          vals3_smem_bytes(nc, p->pc.kf, true) <= 200 * 1024;
   for (int a = 0; a < num_dm; ++a)
     for (int b = 0; b < num_sc; ++b) {
       // the whole sweep is enqueued without a host round trip: the grid point is written into
@@ -2145,17 +2166,27 @@ extern "C" int fb_chisq_grid(fb_plan_t p, const double* data_dev, const double* 
       } else if (fast_grid && sc_values_host[b] > 0.0) {
         rc = ensure_tables(p, st, true);
         if (rc != FB_OK) return rc;
-        rc = ensure_capacity(&p->d_vals, &p->vals_cap, (size_t)p->num_good * nc * p->pc.num_time);
-        if (rc == FB_OK) rc = ensure_capacity(&p->d_partials, &p->partials_cap, (size_t)p->num_good);
-        if (rc != FB_OK) return rc;
-        A.chi2_partials = p->d_partials;
-        rc = launch_vals3(p, A, p->d_vals, st, nullptr);
-        if (rc != FB_OK) return rc;
-        k_chi2_vals<<<p->num_good, 256, 0, st>>>(A, p->d_vals);
-        CUDA_TRY(cudaGetLastError());
-        p->launches += 1;
-        grid = p->num_good;
-        p->vals_match_cache = false;
+        if (fused_grid) {
+          // one kernel: spectrum values and residual sums, nothing stored in between
+          rc = ensure_capacity(&p->d_partials, &p->partials_cap, (size_t)p->sm_count * 16 * kFastWarps);
+          if (rc != FB_OK) return rc;
+          A.chi2_partials = p->d_partials;
+          rc = launch_chisq3(p, A, st, &grid);
+          if (rc != FB_OK) return rc;
+          grid *= kFastWarps;
+        } else {
+          rc = ensure_capacity(&p->d_vals, &p->vals_cap, (size_t)p->num_good * nc * p->pc.num_time);
+          if (rc == FB_OK) rc = ensure_capacity(&p->d_partials, &p->partials_cap, (size_t)p->num_good);
+          if (rc != FB_OK) return rc;
+          A.chi2_partials = p->d_partials;
+          rc = launch_vals3(p, A, p->d_vals, st, nullptr);
+          if (rc != FB_OK) return rc;
+          k_chi2_vals<<<p->num_good, 256, 0, st>>>(A, p->d_vals);
+          CUDA_TRY(cudaGetLastError());
+          p->launches += 1;
+          grid = p->num_good;
+          p->vals_match_cache = false;
+        }
       } else {
         rc = ensure_tables(p, st, true);
         if (rc != FB_OK) return rc;

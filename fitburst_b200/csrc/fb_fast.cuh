@@ -107,14 +107,18 @@ static_assert(kSpl % 2 == 0 && kSpl >= 2 && kSpl <= 8, "k_vals3 handles samples 
 struct TayTab {
   double d_bar, rho_bar, dz_max;
   double c0, c1z, c1r, c2zz, c2zr, c2rr, c3zzz, c3zzr, c3zrr, c3rrr;
-  int ok, pad_;
+  int ok, ser_ok;  // moment expansion usable / per-sub-frequency series usable (series_eval)
 };
 
 
 __host__ __device__ inline int vals3_bw_stride(int nck) { return (nck + 31) & ~31; }
 
-__host__ __device__ inline size_t vals3_smem_bytes(int nc, int kf) {
+// chi^2 variant of k_vals3: residuals of samples that wait for a queued rise-region value
+constexpr int kChiSlots = 128;  // per warp and channel (= its queue length in that variant)
+
+__host__ __device__ inline size_t vals3_smem_bytes(int nc, int kf, bool chi2 = false) {
   size_t n = 0;
+  if (chi2) n += sizeof(double) * (size_t)kFastWarps * kChiSlots * (1 + nc) + sizeof(int) * kFastWarps * (kChiSlots + kVTile);
   n += sizeof(CompTab) * nc;
   n += 2 * (sizeof(ChanTab) * nc + sizeof(SubTab) * nc * kf);  // double-buffered channel tables
   n += sizeof(double) * (size_t)nc * kf * (kVTile + 1);       // R (sample offsets of a tile), D
@@ -196,7 +200,13 @@ __device__ inline void make_tay_tab(const PlanConst& pc, const CompTab& ct, cons
   const double s = fabs(rho_bar) + 8.5, d = dz_max + dr_max;
   const double bound = (s * s) * (s * s) * (1.0 / 24.0) * (d * d) * (d * d);
   t.ok = ch.fast_ok && !pc.is_folded && bound < FB_TAY_BOUND && rho_bar > 0.0;
-  t.pad_ = 0;
+  // series_eval: order-7 remainder of erfcx about the mean argument, |erfcx^(8) / erfcx| <= 12.75^8
+  // for arguments >= -6.1 (the rise region ends at z = rho + 6 sqrt 2); 15 leaves a margin
+  const double sd = 15.0 * kSqrtHalf * d, sd2 = sd * sd, sd4 = sd2 * sd2;
+  t.ser_ok = ch.fast_ok && !pc.is_folded && rho_bar > 0.0 && sd4 * sd4 * (1.0 / 40320.0) < FB_TAY_BOUND;
+#ifdef FB_NO_SERIES  // comparison builds (scripts/build_variant.sh)
+  t.ser_ok = 0;
+#endif
 }
 
 // sum_a c_a E(z - dz_a, rho_a) by the expansion about (z, rho_bar); z = (T - d_bar) / w unclamped.
@@ -240,7 +250,8 @@ __device__ __forceinline__ void vals3_component_tile(const PlanConst& pc, const 
                                                      const SubTab* __restrict__ sb, const double* __restrict__ r_lane,
                                                      const double* __restrict__ bw, int c, int jp, int jt, int j0,
                                                      int lane, int nt, bool tail_dot_ok, int* __restrict__ queue,
-                                                     int& qcount, double (&out)[kSpl], bool (&deferred)[kSpl]) {
+                                                     int& qcount, double (&out)[kSpl], bool (&deferred)[kSpl],
+                                                     int qcap = kValsQueue) {
   const int kf = KF > 0 ? KF : pc.kf, kt = pc.kt;
 #pragma unroll
   for (int s = 0; s < kSpl; ++s) deferred[s] = false;
@@ -306,7 +317,7 @@ __device__ __forceinline__ void vals3_component_tile(const PlanConst& pc, const 
         // its tiles): the counter is a warp-uniform register, a request that does not fit is
         // refused whole and its samples are evaluated in place
         const int cnt = __popc(gm);
-        if (ch.fast_ok && qcount + cnt <= kValsQueue) {
+        if (ch.fast_ok && qcount + cnt <= qcap) {
           if (general) queue[qcount + __popc(gm & ((1u << lane) - 1u))] = (c << 27) | j;
           qcount += cnt;
           deferred[s] = general;
@@ -325,12 +336,61 @@ __device__ __forceinline__ void vals3_component_tile(const PlanConst& pc, const 
   }
 }
 
+// The same sum where the sub-frequencies of a channel are too far apart for the third-order
+// moments (narrow scattering: rho = w / tau large; DM offsets of a grid sweep at the bottom of the
+// band): E depends on the sub-frequency only through the Gaussian factor -- exact ratio
+// exp(z dz_a - dz_a^2 / 2) to the mean one -- and through the erfcx argument u_a = u + du_a with
+// du_a = (d rho_a + dz_a) / sqrt 2 independent of the sample, so ONE erfcx per sub-time and its
+// derivatives (x_{n+1} = 2 u x_n + 2 n x_{n-1}) give every erfcx(u_a) by a Taylor polynomial of
+// order 7; one short exp per sub-frequency remains. Measured worst relative error 1.5e-13 over
+// rho in [0.01, 300] at the largest admitted spread (the conditioning of exp(-z^2/2) itself).
+template <int KF>
+__device__ __forceinline__ double series_eval(const PlanConst& pc, const TayTab& t, const CompTab& ct,
+                                              const SubTab* __restrict__ sb, double z) {
+  const int kf = KF > 0 ? KF : pc.kf;
+  const double h = kSqrtHalf;
+  const double u = (t.rho_bar - z) * h, u2 = 2.0 * u;
+  const double x0 = erfcx(u);
+  const double x1 = fma(u2, x0, -kTwoOverSqrtPi);
+  const double x2 = fma(u2, x1, 2.0 * x0);
+  const double x3 = fma(u2, x2, 4.0 * x1);
+  const double x4 = fma(u2, x3, 6.0 * x2);
+  const double x5 = fma(u2, x4, 8.0 * x3);
+  const double x6 = fma(u2, x5, 10.0 * x4);
+  const double x7 = fma(u2, x6, 12.0 * x5);
+  const double q2 = 0.5 * x2, q3 = x3 * (1.0 / 6.0), q4 = x4 * (1.0 / 24.0), q5 = x5 * (1.0 / 120.0),
+               q6 = x6 * (1.0 / 720.0), q7 = x7 * (1.0 / 5040.0);
+  double s = 0.0;
+#pragma unroll
+  for (int a = 0; a < kf; ++a) {
+    const double dz = (sb[a].delay - t.d_bar) * ct.inv_w;  // z_a = z - dz
+    const double du = ((sb[a].ratio - t.rho_bar) + dz) * h;
+    double q = fma(q7, du, q6);
+    q = fma(q, du, q5);
+    q = fma(q, du, q4);
+    q = fma(q, du, q3);
+    q = fma(q, du, q2);
+    q = fma(q, du, x1);
+    q = fma(q, du, x0);
+    const double e = fb_exp(dz * fma(-0.5, dz, z));
+    s = fma((sb[a].amp_term * sb[a].sed) * e, q, s);
+  }
+  return fb_exp(-0.5 * z * z) * s;
+}
+
 // Stores the spectrum value of every (good channel, component, sample):
 // gvals[(chi * nc + c) * num_time + j].
 // NC > 0: the number of components is a compile-time constant (the component loops unroll and
 // their address arithmetic is hoisted: the source-line profile put a fifth of the stall samples on
 // per-(tile, component) pointer and index arithmetic); NC = 0: run-time value.
-template <int KF, int NC = 0>
+//
+// CHI2 = true (grid sweeps, BASELINE.json config 4): nothing is stored; the kernel sums the
+// weighted squared residuals sum_j (w_i (d_ij - sum_c v_c))^2 (analysis/fitter.py:231-266) of its
+// channels instead, one partial per (block, warp) in A.chi2_partials[blockIdx.x * kFastWarps + warp]
+// (the channels of a block are fixed by the grid size: deterministic).
+// A sample with a queued rise-region component parks its partial residual in a slot of the warp
+// until phase B has the missing values (components subtracted in order: deterministic).
+template <int KF, int NC = 0, bool CHI2 = false>
 __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs A, double* __restrict__ gvals) {
   extern __shared__ __align__(16) unsigned char fast_smem[];
   const PlanConst& pc = A.pc;
@@ -354,6 +414,20 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
   int* queue = reinterpret_cast<int*>(sp) + warp * kValsQueue;  // this warp's rise-region items
   int* bounds = reinterpret_cast<int*>(sp) + kFastWarps * kValsQueue + 1;  // [nc][2]: jp, jt
   TayTab* tay = reinterpret_cast<TayTab*>((reinterpret_cast<uintptr_t>(bounds + 2 * FB_MAX_COMPONENTS + 2) + 15) & ~(uintptr_t)15);
+  // CHI2: per-warp slots behind everything else
+  double* slot_r = nullptr;  // [kChiSlots] partial residual d - sum of the values known in phase A
+  double* slot_v = nullptr;  // [kChiSlots][nc] queued values (0 where the component was not queued)
+  int* qslot = nullptr;      // [kChiSlots] slot of queue item q
+  int* tile_slot = nullptr;  // [kVTile] slot of a sample of the current tile
+  if constexpr (CHI2) {
+    double* base = reinterpret_cast<double*>((reinterpret_cast<uintptr_t>(tay + nc) + 15) & ~(uintptr_t)15);
+    slot_r = base + (size_t)warp * kChiSlots * (1 + nc);
+    slot_v = slot_r + kChiSlots;
+    int* ibase = reinterpret_cast<int*>(base + (size_t)kFastWarps * kChiSlots * (1 + nc));
+    qslot = ibase + warp * (kChiSlots + kVTile);
+    tile_slot = qslot + kChiSlots;
+  }
+  constexpr int kQueueCap = CHI2 ? kChiSlots : kValsQueue;
 
   {
     const double* src = reinterpret_cast<const double*>(A.g_comp);
@@ -383,6 +457,7 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
   int i_next = channel_of(blockIdx.x + gridDim.x);
   prefetch_tables(channel_of(blockIdx.x), 0);
   int buf = 0;
+  double acc = 0.0;  // CHI2: this lane's sum of squared weighted residuals over the block's channels
   for (int chi = blockIdx.x; chi < A.num_chan; chi += gridDim.x, buf ^= 1) {
     const int i_after = channel_of(chi + 2 * gridDim.x);
     cp_async_wait<0>();
@@ -414,7 +489,11 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
     for (int e = tid; e < nck; e += kFastBlock)
       D[e] = fb_exp(-((double)(kVTile * kFastWarps * kt) * comp[e / kf].t_step) * sub[e].inv_tau);
     __syncthreads();
-    double* out = gvals + (size_t)chi * nc * nt;
+    double* out = CHI2 ? nullptr : gvals + (size_t)chi * nc * nt;
+    const int i_chan = CHI2 ? (A.chan_list ? __ldg(A.chan_list + chi) : chi) : 0;
+    const double* drow = CHI2 ? A.data + (size_t)i_chan * nt : nullptr;
+    const double wi = CHI2 ? __ldg(A.weights + i_chan) : 0.0;
+    int scount = 0;    // CHI2: slots in use (warp-uniform)
     // phase A: closed-form regimes tile by tile (uniform cost), rise-region samples queued
     for (int wt = warp, k = 0; wt < wtiles; wt += kFastWarps, ++k) {
       const int j0 = wt * kVTile, j = j0 + kSpl * lane;
@@ -442,13 +521,43 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
       // meaningful when the nc * kf factors fit one pass of the warp
       const unsigned bmask = nck <= 32 ? __ballot_sync(kFullMask, b_finite) : 0u;
       __syncwarp();
+      double dval[kSpl], msum[kSpl];
+      bool parked[kSpl];
+      const int q_before = qcount;
+      if constexpr (CHI2) {
+#pragma unroll
+        for (int h = 0; h < kSpl / 2; ++h) {
+          if (pair_store && j + 2 * h + 1 < nt) {
+            const double2 d2 = *reinterpret_cast<const double2*>(drow + j + 2 * h);
+            dval[2 * h] = d2.x;
+            dval[2 * h + 1] = d2.y;
+          } else {
+            dval[2 * h] = j + 2 * h < nt ? drow[j + 2 * h] : 0.0;
+            dval[2 * h + 1] = j + 2 * h + 1 < nt ? drow[j + 2 * h + 1] : 0.0;
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < kSpl; ++s) {
+          msum[s] = 0.0;
+          parked[s] = false;
+        }
+      }
 #pragma unroll
       for (int c = 0; c < nc; ++c) {
         bool deferred[kSpl];
         double v[kSpl];
         vals3_component_tile<KF>(pc, comp[c], chan[c], sub + c * kf, R + (size_t)c * kf * kVTile + kSpl * lane,
                                  bw + c * kf, c, bounds[2 * c], bounds[2 * c + 1], j0, lane, nt,
-                                 nck <= 32 && ((bmask >> (c * kf)) & kf_mask) == kf_mask, queue, qcount, v, deferred);
+                                 nck <= 32 && ((bmask >> (c * kf)) & kf_mask) == kf_mask, queue, qcount, v, deferred,
+                                 kQueueCap);
+        if constexpr (CHI2) {
+#pragma unroll
+          for (int s = 0; s < kSpl; ++s) {
+            if (!deferred[s]) msum[s] += v[s];
+            parked[s] = parked[s] || deferred[s];
+          }
+          continue;
+        }
         double* dst = out + (size_t)c * nt + j;
 #pragma unroll
         for (int h = 0; h < kSpl / 2; ++h) {
@@ -458,6 +567,31 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
             if (j + 2 * h < nt && !deferred[2 * h]) dst[2 * h] = v[2 * h];
             if (j + 2 * h + 1 < nt && !deferred[2 * h + 1]) dst[2 * h + 1] = v[2 * h + 1];
           }
+        }
+      }
+      if constexpr (CHI2) {
+        // samples without queued components are finished here; the others take a slot
+#pragma unroll
+        for (int s = 0; s < kSpl; ++s) {
+          const double r = dval[s] - msum[s];
+          const unsigned pm = __ballot_sync(kFullMask, parked[s]);
+          if (pm != 0u) {
+            if (parked[s]) {
+              const int slot = scount + __popc(pm & ((1u << lane) - 1u));
+              slot_r[slot] = r;
+              for (int c = 0; c < nc; ++c) slot_v[slot * nc + c] = 0.0;
+              tile_slot[kSpl * lane + s] = slot;
+            }
+            scount += __popc(pm);
+          }
+          if (!parked[s] && j + s < nt) {
+            const double rw = r * wi;
+            acc = fma(rw, rw, acc);
+          }
+        }
+        if (qcount > q_before) {  // items queued by this tile learn their slots
+          __syncwarp();
+          for (int q = q_before + lane; q < qcount; q += 32) qslot[q] = tile_slot[(queue[q] & ((1 << 27) - 1)) - j0];
         }
       }
       __syncwarp();
@@ -482,11 +616,12 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
         c = item >> 27;
         jj = item & ((1 << 27) - 1);
         const TayTab& t = tay[c];
-        expanded = t.ok && kt <= 32;
+        expanded = (t.ok || t.ser_ok) && kt <= 32;
         if (expanded && b < kt) {
           const CompTab& ct = comp[c];
           const double z = (linspace_at(ct.t_start, ct.t_step, ct.t_stop, jj * kt + b, pc.ntk) - t.d_bar) * ct.inv_w;
-          if (z - t.dz_max >= -5.0) v = tay_eval(t, z);  // no sub-frequency clamped at -5 w
+          if (z - t.dz_max >= -5.0)  // no sub-frequency clamped at -5 w
+            v = t.ok ? tay_eval(t, z) : series_eval<KF>(pc, t, ct, sub + c * kf, z);
           else expanded = false;
         }
       }
@@ -495,7 +630,11 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
       for (int off = lpi >> 1; off > 0; off >>= 1) v += __shfl_xor_sync(kFullMask, v, off);
       const unsigned group = (lpi == 32 ? kFullMask : ((1u << lpi) - 1u)) << (lane / lpi * lpi);
       const bool item_fail = (fail & group) != 0u;
-      if (have && !item_fail && b == 0) out[(size_t)c * nt + jj] = comp[c].amp10 * (v * inv_n);
+      if (have && !item_fail && b == 0) {
+        const double value = comp[c].amp10 * (v * inv_n);
+        if constexpr (CHI2) slot_v[qslot[q] * nc + c] = value;
+        else out[(size_t)c * nt + jj] = value;
+      }
       // exact sub-grid for the rest, whole warp per item
       unsigned todo = __ballot_sync(kFullMask, have && item_fail && b == 0);
       while (todo) {
@@ -503,11 +642,31 @@ __global__ void __launch_bounds__(kFastBlock, FB_V3_MINB) k_vals3(const EvalArgs
         todo &= todo - 1;
         const int c2 = __shfl_sync(kFullMask, c, src), j2 = __shfl_sync(kFullMask, jj, src);
         const double v2 = vals3_general_warp<KF>(pc, comp[c2], chan[c2], sub + c2 * kf, j2, lane);
-        if (lane == 0) out[(size_t)c2 * nt + j2] = v2;
+        if constexpr (CHI2) {
+          const int q2 = __shfl_sync(kFullMask, q, src);
+          if (lane == 0) slot_v[qslot[q2] * nc + c2] = v2;
+        } else {
+          if (lane == 0) out[(size_t)c2 * nt + j2] = v2;
+        }
+      }
+    }
+    if constexpr (CHI2) {
+      // phase C: parked residuals, queued components subtracted in component order
+      __syncwarp();
+      for (int slot = lane; slot < scount; slot += 32) {
+        double r = slot_r[slot];
+        for (int c = 0; c < nc; ++c) r -= slot_v[slot * nc + c];
+        const double rw = r * wi;
+        acc = fma(rw, rw, acc);
       }
     }
   }
   cp_async_wait<0>();
+  if constexpr (CHI2) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(kFullMask, acc, off);
+    if (lane == 0) A.chi2_partials[(size_t)blockIdx.x * kFastWarps + warp] = acc;
+  }
 }
 
 // Model spectrum from the stored rows: model[i, j] = sum_c gvals[(i * nc + c) * nt + j], components

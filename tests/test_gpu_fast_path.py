@@ -186,6 +186,36 @@ def test_chisq_grid_fast_vs_general(native_lib):
     np.testing.assert_allclose(fast, general, rtol=1e-12)
 
 
+@pytest.mark.parametrize("case", [
+    dict(num_freq=16, num_time=512),
+    dict(num_freq=24, num_time=1024, num_comp=4),
+    dict(num_freq=10, num_time=301, num_comp=2, kf=4, kt=2),       # odd row length: no 16-byte pairs
+    dict(num_freq=8, num_time=256, num_comp=1, kf=1, kt=1),        # in-place rise region (small sub-grid)
+    dict(num_freq=8, num_time=640, widths=[4.0e-3, 6.0e-3, 5.0e-3]),  # long rise regions: queue overflows
+], ids=["three_components", "four_components", "odd_length", "no_upsampling", "queue_overflow"])
+def test_chisq_grid_fused_kernel(native_lib, case):
+    """The one-kernel sweep (k_vals3<.., CHI2>) against the stored-values sweep of round 1, the
+    general kernels and the reference's definition sum(compute_residuals(x)**2)
+    (analysis/fitter.py:231-266) evaluated by the oracle."""
+    from fitburst_b200.batch import chisq_grid
+    fc, fo = _fitters(case, ["dm_index", "scattering_index"])
+    dm_values = np.linspace(-0.04, 0.06, 3)
+    sc_values = np.logspace(-3.5, -2.0, 4)
+    fused = chisq_grid(fc, dm_values, sc_values)
+    os.environ["FITBURST_B200_GRID_FUSED"] = "0"
+    try:
+        stored = chisq_grid(fc, dm_values, sc_values)
+    finally:
+        del os.environ["FITBURST_B200_GRID_FUSED"]
+    with general_kernels():
+        general = chisq_grid(fc, dm_values, sc_values)
+    np.testing.assert_allclose(fused, stored, rtol=1e-13)
+    np.testing.assert_allclose(fused, general, rtol=1e-12)
+    fo.fit_parameters = ["dm", "scattering_timescale"]
+    want = np.array([[np.sum(fo.compute_residuals([dm, sc]) ** 2) for sc in sc_values] for dm in dm_values])
+    np.testing.assert_allclose(fused, want, rtol=1e-10)
+
+
 def test_fit_stream_matches_individual_fits(native_lib):
     from fitburst_b200.analysis.fitter import LSFitter
     from fitburst_b200.batch import fit_stream, pinned_like
@@ -293,8 +323,13 @@ MODEL_REGIMES = {
     # region is taken or refused by its truncation bound; either way the model must hold 1e-10
     "expansion_config2": (0.0, 2e-3, None),
     "expansion_small_dm_offset": (0.02, 2e-3, None),
-    "exact_large_dm_offset": (0.5, 2e-3, None),
-    "exact_weak_scattering": (0.0, 2e-4, None),
+    # beyond the moment bound: the per-sub-frequency series (series_eval) takes over
+    "series_large_dm_offset": (0.5, 2e-3, None),
+    "series_weak_scattering": (0.0, 2e-4, None),
+    "series_very_weak_scattering": (0.0, 2e-5, None),
+    "series_weak_scattering_and_dm_offset": (-0.3, 1e-4, None),
+    # beyond the series bound as well: exact sub-grid
+    "exact_huge_dm_offset_narrow_components": (4.0, 5e-4, [2e-4, 3e-4, 2e-4]),
     "expansion_strong_scattering": (0.01, 2e-2, None),
     "mixed_wide_and_narrow": (0.005, 1e-3, [3e-3, 4e-4, 1e-3]),
     # a component wider than the window: every sample is a rise-region sample, the per-channel
