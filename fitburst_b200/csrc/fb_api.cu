@@ -51,6 +51,9 @@ struct fb_plan_s {
   double* d_weights = nullptr;
   double* d_chan_sumsq = nullptr;
   double* d_partials = nullptr;
+  double* d_scint_amps = nullptr;      // (num_freq, num_comp) scintillation amplitudes (k_scint_solve)
+  double* d_scint_partials = nullptr;  // chunk partials of the per-channel systems
+  size_t scint_partials_cap = 0;
   size_t partials_cap = 0;
   double* d_gram = nullptr;  // (FB_MAX_FREE+1)^2
   double* h_gram = nullptr;  // pinned
@@ -241,6 +244,8 @@ extern "C" int fb_plan_destroy(fb_plan_t p) {
   cudaFree(p->d_err);
   cudaFree(p->d_gram);
   cudaFree(p->d_partials);
+  cudaFree(p->d_scint_amps);
+  cudaFree(p->d_scint_partials);
   cudaFree(p->d_hess_partials);
   cudaFree(p->d_pairs);
   cudaFree(p->d_comp_list);
@@ -340,11 +345,56 @@ static EvalArgs base_args(fb_plan_s* p) {
   return A;
 }
 
+static int ensure_capacity(double** buf, size_t* cap, size_t need);
+
+static bool env_off(const char* name) {
+  const char* v = getenv(name);
+  return v && !strcmp(v, "0");
+}
+
+// Scintillation amplitudes of the channels in A (routines/ism.py:11-48) ahead of an evaluation:
+// (channel, chunk) partial systems on the whole GPU, then one small solve per channel. The tables
+// must be current. On return A.scint_amps points at the plan's (num_freq, num_comp) block.
+// FITBURST_B200_SCINT_PRESOLVE=0: one block per channel solves in place (round-1 behaviour).
+static int presolve_scint_amps(fb_plan_s* p, EvalArgs& A, cudaStream_t st) {
+  if (!p->pc.scintillation || A.scint_amps != nullptr || A.num_chan < 1 || !A.data) return FB_OK;
+  if (env_off("FITBURST_B200_SCINT_PRESOLVE")) return FB_OK;
+  const int nc = p->pc.num_comp, kf = p->pc.kf;
+  if (!p->d_scint_amps) CUDA_TRY(cudaMalloc(&p->d_scint_amps, sizeof(double) * (size_t)p->desc.num_freq * nc));
+  const size_t smem = smem_bytes(nc, kf, 1, true);
+  if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request %zu B exceeds 227 KB", smem);
+  if (smem > 48 * 1024)
+    CUDA_TRY(cudaFuncSetAttribute(k_scint_partials, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 1;
+  CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scint_partials, kBlock, smem));
+  if (occ < 1) occ = 1;
+  const int tiles = (p->pc.num_time + kBlock - 1) / kBlock;
+  const long long slots = (long long)p->sm_count * occ * 4;  // a few items per resident block: balance
+  const int nchunks = (int)std::min<long long>(tiles, std::max<long long>(1, (slots + A.num_chan - 1) / A.num_chan));
+  const size_t nent = (size_t)gram_ntiles(nc + 1) * kTile * kTile;
+  const int rc = ensure_capacity(&p->d_scint_partials, &p->scint_partials_cap, (size_t)A.num_chan * nchunks * nent);
+  if (rc != FB_OK) return rc;
+  const long long items = (long long)A.num_chan * nchunks;
+  const int grid = (int)std::min<long long>(items, (long long)p->sm_count * occ);
+  k_scint_partials<<<grid, kBlock, smem, st>>>(A, nchunks, p->d_scint_partials);
+  CUDA_TRY(cudaGetLastError());
+  k_scint_solve<<<A.num_chan, 64, 0, st>>>(A, nchunks, p->d_scint_partials, p->d_scint_amps);
+  CUDA_TRY(cudaGetLastError());
+  p->launches += 2;
+  A.scint_amps = p->d_scint_amps;
+  return FB_OK;
+}
+
 template <int MODE>
-static int launch_eval(fb_plan_s* p, const EvalArgs& A, int ncols_main, cudaStream_t st, int* grid_out) {
+static int launch_eval(fb_plan_s* p, const EvalArgs& A_in, int ncols_main, cudaStream_t st, int* grid_out) {
   {
-    const int rc_t = ensure_tables(p, st, A.chan_list != nullptr && A.chan_list == p->d_chan_list);
+    const int rc_t = ensure_tables(p, st, A_in.chan_list != nullptr && A_in.chan_list == p->d_chan_list);
     if (rc_t != FB_OK) return rc_t;
+  }
+  EvalArgs A = A_in;
+  {
+    const int rc_s = presolve_scint_amps(p, A, st);
+    if (rc_s != FB_OK) return rc_s;
   }
   const size_t smem = smem_bytes(p->pc.num_comp, p->pc.kf, ncols_main, p->pc.scintillation != 0);
   if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request %zu B exceeds 227 KB", smem);
@@ -355,7 +405,7 @@ static int launch_eval(fb_plan_s* p, const EvalArgs& A, int ncols_main, cudaStre
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_eval<MODE>, kBlock, smem));
   if (occ < 1) occ = 1;
   const int tiles = (p->pc.num_time + kBlock - 1) / kBlock;
-  long long items = p->pc.scintillation ? (long long)A.num_chan : (long long)A.num_chan * tiles;
+  long long items = (p->pc.scintillation && !A.scint_amps) ? (long long)A.num_chan : (long long)A.num_chan * tiles;
   if (items < 1) items = 1;
   long long grid = (long long)p->sm_count * occ;
   if (MODE != MODE_GRAM) grid *= 8;  // short blocks balance better when nothing is kept in registers
@@ -393,7 +443,6 @@ static int check_err_flag(fb_plan_s* p, cudaStream_t st) {
 
 static bool fast_path_ok(const fb_plan_s* p, bool for_gram);
 static int launch_vals3(fb_plan_s* p, const EvalArgs& A, double* out, cudaStream_t st, int* grid_out);
-static int ensure_capacity(double** buf, size_t* cap, size_t need);
 
 extern "C" int fb_model_eval(fb_plan_t p, const double* data_dev, double* model_dev,
                              double* amplitude_dev, double* spectrum_dev, double* timediff_dev,
@@ -515,10 +564,6 @@ extern "C" int fb_set_free_parameters(fb_plan_t p, const int32_t* free_mask, int
 }
 
 // ---- fast evaluation (fb_fast.cuh) ---------------------------------------------------------------
-static bool env_off(const char* name) {
-  const char* v = getenv(name);
-  return v && !strcmp(v, "0");
-}
 
 static int ensure_capacity(double** buf, size_t* cap, size_t need) {
   if (need <= *cap) return FB_OK;
@@ -853,7 +898,7 @@ static int launch_fast_gram(fb_plan_s* p, EvalArgs& A, int ncols, double* gram_d
 template <int NB>
 static int launch_gram2_mma(fb_plan_s* p, const EvalArgs& A, int ncols, long long items, cudaStream_t st, int* warps_out) {
   const int nc = p->pc.num_comp, kf = p->pc.kf;
-  const size_t smem = gram_mma_smem_bytes(nc, kf, ncols);
+  const size_t smem = gram_mma_smem_bytes(nc, kf, ncols, A.vals_spc == 2 ? 2 : 3);
   if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "shared-memory request exceeds 227 KB");
   if (smem > 48 * 1024)
     CUDA_TRY(cudaFuncSetAttribute(k_gram2_mma<NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -883,8 +928,9 @@ static int launch_split_gram(fb_plan_s* p, EvalArgs& A, int ncols, cudaStream_t 
   const int nc = p->pc.num_comp, kf = p->pc.kf;
   const int tiles = (p->pc.num_time + kBlock - 1) / kBlock;
   const long long items = (long long)A.num_chan * tiles;
-  A.vals_spc = 2;  // the fit needs spectrum + time difference only
-  const size_t need_vals = (size_t)items * kBlock * 2 * nc;
+  const bool scint = p->pc.scintillation != 0;
+  A.vals_spc = scint ? 3 : 2;  // the fit needs spectrum + time difference only; scintillation also the mean profile
+  const size_t need_vals = (size_t)items * kBlock * A.vals_spc * nc;
   if (need_vals > p->vals_cap) {
     cudaFree(p->d_vals);
     p->d_vals = nullptr;
@@ -901,6 +947,28 @@ static int launch_split_gram(fb_plan_s* p, EvalArgs& A, int ncols, cudaStream_t 
   k_vals<<<(int)grid1, kBlock, smem1, st>>>(A, p->d_vals);
   CUDA_TRY(cudaGetLastError());
   p->launches += 2;
+  if (scint) {
+    // per-channel amplitudes (routines/ism.py:11-48) from the stored mean profiles
+    if (!p->d_scint_amps) CUDA_TRY(cudaMalloc(&p->d_scint_amps, sizeof(double) * (size_t)p->desc.num_freq * nc));
+    const size_t smem_s = scint_vals_smem_bytes(nc);
+    if (smem_s > 48 * 1024)
+      CUDA_TRY(cudaFuncSetAttribute(k_scint_partials_vals, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));
+    int occ_s = 1;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_s, k_scint_partials_vals, kBlock, smem_s));
+    if (occ_s < 1) occ_s = 1;
+    const long long slots = (long long)p->sm_count * occ_s * 4;
+    const int nchunks = (int)std::min<long long>(tiles, std::max<long long>(1, (slots + A.num_chan - 1) / A.num_chan));
+    const size_t nent = (size_t)gram_ntiles(nc + 1) * kTile * kTile;
+    rc = ensure_capacity(&p->d_scint_partials, &p->scint_partials_cap, (size_t)A.num_chan * nchunks * nent);
+    if (rc != FB_OK) return rc;
+    const int grid_s = (int)std::min<long long>((long long)A.num_chan * nchunks, (long long)p->sm_count * occ_s);
+    k_scint_partials_vals<<<grid_s, kBlock, smem_s, st>>>(A, nchunks, p->d_vals, p->d_scint_partials);
+    CUDA_TRY(cudaGetLastError());
+    k_scint_solve<<<A.num_chan, 64, 0, st>>>(A, nchunks, p->d_scint_partials, p->d_scint_amps);
+    CUDA_TRY(cudaGetLastError());
+    p->launches += 2;
+    A.scint_amps = p->d_scint_amps;
+  }
   *mma_warps_out = 0;
   const int nb = (ncols + 7) / 8;
   const char* mma_env = getenv("FITBURST_B200_DMMA");
@@ -949,9 +1017,14 @@ static int normal_equations_async(fb_plan_s* p, const double* data_dev, double* 
   int grid = 0;
   int rc = FB_OK;
   const char* split_env = getenv("FITBURST_B200_SPLIT");
-  const bool split = !p->pc.scintillation && !(split_env && !strcmp(split_env, "0"));
+  // scintillation: split as well unless the amplitudes are to be solved in place
+  // (FITBURST_B200_SCINT_PRESOLVE=0) or the stored values would not fit (3 doubles per (sample, component))
+  const bool scint_split = !p->pc.scintillation ||
+                           (!env_off("FITBURST_B200_SCINT_PRESOLVE") &&
+                            (size_t)p->num_good * p->pc.num_time * p->pc.num_comp * 24 <= ((size_t)64 << 30));
+  const bool split = scint_split && !(split_env && !strcmp(split_env, "0"));
   int mma_warps = 0;
-  p->last_eval_split = split;
+  p->last_eval_split = split && !p->pc.scintillation;  // (scintillation stores 3 planes: never reused)
   p->vals_match_cache = false;
   if (split && fast_path_ok(p, true)) {
     p->vals_layout = 3;
@@ -1715,6 +1788,10 @@ static int launch_hessian(fb_plan_s* p, HessArgs& H, cudaStream_t st, int* grid_
     const int rc_t = ensure_tables(p, st, H.E.chan_list != nullptr && H.E.chan_list == p->d_chan_list);
     if (rc_t != FB_OK) return rc_t;
   }
+  {
+    const int rc_s = presolve_scint_amps(p, H.E, st);
+    if (rc_s != FB_OK) return rc_s;
+  }
   const size_t smem = hess_smem_bytes(p->pc.num_comp, p->pc.kf, MAP ? 0 : H.num_pairs);
   if (smem > 227 * 1024) return fail(FB_ERR_INVALID, "Hessian shared-memory request %zu B exceeds 227 KB", smem);
   if (smem > 48 * 1024)
@@ -1723,7 +1800,7 @@ static int launch_hessian(fb_plan_s* p, HessArgs& H, cudaStream_t st, int* grid_
   CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_hessian<MAP>, kBlock, smem));
   if (occ < 1) occ = 1;
   const int tiles = (p->pc.num_time + kBlock - 1) / kBlock;
-  long long items = p->pc.scintillation ? (long long)H.E.num_chan : (long long)H.E.num_chan * tiles;
+  long long items = (p->pc.scintillation && !H.E.scint_amps) ? (long long)H.E.num_chan : (long long)H.E.num_chan * tiles;
   if (items < 1) items = 1;
   long long grid = (long long)p->sm_count * occ;
   if (MAP) grid *= 8;

@@ -266,18 +266,20 @@ __global__ void __launch_bounds__(kBlock, 2) k_hessian(const HessArgs H) {
   const double tau0 = global_param(A.params, nc, FB_SCATTERING_TIMESCALE);
 
   // scintillation needs whole channels per block (two passes); otherwise (channel, tile) items.
-  const long long total = pc.scintillation ? (long long)A.num_chan : (long long)A.num_chan * tiles;
+  // (amplitudes already solved by k_scint_solve: items like the non-scintillating model)
+  const bool whole = pc.scintillation && A.scint_amps == nullptr;
+  const long long total = whole ? (long long)A.num_chan : (long long)A.num_chan * tiles;
   const long long begin = total * blockIdx.x / gridDim.x, end = total * (blockIdx.x + 1) / gridDim.x;
   int cur = -1;
   for (long long item = begin; item < end; ++item) {
-    const int chi = pc.scintillation ? (int)item : (int)(item / tiles);
+    const int chi = whole ? (int)item : (int)(item / tiles);
     const int i = A.chan_list ? A.chan_list[chi] : chi;
-    const int tile_lo = pc.scintillation ? 0 : (int)(item % tiles);
-    const int tile_hi = pc.scintillation ? tiles : tile_lo + 1;
+    const int tile_lo = whole ? 0 : (int)(item % tiles);
+    const int tile_hi = whole ? tiles : tile_lo + 1;
     if (chi != cur) {
       load_channel_tables(A, L, i);
       cur = chi;
-      if (pc.scintillation) {
+      if (whole) {
         // amplitudes from the per-channel least-squares solve (routines/ism.py:11-48)
         const int ncols2 = nc + 1, stride2 = gram_stride(ncols2), side2 = gram_side(ncols2);
         const int ntiles2 = gram_ntiles(ncols2), nslices2 = kBlock / ntiles2;

@@ -48,6 +48,9 @@ struct EvalArgs {
   // k_gram3: the spectrum-row / data tiles are fetched with cp.async.bulk (one elected lane, completion
   // on an mbarrier per ring slot) instead of one 8-byte cp.async per lane; needs an even num_time
   int bulk_rows;
+  // scintillation: per-(channel, component) amplitudes solved beforehand (k_scint_partials +
+  // k_scint_solve), (num_freq, num_comp). nullptr: a block owns whole channels and solves in place.
+  const double* scint_amps;
 };
 
 __host__ __device__ inline bool is_fit_global(int p) {
@@ -336,6 +339,8 @@ __device__ inline void load_channel_tables(const EvalArgs& A, const SmemLayout& 
     const int nd = nc * (int)(sizeof(ChanTab) / sizeof(double));
     for (int e = threadIdx.x; e < nd; e += blockDim.x) dst[e] = src[e];
   }
+  if (pc.scintillation && A.scint_amps != nullptr && (int)threadIdx.x < nc)
+    L.scint_amp[threadIdx.x] = A.scint_amps[(size_t)i * nc + threadIdx.x];
   __syncthreads();
 }
 
@@ -563,7 +568,7 @@ __device__ __forceinline__ void eval_body(const EvalArgs& A, const int block_id,
   double* row = L.X + (size_t)tid * stride;
   double chi2_acc = 0.0;
 
-  if (!pc.scintillation) {
+  if (!pc.scintillation || A.scint_amps != nullptr) {
     const long long total = (long long)A.num_chan * tiles;
     const long long begin = total * block_id / num_blocks;
     const long long end = total * (block_id + 1) / num_blocks;
@@ -587,7 +592,8 @@ __device__ __forceinline__ void eval_body(const EvalArgs& A, const int block_id,
     }
   } else {
     // Scintillation: per-channel amplitudes come from a least-squares solve over ALL samples of
-    // the channel (routines/ism.py:11-48), so a block owns whole channels and makes two passes.
+    // the channel (routines/ism.py:11-48), so a block owns whole channels and makes two passes
+    // (batched small bursts; single spectra take the amplitudes from k_scint_solve instead).
     const int ncols2 = nc + 1;
     const int stride2 = gram_stride(ncols2);
     const int side2 = gram_side(ncols2);
@@ -674,6 +680,151 @@ __device__ __forceinline__ void eval_body(const EvalArgs& A, const int block_id,
     for (int k = 0; k < kTile * kTile; ++k) acc[k] = L.park[k * kBlock + tid];
     gram_block_reduce(L.X, ntiles, nslices, g_tile, g_slice, g_active, acc,
                       A.partials + (size_t)block_id * ntiles * kTile * kTile);
+  }
+}
+
+// Scintillation amplitudes ahead of the evaluation (routines/ism.py:11-48), parallel over
+// (channel, chunk of tiles) instead of one block per channel: a long channel (config 5: 262144
+// samples) no longer runs on a single block, a short channel list no longer leaves SMs idle.
+// k_scint_partials: block-summed Gram tiles of [timeprof_1 .. timeprof_nc, data] of one chunk,
+// partials[(chi * nchunks + k)][ntiles2 * 64] in the tile-major layout of gram_block_reduce.
+__global__ void __launch_bounds__(kBlock, 4) k_scint_partials(const EvalArgs A, int nchunks,
+                                                              double* __restrict__ partials) {
+  extern __shared__ double smem_raw[];
+  const PlanConst& pc = A.pc;
+  if (fit_stopped(pc)) return;
+  const int nc = pc.num_comp, kf = pc.kf, tid = threadIdx.x;
+  SmemLayout L = carve(smem_raw, nc, kf);
+  load_comp_tables(A, L);
+  const int tiles = (pc.num_time + kBlock - 1) / kBlock;
+  const int ncols2 = nc + 1;
+  const int stride2 = gram_stride(ncols2), side2 = gram_side(ncols2), ntiles2 = gram_ntiles(ncols2);
+  const int nslices2 = kBlock / ntiles2;
+  const int s_tile = tid % ntiles2, s_slice = tid / ntiles2;
+  const bool s_active = s_slice < nslices2;
+  int s_ti, s_tj;
+  tile_coords(s_tile, side2, s_ti, s_tj);
+  double* row2 = L.X + (size_t)tid * stride2;
+  const long long total = (long long)A.num_chan * nchunks;
+  int cur = -1;
+  for (long long item = blockIdx.x; item < total; item += gridDim.x) {
+    const int chi = (int)(item / nchunks), k = (int)(item % nchunks);
+    const int i = A.chan_list ? A.chan_list[chi] : chi;
+    if (chi != cur) {
+      load_channel_tables(A, L, i);
+      cur = chi;
+    }
+    const int tile_lo = (int)((long long)tiles * k / nchunks), tile_hi = (int)((long long)tiles * (k + 1) / nchunks);
+    double acc2[kTile * kTile];
+#pragma unroll
+    for (int q = 0; q < kTile * kTile; ++q) acc2[q] = 0.0;
+    for (int tile = tile_lo; tile < tile_hi; ++tile) {
+      const int j = tile * kBlock + tid;
+      eval_tile(A, L, i, tile);
+      for (int q = 0; q < stride2; ++q) row2[q] = 0.0;
+      if (j < pc.num_time) {
+        const double* vrow = L.vals + (size_t)tid * val_stride(nc);
+        for (int c = 0; c < nc; ++c) row2[c] = vrow[3 * c + 2];
+        row2[nc] = A.data[(size_t)i * pc.num_time + j];
+      }
+      __syncthreads();
+      gram_accumulate(L.X, stride2, kBlock, ntiles2, nslices2, s_ti, s_tj, s_slice, s_active, acc2);
+      __syncthreads();
+    }
+    gram_block_reduce(L.X, ntiles2, nslices2, s_tile, s_slice, s_active, acc2,
+                      partials + (size_t)item * ntiles2 * kTile * kTile);
+  }
+}
+
+// The same partial systems from the values k_vals stored (split evaluation, vals_spc = 3: the mean
+// profile is slot 3 c + 2 of item chi * tiles + tile): no second evaluation of the profiles.
+__global__ void __launch_bounds__(kBlock, 4) k_scint_partials_vals(const EvalArgs A, int nchunks,
+                                                                   const double* __restrict__ gvals,
+                                                                   double* __restrict__ partials) {
+  extern __shared__ double smem_raw[];
+  const PlanConst& pc = A.pc;
+  if (fit_stopped(pc)) return;
+  const int nc = pc.num_comp, tid = threadIdx.x;
+  double* X = smem_raw;  // [kBlock][stride2] staged rows, then the scratch of the block reduction
+  const int tiles = (pc.num_time + kBlock - 1) / kBlock;
+  const int ncols2 = nc + 1;
+  const int stride2 = gram_stride(ncols2), side2 = gram_side(ncols2), ntiles2 = gram_ntiles(ncols2);
+  const int nslices2 = kBlock / ntiles2;
+  const int s_tile = tid % ntiles2, s_slice = tid / ntiles2;
+  const bool s_active = s_slice < nslices2;
+  int s_ti, s_tj;
+  tile_coords(s_tile, side2, s_ti, s_tj);
+  double* row2 = X + (size_t)tid * stride2;
+  const int vs = 3 * nc;
+  const long long total = (long long)A.num_chan * nchunks;
+  for (long long item = blockIdx.x; item < total; item += gridDim.x) {
+    const int chi = (int)(item / nchunks), k = (int)(item % nchunks);
+    const int i = A.chan_list ? A.chan_list[chi] : chi;
+    const int tile_lo = (int)((long long)tiles * k / nchunks), tile_hi = (int)((long long)tiles * (k + 1) / nchunks);
+    double acc2[kTile * kTile];
+#pragma unroll
+    for (int q = 0; q < kTile * kTile; ++q) acc2[q] = 0.0;
+    for (int tile = tile_lo; tile < tile_hi; ++tile) {
+      const int j = tile * kBlock + tid;
+      const double* v = gvals + ((size_t)chi * tiles + tile) * kBlock * vs + tid;
+      for (int q = 0; q < stride2; ++q) row2[q] = 0.0;
+      if (j < pc.num_time) {
+        for (int c = 0; c < nc; ++c) row2[c] = v[(size_t)(3 * c + 2) * kBlock];
+        row2[nc] = A.data[(size_t)i * pc.num_time + j];
+      }
+      __syncthreads();
+      gram_accumulate(X, stride2, kBlock, ntiles2, nslices2, s_ti, s_tj, s_slice, s_active, acc2);
+      __syncthreads();
+    }
+    gram_block_reduce(X, ntiles2, nslices2, s_tile, s_slice, s_active, acc2,
+                      partials + (size_t)item * ntiles2 * kTile * kTile);
+  }
+}
+
+__host__ __device__ inline size_t scint_vals_smem_bytes(int nc) {
+  size_t rows = (size_t)kBlock * gram_stride(nc + 1);
+  if (rows < (size_t)kBlock * kTile * kTile) rows = (size_t)kBlock * kTile * kTile;
+  return sizeof(double) * rows;
+}
+
+// k_scint_solve: one block per channel; chunk partials summed in chunk order, then the nc x nc
+// system of routines/ism.py:40-46 by Gaussian elimination with partial pivoting (solve_small).
+__global__ void __launch_bounds__(64) k_scint_solve(const EvalArgs A, int nchunks, const double* __restrict__ partials,
+                                                    double* __restrict__ amps) {
+  __shared__ double sums[((FB_MAX_COMPONENTS + 1 + kTile - 1) / kTile) * ((FB_MAX_COMPONENTS + 1 + kTile - 1) / kTile + 1) / 2 *
+                         kTile * kTile];
+  __shared__ double G[FB_MAX_COMPONENTS * FB_MAX_COMPONENTS];
+  __shared__ double b[FB_MAX_COMPONENTS];
+  if (fit_stopped(A.pc)) return;
+  const int nc = A.pc.num_comp, chi = blockIdx.x, tid = threadIdx.x;
+  const int i = A.chan_list ? A.chan_list[chi] : chi;
+  const int side2 = gram_side(nc + 1), ntiles2 = gram_ntiles(nc + 1);
+  const int nent = ntiles2 * kTile * kTile;
+  for (int e = tid; e < nent; e += blockDim.x) {
+    double acc = 0.0;
+    for (int k = 0; k < nchunks; ++k) acc += partials[((size_t)chi * nchunks + k) * nent + e];
+    sums[e] = acc;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int t = 0; t < ntiles2; ++t) {
+      int ti, tj;
+      tile_coords(t, side2, ti, tj);
+      for (int r = 0; r < kTile; ++r)
+        for (int q = 0; q < kTile; ++q) {
+          const int gr = ti * kTile + r, gc = tj * kTile + q;
+          const double v = sums[t * kTile * kTile + r * kTile + q];
+          if (gr < nc && gc < nc) {
+            G[gr * nc + gc] = v;
+            G[gc * nc + gr] = v;
+          } else if (gr < nc && gc == nc) {
+            b[gr] = v;
+          }
+        }
+    }
+    const bool ok = solve_small(G, b, nc, nc);
+    for (int c = 0; c < nc; ++c) amps[(size_t)i * nc + c] = ok ? b[c] : nan("");
+    if (!ok && A.err_flag) atomicExch(A.err_flag, 1);
   }
 }
 
@@ -815,10 +966,10 @@ __device__ __forceinline__ void dmma8x8x4(double& c0, double& c1, double a, doub
                : "d"(a), "d"(b));
 }
 
-__host__ __device__ inline size_t gram_mma_smem_bytes(int nc, int kf, int ncols) {
+__host__ __device__ inline size_t gram_mma_smem_bytes(int nc, int kf, int ncols, int spc = 2) {
   const int nb = (ncols + 7) / 8;
   return smem_bytes(nc, kf, 1, false, false, 0) + sizeof(double) * (size_t)(kBlock / 32) * nb * 8 * kMmaRowStride +
-         sizeof(double) * 2 * (size_t)(2 * nc + 1) * kBlock;  // double-buffered value + data prefetch
+         sizeof(double) * 2 * (size_t)(spc * nc + 1) * kBlock;  // double-buffered value + data prefetch
 }
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {

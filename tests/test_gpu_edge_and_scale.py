@@ -159,6 +159,66 @@ def test_scintillation_fit(native_lib):
     np.testing.assert_allclose(fc.results.x, fo.results.x, rtol=1e-6)
 
 
+@pytest.mark.parametrize("shape", [dict(num_freq=6, num_time=3000, num_comp=3), dict(num_freq=40, num_time=200, num_comp=2)],
+                         ids=["few_long_channels", "many_short_channels"])
+def test_scintillation_amplitude_routes(native_lib, shape):
+    """The per-channel amplitude systems (routines/ism.py:11-48) are solved ahead of the evaluation,
+    split over (channel, chunk) blocks: from the stored profiles (split evaluation, default), by an
+    evaluation of their own (FITBURST_B200_SPLIT=0) or inside one block per channel
+    (FITBURST_B200_SCINT_PRESOLVE=0, the batched kernels' route). All three against the oracle:
+    [J r]^T [J r], the exact Hessian, the model and the amplitudes."""
+    import os
+    from fitburst_b200 import _lib
+    from fitburst_b200.analysis.fitter import LSFitter
+    from oracle.fitburst_oracle import OracleFitter
+    case = dict(scint=True, kf=1, kt=1, **shape)
+    freqs, times, truth, kwargs = make_case(**case)
+    cuda, oracle = model_pair(freqs, times, kwargs, truth)
+    _, plain = model_pair(freqs, times, dict(kwargs, scintillation=False), truth)
+    rng = np.random.default_rng(11)
+    good = np.ones(len(freqs), dtype=bool)
+    good[1] = False
+    data = plain.compute_model() * np.exp(rng.normal(0, 0.4, size=(len(freqs), 1))) + rng.normal(0, 0.05, size=(len(freqs), len(times)))
+    start = syn.config2_start(truth)
+    cuda.update_parameters(start)
+    oracle.update_parameters(start)
+    with quiet():
+        fc = LSFitter(data, cuda, good)
+        fc.fix_parameter(["dm_index", "scattering_index"])
+    fo = OracleFitter(data, oracle, good)
+    fo.fix_parameter(["dm_index", "scattering_index"])
+    x0 = fo.get_fit_parameters_list()
+    ro = fo.compute_residuals(x0)  # first: the Jacobian reads the caches this evaluation leaves (fitter.py:180-229)
+    jo = fo.compute_jacobian(x0)
+    jr = np.column_stack([jo, ro])
+    want = jr.T @ jr
+    scale = np.sqrt(np.outer(np.diag(want), np.diag(want)))
+    want_model = oracle.compute_model(data=data)
+    lib = _lib.load_library()
+    routes = {"stored_profiles": {}, "own_evaluation": {"FITBURST_B200_SPLIT": "0"},
+              "in_place": {"FITBURST_B200_SCINT_PRESOLVE": "0"}}
+    hessians = {}
+    for name, env in routes.items():
+        os.environ.update(env)
+        try:
+            plan, n = fc._prepare()
+            cuda._push_parameters()
+            gram = np.zeros((n + 1, n + 1))
+            _lib.check(lib.fb_normal_equations(plan, fc._data_on_device().data_ptr(), _lib.dptr(gram), fc._stream()))
+            assert np.max(np.abs(gram - want) / scale) < 1e-9, name
+            with quiet():
+                hessians[name], _ = fc.compute_hessian(fc.data, fc.fit_parameters)
+            got_model = cuda.compute_model(data=data)
+            assert_close(got_model[good], want_model[good], 1e-10, name)
+            assert_close(cuda.amplitude_per_component[good], oracle.amplitude_per_component[good], 1e-10, name)
+        finally:
+            for key in env:
+                del os.environ[key]
+    hs = np.sqrt(np.outer(np.abs(np.diag(hessians["in_place"])), np.abs(np.diag(hessians["in_place"]))))
+    for name in ("stored_profiles", "own_evaluation"):
+        assert np.max(np.abs(hessians[name] - hessians["in_place"]) / hs) < 1e-9, name
+
+
 # ---------------------------------------------------------------------------- full size
 @pytest.fixture(scope="module")
 def full_size(native_lib):
