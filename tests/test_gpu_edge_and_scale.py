@@ -217,6 +217,27 @@ def test_scintillation_amplitude_routes(native_lib, shape):
     hs = np.sqrt(np.outer(np.abs(np.diag(hessians["in_place"])), np.abs(np.diag(hessians["in_place"]))))
     for name in ("stored_profiles", "own_evaluation"):
         assert np.max(np.abs(hessians[name] - hessians["in_place"]) / hs) < 1e-9, name
+    # a component whose profile has underflowed to exactly zero everywhere makes every channel's
+    # system singular: numpy.linalg.LinAlgError like np.linalg.solve (routines/ism.py:46), on every route
+    dead = {k: list(v) for k, v in start.items()}
+    dead["arrival_time"][0] = -1.0e4
+    cuda.update_parameters(dead)
+    oracle.update_parameters(dead)
+    with pytest.raises(np.linalg.LinAlgError):
+        oracle.compute_model(data=data)
+    for name, env in routes.items():
+        os.environ.update(env)
+        try:
+            with pytest.raises(np.linalg.LinAlgError):
+                cuda.compute_model(data=data)
+            plan, n = fc._prepare()
+            cuda._push_parameters()
+            gram = np.zeros((n + 1, n + 1))
+            with pytest.raises(np.linalg.LinAlgError):
+                _lib.check(lib.fb_normal_equations(plan, fc._data_on_device().data_ptr(), _lib.dptr(gram), fc._stream()))
+        finally:
+            for key in env:
+                del os.environ[key]
 
 
 # ---------------------------------------------------------------------------- full size
