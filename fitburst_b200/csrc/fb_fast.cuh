@@ -118,7 +118,8 @@ constexpr int kChiSlots = 128;  // per warp and channel (= its queue length in t
 
 __host__ __device__ inline size_t vals3_smem_bytes(int nc, int kf, bool chi2 = false) {
   size_t n = 0;
-  if (chi2) n += sizeof(double) * (size_t)kFastWarps * kChiSlots * (1 + nc) + sizeof(int) * kFastWarps * (kChiSlots + kVTile);
+  if (chi2)  // + 16: the slot block is re-aligned behind the expansion tables
+    n += sizeof(double) * (size_t)kFastWarps * kChiSlots * (1 + nc) + sizeof(int) * kFastWarps * (kChiSlots + kVTile) + 16;
   n += sizeof(CompTab) * nc;
   n += 2 * (sizeof(ChanTab) * nc + sizeof(SubTab) * nc * kf);  // double-buffered channel tables
   n += sizeof(double) * (size_t)nc * kf * (kVTile + 1);       // R (sample offsets of a tile), D
