@@ -552,7 +552,7 @@ def run_cuda(args):
         # opt-in fb_upload_rows: only the usable channels cross the host link (rows of the good
         # channels + their int32 index list + the flag mask for the weights)
         num_good_0 = int(np.sum(bursts[0][2]))
-        h2d = int(num_good_0 * args.ntime * 8 + 4 * num_good_0 + args.nfreq)
+        h2d = int(num_good_0 * args.ntime * host_data[0].itemsize + 4 * num_good_0 + args.nfreq)
     # device loop: per evaluation one 32-byte flag block; at the end two (n+1)^2 matrices, the result
     # struct, the parameter block, the Hessian sums; per fitter the weights and per-channel sums
     d2h = int(32 * (nfev + 2) + 8 * (2 * (n_free + 1) ** 2 + 3 * 67 + 8 + n_free * n_free + 2 * args.nfreq

@@ -144,7 +144,8 @@ def _upload(buffer, source, staging, good_freq=None):
     read by the fit; their rows of `buffer` keep whatever an earlier burst left there, the buffers
     start zeroed), read by a kernel straight from the pinned array, float32 widened on the way.
     Meant for hosts whose link is the bound (eight GPUs uploading at once); on one GPU the copy
-    engine is faster than the kernel (297 vs 220 fits/s end to end), hence off by default."""
+    engine is faster than the kernel (287 vs 251 fits/s end to end with the uploads on the workers'
+    copy streams; 297 vs 220 in round 1), hence off by default."""
     if good_freq is not None and os.environ.get("FITBURST_B200_ROW_UPLOAD", "0") == "1" and source.is_pinned():
         rows = np.flatnonzero(np.asarray(good_freq, dtype=bool)).astype(np.int32)
         rows_dev = torch.from_numpy(rows).to(buffer.device, non_blocking=True)
