@@ -291,6 +291,20 @@ def test_fit_stream_concurrent_workers_identical(native_lib):
     first = next(stream)
     stream.close()
     np.testing.assert_array_equal(first["results"].x, serial[0]["results"].x)
+    # a slow consumer fills the look-ahead window (the workers' non-blocking take comes back
+    # empty and they upload after publishing instead); host and device inputs mixed in one list,
+    # every worker alternating between its two upload buffers many times
+    import time
+    mixed = [(resident[k % 9] if k % 4 == 3 else pinned[k % 9]) for k in range(22)]
+    got = []
+    for k, out in enumerate(fit_stream(cuda, mixed, fixed, workers=2)):
+        if k < 4:
+            time.sleep(0.05)
+        got.append(out)
+    assert len(got) == len(mixed)
+    for k, out in enumerate(got):
+        np.testing.assert_array_equal(out["results"].x, serial[k % 9]["results"].x)
+        assert out["fit_statistics"] == serial[k % 9]["fit_statistics"]
 
 
 def test_full_size_fast_vs_general(native_lib):
