@@ -285,6 +285,11 @@ extern "C" int fb_set_parameters(fb_plan_t p, const double* params_host, void* s
   return FB_OK;
 }
 
+static bool env_off(const char* name) {
+  const char* v = getenv(name);
+  return v && !strcmp(v, "0");
+}
+
 // Rebuilds the per-channel tables when the parameters changed since the last build. The fit only
 // ever reads the tables of the good channels (good_only); everything else needs all of them.
 template <int KF>
@@ -346,11 +351,6 @@ static EvalArgs base_args(fb_plan_s* p) {
 }
 
 static int ensure_capacity(double** buf, size_t* cap, size_t need);
-
-static bool env_off(const char* name) {
-  const char* v = getenv(name);
-  return v && !strcmp(v, "0");
-}
 
 // Scintillation amplitudes of the channels in A (routines/ism.py:11-48) ahead of an evaluation:
 // (channel, chunk) partial systems on the whole GPU, then one small solve per channel. The tables

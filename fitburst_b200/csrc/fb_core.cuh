@@ -285,8 +285,17 @@ __device__ inline void make_sub_tab(const PlanConst& pc, const double* params, c
   st.sed = exp(sp_idx * lf + sp_run * (lf * lf));
   st.inv_tau = 1.0 / sc_time;
   st.tail_e = 0.5 * st.ratio * st.ratio + delay * st.inv_tau;
+  // sum_b exp(-b step / tau) over the kt sub-times: one exp, the powers by multiplication
+  // (kt <= a few dozen: the accumulated rounding stays below 1e-14 relative)
   double geom = 0.0;
-  for (int b = 0; b < kt; ++b) geom += exp(-(double)b * ct.t_step * st.inv_tau);
+  {
+    const double r = exp(-ct.t_step * st.inv_tau);
+    double rb = 1.0;
+    for (int b = 0; b < kt; ++b) {
+      geom += rb;
+      rb *= r;
+    }
+  }
   st.tail_c = 2.0 * st.amp_term * geom / ((double)kt * (double)kf);
   if (pc.is_folded) {
     // analysis/model.py:327-331 on the delay-corrected labels of this sub-frequency row.

@@ -269,18 +269,34 @@ __global__ void __launch_bounds__(128) k_tables_group(const PlanConst pc, const 
                                                       CompTab* __restrict__ g_comp, SubTab* __restrict__ g_sub,
                                                       ChanTab* __restrict__ g_chan, const int* __restrict__ chan_list,
                                                       int num_chan) {
+  // ncu (round 2): 2.3e7 warp instructions, 23 of 32 lanes active -- every thread repeated the
+  // per-component table (a pow), and the channel-level part ran on one lane of eight. Now the
+  // component tables are made once per block and the channel-level part of the block's 128 / KF
+  // (channel, component) items is finished by its first 128 / KF threads together: 1.6e7
+  // instructions, 29 lanes active. The kernel stays latency-bound (42 us either way: chains of
+  // pow / exp / erfcx calls at 20 warps per SM; finishing in a second, full-warp kernel measured
+  // 34 + 13 us) -- the saving is issue slots for the kernels of the other fits in flight.
+  constexpr int kGroups = 128 / KF;
+  __shared__ CompTab s_ct[FB_MAX_COMPONENTS];
+  __shared__ SubSummary s_sm[kGroups];
+  __shared__ ChanPowers s_cp[kGroups];
   if (fit_stopped(pc)) return;
   const int nc = pc.num_comp;
+  if ((int)threadIdx.x < nc) {
+    CompTab t;
+    make_comp_tab(pc, params, threadIdx.x, t);
+    s_ct[threadIdx.x] = t;
+    if (blockIdx.x == 0) g_comp[threadIdx.x] = t;
+  }
+  __syncthreads();
   const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int a = (int)(gid % KF), lane = threadIdx.x & 31;
+  const int a = (int)(gid % KF), lane = threadIdx.x & 31, group = threadIdx.x / KF;
   long long item = gid / KF;
   const bool active = item < (long long)num_chan * nc;
   if (!active) item = 0;  // keeps the lane in the shuffles below
   const int chi = (int)(item / nc), c = (int)(item % nc);
   const int i = chan_list ? chan_list[chi] : chi;
-  CompTab ct;
-  make_comp_tab(pc, params, c, ct);
-  if (active && chi == 0 && a == 0) g_comp[c] = ct;
+  const CompTab& ct = s_ct[c];
   const int base = lane & ~(KF - 1);
   // the four channel-level powers, one per lane of the group (same pow calls as make_chan_powers)
   ChanPowers cp;
@@ -319,7 +335,19 @@ __global__ void __launch_bounds__(128) k_tables_group(const PlanConst pc, const 
     if (sck > 0.0) sm.scattered = 1;
     sm.add(delay, ratio, sed, ct.w, pk);
   }
-  if (active && a == 0) finish_chan_tab(pc, params, ct, i, c, sm, cp, g_chan[(size_t)i * nc + c]);
+  if (a == 0) {
+    s_sm[group] = sm;
+    s_cp[group] = cp;
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < kGroups) {
+    const long long item2 = (long long)blockIdx.x * kGroups + threadIdx.x;
+    if (item2 < (long long)num_chan * nc) {
+      const int chi2 = (int)(item2 / nc), c2 = (int)(item2 % nc);
+      const int i2 = chan_list ? chan_list[chi2] : chi2;
+      finish_chan_tab(pc, params, s_ct[c2], i2, c2, s_sm[threadIdx.x], s_cp[threadIdx.x], g_chan[(size_t)i2 * nc + c2]);
+    }
+  }
 }
 
 // Stages one channel's tables from global memory (L2-resident, written by k_tables).
