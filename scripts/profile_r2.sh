@@ -13,6 +13,7 @@ ncu -i /tmp/r2_hot.ncu-rep --page raw --csv > $O/r2_end_hot_raw.csv
 ncu --set full --clock-control none -k regex:'k_tables_group|k_trf_chol|k_hess3|k_gram3_finish' -s 12 -c 8 -f -o /tmp/r2_small $CMD > $O/r2_prof_ncu3.log 2>&1
 echo "small EXIT $?"
 ncu -i /tmp/r2_small.ncu-rep --page raw --csv > $O/r2_end_small_raw.csv
+[ -n "$SKIP_GEN4" ] && { ls -la $O/r2_*csv; exit 0; }
 FITBURST_B200_EVAL=4 $CMD > $O/r2_prof_plain4.log 2>&1 || { echo "plain gen4 run failed"; exit 1; }
 FITBURST_B200_EVAL=4 ncu --set full --clock-control none --import-source on -k regex:'k_rise3|k_gram4' -s 6 -c 4 -f -o /tmp/r2_gen4 $CMD > $O/r2_prof_ncu4.log 2>&1
 echo "gen4 EXIT $?"
