@@ -929,8 +929,8 @@ static int launch_split_gram(fb_plan_s* p, EvalArgs& A, int ncols, cudaStream_t 
   const int tiles = (p->pc.num_time + kBlock - 1) / kBlock;
   const long long items = (long long)A.num_chan * tiles;
   const bool scint = p->pc.scintillation != 0;
-  A.vals_spc = scint ? 3 : 2;  // the fit needs spectrum + time difference only; scintillation also the mean profile
-  const size_t need_vals = (size_t)items * kBlock * A.vals_spc * nc;
+  A.vals_spc = 2;  // spectrum (scintillation: mean profile, see EvalArgs.vals_spc) + time difference
+  const size_t need_vals = (size_t)items * kBlock * 2 * nc;
   if (need_vals > p->vals_cap) {
     cudaFree(p->d_vals);
     p->d_vals = nullptr;
@@ -1018,10 +1018,10 @@ static int normal_equations_async(fb_plan_s* p, const double* data_dev, double* 
   int rc = FB_OK;
   const char* split_env = getenv("FITBURST_B200_SPLIT");
   // scintillation: split as well unless the amplitudes are to be solved in place
-  // (FITBURST_B200_SCINT_PRESOLVE=0) or the stored values would not fit (3 doubles per (sample, component))
+  // (FITBURST_B200_SCINT_PRESOLVE=0) or the stored values would not fit (2 doubles per (sample, component))
   const bool scint_split = !p->pc.scintillation ||
                            (!env_off("FITBURST_B200_SCINT_PRESOLVE") &&
-                            (size_t)p->num_good * p->pc.num_time * p->pc.num_comp * 24 <= ((size_t)64 << 30));
+                            (size_t)p->num_good * p->pc.num_time * p->pc.num_comp * 16 <= ((size_t)64 << 30));
   const bool split = scint_split && !(split_env && !strcmp(split_env, "0"));
   int mma_warps = 0;
   p->last_eval_split = split && !p->pc.scintillation;  // (scintillation stores 3 planes: never reused)

@@ -44,6 +44,8 @@ struct EvalArgs {
   double* chi2_partials;
   // values stored per (sample, component): 3 = spectrum, timediff, timeprof; 2 = without timeprof
   // (only the caches and the scintillation solve need the mean profile). 0 means 3.
+  // Scintillation mode with 2: slot 0 holds the mean PROFILE instead (the spectrum there is
+  // amplitude * profile with the amplitude of the per-channel solve: analysis/model.py:274-277).
   int vals_spc;
   // k_gram3: the spectrum-row / data tiles are fetched with cp.async.bulk (one elected lane, completion
   // on an mbarrier per ring slot) instead of one 8-byte cp.async per lane; needs an even num_time
@@ -401,19 +403,20 @@ __device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, 
   double* vals = vals_out ? vals_out : L.vals;
   const int ts = soa ? 1 : vs, ss = soa ? kBlock : 1;
   const int spc = A.vals_spc == 2 ? 2 : 3;
+  const bool prof_first = spc == 2 && pc.scintillation != 0;  // slot 0 = mean profile
   double* v = vals + (size_t)tid * ts;
   if (j < pc.num_time) {
     for (int c = 0; c < nc; ++c) {
       SampleComp sc;
       if (eval_sample_fast(pc, L.comp[c], L.chan[c], L.sub + c * kf, j, sc)) {
-        v[(spc * c) * ss] = sc.spectrum;
+        v[(spc * c) * ss] = prof_first ? sc.timeprof : sc.spectrum;
         v[(spc * c + 1) * ss] = sc.timediff;
         if (spc == 3) v[(spc * c + 2) * ss] = sc.timeprof;
       } else if (use_queue) {
         L.queue[atomicAdd(L.qcount, 1)] = (tid << 5) | c;
       } else {
         sc = eval_sample_general(pc, L.comp[c], L.chan[c], L.sub + c * kf, j);
-        v[(spc * c) * ss] = sc.spectrum;
+        v[(spc * c) * ss] = prof_first ? sc.timeprof : sc.spectrum;
         v[(spc * c + 1) * ss] = sc.timediff;
         if (spc == 3) v[(spc * c + 2) * ss] = sc.timeprof;
       }
@@ -451,7 +454,7 @@ __device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, 
         for (int pe = gl; pe < npe; pe += gs) {
           double t, p;
           eval_subsample(pc, ct, scattered, sub[a], jj * kt + b, t, p);
-          if (spc == 3) s_p += p;
+          if (spc == 3 || prof_first) s_p += p;
           s_ps = fma(p, sub[a].sed, s_ps);
           b += db;
           a += da;
@@ -462,14 +465,14 @@ __device__ inline void eval_tile(const EvalArgs& A, const SmemLayout& L, int i, 
         }
       }
       for (int off = gs >> 1; off > 0; off >>= 1) {
-        if (spc == 3) s_p += __shfl_xor_sync(0xffffffffu, s_p, off);
+        if (spc == 3 || prof_first) s_p += __shfl_xor_sync(0xffffffffu, s_p, off);
         s_ps += __shfl_xor_sync(0xffffffffu, s_ps, off);
       }
       if (active && gl == 0) {
         const CompTab& ct = L.comp[c];
         const int jj = tile * kBlock + t_idx;
         double* o = vals + (size_t)t_idx * ts + (size_t)(spc * c) * ss;
-        o[0] = ct.amp10 * (s_ps * inv_n);
+        o[0] = prof_first ? s_p * inv_n : ct.amp10 * (s_ps * inv_n);
         o[ss] = fma(ct.t_step, (double)(jj * kt) + 0.5 * (double)(kt - 1), ct.t_start) - L.chan[c].mean_delay;
         if (spc == 3) o[2 * ss] = s_p * inv_n;
       }
@@ -513,7 +516,7 @@ __device__ __forceinline__ void process_sample(const EvalArgs& A, const SmemLayo
     const int spc = A.vals_spc == 2 ? 2 : 3;
     sc.spectrum = vrow[(spc * c) * vss];
     sc.timediff = vrow[(spc * c + 1) * vss];
-    sc.timeprof = spc == 3 ? vrow[(spc * c + 2) * vss] : 0.0;
+    sc.timeprof = spc == 3 ? vrow[(spc * c + 2) * vss] : (pc.scintillation ? sc.spectrum : 0.0);
     double amp = ch.amp;
     if (pc.scintillation) {  // analysis/model.py:274-277
       amp = L.scint_amp[c];
@@ -764,8 +767,9 @@ __global__ void __launch_bounds__(kBlock, 4) k_scint_partials(const EvalArgs A, 
   }
 }
 
-// The same partial systems from the values k_vals stored (split evaluation, vals_spc = 3: the mean
-// profile is slot 3 c + 2 of item chi * tiles + tile): no second evaluation of the profiles.
+// The same partial systems from the values k_vals stored (split evaluation, vals_spc = 2 in
+// scintillation mode: the mean profile is slot 2 c of item chi * tiles + tile): no second
+// evaluation of the profiles.
 __global__ void __launch_bounds__(kBlock, 4) k_scint_partials_vals(const EvalArgs A, int nchunks,
                                                                    const double* __restrict__ gvals,
                                                                    double* __restrict__ partials) {
@@ -783,7 +787,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_scint_partials_vals(const EvalArg
   int s_ti, s_tj;
   tile_coords(s_tile, side2, s_ti, s_tj);
   double* row2 = X + (size_t)tid * stride2;
-  const int vs = 3 * nc;
+  const int vs = 2 * nc;
   const long long total = (long long)A.num_chan * nchunks;
   for (long long item = blockIdx.x; item < total; item += gridDim.x) {
     const int chi = (int)(item / nchunks), k = (int)(item % nchunks);
@@ -797,7 +801,7 @@ __global__ void __launch_bounds__(kBlock, 4) k_scint_partials_vals(const EvalArg
       const double* v = gvals + ((size_t)chi * tiles + tile) * kBlock * vs + tid;
       for (int q = 0; q < stride2; ++q) row2[q] = 0.0;
       if (j < pc.num_time) {
-        for (int c = 0; c < nc; ++c) row2[c] = v[(size_t)(3 * c + 2) * kBlock];
+        for (int c = 0; c < nc; ++c) row2[c] = v[(size_t)(2 * c) * kBlock];
         row2[nc] = A.data[(size_t)i * pc.num_time + j];
       }
       __syncthreads();
