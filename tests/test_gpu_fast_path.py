@@ -365,6 +365,41 @@ def test_model_rise_region_regimes(name, native_lib):
     assert rel_to_max(got, want) < 2e-12
 
 
+@pytest.mark.parametrize("seed", range(16))
+def test_model_random_regimes(seed, native_lib):
+    """Random scattering times, widths and DM offsets across the moment / series / exact domains of
+    the rise-region evaluation (make_tay_tab, series_eval): model within 1e-10 of the oracle and
+    the fused chi^2 kernel equal to the stored-values sweep."""
+    from fitburst_b200.analysis.fitter import LSFitter
+    from fitburst_b200.batch import chisq_grid
+    from tests.helpers import assert_close
+    rng = np.random.default_rng(1000 + seed)
+    tau = float(10 ** rng.uniform(np.log10(2e-5), np.log10(3e-2)))
+    dm = float(rng.uniform(-0.6, 0.6))
+    widths = [float(10 ** rng.uniform(np.log10(2e-4), np.log10(5e-3))) for _ in range(3)]
+    freqs, times, truth, kwargs = _case(num_freq=24, num_time=512, dm=dm, widths=widths)
+    truth["scattering_timescale"] = [tau] * 3
+    cuda, oracle = model_pair(freqs, times, kwargs, truth)
+    got, want = cuda.compute_model(), oracle.compute_model()
+    what = f"tau={tau:.3g} dm={dm:.3g} widths={widths}"
+    assert_close(got, want, 1e-10, what)
+    assert rel_to_max(got, want) < 2e-12, what
+    good = syn.make_good_freq(len(freqs), 0.2, seed)
+    data = syn.add_noise(want, good, 0.1, seed)
+    with contextlib.redirect_stdout(io.StringIO()):
+        fitter = LSFitter(data, cuda, good)
+    dm_values, sc_values = np.array([dm, 0.5 * dm]), np.array([tau, 2.0 * tau])
+    fused = chisq_grid(fitter, dm_values, sc_values)
+    os.environ["FITBURST_B200_GRID_FUSED"] = "0"
+    try:
+        stored = chisq_grid(fitter, dm_values, sc_values)
+    finally:
+        del os.environ["FITBURST_B200_GRID_FUSED"]
+    np.testing.assert_allclose(fused, stored, rtol=1e-13, err_msg=what)
+    resid = (data - want) * fitter.weights[:, None]
+    np.testing.assert_allclose(fused[0, 0], np.sum(resid[good] ** 2), rtol=1e-9, err_msg=what)
+
+
 def test_normal_equations_queue_overflow(native_lib):
     """Trial points far from the burst (a component wider than the window, arrival outside it --
     seen on weak components of config-3 bursts): fast and general kernels agree, nothing faults."""
